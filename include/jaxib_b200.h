@@ -1,0 +1,182 @@
+/*
+ * jaxib_b200.h -- C ABI of the B200-native jax_ib per-timestep hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one pluggable callable (or a fused
+ * group of them) of hashimmg/jax_IB's step function.  Citations are to files under the reference
+ * tree (jax_ib/base/...).  The reference is pure Python/JAX and has no FFI of its own; the
+ * binding a maintainer would add is an XLA-FFI custom call per entry point (see INTEGRATION.md,
+ * jax_ib_b200/csrc/xla_ffi_shim.cc) or the ctypes stub in jax_ib_b200/_lib.py.
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers to float32, C-order [batch][nx][ny] (axis 1 = y is
+ *     contiguous), exactly the reference's GridArray.data layout (grids.py:718 indexing='ij').
+ *     Staggering (grids.py:632-637): u at offset (1, .5), v at (.5, 1), p at (.5, .5).
+ *   - Every call only ENQUEUES work on `stream` (a cudaStream_t); none synchronises.
+ *   - Return value: 0 on success, negative jaxib_status otherwise; jaxib_last_error() gives text.
+ *   - No mutable globals: all state lives in the caller's buffers or in a jaxib_plan.
+ *   - Inputs are const; in-place use is allowed only where stated.
+ */
+#ifndef JAXIB_B200_H_
+#define JAXIB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* jaxib_stream_t; /* cudaStream_t */
+
+typedef enum {
+  JAXIB_OK = 0,
+  JAXIB_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) */
+  JAXIB_ERR_UNSUPPORTED = -2, /* size / option outside what the kernels implement */
+  JAXIB_ERR_SCRATCH = -3,     /* scratch buffer too small */
+  JAXIB_ERR_CUDA = -4         /* CUDA runtime error (launch, allocation) */
+} jaxib_status;
+
+/* Boundary-condition families (boundaries.py:852-879 periodic; :636-663 moving wall / channel). */
+typedef enum {
+  JAXIB_BC_PERIODIC = 0, /* periodic x and y; pressure periodic                                  */
+  JAXIB_BC_CHANNEL = 1   /* periodic x; Dirichlet velocity / homogeneous-Neumann pressure in y   */
+} jaxib_bc;
+
+/* Advection schemes (advection.py:120-124, :206-280, :325-333). */
+typedef enum {
+  JAXIB_CONVECT_UPWIND = 0,
+  JAXIB_CONVECT_VAN_LEER = 1,
+  JAXIB_CONVECT_VAN_LEER_LIMITERS = 2,
+  JAXIB_CONVECT_NONE = 3
+} jaxib_convect;
+
+/* Grid + physics of one step.  Scalars are doubles because the reference holds them as Python
+ * floats and rounds them to float32 only where they meet an array (e.g. float32(dt/dx), not
+ * float32(dt)/float32(dx)); the library does the same rounding internally. */
+typedef struct {
+  int32_t nx, ny;      /* cells per axis (grids.py:563-624)                                      */
+  int32_t batch;       /* independent simulations stacked on the leading axis (>= 1)            */
+  double lower_x, lower_y; /* domain lower corner                                              */
+  double dx, dy;       /* grid step = (upper - lower) / n                                       */
+  double dt;           /* time step                                                             */
+  double nu;           /* viscosity / density (equations.py:73); < 0 disables diffusion        */
+  double density;      /* forcing is divided by it (equations.py:75)                            */
+  int32_t bc;          /* jaxib_bc                                                              */
+  int32_t convect;     /* jaxib_convect                                                         */
+  double u_wall[2];    /* channel: u at the lower / upper y wall (bc_values[1] of velocity[0])  */
+  double v_wall[2];    /* channel: v at the lower / upper y wall                                */
+  double force[2];     /* constant body force (forcing(v) of the Taylor demo), per component    */
+  int32_t ib_window;   /* Gaussian truncation radius R in cells (window 2R x 2R); default 6     */
+  int32_t reserved;
+} jaxib_grid;
+
+/* Rigid bodies of ONE simulation (identical marker topology across the batch).
+ * x0/y0: body-frame marker coordinates returned by the reference's shape_fn (IBM_Force.py:29);
+ * body_offset[b]..body_offset[b+1] is body b's (closed-curve) marker range. */
+typedef struct {
+  int32_t n_bodies;
+  int32_t n_markers;
+  const int32_t* body_offset; /* device [n_bodies + 1]                                         */
+  const float* x0;            /* device [n_markers]                                             */
+  const float* y0;            /* device [n_markers]                                             */
+  double max_radius;          /* max over markers of hypot(x0, y0): bounds every body's extent  */
+} jaxib_bodies;
+
+/* Per-step, per-body kinematic state, evaluated by the HOST from the user's Displacement_EQ /
+ * Rotation_EQ callables (kinematics.py; jacrev at IBM_Force.py:101-104): 8 floats per body
+ *   [cos(theta), sin(theta), xc, yc, U0x, U0y, Omega, 0]
+ * laid out [step][batch][n_bodies][8]. */
+#define JAXIB_BODY_STATE_STRIDE 8
+
+typedef struct jaxib_plan jaxib_plan; /* opaque: FFT twiddles, Laplacian eigenvalues, radix plan */
+
+const char* jaxib_version(void);
+const char* jaxib_last_error(void);
+/* Compute capability the kernels were compiled for (100 => sm_100a). */
+int jaxib_compiled_arch(void);
+
+/* ---- plan ------------------------------------------------------------------------------- */
+/* Replaces the host-side set-up of pressure.py:94-130 (array_utils.laplacian_matrix :168-182 +
+ * jax_cfd fast_diagonalization.pseudoinverse): eigenvalues in float64, inverse cutoff 10*eps32. */
+int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out);
+int jaxib_plan_destroy(jaxib_plan* plan);
+/* Bytes of device scratch jaxib_step / jaxib_project / jaxib_ib_force need for this plan
+ * (n_markers = total markers per simulation, 0 if no bodies). */
+size_t jaxib_scratch_bytes(const jaxib_plan* plan, int32_t n_markers);
+
+/* ---- stage: explicit terms + predictor ---------------------------------------------------- */
+/* equations.py:42-83 navier_stokes_explicit_terms: (du, dv) = convect(v) + nu*laplacian(v) +
+ * force/density [- perm*v/density when perm != NULL: penalty/util_funs.py:6-16].             */
+int jaxib_explicit_terms(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
+                         const float* perm, float* du, float* dv);
+/* time_stepping.py:191-208: u* = u + dt*F(u) - forward_difference(p) (p == NULL: no gradient,
+ * the penalty stepper time_stepping.py:345).  Outputs must not alias inputs.                  */
+int jaxib_explicit_predict(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
+                           const float* p, const float* perm, float* u_star, float* v_star);
+
+/* ---- stage: immersed boundary -------------------------------------------------------------- */
+/* convolution_functions.py:11-37 new_surf_fn (the `surface_fn` plug-in): Gaussian E->L
+ * interpolation of `field` (offset = (off_x, off_y)) at n points; also returns the owning cell
+ * floor(xp/dx - off_x), floor(yp/dy - off_y) (IBM_Force.py:35) when ci/cj != NULL.  batch = 1.  */
+int jaxib_ib_interp(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y,
+                    const float* field, const float* xp, const float* yp, int32_t n, float* out,
+                    int32_t* ci, int32_t* cj);
+/* IBM_Force.py:66-87: out[i,j] += scale * sum_k F_k * delta(r_k; dx) * dS_k.  Cells outside every
+ * marker window are left untouched (zero `out` first to obtain the bare force field).  Needs 16
+ * bytes of device scratch (bounding box of the point cloud).  batch = 1.                       */
+int jaxib_ib_spread(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y,
+                    const float* F, const float* xp, const float* yp, const float* dS, int32_t n,
+                    double scale, float* out, void* scratch, size_t scratch_bytes);
+/* IBM_Force.py:109-115 calc_IBM_force_NEW_MULTIPLE fused with time_stepping.py:223:
+ * u** = u* + dt * f_IB, in place on (u_star, v_star).  body_state: [batch][n_bodies][8].
+ * Marker arrays (xp, yp, dS, Fx, Fy: 5 * batch * n_markers floats) are left in `scratch`.     */
+int jaxib_ib_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
+                   const float* body_state, float* u_star, float* v_star, void* scratch, size_t scratch_bytes);
+
+/* ---- stage: pressure projection ------------------------------------------------------------ */
+/* pressure.py:94-130 solve_fast_diag / solve_fast_diag_moving_wall (the `pressure_solve`
+ * plug-in): q = pinv(Laplacian)(divergence(u, v)).                                            */
+int jaxib_pressure_solve(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v,
+                         float* q, void* scratch, size_t scratch_bytes);
+/* pressure.py:58-91 projection_and_update_pressure: q = solve; p_out = q + p; (u,v)_out =
+ * (u,v) - forward_difference(q) [+ impose_bc for channel].  Outputs may alias the inputs.     */
+int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v, const float* p,
+                  float* u_out, float* v_out, float* p_out, void* scratch, size_t scratch_bytes);
+
+/* ---- fused step ------------------------------------------------------------------------------ */
+/* time_stepping.py:144-255 step_fn, `nsteps` times, in place on (u, v, p):
+ *   predict -> [IB interp / force / spread] -> project.
+ * bodies == NULL skips the IB stage.  body_table: [nsteps][batch][n_bodies][8] (device).
+ * perm (may be NULL): [batch][nx][ny] Brinkman permeability.  incremental_pressure == 0 selects
+ * the penalty stepper (no -grad p_old in the predictor, time_stepping.py:345).
+ * The clock / wall values / body centres are host-side state (boundaries.py:519-542,
+ * particle_motion.py:38-66) and are not touched here.                                         */
+int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
+               const float* perm, int32_t incremental_pressure, int32_t nsteps, float* u, float* v, float* p,
+               void* scratch, size_t scratch_bytes);
+
+/* ---- tracers (MD/CFD_MD_coupling.py:7-27 + MD/simulate.py:81-97, kT = 0 or caller noise) ----- */
+/* R[n][2] += (F_pair + [u,v](R)) * dt/(mass*gamma) + sqrt(2 kT dt/(mass gamma)) * xi, masked
+ * by is_mobile (NULL = all mobile).  pair_force / xi may be NULL.                              */
+int jaxib_tracer_step(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
+                      const float* pair_force, const float* xi, const uint8_t* is_mobile, double dt_md,
+                      double mass_gamma, double kT, int32_t n, float* R);
+/* Bilinear E->L sample of one field at n points (CFD_MD_coupling.py:7-19 interpolate_pbc).     */
+int jaxib_bilinear_sample(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y,
+                          const float* field, const float* R, int32_t n, float* out);
+/* Species-masked all-pairs harmonic/Morse force (MD/interaction_potential.py:6-22 through
+ * jax_md smap.pair + quantity.force): h, r0 are [n_species][n_species] device matrices.        */
+int jaxib_pair_force(jaxib_stream_t stream, const float* R, const int32_t* species, int32_t n, int32_t n_species,
+                     const float* h, const float* r0, double D0, double alpha, double k, double box_x, double box_y,
+                     float* F);
+
+/* ---- penalty mask (penalty/util_funs.py:26-123) ----------------------------------------------- */
+/* perm[i,j] = sum_b K/2 * (1 + tanh((R_b(theta)^2 - r^2)/width)); Rtheta: [n_bodies][ntheta],
+ * centers: [n_bodies][2] (device).                                                              */
+int jaxib_penalty_perm(jaxib_stream_t stream, const jaxib_grid* grid, const float* centers, const float* Rtheta,
+                       int32_t n_bodies, int32_t ntheta, double K, double width, float* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXIB_B200_H_ */

@@ -1,0 +1,222 @@
+// extern "C" entry points declared in include/jaxib_b200.h: argument checking, scratch carving
+// and the fused step driver.  Nothing here synchronises; every call only enqueues on `stream`.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace jaxib {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return JAXIB_ERR_CUDA;
+  }
+  return JAXIB_OK;
+}
+
+int check_grid(const jaxib_grid* g) {
+  if (!g) { set_error("grid is null"); return JAXIB_ERR_INVALID; }
+  if (g->nx <= 0 || g->ny <= 0 || g->batch < 1) {
+    set_error("grid: nx=%d ny=%d batch=%d must be positive", g->nx, g->ny, g->batch);
+    return JAXIB_ERR_INVALID;
+  }
+  if (!(g->dx > 0.0) || !(g->dy > 0.0)) { set_error("grid: dx, dy must be positive"); return JAXIB_ERR_INVALID; }
+  if (g->bc != JAXIB_BC_PERIODIC && g->bc != JAXIB_BC_CHANNEL) {
+    set_error("grid: unknown bc %d", g->bc);
+    return JAXIB_ERR_INVALID;
+  }
+  if (g->convect < 0 || g->convect > JAXIB_CONVECT_NONE) {
+    set_error("grid: unknown convect scheme %d", g->convect);
+    return JAXIB_ERR_INVALID;
+  }
+  return JAXIB_OK;
+}
+
+static int check_ptrs(const char* who, std::initializer_list<const void*> ptrs) {
+  for (const void* p : ptrs)
+    if (!p) { set_error("%s: null device pointer", who); return JAXIB_ERR_INVALID; }
+  return JAXIB_OK;
+}
+
+struct Scratch {
+  float* u_star;
+  float* v_star;
+  float* spectrum;
+  float* markers;
+};
+
+static size_t scratch_need(const GridF& g, int n_markers) {
+  size_t plane = (size_t)g.batch * g.nx * g.ny;
+  return (3 * plane + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256;
+}
+
+static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scratch* out) {
+  size_t need = scratch_need(g, n_markers);
+  if (!scratch || bytes < need) {
+    set_error("scratch too small: have %zu bytes, need %zu", bytes, need);
+    return JAXIB_ERR_SCRATCH;
+  }
+  uintptr_t a = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255);
+  float* base = reinterpret_cast<float*>(a);
+  size_t plane = (size_t)g.batch * g.nx * g.ny;
+  out->u_star = base;
+  out->v_star = base + plane;
+  out->spectrum = base + 2 * plane;
+  out->markers = base + 3 * plane;
+  return JAXIB_OK;
+}
+
+}  // namespace jaxib
+
+using namespace jaxib;
+
+extern "C" {
+
+const char* jaxib_version(void) { return "jax_ib_b200 0.1 (sm_100a)"; }
+const char* jaxib_last_error(void) { return g_err; }
+int jaxib_compiled_arch(void) {
+#ifdef JAXIB_ARCH
+  return JAXIB_ARCH;
+#else
+  return 100;
+#endif
+}
+
+size_t jaxib_scratch_bytes(const jaxib_plan* plan, int32_t n_markers) {
+  if (!plan) return 0;
+  return scratch_need(plan_grid(plan), n_markers);
+}
+
+int jaxib_explicit_terms(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
+                         const float* perm, float* du, float* dv) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if ((rc = check_ptrs("explicit_terms", {u, v, du, dv}))) return rc;
+  return launch_explicit((cudaStream_t)stream, make_gridf(*grid), u, v, nullptr, perm, du, dv, false);
+}
+
+int jaxib_explicit_predict(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
+                           const float* p, const float* perm, float* u_star, float* v_star) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if ((rc = check_ptrs("explicit_predict", {u, v, u_star, v_star}))) return rc;
+  if (u_star == u || v_star == v || u_star == v || v_star == u) {
+    set_error("explicit_predict: outputs must not alias inputs");
+    return JAXIB_ERR_INVALID;
+  }
+  return launch_explicit((cudaStream_t)stream, make_gridf(*grid), u, v, p, perm, u_star, v_star, true);
+}
+
+int jaxib_ib_interp(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y, const float* field,
+                    const float* xp, const float* yp, int32_t n, float* out, int32_t* ci, int32_t* cj) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if (n < 0) { set_error("ib_interp: n < 0"); return JAXIB_ERR_INVALID; }
+  if (n == 0) return JAXIB_OK;
+  if ((rc = check_ptrs("ib_interp", {field, xp, yp, out}))) return rc;
+  if ((ci == nullptr) != (cj == nullptr)) { set_error("ib_interp: ci and cj must both be given"); return JAXIB_ERR_INVALID; }
+  return launch_ib_interp((cudaStream_t)stream, make_gridf(*grid), (float)off_x, (float)off_y, field, xp, yp, n, out,
+                          ci, cj);
+}
+
+int jaxib_ib_spread(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y, const float* F,
+                    const float* xp, const float* yp, const float* dS, int32_t n, double scale, float* out,
+                    void* scratch, size_t scratch_bytes) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if (n < 0) { set_error("ib_spread: n < 0"); return JAXIB_ERR_INVALID; }
+  if (n == 0) return JAXIB_OK;
+  if ((rc = check_ptrs("ib_spread", {F, xp, yp, dS, out}))) return rc;
+  if (!scratch || scratch_bytes < 16) { set_error("ib_spread: needs 16 bytes of scratch"); return JAXIB_ERR_SCRATCH; }
+  return launch_ib_spread((cudaStream_t)stream, make_gridf(*grid), (float)off_x, (float)off_y, F, xp, yp, dS, n,
+                          (float)scale, out, reinterpret_cast<int*>(scratch));
+}
+
+static int check_bodies(const jaxib_bodies* b) {
+  if (!b) { set_error("bodies is null"); return JAXIB_ERR_INVALID; }
+  if (b->n_bodies < 0 || b->n_markers < 0) { set_error("bodies: negative counts"); return JAXIB_ERR_INVALID; }
+  if (b->n_markers > 0 && (!b->body_offset || !b->x0 || !b->y0)) {
+    set_error("bodies: null marker arrays");
+    return JAXIB_ERR_INVALID;
+  }
+  if (b->n_markers > 0 && !(b->max_radius > 0.0)) { set_error("bodies: max_radius must be positive"); return JAXIB_ERR_INVALID; }
+  return JAXIB_OK;
+}
+
+int jaxib_ib_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies, const float* body_state,
+                   float* u_star, float* v_star, void* scratch, size_t scratch_bytes) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if ((rc = check_bodies(bodies))) return rc;
+  if ((rc = check_ptrs("ib_force", {body_state, u_star, v_star}))) return rc;
+  GridF g = make_gridf(*grid);
+  size_t need = (size_t)5 * g.batch * bodies->n_markers * sizeof(float) + 256;
+  if (!scratch || scratch_bytes < need) {
+    set_error("ib_force: scratch too small: have %zu, need %zu", scratch_bytes, need);
+    return JAXIB_ERR_SCRATCH;
+  }
+  uintptr_t a = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255);
+  return launch_ib_force((cudaStream_t)stream, g, *bodies, body_state, u_star, v_star, reinterpret_cast<float*>(a));
+}
+
+int jaxib_pressure_solve(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v, float* q,
+                         void* scratch, size_t scratch_bytes) {
+  if (!plan) { set_error("pressure_solve: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("pressure_solve", {u, v, q});
+  if (rc) return rc;
+  Scratch sc;
+  if ((rc = carve(plan_grid(plan), 0, scratch, scratch_bytes, &sc))) return rc;
+  return launch_project((cudaStream_t)stream, plan, u, v, nullptr, nullptr, nullptr, nullptr, q, sc.spectrum);
+}
+
+int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v, const float* p,
+                  float* u_out, float* v_out, float* p_out, void* scratch, size_t scratch_bytes) {
+  if (!plan) { set_error("project: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("project", {u, v, p, u_out, v_out, p_out});
+  if (rc) return rc;
+  Scratch sc;
+  if ((rc = carve(plan_grid(plan), 0, scratch, scratch_bytes, &sc))) return rc;
+  return launch_project((cudaStream_t)stream, plan, u, v, p, u_out, v_out, p_out, nullptr, sc.spectrum);
+}
+
+int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
+               const float* perm, int32_t incremental_pressure, int32_t nsteps, float* u, float* v, float* p,
+               void* scratch, size_t scratch_bytes) {
+  if (!plan) { set_error("step: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("step", {u, v, p});
+  if (rc) return rc;
+  if (nsteps < 0) { set_error("step: nsteps < 0"); return JAXIB_ERR_INVALID; }
+  const bool has_ib = bodies && bodies->n_markers > 0;
+  if (has_ib) {
+    if ((rc = check_bodies(bodies))) return rc;
+    if (!body_table) { set_error("step: bodies given without body_table"); return JAXIB_ERR_INVALID; }
+  }
+  const GridF& g = plan_grid(plan);
+  Scratch sc;
+  if ((rc = carve(g, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
+  for (int n = 0; n < nsteps; ++n) {
+    // time_stepping.py:191-208
+    if ((rc = launch_explicit(s, g, u, v, incremental_pressure ? p : nullptr, perm, sc.u_star, sc.v_star, true))) return rc;
+    // time_stepping.py:210-223
+    if (has_ib && (rc = launch_ib_force(s, g, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
+      return rc;
+    // time_stepping.py:246
+    if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum))) return rc;
+  }
+  return JAXIB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Internal declarations shared by the jax_ib_b200 CUDA translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/jaxib_b200.h"
+
+namespace jaxib {
+
+// float32 view of jaxib_grid with the roundings the reference performs (JAX weak typing:
+// Python-float scalars are rounded to float32 where they meet an array).
+struct GridF {
+  int nx, ny, batch;
+  float lower_x, lower_y;
+  float dx, dy;          // float32(step)
+  float inv_dx, inv_dy;  // 1 / float32(step)
+  float dt;
+  float nu;              // float32(viscosity / density); diffusion disabled when has_nu == 0
+  int has_nu;
+  float dt_over_dx, dt_over_dy;  // float32(dt / step) computed in double (advection.py:273)
+  float sx, sy, ssum;    // finite_differences.py:131: square(1 / float32(step)), and their sum
+  float fx, fy;          // float32(force) / float32(density)
+  float inv_rho;
+  int bc, convect;
+  float uw_lo, uw_hi, vw_lo, vw_hi;
+  int R;                 // IB window radius
+};
+
+inline GridF make_gridf(const jaxib_grid& g) {
+  GridF f;
+  f.nx = g.nx; f.ny = g.ny; f.batch = g.batch < 1 ? 1 : g.batch;
+  f.lower_x = (float)g.lower_x; f.lower_y = (float)g.lower_y;
+  f.dx = (float)g.dx; f.dy = (float)g.dy;
+  f.inv_dx = 1.0f / f.dx; f.inv_dy = 1.0f / f.dy;
+  f.dt = (float)g.dt;
+  f.has_nu = g.nu >= 0.0;
+  f.nu = f.has_nu ? (float)g.nu : 0.0f;
+  f.dt_over_dx = (float)(g.dt / g.dx); f.dt_over_dy = (float)(g.dt / g.dy);
+  f.sx = f.inv_dx * f.inv_dx; f.sy = f.inv_dy * f.inv_dy; f.ssum = f.sx + f.sy;
+  float rho = g.density > 0.0 ? (float)g.density : 1.0f;
+  f.inv_rho = 1.0f / rho;
+  f.fx = (float)g.force[0] / rho; f.fy = (float)g.force[1] / rho;
+  f.bc = g.bc; f.convect = g.convect;
+  f.uw_lo = (float)g.u_wall[0]; f.uw_hi = (float)g.u_wall[1];
+  f.vw_lo = (float)g.v_wall[0]; f.vw_hi = (float)g.v_wall[1];
+  f.R = g.ib_window > 0 ? g.ib_window : 6;
+  return f;
+}
+
+void set_error(const char* fmt, ...);
+int check_grid(const jaxib_grid* g);
+int check_launch(const char* what);
+
+// ---- FFT plan (poisson.cu) ----------------------------------------------------------------
+constexpr int kMaxStages = 16;
+struct FftPlan {
+  int n;                   // complex length
+  int nstages;
+  int radix[kMaxStages];   // DIF order: first pass acts on the whole length
+};
+
+// stage launchers (each only enqueues on `stream`)
+int launch_explicit(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
+                    const float* perm, float* out_u, float* out_v, bool predictor);
+int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
+                    float* u_star, float* v_star, float* marker_scratch);
+int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
+                     const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
+int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,
+                     const float* xp, const float* yp, const float* dS, int n, float scale, float* out,
+                     int* box_scratch);
+int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
+                   float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum);
+size_t spectrum_floats(const jaxib_plan* plan);
+const GridF& plan_grid(const jaxib_plan* plan);
+
+}  // namespace jaxib

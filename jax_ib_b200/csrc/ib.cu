@@ -1,0 +1,341 @@
+// K2/K3: immersed-boundary interpolation (E->L), direct forcing and spreading (L->E).
+//
+// Reference arithmetic (all float32):
+//   delta(x, x0, w) = 1/(w sqrt(2 pi)) exp(-0.5 ((x - x0)/w)^2)              convolution_functions.py:5-7
+//   U_k  = sum_ij field_ij * delta(xp_k, X_ij, dx) * delta(yp_k, Y_ij, dy) * dx * dy   :11-37
+//   xp   = x0 cos(th) - y0 sin(th) + xc ; yp = x0 sin(th) + y0 cos(th) + yc   IBM_Force.py:33-34
+//   UP_k = U0[Xi] + Omega * r_k, r = -(yp - yc) | (xp - xc) ; F_k = (UP_k - U_k)/dt      :39-50
+//   dS_k = |x_{k+1} - x_k| (closed curve, roll(-1))                                       :59-63
+//   f_ij = sum_k F_k * delta(sqrt((xp_k-X_ij)^2 + (yp_k-Y_ij)^2), 0, dx) * dS_k           :66-87
+//   u**  = u* + dt * f                                                        time_stepping.py:223
+//
+// The reference evaluates every marker against the WHOLE grid; here each marker touches the
+// 2R x 2R cells i in [i_k-R+1, i_k+R] around its owning cell i_k = floor(xp/dx - offset)
+// (IBM_Force.py:35), R = 6 by default (truncation error 6e-9).  No periodic image is
+// taken (the reference uses raw xp - X).
+//
+// Interpolation: one warp per marker; separable weights are computed once by 2R lanes and
+// broadcast by shuffles; the window sum is a shuffle-tree reduction.
+// Spreading: a deterministic GATHER -- one CTA per 16x16 cell tile of a body's bounding box, the
+// body's markers are culled against the tile (order-preserving ballot compaction into shared
+// memory) and every cell sums its contributions in marker order.  No float atomics anywhere.
+// Marker coordinates and cell indices use explicitly rounded (non-contracted) float ops so that
+// they match a NumPy float32 evaluation bit for bit.
+#include "common.cuh"
+
+namespace jaxib {
+namespace {
+
+constexpr int TS = 16;          // spread tile edge (cells)
+constexpr int SPREAD_THREADS = TS * TS;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float mesh_coord(float lower, int i, float off, float h) {
+  // grids.py:665: lower + (arange + offset) * step, each op rounded to float32
+  return __fadd_rn(lower, __fmul_rn(__fadd_rn((float)i, off), h));
+}
+__device__ __forceinline__ int cell_index(float x, float h, float off) {
+  // IBM_Force.py:35: floor(xp/dx - offset)
+  return (int)floorf(__fsub_rn(__fdiv_rn(x, h), off));
+}
+__device__ __forceinline__ float gauss(float x, float x0, float w, float pref) {
+  float z = __fdiv_rn(__fsub_rn(x, x0), w);
+  return __fmul_rn(pref, expf(__fmul_rn(-0.5f, __fmul_rn(z, z))));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+struct Mesh {
+  float lower_x, lower_y, dx, dy, off_x, off_y, pref_x, pref_y;
+  int nx, ny, R;
+};
+
+__device__ __forceinline__ Mesh make_mesh(const GridF& g, float off_x, float off_y) {
+  Mesh m;
+  m.lower_x = g.lower_x; m.lower_y = g.lower_y; m.dx = g.dx; m.dy = g.dy;
+  m.off_x = off_x; m.off_y = off_y;
+  const float s2pi = sqrtf(6.283185307179586f);
+  m.pref_x = __fdiv_rn(1.0f, __fmul_rn(g.dx, s2pi));
+  m.pref_y = __fdiv_rn(1.0f, __fmul_rn(g.dy, s2pi));
+  m.nx = g.nx; m.ny = g.ny; m.R = g.R;
+  return m;
+}
+
+// Window sum for one marker, executed by a full warp.  Returns the sum in every lane.
+__device__ float interp_marker(const Mesh& m, const float* __restrict__ field, float xp, float yp, int* ik_out,
+                               int* jk_out) {
+  const int lane = threadIdx.x & 31;
+  const int W = 2 * m.R;
+  const int ik = cell_index(xp, m.dx, m.off_x), jk = cell_index(yp, m.dy, m.off_y);
+  if (ik_out) { *ik_out = ik; *jk_out = jk; }
+  const int ia = ik - m.R + 1, ja = jk - m.R + 1;
+  float gx = 0.0f, gy = 0.0f;
+  if (lane < W) {
+    gx = gauss(xp, mesh_coord(m.lower_x, ia + lane, m.off_x, m.dx), m.dx, m.pref_x);
+    gy = gauss(yp, mesh_coord(m.lower_y, ja + lane, m.off_y, m.dy), m.dy, m.pref_y);
+  }
+  float acc = 0.0f;
+  const int cells = W * W;
+  for (int base = 0; base < cells; base += 32) {
+    int e = base + lane;
+    int wi = e / W, wj = e - wi * W;
+    bool in = e < cells;
+    float wx = __shfl_sync(FULL, gx, in ? wi : 0);
+    float wy = __shfl_sync(FULL, gy, in ? wj : 0);
+    int i = ia + wi, j = ja + wj;
+    if (in && i >= 0 && i < m.nx && j >= 0 && j < m.ny) {
+      float f = __ldg(field + (size_t)i * m.ny + j);
+      // convolution_functions.py:19: ((((f * dx_delta) * dy_delta) * dx) * dy)
+      acc += __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(f, wx), wy), m.dx), m.dy);
+    }
+  }
+  return warp_sum(acc);
+}
+
+// ---- generic E->L interpolation (the `surface_fn` plug-in) -----------------------------------
+__global__ void interp_points_kernel(GridF g, float off_x, float off_y, const float* __restrict__ field,
+                                     const float* __restrict__ xp, const float* __restrict__ yp, int n,
+                                     float* __restrict__ out, int32_t* __restrict__ ci, int32_t* __restrict__ cj) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n) return;
+  Mesh m = make_mesh(g, off_x, off_y);
+  int ik, jk;
+  float s = interp_marker(m, field, xp[k], yp[k], &ik, &jk);
+  if ((threadIdx.x & 31) == 0) {
+    out[k] = s;
+    if (ci) { ci[k] = ik; cj[k] = jk; }
+  }
+}
+
+// ---- fused marker kinematics + interpolation + direct forcing --------------------------------
+// scratch layout: [5][batch][n_markers] = xp, yp, dS, Fx, Fy
+__global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
+                                    const float* __restrict__ x0, const float* __restrict__ y0,
+                                    const float* __restrict__ body_state, const float* __restrict__ u_star,
+                                    const float* __restrict__ v_star, float* __restrict__ markers) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int total = g.batch * n_markers;
+  if (gw >= total) return;
+  const int s = gw / n_markers, k = gw - s * n_markers;
+  int b = 0;
+  while (b + 1 < n_bodies && k >= body_offset[b + 1]) ++b;
+  const int k0 = body_offset[b], k1 = body_offset[b + 1];
+  const int kn = (k + 1 < k1) ? k + 1 : k0;  // roll(-1) within the body's closed curve
+  const float* st = body_state + ((size_t)s * n_bodies + b) * JAXIB_BODY_STATE_STRIDE;
+  const float c = st[0], sn = st[1], xc = st[2], yc = st[3], U0x = st[4], U0y = st[5], om = st[6];
+  const float ax = x0[k], ay = y0[k], bx = x0[kn], by = y0[kn];
+  const float xp = __fadd_rn(__fsub_rn(__fmul_rn(ax, c), __fmul_rn(ay, sn)), xc);
+  const float yp = __fadd_rn(__fadd_rn(__fmul_rn(ax, sn), __fmul_rn(ay, c)), yc);
+  const float xq = __fadd_rn(__fsub_rn(__fmul_rn(bx, c), __fmul_rn(by, sn)), xc);
+  const float yq = __fadd_rn(__fadd_rn(__fmul_rn(bx, sn), __fmul_rn(by, c)), yc);
+  const size_t plane = (size_t)g.nx * g.ny;
+  Mesh mu = make_mesh(g, 1.0f, 0.5f), mv = make_mesh(g, 0.5f, 1.0f);
+  const float Uu = interp_marker(mu, u_star + s * plane, xp, yp, nullptr, nullptr);
+  const float Uv = interp_marker(mv, v_star + s * plane, xp, yp, nullptr, nullptr);
+  if ((threadIdx.x & 31) == 0) {
+    const float rx = -(__fsub_rn(yp, yc));
+    const float ry = __fsub_rn(xp, xc);
+    const float UPx = __fadd_rn(U0x, __fmul_rn(om, rx));
+    const float UPy = __fadd_rn(U0y, __fmul_rn(om, ry));
+    const float dxl = __fsub_rn(xq, xp), dyl = __fsub_rn(yq, yp);
+    const size_t stride = (size_t)total;
+    float* mk = markers + gw;
+    mk[0] = xp;
+    mk[stride] = yp;
+    mk[2 * stride] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
+    mk[3 * stride] = __fdiv_rn(__fsub_rn(UPx, Uu), g.dt);
+    mk[4 * stride] = __fdiv_rn(__fsub_rn(UPy, Uv), g.dt);
+  }
+}
+
+// ---- spreading: tile gather ---------------------------------------------------------------------
+struct SpreadShared {
+  float xp[SPREAD_THREADS], yp[SPREAD_THREADS], F[SPREAD_THREADS], dS[SPREAD_THREADS];
+  int ik[SPREAD_THREADS], jk[SPREAD_THREADS];
+  int warp_count[SPREAD_THREADS / 32];
+  int count;
+};
+
+// Culls markers [k0, k1) against the tile [ti0, ti0+TS) x [tj0, tj0+TS) and accumulates this
+// thread's cell (i, j).  Sum order = marker order (deterministic).
+__device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __restrict__ mxp,
+                                const float* __restrict__ myp, const float* __restrict__ mF,
+                                const float* __restrict__ mdS, int k0, int k1, int ti0, int tj0, int i, int j,
+                                bool valid) {
+  const int tid = threadIdx.y * TS + threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float X = mesh_coord(m.lower_x, i, m.off_x, m.dx);
+  const float Y = mesh_coord(m.lower_y, j, m.off_y, m.dy);
+  float acc = 0.0f;
+  for (int base = k0; base < k1; base += SPREAD_THREADS) {
+    const int k = base + tid;
+    bool keep = false;
+    float xp = 0.f, yp = 0.f, F = 0.f, dS = 0.f;
+    int ik = 0, jk = 0;
+    if (k < k1) {
+      xp = mxp[k]; yp = myp[k]; F = mF[k]; dS = mdS[k];
+      ik = cell_index(xp, m.dx, m.off_x);
+      jk = cell_index(yp, m.dy, m.off_y);
+      keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
+    }
+    const unsigned ballot = __ballot_sync(FULL, keep);
+    if (lane == 0) sh.warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    int offset = 0, totalc = 0;
+#pragma unroll
+    for (int w = 0; w < SPREAD_THREADS / 32; ++w) {
+      int cw = sh.warp_count[w];
+      if (w < warp) offset += cw;
+      totalc += cw;
+    }
+    if (keep) {
+      const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
+      sh.xp[pos] = xp; sh.yp[pos] = yp; sh.F[pos] = F; sh.dS[pos] = dS; sh.ik[pos] = ik; sh.jk[pos] = jk;
+    }
+    __syncthreads();
+    if (valid) {
+      for (int q = 0; q < totalc; ++q) {
+        const int di = i - sh.ik[q], dj = j - sh.jk[q];
+        if (di > -m.R && di <= m.R && dj > -m.R && dj <= m.R) {
+          const float ddx = __fsub_rn(sh.xp[q], X), ddy = __fsub_rn(sh.yp[q], Y);
+          const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+          // IBM_Force.py:67: F * delta(r, 0, dx) * dS  -- width dx on both axes
+          const float gk = gauss(r, 0.0f, m.dx, m.pref_x);
+          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(sh.F[q], gk), sh.dS[q]));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic, int& jc) {
+  ic = cell_index(st[2], m.dx, m.off_x);
+  jc = cell_index(st[3], m.dy, m.off_y);
+}
+
+// grid = (tiles_per_axis^2, n_bodies, batch * 2); block = (TS, TS)
+__global__ void __launch_bounds__(SPREAD_THREADS)
+spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
+                     const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
+                     int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star) {
+  __shared__ SpreadShared sh;
+  const int b = blockIdx.y;
+  const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
+  const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
+  const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
+  int ic, jc;
+  body_box(states + b * JAXIB_BODY_STATE_STRIDE, m, ic, jc);
+  const int ty = blockIdx.x / tiles_per_axis, tx = blockIdx.x - ty * tiles_per_axis;
+  const int ti0 = ic - half_extent + ty * TS, tj0 = jc - half_extent + tx * TS;
+  if (ti0 >= g.nx || ti0 + TS <= 0 || tj0 >= g.ny || tj0 + TS <= 0) return;  // tile fully outside: no image
+  const int i = ti0 + threadIdx.y, j = tj0 + threadIdx.x;
+  bool valid = i >= 0 && i < g.nx && j >= 0 && j < g.ny && i <= ic + half_extent && j <= jc + half_extent;
+  // a cell covered by several bounding boxes belongs to the lowest-numbered body
+  for (int b2 = 0; b2 < b && valid; ++b2) {
+    int ic2, jc2;
+    body_box(states + b2 * JAXIB_BODY_STATE_STRIDE, m, ic2, jc2);
+    if (abs(i - ic2) <= half_extent && abs(j - jc2) <= half_extent) valid = false;
+  }
+  const size_t total = (size_t)g.batch * n_markers;
+  const float* mk = markers + (size_t)s * n_markers;
+  const float* mF = mk + (comp == 0 ? 3 : 4) * total;
+  float f_total = 0.0f;
+  bool touched = false;
+  for (int b2 = b; b2 < n_bodies; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
+    int ic2, jc2;
+    body_box(states + b2 * JAXIB_BODY_STATE_STRIDE, m, ic2, jc2);
+    if (b2 != b && (ic2 + half_extent < ti0 || ic2 - half_extent >= ti0 + TS || jc2 + half_extent < tj0 ||
+                    jc2 - half_extent >= tj0 + TS))
+      continue;  // block-uniform
+    float fb = gather_markers(sh, m, mk, mk + total, mF, mk + 2 * total, body_offset[b2], body_offset[b2 + 1], ti0,
+                              tj0, i, j, valid);
+    f_total = __fadd_rn(f_total, fb);
+    touched = true;
+  }
+  if (valid && touched && f_total != 0.0f) {
+    float* out = (comp == 0 ? u_star : v_star) + (size_t)s * g.nx * g.ny + (size_t)i * g.ny + j;
+    *out = __fadd_rn(*out, __fmul_rn(g.dt, f_total));  // time_stepping.py:223
+  }
+}
+
+// ---- generic L->E spreading of a point cloud (plug-in granularity, batch = 1) -------------------
+__global__ void bbox_kernel(GridF g, float off_x, float off_y, const float* __restrict__ xp,
+                            const float* __restrict__ yp, int n, int* __restrict__ box) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int ik = cell_index(xp[k], g.dx, off_x), jk = cell_index(yp[k], g.dy, off_y);
+  atomicMin(box + 0, ik); atomicMax(box + 1, ik);
+  atomicMin(box + 2, jk); atomicMax(box + 3, jk);
+}
+__global__ void bbox_init_kernel(int* box) {
+  box[0] = box[2] = 0x7fffffff;
+  box[1] = box[3] = (int)0x80000000;
+}
+
+// grid = (ceil(ny/TS), ceil(nx/TS)); every tile culls all n points (early exit outside the bbox)
+__global__ void __launch_bounds__(SPREAD_THREADS)
+spread_points_kernel(GridF g, float off_x, float off_y, const float* __restrict__ F, const float* __restrict__ xp,
+                     const float* __restrict__ yp, const float* __restrict__ dS, int n, float scale,
+                     const int* __restrict__ box, float* __restrict__ out) {
+  __shared__ SpreadShared sh;
+  const int ti0 = blockIdx.y * TS, tj0 = blockIdx.x * TS;
+  if (ti0 > box[1] + g.R || ti0 + TS <= box[0] - g.R || tj0 > box[3] + g.R || tj0 + TS <= box[2] - g.R) return;
+  const Mesh m = make_mesh(g, off_x, off_y);
+  const int i = ti0 + threadIdx.y, j = tj0 + threadIdx.x;
+  const bool valid = i < g.nx && j < g.ny;
+  float f = gather_markers(sh, m, xp, yp, F, dS, 0, n, ti0, tj0, i, j, valid);
+  if (valid && f != 0.0f) {
+    float* o = out + (size_t)i * g.ny + j;
+    *o = __fadd_rn(*o, __fmul_rn(scale, f));
+  }
+}
+
+}  // namespace
+
+int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field, const float* xp,
+                     const float* yp, int n, float* out, int32_t* ci, int32_t* cj) {
+  if (n <= 0) return JAXIB_OK;
+  if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
+  const int threads = 128;
+  const long long total = (long long)n * 32;
+  interp_points_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(g, off_x, off_y, field, xp, yp,
+                                                                                       n, out, ci, cj);
+  return check_launch("interp_points_kernel");
+}
+
+int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state, float* u_star,
+                    float* v_star, float* markers) {
+  if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
+  if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
+  const int threads = 128;
+  const long long total = (long long)g.batch * b.n_markers * 32;
+  interp_force_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+      g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state, u_star, v_star, markers);
+  int rc = check_launch("interp_force_kernel");
+  if (rc) return rc;
+  const float hmin = g.dx < g.dy ? g.dx : g.dy;
+  const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
+  const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
+  dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(TS, TS);
+  spread_bodies_kernel<<<grid, block, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
+                                              half_extent, tiles, u_star, v_star);
+  return check_launch("spread_bodies_kernel");
+}
+
+int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F, const float* xp,
+                     const float* yp, const float* dS, int n, float scale, float* out, int* box_scratch) {
+  if (n <= 0) return JAXIB_OK;
+  if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
+  bbox_init_kernel<<<1, 1, 0, s>>>(box_scratch);
+  bbox_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, off_x, off_y, xp, yp, n, box_scratch);
+  dim3 grid((g.ny + TS - 1) / TS, (g.nx + TS - 1) / TS), block(TS, TS);
+  spread_points_kernel<<<grid, block, 0, s>>>(g, off_x, off_y, F, xp, yp, dS, n, scale, box_scratch, out);
+  return check_launch("spread_points_kernel");
+}
+
+}  // namespace jaxib

@@ -1,0 +1,401 @@
+// K4/K5/K6: pressure projection by fast diagonalisation with a hand-written FFT.
+//
+// Reference: pressure.py:58-130 (projection_and_update_pressure, solve_fast_diag,
+// solve_fast_diag_moving_wall) over jax_cfd.fast_diagonalization.pseudoinverse:
+//     rhs = divergence(v);  q = irfftn( D * rfftn(rhs) );  D = 1/(lx_k + ly_l) if |.| > 10 eps32 else 0
+//     p += q;  u -= (q[i+1,j]-q[i,j])/dx;  v -= (q[i,j+1]-q[i,j])/dy        (A4 of SURVEY.md)
+// with lx_k = (2cos(2 pi k/Nx) - 2)/dx^2 (eigenvalues of array_utils.laplacian_matrix :168-173).
+//
+// Three kernels, 68 B/cell-step of algorithmic HBM traffic together with K1:
+//   rows_fwd  (K4): divergence fused into a real FFT along y (contiguous axis).  A real row of Ny
+//                   values is transformed as Ny/2 packed complex values and untangled; the real
+//                   Nyquist coefficient is packed into the imaginary part of the DC coefficient, so
+//                   the half spectrum is exactly [Nx][Ny/2] complex = one word per cell.
+//   cols      (K5): complex FFT along x (strided axis) of a group of adjacent ky columns held in
+//                   shared memory, multiply by D (computed in float64 from the two eigenvalue
+//                   vectors, rounded once to float32 as the reference does), inverse FFT, in place.
+//                   The packed DC/Nyquist column is separated through its Hermitian symmetry.
+//   rows_inv  (K6): inverse real FFT along y fused with the gradient, the velocity correction
+//                   and the pressure update.  Row i needs q[i+1], so a CTA that owns rows
+//                   [i0, i1) transforms rows i0..i1 and finalises row i-1 when row i is ready.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fft.cuh"
+
+struct jaxib_plan {
+  jaxib_grid grid;
+  jaxib::GridF gf;
+  jaxib::FftPlan row;  // complex length ny/2
+  jaxib::FftPlan col;  // complex length nx
+  float2* tw_row;      // W_ny^k,  k < ny
+  float2* tw_col;      // W_nx^k,  k < nx
+  int* row_pos;        // position of frequency k after the forward row transform, k < ny/2
+  int* col_pos;        // same for the column transform, k < nx
+  double* lam_x_pos;   // lx[freq(p)] indexed by position p (digit-reversed), p < nx
+  double* lam_y;       // ly_l, l <= ny/2
+  int row_threads, col_threads, cols_per_cta, rows_per_cta;
+  size_t row_smem, col_smem;
+};
+
+namespace jaxib {
+namespace {
+
+constexpr double kCutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps
+
+bool factor_plan(int n, FftPlan* pl) {
+  pl->n = n;
+  pl->nstages = 0;
+  int e2 = 0, e3 = 0, e5 = 0;
+  while (n % 2 == 0) { n /= 2; ++e2; }
+  while (n % 3 == 0) { n /= 3; ++e3; }
+  while (n % 5 == 0) { n /= 5; ++e5; }
+  if (n != 1) return false;
+  auto push = [&](int r) { pl->radix[pl->nstages++] = r; };
+  // small odd radices first (they act on long, conflict-free strides), then 16/8/4/2
+  for (int i = 0; i < e3; ++i) push(3);
+  for (int i = 0; i < e5; ++i) push(5);
+  while (e2 >= 7 || e2 == 4) { push(16); e2 -= 4; }
+  while (e2 >= 3) { push(8); e2 -= 3; }
+  if (e2 == 2) push(4);
+  if (e2 == 1) push(2);
+  return pl->nstages <= kMaxStages && pl->nstages > 0;
+}
+
+int pos_of_freq(const FftPlan& pl, int k) {
+  int p = 0, len = pl.n;
+  for (int s = 0; s < pl.nstages; ++s) {
+    int r = pl.radix[s];
+    len /= r;
+    p += (k % r) * len;
+    k /= r;
+  }
+  return p;
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+  if (cudaMalloc((void**)dst, src.size() * sizeof(T)) != cudaSuccess) return JAXIB_ERR_CUDA;
+  if (cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+    return JAXIB_ERR_CUDA;
+  return JAXIB_OK;
+}
+
+struct RowParams {
+  GridF g;
+  FftPlan pl;
+  const float2* tw;
+  const int* pos;
+  int rows_per_cta;
+  float scale;  // 1 / (nx * ny/2)
+};
+
+__device__ __forceinline__ int wrapi(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+// ---- K4 -------------------------------------------------------------------------------------------
+__global__ void rows_fwd_kernel(RowParams P, const float* __restrict__ u, const float* __restrict__ v,
+                                float2* __restrict__ spec) {
+  extern __shared__ float2 buf[];
+  const GridF& g = P.g;
+  const int n2 = g.ny >> 1;
+  const size_t plane = (size_t)g.nx * g.ny;
+  const int b = blockIdx.y;
+  u += b * plane; v += b * plane; spec += (size_t)b * g.nx * n2;
+  const int i0 = blockIdx.x * P.rows_per_cta;
+  const int i1 = min(i0 + P.rows_per_cta, g.nx);
+  for (int i = i0; i < i1; ++i) {
+    const float2* ur = reinterpret_cast<const float2*>(u + (size_t)i * g.ny);
+    const float2* um = reinterpret_cast<const float2*>(u + (size_t)wrapi(i - 1, g.nx) * g.ny);
+    const float* vrow = v + (size_t)i * g.ny;
+    const float2* vr = reinterpret_cast<const float2*>(vrow);
+    for (int n = threadIdx.x; n < n2; n += blockDim.x) {
+      float2 a = ur[n], c = um[n], d = vr[n];
+      float vm;  // v[i][2n-1]
+      if (n > 0) vm = vrow[2 * n - 1];
+      else vm = g.bc == JAXIB_BC_PERIODIC ? vrow[g.ny - 1] : g.vw_lo;
+      // finite_differences.py:139-146: backward differences, summed
+      float r0 = (a.x - c.x) * g.inv_dx + (d.x - vm) * g.inv_dy;
+      float r1 = (a.y - c.y) * g.inv_dx + (d.y - d.x) * g.inv_dy;
+      buf[padi(n)] = make_float2(r0, r1);
+    }
+    __syncthreads();
+    fft_forward(P.pl, buf, 1, 0, P.tw, 2);
+    // untangle the packed real transform and store the half spectrum (DC.im carries Nyquist)
+    float2* out = spec + (size_t)i * n2;
+    for (int k = threadIdx.x; k <= n2 / 2; k += blockDim.x) {
+      if (k == 0) {
+        float2 z = buf[padi(P.pos[0])];
+        out[0] = make_float2(z.x + z.y, z.x - z.y);
+      } else {
+        const int km = n2 - k;
+        float2 zk = buf[padi(P.pos[k])], zm = cconj(buf[padi(P.pos[km])]);
+        float2 e = cscale(cadd(zk, zm), 0.5f);
+        float2 o = cscale(mul_mi(csub(zk, zm)), 0.5f);
+        float2 t = cmul(__ldg(P.tw + k), o);
+        out[k] = cadd(e, t);
+        if (km != k) out[km] = cconj(csub(e, t));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K6 -------------------------------------------------------------------------------------------
+template <bool PROJECT>
+__global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, const float* u, const float* v,
+                                const float* p, float* u_out, float* v_out, float* p_out) {
+  extern __shared__ float2 smem[];
+  const GridF& g = P.g;
+  const int n2 = g.ny >> 1;
+  const int pitch = padi(n2) + 1;
+  const size_t plane = (size_t)g.nx * g.ny;
+  const int b = blockIdx.y;
+  spec += (size_t)b * g.nx * n2;
+  if (PROJECT) { u += b * plane; v += b * plane; p += b * plane; u_out += b * plane; v_out += b * plane; }
+  p_out += b * plane;
+  const int i0 = blockIdx.x * P.rows_per_cta;
+  const int i1 = min(i0 + P.rows_per_cta, g.nx);
+  const int last = PROJECT ? i1 : i1 - 1;  // projection needs q of the row after the last owned one
+  for (int ii = i0; ii <= last; ++ii) {
+    const int i = ii >= g.nx ? ii - g.nx : ii;
+    float2* cur = smem + ((ii - i0) & 1) * pitch;
+    const float2* in = spec + (size_t)i * n2;
+    for (int k = threadIdx.x; k <= n2 / 2; k += blockDim.x) {
+      if (k == 0) {
+        float2 x = in[0];  // (X[0], X[ny/2]) both real
+        cur[padi(P.pos[0])] = make_float2(0.5f * (x.x + x.y), 0.5f * (x.x - x.y));
+      } else {
+        const int km = n2 - k;
+        float2 xk = in[k], xm = cconj(in[km]);
+        float2 e = cscale(cadd(xk, xm), 0.5f);
+        float2 o = cmulc(cscale(csub(xk, xm), 0.5f), __ldg(P.tw + k));
+        cur[padi(P.pos[k])] = cadd(e, mul_pi(o));
+        if (km != k) cur[padi(P.pos[km])] = cadd(cconj(e), mul_pi(cconj(o)));
+      }
+    }
+    __syncthreads();
+    fft_inverse(P.pl, cur, 1, 0, P.tw, 2);
+    if (!PROJECT) {
+      float2* qo = reinterpret_cast<float2*>(p_out + (size_t)i * g.ny);
+      for (int n = threadIdx.x; n < n2; n += blockDim.x) qo[n] = cscale(cur[padi(n)], P.scale);
+    } else if (ii > i0) {
+      const int im = ii - 1;  // owned row to finalise
+      const float2* prv = smem + ((ii - 1 - i0) & 1) * pitch;
+      const size_t ro = (size_t)im * g.ny;
+      const float2* u2 = reinterpret_cast<const float2*>(u + ro);
+      const float2* v2 = reinterpret_cast<const float2*>(v + ro);
+      const float2* p2 = reinterpret_cast<const float2*>(p + ro);
+      float2* uo = reinterpret_cast<float2*>(u_out + ro);
+      float2* vo = reinterpret_cast<float2*>(v_out + ro);
+      float2* po = reinterpret_cast<float2*>(p_out + ro);
+      for (int n = threadIdx.x; n < n2; n += blockDim.x) {
+        float2 q0 = cscale(prv[padi(n)], P.scale);
+        float2 q1 = cscale(cur[padi(n)], P.scale);
+        float qn;  // q[im][2n+2]
+        if (n + 1 < n2) qn = prv[padi(n + 1)].x * P.scale;
+        else qn = g.bc == JAXIB_BC_PERIODIC ? prv[padi(0)].x * P.scale : q0.y;  // Neumann ghost = edge
+        float2 uu = u2[n], vv = v2[n], pp = p2[n];
+        uu.x -= (q1.x - q0.x) * g.inv_dx;
+        uu.y -= (q1.y - q0.y) * g.inv_dx;
+        vv.x -= (q0.y - q0.x) * g.inv_dy;
+        vv.y -= (qn - q0.y) * g.inv_dy;
+        if (g.bc == JAXIB_BC_CHANNEL && n + 1 == n2) vv.y = g.vw_hi;  // impose_bc (boundaries.py:405-419)
+        uo[n] = uu;
+        vo[n] = vv;
+        po[n] = make_float2(q0.x + pp.x, q0.y + pp.y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K5 -------------------------------------------------------------------------------------------
+struct ColParams {
+  int nx, n2, ncols;      // spectrum is [nx][n2]; ncols = number of stored columns (n2)
+  FftPlan pl;
+  const float2* tw;
+  const int* pos;
+  const double* lam_x_pos;
+  const double* lam_y;
+  int cols_per_cta;
+  int packed_all;         // channel: every stored column is a pair of real (DCT) columns
+  int nyq;                // periodic: index of the Nyquist eigenvalue paired with column 0
+};
+
+__device__ __forceinline__ float inv_eig(double lx, double ly) {
+  double l = lx + ly;
+  return fabs(l) > kCutoff ? (float)(1.0 / l) : 0.0f;
+}
+
+__global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
+  extern __shared__ float2 buf[];
+  const int nx = P.nx;
+  const int pitch = padi(nx) + 1;
+  spec += (size_t)blockIdx.y * nx * P.n2;
+  const int c0 = blockIdx.x * P.cols_per_cta;
+  const int nc = min(P.cols_per_cta, P.ncols - c0);
+  const int total = nx * nc;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int i = e / nc, c = e - i * nc;
+    buf[c * pitch + padi(i)] = spec[(size_t)i * P.n2 + c0 + c];
+  }
+  __syncthreads();
+  fft_forward(P.pl, buf, nc, pitch, P.tw, 1);
+  for (int c = 0; c < nc; ++c) {
+    float2* col = buf + c * pitch;
+    const int ky = c0 + c;
+    const bool packed = P.packed_all || ky == 0;
+    if (!packed) {
+      const double ly = P.lam_y[ky];
+      for (int q = threadIdx.x; q < nx; q += blockDim.x) {
+        float d = inv_eig(P.lam_x_pos[q], ly);
+        col[padi(q)] = cscale(col[padi(q)], d);
+      }
+    } else {
+      // column holds A + iB with A, B the transforms of two REAL sequences a (eigenvalue ly_a) and
+      // b (ly_b): A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)
+      const double lya = P.packed_all ? P.lam_y[2 * ky] : P.lam_y[0];
+      const double lyb = P.packed_all ? P.lam_y[2 * ky + 1] : P.lam_y[P.nyq];
+      for (int k = threadIdx.x; k <= nx / 2; k += blockDim.x) {
+        const int km = k == 0 ? 0 : nx - k;
+        const int p1 = P.pos[k], p2 = P.pos[km];
+        const double lx = P.lam_x_pos[p1];
+        const float da = inv_eig(lx, lya), db = inv_eig(lx, lyb);
+        float2 z1 = col[padi(p1)], z2 = cconj(col[padi(p2)]);
+        float2 a = cscale(cadd(z1, z2), 0.5f * da);
+        float2 bq = cscale(mul_mi(csub(z1, z2)), 0.5f * db);
+        col[padi(p1)] = cadd(a, mul_pi(bq));
+        if (p2 != p1) col[padi(p2)] = cadd(cconj(a), mul_pi(cconj(bq)));
+      }
+    }
+  }
+  __syncthreads();
+  fft_inverse(P.pl, buf, nc, pitch, P.tw, 1);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int i = e / nc, c = e - i * nc;
+    spec[(size_t)i * P.n2 + c0 + c] = buf[c * pitch + padi(i)];
+  }
+}
+
+}  // namespace
+
+const GridF& plan_grid(const jaxib_plan* plan) { return plan->gf; }
+size_t spectrum_floats(const jaxib_plan* plan) {
+  return (size_t)plan->gf.batch * plan->gf.nx * plan->gf.ny;  // [nx][ny/2] complex
+}
+
+int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
+                   float* v_out, float* p_out, float* q_only, float* spectrum) {
+  const GridF& g = pl->gf;
+  const int n2 = g.ny / 2;
+  RowParams rp;
+  rp.g = g; rp.pl = pl->row; rp.tw = pl->tw_row; rp.pos = pl->row_pos; rp.rows_per_cta = pl->rows_per_cta;
+  rp.scale = (float)(1.0 / ((double)g.nx * (double)n2));
+  float2* spec = reinterpret_cast<float2*>(spectrum);
+  dim3 rgrid((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
+  rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
+  int rc = check_launch("rows_fwd_kernel");
+  if (rc) return rc;
+  ColParams cp;
+  cp.nx = g.nx; cp.n2 = n2; cp.ncols = n2; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
+  cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
+  cp.packed_all = g.bc == JAXIB_BC_CHANNEL; cp.nyq = n2;
+  dim3 cgrid((n2 + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
+  cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
+  rc = check_launch("cols_kernel");
+  if (rc) return rc;
+  if (q_only) {
+    rows_inv_kernel<false><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, nullptr, nullptr, nullptr,
+                                                                           nullptr, nullptr, q_only);
+  } else {
+    rows_inv_kernel<true><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, u, v, p, u_out, v_out, p_out);
+  }
+  return check_launch("rows_inv_kernel");
+}
+
+}  // namespace jaxib
+
+using namespace jaxib;
+
+extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
+  if (!out) { set_error("plan_create: out is null"); return JAXIB_ERR_INVALID; }
+  *out = nullptr;
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if (grid->bc == JAXIB_BC_CHANNEL) {
+    set_error("channel (DCT) Poisson plan is not implemented yet");
+    return JAXIB_ERR_UNSUPPORTED;
+  }
+  if (grid->ny % 2) { set_error("ny=%d must be even for the packed real FFT", grid->ny); return JAXIB_ERR_UNSUPPORTED; }
+  jaxib_plan* pl = new jaxib_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->grid = *grid;
+  pl->gf = make_gridf(*grid);
+  const int nx = grid->nx, ny = grid->ny, n2 = ny / 2;
+  if (!factor_plan(n2, &pl->row) || !factor_plan(nx, &pl->col)) {
+    set_error("grid %dx%d: sizes must factor into 2, 3 and 5", nx, ny);
+    delete pl;
+    return JAXIB_ERR_UNSUPPORTED;
+  }
+  const double two_pi = 6.283185307179586476925286766559;
+  std::vector<float2> twr(ny), twc(nx);
+  for (int k = 0; k < ny; ++k) twr[k] = make_float2((float)cos(two_pi * k / ny), (float)-sin(two_pi * k / ny));
+  for (int k = 0; k < nx; ++k) twc[k] = make_float2((float)cos(two_pi * k / nx), (float)-sin(two_pi * k / nx));
+  std::vector<int> rpos(n2), cpos(nx);
+  for (int k = 0; k < n2; ++k) rpos[k] = pos_of_freq(pl->row, k);
+  for (int k = 0; k < nx; ++k) cpos[k] = pos_of_freq(pl->col, k);
+  // eigenvalues of the circulant 1-D Laplacians (array_utils.py:168-173), float64
+  std::vector<double> lxp(nx), ly(n2 + 1);
+  for (int k = 0; k < nx; ++k) lxp[cpos[k]] = (2.0 * cos(two_pi * k / nx) - 2.0) / (grid->dx * grid->dx);
+  for (int l = 0; l <= n2; ++l) ly[l] = (2.0 * cos(two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
+  rc = upload(&pl->tw_row, twr);
+  if (!rc) rc = upload(&pl->tw_col, twc);
+  if (!rc) rc = upload(&pl->row_pos, rpos);
+  if (!rc) rc = upload(&pl->col_pos, cpos);
+  if (!rc) rc = upload(&pl->lam_x_pos, lxp);
+  if (!rc) rc = upload(&pl->lam_y, ly);
+  if (rc) { set_error("plan_create: device allocation failed"); jaxib_plan_destroy(pl); return rc; }
+
+  int dev = 0, sms = 148, max_smem = 227 * 1024;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  auto pick_threads = [](int n) {
+    int t = ((n / 8 + 31) / 32) * 32;
+    return t < 64 ? 64 : (t > 256 ? 256 : t);
+  };
+  pl->row_threads = pick_threads(n2);
+  pl->row_smem = (size_t)(padi(n2) + 1) * sizeof(float2);
+  long long rows_total = (long long)nx * pl->gf.batch;
+  int rpc = (int)(rows_total / (3LL * sms));
+  pl->rows_per_cta = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
+  const size_t col_bytes = (size_t)(padi(nx) + 1) * sizeof(float2);
+  int cpc = 4;
+  while (cpc > 1 && cpc * col_bytes > (size_t)max_smem) cpc /= 2;
+  if (cpc * col_bytes > (size_t)max_smem) {
+    set_error("nx=%d: one column (%zu B) exceeds shared memory", nx, col_bytes);
+    jaxib_plan_destroy(pl);
+    return JAXIB_ERR_UNSUPPORTED;
+  }
+  pl->cols_per_cta = cpc;
+  pl->col_smem = cpc * col_bytes;
+  pl->col_threads = 256;
+  cudaFuncSetAttribute(cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
+  cudaFuncSetAttribute(rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
+  cudaFuncSetAttribute(rows_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
+  cudaFuncSetAttribute(rows_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
+  cudaGetLastError();
+  *out = pl;
+  return JAXIB_OK;
+}
+
+extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
+  if (!pl) return JAXIB_OK;
+  cudaFree(pl->tw_row); cudaFree(pl->tw_col); cudaFree(pl->row_pos); cudaFree(pl->col_pos);
+  cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y);
+  delete pl;
+  return JAXIB_OK;
+}

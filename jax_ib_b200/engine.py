@@ -1,0 +1,129 @@
+"""Device-resident fused stepping: the B200 replacement of the reference's `step_fn`
+(time_stepping.py:144-255) and of `funcutils.repeated(step_fn, n)`.
+
+One `FusedStepper` owns a jaxib_plan + scratch for a grid and advances (u, v, p) on the GPU for a
+block of steps with a single host round: the host evaluates the user's kinematic callables for the
+whole block (kinematics.body_schedule -> a [nsteps, B, 8] float32 table, uploaded once), the kernels
+run back to back on the current CUDA stream, and the host-side members of All_Variables (clock in
+the velocity BC, body centres, Step_count) are advanced with the reference's float32 arithmetic.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import boundaries, grids, kinematics, ops, particle_class
+
+
+def grid_spec_from(grid: grids.Grid, dt, viscosity, density, bc_kind, convect, v=None, force=(0.0, 0.0), ib_window=6,
+                   batch=1) -> ops.GridSpec:
+    u_wall = v_wall = (0.0, 0.0)
+    if v is not None and bc_kind == "channel":
+        u_wall = tuple(float(x) for x in v[0].bc.bc_values[1])
+        v_wall = tuple(float(x) for x in v[1].bc.bc_values[1])
+    return ops.GridSpec(
+        nx=grid.shape[0], ny=grid.shape[1], lower=(grid.domain[0][0], grid.domain[1][0]), step=grid.step, dt=dt,
+        nu=None if viscosity is None else viscosity / density, density=density, bc=bc_kind, convect=convect,
+        u_wall=u_wall, v_wall=v_wall, force=force, ib_window=ib_window, batch=batch)
+
+
+def bc_kind_of(v) -> str:
+    if boundaries.has_all_periodic_boundary_conditions(*v):
+        return "periodic"
+    t = v[0].bc.types
+    if t[0][0] == boundaries.BCType.PERIODIC and t[1][0] == boundaries.BCType.DIRICHLET:
+        return "channel"
+    raise NotImplementedError(f"no CUDA path for velocity BC types {t}")
+
+
+class FusedStepper:
+    def __init__(self, spec: ops.GridSpec, particles: Optional[particle_class.particle] = None, perm=None,
+                 incremental_pressure: bool = True, md_step: Optional[Callable] = None, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("jax_ib_b200 needs a CUDA device: there is no CPU fallback")
+        self.spec = spec
+        self.device = torch.device(device)
+        self.particles_template = particles
+        self.bodies = None
+        if particles is not None:
+            x0s, y0s = [], []
+            grid_p = particles.generate_grid()
+            for gp in particles.geometry_param:
+                x0, y0 = particles.shape(gp, grid_p)
+                x0s.append(np.asarray(x0, dtype=np.float32))
+                y0s.append(np.asarray(y0, dtype=np.float32))
+            self.bodies = ops.DeviceBodies(x0s, y0s, self.device)
+        self.plan = ops.Plan(spec, self.bodies.n_markers if self.bodies else 0, self.device)
+        self.perm = perm
+        self.incremental_pressure = incremental_pressure
+        self.md_step = md_step
+        self.launches_per_step = 4 + (2 if self.bodies else 0)
+
+    # -- raw device-level block ---------------------------------------------------------------
+    def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor]):
+        """In place on CUDA tensors (u, v, p)."""
+        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure)
+
+    # -- All_Variables-level --------------------------------------------------------------------
+    def advance(self, all_variables, nsteps: int):
+        vel = all_variables.velocity
+        dev = self.device
+        in_dev = vel[0].data.device
+        # first touch: copy (functional semantics: the caller's arrays are never modified)
+        u = vel[0].data.to(dev, dtype=torch.float32, copy=True).contiguous()
+        v = vel[1].data.to(dev, dtype=torch.float32, copy=True).contiguous()
+        p = all_variables.pressure.data.to(dev, dtype=torch.float32, copy=True).contiguous()
+        t0 = vel[0].bc.time_stamp
+        dt = self.spec.dt
+        particles = all_variables.particles
+        state = all_variables
+        if self.md_step is None:
+            table_dev, times, centers = self._schedule(particles, t0, dt, nsteps)
+            self.run_block(u, v, p, nsteps, table_dev)
+        else:
+            table_dev, times, centers = self._schedule(particles, t0, dt, nsteps)
+            md = all_variables.MD_var
+            for n in range(nsteps):
+                self.run_block(u, v, p, 1, None if table_dev is None else table_dev[n:n + 1])
+                md = self.md_step(self._view(all_variables, u, v, p, times[n + 1], particles, md))
+            state = dataclasses.replace(state, MD_var=md)
+        new_particles = particles
+        if particles is not None:
+            new_particles = dataclasses.replace(particles, particle_center=_like(particles.particle_center, centers[-1]))
+        out = self._view(state, u.to(in_dev), v.to(in_dev), p.to(in_dev), times[-1], new_particles, state.MD_var)
+        return dataclasses.replace(out, Step_count=all_variables.Step_count + nsteps)
+
+    def _schedule(self, particles, t0, dt, nsteps):
+        f32 = np.float32
+        if particles is None:
+            times = np.add.accumulate(np.concatenate([[f32(t0)], np.full(nsteps, f32(dt), f32)]).astype(f32), dtype=f32)
+            return None, times, None
+        table, times, centers = kinematics.body_schedule(particles, t0, dt, nsteps)
+        table = np.ascontiguousarray(np.broadcast_to(table[:, None], (nsteps, self.spec.batch) + table.shape[1:]))
+        return torch.from_numpy(table).to(self.device, non_blocking=True), times, centers
+
+    def _view(self, all_variables, u, v, p, t, particles, md):
+        vel = all_variables.velocity
+        new_v = []
+        for comp, data in zip(vel, (u, v)):
+            bc = comp.bc
+            fns = bc.boundary_fn
+            values = bc.bc_values
+            try:
+                values = ((fns[0](t), fns[1](t)), (fns[2](t), fns[3](t)))
+            except TypeError:
+                pass
+            nbc = boundaries.ConstantBoundaryConditions(values=values, time_stamp=t, types=bc.types, boundary_fn=fns)
+            new_v.append(grids.GridVariable(grids.GridArray(data, comp.offset, comp.grid), nbc))
+        pr = all_variables.pressure
+        new_p = grids.GridVariable(grids.GridArray(p, pr.offset, pr.grid), pr.bc)
+        return dataclasses.replace(all_variables, particles=particles, velocity=tuple(new_v), pressure=new_p, MD_var=md)
+
+
+def _like(template, arr: np.ndarray):
+    if isinstance(template, torch.Tensor):
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(template.dtype)
+    return np.asarray(arr, dtype=np.float32)
