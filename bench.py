@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-steps/s of the full IB step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ib2048]
+
+A "step" is one full immersed-boundary time step (explicit predict -> IB interpolate / force /
+spread -> FFT pressure projection) of the `ib2048` workload: a 2048^2 periodic grid at the Flapping
+demo's resolution with 4 flapping ellipses (1192 markers), upwind advection (configs.ib_periodic).
+N > 1 runs one independent simulation per GPU (ensemble sweep, no data-path collective): weak scaling.
+
+`value`     device-resident throughput, per-step CUDA-event brackets, L2 flushed between steps.
+`e2e`       same metric through the public All_Variables -> All_Variables API with HOST (pinned)
+            arrays: H2D of (u, v, p) and D2H of the result inside every timed step.
+`roofline`  dominant kernel, algorithmic bytes / CUDA-event duration / measured HBM peak.
+`cpu_baseline` / `--impl reference`: the NumPy oracle (a faithful restatement of the reference's
+            dense algorithm; the reference's JAX path cannot run in this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mcell-steps/s (full IB step)"
+UNIT = "Mcell-steps/s"
+# SURVEY.md 8d / DESIGN.md: algorithmic HBM bytes per cell-step of each grid kernel (fp32)
+ALGO_BYTES = {"explicit_predict": 20.0, "rows_fwd": 12.0, "cols": 8.0, "rows_inv": 28.0}
+STEP_BYTES = 68.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ib2048")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_cfg(name):
+    from jax_ib_b200 import configs
+
+    if name == "ib2048":
+        return configs.ib_periodic(2048, 2)
+    if name == "ib4096":
+        return configs.ib_periodic(4096, 4)
+    if name == "ib1024":
+        return configs.ib_periodic(1024, 1)
+    if name == "flap600":
+        return configs.flap600()
+    raise SystemExit(f"unknown workload {name}")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _oracle_worker(args):
+    n, steps = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from jax_ib_b200 import configs
+    from _adapter import oracle_state, oracle_step
+
+    cfg = configs.ib_periodic(n, 1)
+    st = oracle_state(cfg)
+    step = oracle_step(cfg, ib_window=None)  # dense O(M Nx Ny) sums, as the reference does
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st = step(st)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(steps, procs, n=512):
+    """Oracle (NumPy port of the reference's dense algorithm) on the host cores: `procs` independent
+    ensemble members in parallel processes.  Returns (Mcell-steps/s, seconds)."""
+    import multiprocessing as mp
+
+    procs = max(1, procs)
+    t0 = time.perf_counter()
+    if procs == 1:
+        _oracle_worker((n, steps))
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(_oracle_worker, [(n, steps)] * procs)
+    wall = time.perf_counter() - t0
+    return procs * n * n * steps / wall / 1e6, wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = min(cores, 32)
+    n = 512
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(1, 1, n)
+    steps = max(1, min(args.steps, 3))
+    val, wall = cpu_reference(steps, procs, n)
+    sample = (f"{procs} independent ensemble members x {steps} steps of a {n}^2 tile of the ib2048 workload "
+              f"(same dx, dt, upwind, FFT Poisson; one 298-marker ellipse per tile; dense O(M*Nx*Ny) IB sums as in "
+              f"IBM_Force.py:66-87) in {procs} processes, NumPy float32 oracle")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "restated-reference CPU (NumPy oracle), not JAX: jax is not installable in this image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from jax_ib_b200 import demo, kinematics, ops
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    cfg = workload_cfg(args.workload)
+    if world > 1:  # ensemble sweep: every rank gets its own kinematic phase
+        b = dict(cfg["bodies"])
+        b["rotation_param"] = [[p[0], p[1], p[2], p[3] + 0.37 * rank] for p in b["rotation_param"]]
+        cfg = dict(cfg, bodies=b)
+    nx, ny = cfg["shape"]
+    cells = nx * ny
+    K, W = args.steps, args.warmup
+    stepper = demo.make_stepper(cfg, device=device)
+    particles = demo.make_particles(cfg)
+    from jax_ib_b200 import configs as _configs
+
+    u0, v0, p0 = (torch.from_numpy(a).to(device) for a in _configs.initial_fields(cfg))
+    table, times, centers = kinematics.body_schedule(particles, 0.0, cfg["dt"], W + K + K)
+    table = torch.from_numpy(np.ascontiguousarray(table[:, None])).to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # 256 MiB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    u, v, p = u0.clone(), v0.clone(), p0.clone()
+    stepper.run_block(u, v, p, W, table[:W])  # warm-up (untimed)
+    # ---- timed region 1: K steps, per-step event brackets, L2 flushed between steps ------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    prof = ops.step_profile(stepper.plan, u, v, p, K, stepper.bodies, table[W:W + K], flush=flush)
+    barrier()
+    # ---- timed region 2: K steps back to back (L2 warm, as consecutive time steps really run) ---
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    stepper.run_block(u, v, p, K, table[W + K:W + 2 * K])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_flushed = max_over_ranks(prof["step"])
+    ms_warm = max_over_ranks(e0.elapsed_time(e1))
+    finite = bool(torch.isfinite(u).all().item())
+
+    # ---- e2e: public API with host buffers ---------------------------------------------------
+    Ke = max(3, min(K, 20))
+    av = demo.make_all_variables(cfg, device="cpu")
+    pin = lambda gv: type(gv)(type(gv.array)(gv.data.pin_memory(), gv.offset, gv.grid), gv.bc)
+    av = type(av)(av.particles, tuple(pin(x) for x in av.velocity), pin(av.pressure), av.Drag, av.Step_count, av.MD_var)
+    for _ in range(2):
+        av = stepper.advance(av, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        av = stepper.advance(av, 1)  # H2D (u, v, p) -> step -> D2H (u, v, p)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    if rank != 0:
+        return
+    hbm_peak, peak_src = peaks()
+    value = world * cells * K / (ms_flushed * 1e-3) / 1e6
+    stage_ms = {k: prof[k] / K for k in ops.STAGES}
+    dom = max(ALGO_BYTES, key=lambda k: stage_ms[k])
+    achieved = ALGO_BYTES[dom] * cells / (stage_ms[dom] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": [nx, ny], "bodies": len(cfg["bodies"]["centers"]),
+                   "markers": stepper.bodies.n_markers, "convect": cfg["convect"], "poisson": "periodic FFT",
+                   "ib_window_R": 6, "parallelism": f"ensemble x{world} (one simulation per GPU, no collective)",
+                   "l2": "flushed (256 MiB memset) before every timed step; brackets exclude the flush",
+                   "finite": finite},
+        "value_back_to_back": world * cells * K / (ms_warm * 1e-3) / 1e6,
+        "ms_per_step_back_to_back": ms_warm / K,
+        "step_roofline": {"algorithmic_bytes_per_cell_step": STEP_BYTES,
+                          "achieved_gbs": STEP_BYTES * cells * K / (ms_flushed * 1e-3) / 1e9,
+                          "frac": STEP_BYTES * cells * K / (ms_flushed * 1e-3) / 1e9 / hbm_peak,
+                          "frac_back_to_back": STEP_BYTES * cells * K / (ms_warm * 1e-3) / 1e9 / hbm_peak},
+        "stage_us": {k: round(v * 1e3, 2) for k, v in stage_ms.items()},
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * cells},
+        "clocks": clocks,
+        "gpu_launches": stepper.launches_per_step * K,
+        "e2e": {"value": world * cells * Ke / e2e_s / 1e6, "unit": UNIT, "steps": Ke,
+                "h2d_bytes_per_step": 3 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
+                "api": "FusedStepper.advance(All_Variables on pinned host memory, 1)"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        steps_cpu = 3
+        val, wall = cpu_reference(steps_cpu, 1, 512)
+        line["cpu_baseline"] = {
+            "value": val, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": (f"{steps_cpu} steps of a 512^2 tile of the same workload (same dx, dt, upwind, FFT Poisson, one "
+                       f"298-marker ellipse, dense O(M*Nx*Ny) IB sums as the reference) with the single-threaded NumPy "
+                       f"float32 oracle: {wall:.1f} s on 1 of {os.cpu_count()} host cores")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: spawn it the way the driver would
+        import subprocess
+
+        port = os.environ.get("MASTER_PORT", "29541")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -155,6 +155,17 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
                const float* perm, int32_t incremental_pressure, int32_t nsteps, float* u, float* v, float* p,
                void* scratch, size_t scratch_bytes);
 
+/* Measurement aid (bench.py): runs `nsteps` steps like jaxib_step but brackets every stage of every
+ * step with CUDA events on `stream`, optionally overwrites `flush` (flush_bytes, > L2) before each
+ * step outside the timed brackets, SYNCHRONISES the stream (the only entry point that does) and
+ * returns the summed milliseconds per stage in ms_out[JAXIB_N_STAGES]:
+ *   0 explicit_predict, 1 ib_interp_force, 2 ib_spread, 3 rows_fwd, 4 cols, 5 rows_inv, 6 whole step. */
+#define JAXIB_N_STAGES 7
+int jaxib_step_profile(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies,
+                       const float* body_table, const float* perm, int32_t incremental_pressure, int32_t nsteps,
+                       float* u, float* v, float* p, void* scratch, size_t scratch_bytes, void* flush,
+                       size_t flush_bytes, double* ms_out);
+
 /* ---- tracers (MD/CFD_MD_coupling.py:7-27 + MD/simulate.py:81-97, kT = 0 or caller noise) ----- */
 /* R[n][2] += (F_pair + [u,v](R)) * dt/(mass*gamma) + sqrt(2 kT dt/(mass gamma)) * xi, masked
  * by is_mobile (NULL = all mobile).  pair_force / xi may be NULL.                              */

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <initializer_list>
+#include <vector>
+
 #include "common.cuh"
 
 namespace jaxib {
@@ -217,6 +220,58 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
     if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum))) return rc;
   }
   return JAXIB_OK;
+}
+
+int jaxib_step_profile(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies,
+                       const float* body_table, const float* perm, int32_t incremental_pressure, int32_t nsteps,
+                       float* u, float* v, float* p, void* scratch, size_t scratch_bytes, void* flush,
+                       size_t flush_bytes, double* ms_out) {
+  if (!plan || !ms_out) { set_error("step_profile: plan / ms_out is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("step_profile", {u, v, p});
+  if (rc) return rc;
+  if (nsteps <= 0 || nsteps > 100000) { set_error("step_profile: nsteps out of range"); return JAXIB_ERR_INVALID; }
+  const bool has_ib = bodies && bodies->n_markers > 0;
+  if (has_ib) {
+    if ((rc = check_bodies(bodies))) return rc;
+    if (!body_table) { set_error("step_profile: bodies given without body_table"); return JAXIB_ERR_INVALID; }
+  }
+  const GridF& g = plan_grid(plan);
+  Scratch sc;
+  if ((rc = carve(g, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
+  const int per = JAXIB_N_STAGES;  // start + 6 stage ends
+  std::vector<cudaEvent_t> ev((size_t)per * nsteps);
+  for (auto& e : ev) cudaEventCreate(&e);
+  for (int n = 0; n < nsteps && !rc; ++n) {
+    cudaEvent_t* e = ev.data() + (size_t)n * per;
+    if (flush && flush_bytes) cudaMemsetAsync(flush, n & 0xff, flush_bytes, s);
+    cudaEventRecord(e[0], s);
+    rc = launch_explicit(s, g, u, v, incremental_pressure ? p : nullptr, perm, sc.u_star, sc.v_star, true);
+    cudaEventRecord(e[1], s);
+    StageHook hib{e + 2};
+    if (!rc && has_ib) rc = launch_ib_force(s, g, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers, &hib);
+    if (!has_ib) { cudaEventRecord(e[2], s); cudaEventRecord(e[3], s); }
+    StageHook hp{e + 4};
+    if (!rc) rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum, &hp);
+  }
+  cudaError_t ce = cudaStreamSynchronize(s);
+  for (int k = 0; k < JAXIB_N_STAGES; ++k) ms_out[k] = 0.0;
+  if (!rc && ce == cudaSuccess) {
+    for (int n = 0; n < nsteps; ++n) {
+      cudaEvent_t* e = ev.data() + (size_t)n * per;
+      float ms = 0.f;
+      for (int k = 0; k < 6; ++k) {
+        cudaEventElapsedTime(&ms, e[k], e[k + 1]);
+        ms_out[k] += ms;
+      }
+      cudaEventElapsedTime(&ms, e[0], e[6]);
+      ms_out[6] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (ce != cudaSuccess) { set_error("step_profile: %s", cudaGetErrorString(ce)); return JAXIB_ERR_CUDA; }
+  return rc;
 }
 
 }  // extern "C"

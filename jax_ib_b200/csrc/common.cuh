@@ -64,15 +64,20 @@ struct FftPlan {
 // stage launchers (each only enqueues on `stream`)
 int launch_explicit(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                     const float* perm, float* out_u, float* out_v, bool predictor);
+// optional per-stage event recording (jaxib_step_profile): ev[0..] are recorded after each kernel
+struct StageHook {
+  cudaEvent_t* ev;
+};
 int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                    float* u_star, float* v_star, float* marker_scratch);
+                    float* u_star, float* v_star, float* marker_scratch, const StageHook* hook = nullptr);
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
                      const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,
                      const float* xp, const float* yp, const float* dS, int n, float scale, float* out,
                      int* box_scratch);
 int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
-                   float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum);
+                   float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
+                   const StageHook* hook = nullptr);
 size_t spectrum_floats(const jaxib_plan* plan);
 const GridF& plan_grid(const jaxib_plan* plan);
 

@@ -288,7 +288,7 @@ size_t spectrum_floats(const jaxib_plan* plan) {
 }
 
 int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
-                   float* v_out, float* p_out, float* q_only, float* spectrum) {
+                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook) {
   const GridF& g = pl->gf;
   const int n2 = g.ny / 2;
   RowParams rp;
@@ -299,6 +299,7 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
   int rc = check_launch("rows_fwd_kernel");
   if (rc) return rc;
+  if (hook) cudaEventRecord(hook->ev[0], s);
   ColParams cp;
   cp.nx = g.nx; cp.n2 = n2; cp.ncols = n2; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
   cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
@@ -307,12 +308,14 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
   rc = check_launch("cols_kernel");
   if (rc) return rc;
+  if (hook) cudaEventRecord(hook->ev[1], s);
   if (q_only) {
     rows_inv_kernel<false><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, nullptr, nullptr, nullptr,
                                                                            nullptr, nullptr, q_only);
   } else {
     rows_inv_kernel<true><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, u, v, p, u_out, v_out, p_out);
   }
+  if (hook) cudaEventRecord(hook->ev[2], s);
   return check_launch("rows_inv_kernel");
 }
 

@@ -233,6 +233,23 @@ class Plan:
         return u, v, p
 
 
+STAGES = ("explicit_predict", "ib_interp_force", "ib_spread", "rows_fwd", "cols", "rows_inv", "step")
+
+
+def step_profile(plan: Plan, u, v, p, nsteps, bodies=None, body_table=None, perm=None, incremental_pressure=True,
+                 flush: Optional[torch.Tensor] = None):
+    """Measurement aid: like Plan.step but returns {stage: summed ms} from per-stage CUDA events.
+    `flush` (a device buffer larger than L2) is overwritten before every step, outside the brackets.
+    Synchronises the stream."""
+    b = bodies.c_struct() if bodies is not None else None
+    ms = (C.c_double * len(STAGES))()
+    _lib.check(plan._lib.jaxib_step_profile(
+        _stream(), plan._h, C.byref(b) if b is not None else None, _ptr(body_table), _ptr(perm),
+        1 if incremental_pressure else 0, int(nsteps), _ptr(u), _ptr(v), _ptr(p), _ptr(plan.scratch), plan.scratch_bytes,
+        _ptr(flush), flush.numel() * flush.element_size() if flush is not None else 0, ms), "step_profile")
+    return dict(zip(STAGES, [float(x) for x in ms]))
+
+
 # ---- tracers / penalty ---------------------------------------------------------------------------
 def bilinear_sample(spec: GridSpec, field, offset, R):
     n = R.shape[0]

@@ -1,0 +1,63 @@
+"""Generates the golden fixtures in this directory from the ORACLE (oracle/, float32, the
+reference's dense O(M*Nx*Ny) Gaussian sums exactly as IBM_Force.py / convolution_functions.py do).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference itself cannot run in this image (no JAX), so these are outputs of the
+restatement, not of jax_ib: "parity unpinned" applies (oracle/__init__.py).  Each file holds a crop
+of (u, v, p) around the bodies plus full-field norms / sums, the clock, the body centres and the
+step count, so the fixtures stay small.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from jax_ib_b200 import configs  # noqa: E402
+from _adapter import oracle_state, oracle_step  # noqa: E402
+
+CASES = {
+    # name: (config, steps, dense IB?, crop)
+    "flap600_20": (configs.flap600(), 20, True, (slice(380, 540), slice(220, 380))),
+    "bearing300_20": (configs.bearing300(), 20, True, (slice(70, 230), slice(70, 230))),
+    "channel1024x256_5": (configs.channel(), 5, False, (slice(0, 160), slice(0, 256))),
+    "small64_50": (configs.small_periodic(64), 50, True, (slice(0, 64), slice(0, 64))),
+}
+
+
+def summarize(st, crop):
+    out = {}
+    for name, var in (("u", st.velocity[0]), ("v", st.velocity[1]), ("p", st.pressure)):
+        d = var.data
+        out[name + "_crop"] = d[crop].astype(np.float32)
+        out[name + "_l2"] = np.float64(np.sqrt((d.astype(np.float64) ** 2).sum()))
+        out[name + "_sum"] = np.float64(d.astype(np.float64).sum())
+    out["time"] = np.float32(st.velocity[0].bc.time_stamp)
+    out["step_count"] = np.int64(st.Step_count)
+    if st.particles is not None:
+        out["centers"] = np.asarray(st.particles.centers, dtype=np.float32)
+    return out
+
+
+def main(only=None):
+    for name, (cfg, steps, dense, crop) in CASES.items():
+        if only and name not in only:
+            continue
+        st = oracle_state(cfg)
+        step = oracle_step(cfg, ib_window=None if dense else 6)
+        for _ in range(steps):
+            st = step(st)
+        data = summarize(st, crop)
+        data["crop"] = np.array([crop[0].start, crop[0].stop, crop[1].start, crop[1].stop])
+        data["steps"] = np.int64(steps)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, {k: (v.shape if hasattr(v, "shape") and v.ndim else float(v)) for k, v in data.items()})
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,140 @@
+"""CPU-side checks (no GPU needed): the C-ABI library builds, loads and exports every symbol the
+header declares; the host-side mirror (kinematics table, ghost-cell shift, clock) agrees with the
+oracle; the golden fixtures are what the oracle produces."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from jax_ib_b200 import _lib, boundaries, build, configs, demo, grids, kinematics
+from oracle import field, ib, kinematics as okin
+
+from _adapter import oracle_state, oracle_step, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F = np.float32
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "jaxib_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jaxib_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/jaxib_b200.h but not exported"
+    # and the Python binding covers the same set
+    assert set(names) == set(_lib.exported_symbols())
+    l = _lib.load()
+    assert l.jaxib_compiled_arch() == 100
+    assert b"sm_100a" in l.jaxib_version()
+
+
+def test_argument_errors_without_a_gpu():
+    l = _lib.load()
+    assert l.jaxib_plan_create(None, None) == -1
+    g = _lib.Grid()
+    g.nx, g.ny, g.batch, g.dx, g.dy = 0, 8, 1, 1.0, 1.0
+    h = ctypes.c_void_p()
+    assert l.jaxib_plan_create(ctypes.byref(g), ctypes.byref(h)) == -1
+    assert b"nx" in l.jaxib_last_error()
+    assert l.jaxib_step(None, None, None, None, None, 1, 1, None, None, None, None, 0) == -1
+
+
+def test_sass_is_sm100a_only():
+    out = os.popen(f"cuobjdump -lelf {build.build()} 2>/dev/null").read()
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.parametrize("cfg_fn", [configs.flap600, configs.bearing300])
+def test_body_schedule_matches_oracle_kinematics(cfg_fn):
+    cfg = cfg_fn()
+    particles = demo.make_particles(cfg)
+    n = 40
+    table, times, centers = kinematics.body_schedule(particles, 0.0, cfg["dt"], n)
+    st = oracle_state(cfg)
+    step_t = F(0.0)
+    ob = st.particles
+    for k in range(n):
+        for b in range(len(ob.centers)):
+            th = np.asarray(ob.rotation[0]([ob.rotation_param[b]], step_t), dtype=F).reshape(-1)[0]
+            om = np.asarray(ob.rotation[1]([ob.rotation_param[b]], step_t), dtype=F).reshape(-1)[0]
+            U0 = np.asarray(ob.displacement[1]([ob.displacement_param[b]], step_t), dtype=F).reshape(2, -1)[:, 0]
+            np.testing.assert_allclose(table[k, b, 0], np.cos(th), atol=2e-7)
+            np.testing.assert_allclose(table[k, b, 1], np.sin(th), atol=2e-7)
+            np.testing.assert_allclose(table[k, b, 4:6], U0, rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(table[k, b, 6], om, rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(table[k, b, 2:4], ob.centers[b], rtol=0, atol=2e-6)
+        assert times[k] == step_t
+        step_t = F(step_t + F(cfg["dt"]))  # boundaries.py:530
+        U = np.asarray(ob.displacement[1](list(ob.displacement_param), step_t), dtype=F).reshape(2, -1)
+        c = np.asarray(ob.centers, dtype=F)
+        ob = ob.replace_centers(np.stack([c[:, 0] + F(cfg["dt"]) * U[0], c[:, 1] + F(cfg["dt"]) * U[1]], axis=1))
+    np.testing.assert_allclose(centers[-1], ob.centers, rtol=0, atol=3e-6)
+
+
+def test_grid_and_shift_mirror_the_oracle():
+    g = grids.Grid((6, 5), domain=((0.0, 3.0), (1.0, 2.0)))
+    og = field.Grid((6, 5), ((0.0, 3.0), (1.0, 2.0)))
+    assert g.step == og.step and g.cell_faces == og.cell_faces
+    for off in (g.cell_center,) + g.cell_faces:
+        for a, b in zip(g.axes(off), og.axes(off)):
+            np.testing.assert_array_equal(a.numpy(), b)
+    data = np.random.default_rng(0).standard_normal((6, 5)).astype(F)
+    vals = ((0.0, 0.0), (0.7, -0.4))
+    bc = boundaries.Moving_wall_boundary_conditions(2, vals, 0.0, [lambda t: 0.0] * 4)
+    obc = field.channel_bc(vals)
+    for off in ((1.0, 0.5), (0.5, 1.0)):
+        gv = grids.GridVariable(grids.GridArray(torch.from_numpy(data), off, g), bc)
+        ov = field.Var(data, off, og, obc)
+        for axis in (0, 1):
+            for k in (-2, -1, 1, 2):
+                got = gv.shift(k, axis)
+                want = ov.shift(k, axis)
+                np.testing.assert_allclose(got.data.numpy(), want.data, rtol=0, atol=1e-7)
+                assert got.offset == tuple(want.offset)
+        np.testing.assert_array_equal(gv.impose_bc().data.numpy(), ov.impose_bc().data)
+    pbc = boundaries.get_pressure_bc_from_velocity((gv, gv))
+    assert pbc.types[0][0] == "periodic" and pbc.types[1] == ("neumann", "neumann")
+    with pytest.raises(grids.InconsistentOffsetError):
+        grids.GridArray(data, (1.0, 0.5), g) + grids.GridArray(data, (0.5, 1.0), g)
+
+
+def test_update_bc_advances_the_float32_clock():
+    cfg = configs.flap600()
+    av = demo.make_all_variables(cfg)
+    for _ in range(3):
+        av = boundaries.update_BC(av, cfg["dt"])
+    t = F(0.0)
+    for _ in range(3):
+        t = F(t + F(cfg["dt"]))
+    assert av.velocity[0].bc.time_stamp == t
+
+
+def test_golden_small_fixture_is_reproduced_by_the_oracle():
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "small64_50.npz"))
+    cfg = configs.small_periodic(64)
+    st = oracle_state(cfg)
+    step = oracle_step(cfg, ib_window=None)
+    for _ in range(int(gold["steps"])):
+        st = step(st)
+    np.testing.assert_array_equal(st.velocity[0].data, gold["u_crop"])
+    np.testing.assert_array_equal(st.pressure.data, gold["p_crop"])
+    np.testing.assert_array_equal(st.particles.centers, gold["centers"])
+
+
+def test_product_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        demo.make_stepper(configs.small_periodic(32))

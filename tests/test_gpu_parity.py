@@ -1,0 +1,356 @@
+"""GPU parity: every CUDA stage, called through the C ABI (ctypes -> libjaxib_b200.so), against the
+NumPy oracle on the same seeded inputs.  Bars: bit-exact for marker -> cell indices; float fields
+within the stated tolerance (north star: rel-L2 <= 1e-5 after N steps)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from jax_ib_b200 import configs, demo, engine, kinematics, ops  # noqa: E402
+from oracle import field, ib, poisson, stencils, stepper, tracers, penalty  # noqa: E402
+
+from _adapter import oracle_state, oracle_step, rel_l2  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def random_fields(shape, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return tuple((scale * rng.standard_normal(shape)).astype(F) for _ in range(3))
+
+
+def make_cfg(shape, bc, convect, dt=1e-3, wall_u=(0.0, 0.0), wall_v=(0.0, 0.0), force=(0.0, 0.0)):
+    nx, ny = shape
+    return dict(name="t", shape=shape, domain=((0.5, 0.5 + 0.05 * nx), (0.25, 0.25 + 0.04 * ny)), dt=dt, density=1.3,
+                viscosity=0.07, bc=bc, convect=convect, force=force, wall_u=wall_u, wall_v=wall_v, bodies=None,
+                init="zero")
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("convect", ["upwind", "van_leer", "van_leer_limiters"])
+@pytest.mark.parametrize("bc,shape", [("periodic", (48, 40)), ("periodic", (70, 66)), ("channel", (40, 72)),
+                                      ("channel", (33, 20))])
+def test_explicit_terms_and_predictor(convect, bc, shape):
+    wall_u, wall_v = ((0.3, -0.2), (0.0, 0.0)) if bc == "channel" else ((0.0, 0.0), (0.0, 0.0))
+    cfg = make_cfg(shape, bc, convect, wall_u=wall_u, wall_v=wall_v, force=(0.4, -0.1))
+    u, v, p = random_fields(shape, 11)
+    st = oracle_state(cfg, np.float64, (u, v, p))
+    fx, fy = cfg["force"]
+    forcing = lambda vv: tuple(f * np.ones_like(x.data) for f, x in zip((fx, fy), vv))
+    k = stencils.explicit_terms(st.velocity, cfg["viscosity"], cfg["dt"], convect, forcing, cfg["density"])
+    spec = demo.make_spec(cfg)
+    du, dv = ops.explicit_terms(spec, dev(u), dev(v))
+    scale = max(np.abs(k[0]).max(), np.abs(k[1]).max())
+    assert np.abs(host(du) - k[0]).max() / scale < 3e-5
+    assert np.abs(host(dv) - k[1]).max() / scale < 3e-5
+    # predictor: u* = u + dt k - grad p   (time_stepping.py:208)
+    dP = [stencils.forward_difference(st.pressure, a) for a in range(2)]
+    us, vs = ops.explicit_predict(spec, dev(u), dev(v), dev(p))
+    for got, base, ki, g in zip((us, vs), (u, v), k, dP):
+        want = base.astype(np.float64) + cfg["dt"] * ki - g
+        assert rel_l2(host(got), want) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ K2/K3
+def _g1_like_markers(n=298, seed=0):
+    x0, y0 = configs.ellipse_markers([0.5, 0.06], ntheta=n // 2 + 1)
+    th = F(0.9)
+    xp = (x0 * np.cos(th) - y0 * np.sin(th) + F(7.3)).astype(F)
+    yp = (x0 * np.sin(th) + y0 * np.cos(th) + F(4.1)).astype(F)
+    return xp, yp
+
+
+def test_marker_cell_index_bit_exact():
+    cfg = configs.flap600()
+    spec = demo.make_spec(cfg)
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    xs = rng.uniform(0.0, 15.0, n).astype(F)
+    ys = rng.uniform(0.0, 15.0, n).astype(F)
+    faces = (np.arange(0, 600, dtype=F) * F(0.025)).astype(F)
+    adv = np.concatenate([faces, np.nextafter(faces, F(-1)), np.nextafter(faces, F(100)), faces + F(0.0125)]).astype(F)
+    xs[: adv.size] = adv
+    ys[: adv.size] = adv[::-1]
+    fld = torch.zeros(600, 600, device=DEV)
+    for off in ((1.0, 0.5), (0.5, 1.0), (0.5, 0.5)):
+        _, ci, cj = ops.ib_interp(spec, fld, off, dev(xs), dev(ys), return_cells=True)
+        ei, ej = ib.marker_cell_index(xs, ys, g, off)
+        np.testing.assert_array_equal(host(ci), ei)
+        np.testing.assert_array_equal(host(cj), ej)
+
+
+@pytest.mark.parametrize("R", [4, 6, 8])
+def test_ib_interp_and_spread_match_windowed_oracle(R):
+    cfg = dict(configs.flap600(), shape=(300, 280), domain=((0.0, 7.5 * 2), (0.0, 7.0)))
+    cfg["domain"] = ((0.0, 300 * 0.05), (0.0, 280 * 0.03))
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    spec = demo.make_spec(cfg, ib_window=R)
+    xp, yp = _g1_like_markers()
+    rng = np.random.default_rng(5)
+    fld = rng.standard_normal(cfg["shape"]).astype(F)
+    for off in ((1.0, 0.5), (0.5, 1.0)):
+        var = field.Var(fld, off, g, field.periodic_bc())
+        want = ib.interpolate_windowed(var, xp, yp, R)
+        got = host(ops.ib_interp(spec, dev(fld), off, dev(xp), dev(yp)))
+        assert rel_l2(got, want) < 2e-6
+        Fk = rng.standard_normal(xp.size).astype(F)
+        dS = np.sqrt((np.roll(xp, -1) - xp) ** 2 + (np.roll(yp, -1) - yp) ** 2).astype(F)
+        sw = ib.spread_windowed(Fk, xp, yp, dS, g, off, R)
+        sg = host(ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS)))
+        assert rel_l2(sg, sw) < 1e-6
+        assert np.array_equal(sg != 0, sw != 0)  # identical support
+
+
+def test_ib_interp_partition_of_unity_and_edges():
+    cfg = configs.flap600()
+    spec = demo.make_spec(cfg)
+    ones = torch.ones(600, 600, device=DEV)
+    xp = np.array([7.5, 0.01, 14.99, 3.3333, 0.13], dtype=F)  # interior, both domain edges (clipped window)
+    yp = np.array([7.5, 7.5, 0.02, 14.9, 0.13], dtype=F)
+    got = host(ops.ib_interp(spec, ones, (1.0, 0.5), dev(xp), dev(yp)))
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    want = ib.interpolate_windowed(field.Var(np.ones((600, 600), F), (1.0, 0.5), g, field.periodic_bc()), xp, yp, 6)
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    assert abs(got[0] - 1.0) < 1e-6 and got[1] < 0.9  # no periodic image at the edge
+    # empty input is a no-op
+    e = torch.zeros(0, device=DEV)
+    assert ops.ib_interp(spec, ones, (1.0, 0.5), e, e).numel() == 0
+
+
+@pytest.mark.parametrize("cfg_name", ["small", "bearing", "two_overlap"])
+def test_ib_force_fused_matches_oracle(cfg_name):
+    if cfg_name == "small":
+        cfg = configs.small_periodic(64)
+    elif cfg_name == "bearing":
+        cfg = configs.bearing300()
+    else:  # two bodies whose bounding boxes overlap but are not concentric
+        cfg = configs.small_periodic(96)
+        b = dict(cfg["bodies"])
+        L = cfg["domain"][0][1]
+        b.update(geometry=b["geometry"] * 2, centers=[[L * 0.5, L * 0.5], [L * 0.56, L * 0.47]],
+                 displacement_param=b["displacement_param"] * 2,
+                 rotation_param=[b["rotation_param"][0], [1.0, 0.4, 0.5, 1.1]])
+        cfg["bodies"] = b
+    rng = np.random.default_rng(9)
+    us = (0.3 * rng.standard_normal(cfg["shape"])).astype(F)
+    vs = (0.3 * rng.standard_normal(cfg["shape"])).astype(F)
+    t = F(0.37)
+    st = oracle_state(cfg, fields=(us, vs, np.zeros_like(us)))
+    vel = tuple(x.with_data(x.data, bc=x.bc.with_time(t)) for x in st.velocity)
+    force = ib.ibm_force(vel, st.particles, cfg["dt"], R=6)
+    want = [x.data + F(cfg["dt"]) * f for x, f in zip(vel, force)]
+    # product: host kinematics table for one step at time t
+    particles = demo.make_particles(cfg)
+    table, _, _ = kinematics.body_schedule(particles, t, cfg["dt"], 1)
+    stp = demo.make_stepper(cfg)
+    du, dv = dev(us), dev(vs)
+    mk = ops.ib_force(stp.spec, stp.bodies, dev(table[0]), du, dv)
+    # marker coordinates are bit-identical to the oracle's NumPy evaluation
+    xs, ys = [], []
+    for b in range(len(cfg["bodies"]["centers"])):
+        x, y = ib.body_markers(st.particles, b, t)
+        xs.append(x); ys.append(y)
+    np.testing.assert_array_equal(host(mk[0, 0]), np.concatenate(xs))
+    np.testing.assert_array_equal(host(mk[1, 0]), np.concatenate(ys))
+    for got, w, base in zip((du, dv), want, (us, vs)):
+        delta_w = w - base
+        assert rel_l2(host(got) - base, delta_w) < 2e-5
+        assert rel_l2(host(got), w) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ K4-K6
+@pytest.mark.parametrize("shape", [(64, 64), (60, 100), (128, 64), (30, 36), (256, 512), (600, 600), (1024, 256)])
+def test_pressure_solve_and_projection_periodic(shape):
+    cfg = make_cfg(shape, "periodic", "upwind")
+    u, v, p = random_fields(shape, 21)
+    st = oracle_state(cfg, fields=(u, v, p))
+    q_want = poisson.solve_fast_diag(st.velocity)
+    plan = ops.Plan(demo.make_spec(cfg))
+    q = host(plan.pressure_solve(dev(u), dev(v)))
+    assert rel_l2(q, q_want) < 5e-6
+    new_v, new_p = poisson.projection_and_update_pressure(st.velocity, st.pressure, "periodic")
+    uo, vo, po = plan.project(dev(u), dev(v), dev(p))
+    assert rel_l2(host(uo), new_v[0].data) < 5e-6
+    assert rel_l2(host(vo), new_v[1].data) < 5e-6
+    assert rel_l2(host(po), new_p.data) < 5e-6
+    # in-place aliasing gives the same answer
+    ui, vi, pi = dev(u), dev(v), dev(p)
+    plan.project(ui, vi, pi, inplace=True)
+    assert torch.equal(ui, uo) and torch.equal(vi, vo) and torch.equal(pi, po)
+    # identity: the projected field is discretely divergence free
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    pv = tuple(field.Var(host(x).astype(np.float64), o, g, field.periodic_bc()) for x, o in zip((uo, vo), g.cell_faces))
+    div0 = np.abs(stencils.divergence(tuple(x.with_data(x.data.astype(np.float64)) for x in st.velocity))).max()
+    assert np.abs(stencils.divergence(pv)).max() < 2e-5 * div0
+
+
+def test_pressure_solve_recovers_known_potential():
+    shape = (96, 80)
+    cfg = make_cfg(shape, "periodic", "upwind")
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    rng = np.random.default_rng(4)
+    q0 = rng.standard_normal(shape)
+    q0 -= q0.mean()
+    q = field.Var(q0, (0.5, 0.5), g, field.periodic_bc())
+    gu, gv = (stencils.forward_difference(q, a).astype(F) for a in range(2))
+    plan = ops.Plan(demo.make_spec(cfg))
+    got = host(plan.pressure_solve(dev(gu), dev(gv)))
+    assert rel_l2(got, q0) < 5e-6
+
+
+def test_unsupported_sizes_fail_loudly():
+    from jax_ib_b200._lib import JaxibError
+    with pytest.raises(JaxibError):
+        ops.Plan(demo.make_spec(make_cfg((64, 63), "periodic", "upwind")))  # odd ny
+    with pytest.raises(JaxibError):
+        ops.Plan(demo.make_spec(make_cfg((14, 64), "periodic", "upwind")))  # factor 7
+
+
+# ------------------------------------------------------------------------------------------------ full step
+def _run_product(cfg, steps, fields=None):
+    av = demo.make_all_variables(cfg, device="cpu", fields=fields)
+    stp = demo.make_stepper(cfg)
+    return stp.advance(av, steps)
+
+
+def _compare_state(out, st, tol):
+    errs = {}
+    for name, got, want in (("u", out.velocity[0].data, st.velocity[0].data), ("v", out.velocity[1].data, st.velocity[1].data),
+                            ("p", out.pressure.data, st.pressure.data)):
+        errs[name] = rel_l2(host(got), want)
+    assert max(errs.values()) < tol, errs
+    return errs
+
+
+@pytest.mark.parametrize("steps", [1, 10, 100])
+def test_full_step_small_vs_oracle(steps):
+    cfg = configs.small_periodic(64)
+    st = oracle_state(cfg)
+    step = oracle_step(cfg, ib_window=6)
+    for _ in range(steps):
+        st = step(st)
+    out = _run_product(cfg, steps)
+    _compare_state(out, st, 1e-5)
+    np.testing.assert_allclose(np.asarray(out.particles.particle_center), st.particles.centers, rtol=0, atol=2e-6)
+    assert np.float32(out.velocity[0].bc.time_stamp) == np.float32(st.velocity[0].bc.time_stamp)
+    assert out.Step_count == steps
+
+
+def test_step_is_functional_and_deterministic():
+    cfg = configs.small_periodic(64)
+    av = demo.make_all_variables(cfg, device="cuda")
+    before = av.velocity[0].data.clone()
+    stp = demo.make_stepper(cfg)
+    a = stp.advance(av, 7)
+    b = stp.advance(av, 7)
+    assert torch.equal(av.velocity[0].data, before)  # inputs untouched
+    for x, y in zip((a.velocity[0], a.velocity[1], a.pressure), (b.velocity[0], b.velocity[1], b.pressure)):
+        assert torch.equal(x.data, y.data)  # bit-reproducible (no float atomics)
+    # 3 + 4 steps == 7 steps
+    c = stp.advance(stp.advance(av, 3), 4)
+    assert torch.equal(c.velocity[0].data, a.velocity[0].data)
+    assert torch.equal(torch.as_tensor(np.asarray(c.particles.particle_center)), torch.as_tensor(np.asarray(a.particles.particle_center)))
+
+
+@pytest.mark.parametrize("name,cfg_fn,tol", [
+    ("flap600_20", configs.flap600, 1e-5),
+    ("bearing300_20", configs.bearing300, 1e-5),
+    ("small64_50", lambda: configs.small_periodic(64), 1e-5),
+])
+def test_golden_trajectories(name, cfg_fn, tol):
+    """Fixtures made by tests/golden/make_golden.py with the DENSE (reference-faithful) IB sums."""
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = cfg_fn()
+    out = _run_product(cfg, int(gold["steps"]))
+    a, b, c, d = (int(x) for x in gold["crop"])
+    for key, var in (("u", out.velocity[0]), ("v", out.velocity[1]), ("p", out.pressure)):
+        full = host(var.data)
+        assert rel_l2(full[a:b, c:d], gold[key + "_crop"]) < tol, key
+        l2 = np.sqrt((full.astype(np.float64) ** 2).sum())
+        assert abs(l2 - float(gold[key + "_l2"])) <= tol * float(gold[key + "_l2"]), key
+    np.testing.assert_allclose(np.asarray(out.particles.particle_center), gold["centers"], rtol=0, atol=2e-6)
+    assert np.float32(out.velocity[0].bc.time_stamp) == gold["time"]
+    assert out.Step_count == int(gold["step_count"])
+
+
+def test_batched_ensemble_matches_single():
+    cfg = configs.small_periodic(64)
+    single = _run_product(cfg, 5)
+    stp = demo.make_stepper(cfg, batch=3)
+    u0, v0, p0 = configs.initial_fields(cfg)
+    u = dev(np.stack([u0] * 3)); v = dev(np.stack([v0] * 3)); p = dev(np.stack([p0] * 3))
+    table, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], 5)
+    tb = dev(np.ascontiguousarray(np.broadcast_to(table[:, None], (5, 3) + table.shape[1:])))
+    stp.run_block(u, v, p, 5, tb)
+    for k in range(3):
+        assert torch.equal(u[k].cpu(), single.velocity[0].data.cpu())
+        assert torch.equal(p[k].cpu(), single.pressure.data.cpu())
+
+
+# ------------------------------------------------------------------------------------------------ big-size properties
+def test_properties_at_2048():
+    cfg = configs.ib_periodic(2048)
+    stp = demo.make_stepper(cfg)
+    av = demo.make_all_variables(cfg, device="cuda")
+    out = stp.advance(av, 3)
+    u, v = out.velocity[0].data, out.velocity[1].data
+    dx = cfg["domain"][0][1] / 2048
+    div = (u - torch.roll(u, 1, 0)) / dx + (v - torch.roll(v, 1, 1)) / dx
+    assert torch.isfinite(u).all() and torch.isfinite(out.pressure.data).all()
+    assert float(div.abs().max()) < 1e-3 * float(u.abs().max()) / dx
+    # the no-slip constraint is being enforced: fluid velocity at the markers approaches the body velocity
+    assert out.Step_count == 3
+
+
+# ------------------------------------------------------------------------------------------------ tracers / penalty
+def test_tracers_match_oracle():
+    cfg = configs.bearing300()
+    u, v, _ = random_fields(cfg["shape"], 31, 0.2)
+    spec = demo.make_spec(cfg)
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    U = field.Var(u, (1.0, 0.5), g, field.periodic_bc())
+    V = field.Var(v, (0.5, 1.0), g, field.periodic_bc())
+    rng = np.random.default_rng(8)
+    n = 1401
+    R = rng.uniform(0.2, 4.8, (n, 2)).astype(F)
+    R[:5] = [[0.001, 2.0], [4.999, 2.0], [2.0, 0.001], [2.0, 4.9999], [5.2, 2.0]]  # edges / outside: zero taps
+    got = host(ops.bilinear_sample(spec, dev(u), (1.0, 0.5), dev(R)))
+    np.testing.assert_allclose(got, tracers.interpolate_field(U, R), rtol=1e-5, atol=1e-6)
+    species = np.concatenate([np.zeros(1200), np.ones(200), [2]]).astype(np.int32)
+    h = np.array([[0, 5, 5], [5, 0, 0], [5, 0, 0]], F)
+    r0 = np.array([[0, 0.0314, 0.5], [0.0314, 0, 0], [0.5, 0, 0]], F)
+    Fo = tracers.harmonic_morse_force(R.astype(np.float64), species, h, r0, (5.0, 5.0))
+    Fg = host(ops.pair_force(dev(R), dev(species), dev(h), dev(r0), (5.0, 5.0)))
+    assert rel_l2(Fg, Fo) < 1e-5
+    mobile = (species == 0)
+    st = tracers.brownian_step(tracers.BrownianState(R), (U, V), cfg["dt"], 1.0, 0.0,
+                               lambda RR: Fo.astype(F), mobile)
+    Rg = dev(R.copy())
+    ops.tracer_step(spec, dev(u), dev(v), Rg, cfg["dt"], pair=dev(Fo.astype(F)), is_mobile=dev(mobile.astype(np.uint8)))
+    np.testing.assert_allclose(host(Rg), st.position, rtol=0, atol=1e-6)
+
+
+def test_penalty_mask_matches_oracle():
+    cfg = configs.small_periodic(64, bodies=False)
+    spec = demo.make_spec(cfg)
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    theta = np.linspace(0, 2 * np.pi, 65)
+    Rts = np.stack([penalty.param_ellipse([0.6, 0.3], theta), penalty.param_circle([0.4], theta)]).astype(F)
+    centers = np.array([[1.2, 1.7], [2.3, 1.1]], F)
+    want = penalty.perm_multiple(g, centers, Rts, penalty.tanh_smoothing, (2000.0, 0.05), np.float64)
+    got = host(ops.penalty_perm(spec, dev(centers), dev(Rts), 2000.0, 0.05))
+    assert np.abs(got - want).max() < 2e-2 * 2000.0 * 1e-2  # tanh is steep: compare in absolute terms
