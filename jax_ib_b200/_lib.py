@@ -63,7 +63,7 @@ _SIGNATURES = {
     "jaxib_tracer_step": (C.c_int, [_P, C.POINTER(Grid), _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double,
                                     C.c_int32, _P]),
     "jaxib_bilinear_sample": (C.c_int, [_P, C.POINTER(Grid), C.c_double, C.c_double, _P, _P, C.c_int32, _P]),
-    "jaxib_pair_force": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double,
+    "jaxib_pair_force": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double,
                                    C.c_double, C.c_double, _P]),
     "jaxib_penalty_perm": (C.c_int, [_P, C.POINTER(Grid), _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P]),
 }

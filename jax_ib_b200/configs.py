@@ -116,8 +116,8 @@ def ib_periodic(n=2048, nbodies_axis=2, seed=4, dx=0.025, flow_amp=0.5):
         name=f"ib{n}", shape=(n, n), domain=((0.0, L), (0.0, L)), dt=5e-4, density=1.0, viscosity=0.05,
         bc="periodic", convect="upwind", force=(0.0, 0.0), wall_u=(0.0, 0.0), wall_v=(0.0, 0.0),
         bodies=dict(shape="ellipse", geometry=[[0.5, 0.06]] * B, centers=centers,
-                    displacement="harmonic", displacement_param=[[2.8, 0.25]] * B,
-                    rotation="harmonic",
+                    displacement="harmonic_multi", displacement_param=[[2.8, 0.25]] * B,
+                    rotation="harmonic_multi",
                     rotation_param=[[math.pi / 2, math.pi / 4, 0.25, 2 * math.pi * b / B] for b in range(B)]),
         init=("divfree", seed, flow_amp),
     )

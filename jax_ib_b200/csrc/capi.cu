@@ -61,7 +61,8 @@ struct Scratch {
 
 static size_t scratch_need(const GridF& g, int n_markers) {
   size_t plane = (size_t)g.batch * g.nx * g.ny;
-  return (3 * plane + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256;
+  size_t spectrum = (size_t)g.batch * g.nx * (g.ny + 8);  // [nx][ny/2 + 4] complex
+  return (2 * plane + spectrum + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256;
 }
 
 static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scratch* out) {
@@ -76,7 +77,7 @@ static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scr
   out->u_star = base;
   out->v_star = base + plane;
   out->spectrum = base + 2 * plane;
-  out->markers = base + 3 * plane;
+  out->markers = base + 2 * plane + (size_t)g.batch * g.nx * (g.ny + 8);
   return JAXIB_OK;
 }
 

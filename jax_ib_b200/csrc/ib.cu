@@ -26,8 +26,9 @@
 namespace jaxib {
 namespace {
 
-constexpr int TS = 16;          // spread tile edge (cells)
-constexpr int SPREAD_THREADS = TS * TS;
+constexpr int TS = 8;            // spread tile edge (cells)
+constexpr int SPREAD_SLICES = 4;  // threads cooperating on one cell
+constexpr int SPREAD_THREADS = TS * TS * SPREAD_SLICES;
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float mesh_coord(float lower, int i, float off, float h) {
@@ -153,30 +154,35 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
 
 // ---- spreading: tile gather ---------------------------------------------------------------------
 struct SpreadShared {
-  float xp[SPREAD_THREADS], yp[SPREAD_THREADS], F[SPREAD_THREADS], dS[SPREAD_THREADS];
+  float xp[SPREAD_THREADS], yp[SPREAD_THREADS], c[SPREAD_THREADS], part[SPREAD_THREADS];
   int ik[SPREAD_THREADS], jk[SPREAD_THREADS];
   int warp_count[SPREAD_THREADS / 32];
-  int count;
 };
 
-// Culls markers [k0, k1) against the tile [ti0, ti0+TS) x [tj0, tj0+TS) and accumulates this
-// thread's cell (i, j).  Sum order = marker order (deterministic).
+// Culls markers [k0, k1) against the tile [ti0, ti0+TS) x [tj0, tj0+TS) (order-preserving ballot
+// compaction) and accumulates cell (i, j).  A CTA is TS*TS cells x SPREAD_SLICES threads per cell:
+// slice s sums list entries s, s+4, ... in order and the four partial sums are combined in a fixed
+// order, so the result is deterministic (no atomics) while a body's few tiles still fill the SMs.
 __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __restrict__ mxp,
                                 const float* __restrict__ myp, const float* __restrict__ mF,
                                 const float* __restrict__ mdS, int k0, int k1, int ti0, int tj0, int i, int j,
                                 bool valid) {
-  const int tid = threadIdx.y * TS + threadIdx.x;
+  const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  const int slice = tid / (TS * TS);  // which quarter of the culled list this thread sums
   const float X = mesh_coord(m.lower_x, i, m.off_x, m.dx);
   const float Y = mesh_coord(m.lower_y, j, m.off_y, m.dy);
+  const float mhalf_inv_w2 = -0.5f / (m.dx * m.dx);
   float acc = 0.0f;
   for (int base = k0; base < k1; base += SPREAD_THREADS) {
     const int k = base + tid;
     bool keep = false;
-    float xp = 0.f, yp = 0.f, F = 0.f, dS = 0.f;
+    float xp = 0.f, yp = 0.f, c = 0.f;
     int ik = 0, jk = 0;
     if (k < k1) {
-      xp = mxp[k]; yp = myp[k]; F = mF[k]; dS = mdS[k];
+      xp = mxp[k]; yp = myp[k];
+      // IBM_Force.py:67: F * delta(r, 0, dx) * dS -- the marker's constant factor F * pref * dS
+      c = mF[k] * m.pref_x * mdS[k];
       ik = cell_index(xp, m.dx, m.off_x);
       jk = cell_index(yp, m.dy, m.off_y);
       keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
@@ -193,24 +199,28 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
     }
     if (keep) {
       const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
-      sh.xp[pos] = xp; sh.yp[pos] = yp; sh.F[pos] = F; sh.dS[pos] = dS; sh.ik[pos] = ik; sh.jk[pos] = jk;
+      sh.xp[pos] = xp; sh.yp[pos] = yp; sh.c[pos] = c; sh.ik[pos] = ik; sh.jk[pos] = jk;
     }
     __syncthreads();
     if (valid) {
-      for (int q = 0; q < totalc; ++q) {
+      for (int q = slice; q < totalc; q += SPREAD_SLICES) {
         const int di = i - sh.ik[q], dj = j - sh.jk[q];
         if (di > -m.R && di <= m.R && dj > -m.R && dj <= m.R) {
-          const float ddx = __fsub_rn(sh.xp[q], X), ddy = __fsub_rn(sh.yp[q], Y);
-          const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
-          // IBM_Force.py:67: F * delta(r, 0, dx) * dS  -- width dx on both axes
-          const float gk = gauss(r, 0.0f, m.dx, m.pref_x);
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(sh.F[q], gk), sh.dS[q]));
+          // delta(sqrt(d2), 0, dx) = pref * exp(-0.5 d2 / dx^2): width dx on both axes (IBM_Force.py:67)
+          const float ddx = sh.xp[q] - X, ddy = sh.yp[q] - Y;
+          acc = fmaf(sh.c[q], expf((ddx * ddx + ddy * ddy) * mhalf_inv_w2), acc);
         }
       }
     }
     __syncthreads();
   }
-  return acc;
+  // combine the slices in a fixed order: ((s0 + s1) + (s2 + s3))
+  sh.part[tid] = acc;
+  __syncthreads();
+  const int cell = tid & (TS * TS - 1);
+  float tot = (sh.part[cell] + sh.part[cell + TS * TS]) + (sh.part[cell + 2 * TS * TS] + sh.part[cell + 3 * TS * TS]);
+  __syncthreads();
+  return tot;  // meaningful in slice 0 (every slice computes the same value)
 }
 
 __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic, int& jc) {
@@ -233,7 +243,8 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int ty = blockIdx.x / tiles_per_axis, tx = blockIdx.x - ty * tiles_per_axis;
   const int ti0 = ic - half_extent + ty * TS, tj0 = jc - half_extent + tx * TS;
   if (ti0 >= g.nx || ti0 + TS <= 0 || tj0 >= g.ny || tj0 + TS <= 0) return;  // tile fully outside: no image
-  const int i = ti0 + threadIdx.y, j = tj0 + threadIdx.x;
+  const int cell = threadIdx.x & (TS * TS - 1);
+  const int i = ti0 + cell / TS, j = tj0 + cell % TS;
   bool valid = i >= 0 && i < g.nx && j >= 0 && j < g.ny && i <= ic + half_extent && j <= jc + half_extent;
   // a cell covered by several bounding boxes belongs to the lowest-numbered body
   for (int b2 = 0; b2 < b && valid; ++b2) {
@@ -257,7 +268,7 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
     f_total = __fadd_rn(f_total, fb);
     touched = true;
   }
-  if (valid && touched && f_total != 0.0f) {
+  if (valid && touched && f_total != 0.0f && threadIdx.x < TS * TS) {
     float* out = (comp == 0 ? u_star : v_star) + (size_t)s * g.nx * g.ny + (size_t)i * g.ny + j;
     *out = __fadd_rn(*out, __fmul_rn(g.dt, f_total));  // time_stepping.py:223
   }
@@ -286,10 +297,11 @@ spread_points_kernel(GridF g, float off_x, float off_y, const float* __restrict_
   const int ti0 = blockIdx.y * TS, tj0 = blockIdx.x * TS;
   if (ti0 > box[1] + g.R || ti0 + TS <= box[0] - g.R || tj0 > box[3] + g.R || tj0 + TS <= box[2] - g.R) return;
   const Mesh m = make_mesh(g, off_x, off_y);
-  const int i = ti0 + threadIdx.y, j = tj0 + threadIdx.x;
+  const int cell = threadIdx.x & (TS * TS - 1);
+  const int i = ti0 + cell / TS, j = tj0 + cell % TS;
   const bool valid = i < g.nx && j < g.ny;
   float f = gather_markers(sh, m, xp, yp, F, dS, 0, n, ti0, tj0, i, j, valid);
-  if (valid && f != 0.0f) {
+  if (valid && f != 0.0f && threadIdx.x < TS * TS) {
     float* o = out + (size_t)i * g.ny + j;
     *o = __fadd_rn(*o, __fmul_rn(scale, f));
   }
@@ -322,7 +334,7 @@ int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const
   const float hmin = g.dx < g.dy ? g.dx : g.dy;
   const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
   const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
-  dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(TS, TS);
+  dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
   spread_bodies_kernel<<<grid, block, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
                                               half_extent, tiles, u_star, v_star);
   if (hook) cudaEventRecord(hook->ev[1], s);
@@ -335,7 +347,7 @@ int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, c
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   bbox_init_kernel<<<1, 1, 0, s>>>(box_scratch);
   bbox_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, off_x, off_y, xp, yp, n, box_scratch);
-  dim3 grid((g.ny + TS - 1) / TS, (g.nx + TS - 1) / TS), block(TS, TS);
+  dim3 grid((g.ny + TS - 1) / TS, (g.nx + TS - 1) / TS), block(SPREAD_THREADS);
   spread_points_kernel<<<grid, block, 0, s>>>(g, off_x, off_y, F, xp, yp, dS, n, scale, box_scratch, out);
   return check_launch("spread_points_kernel");
 }

@@ -90,6 +90,7 @@ struct RowParams {
   const float2* tw;
   const int* pos;
   int rows_per_cta;
+  int sp;       // spectrum row pitch in complex values (>= ny/2 + 1, multiple of 4)
   float scale;  // 1 / (nx * ny/2)
 };
 
@@ -103,7 +104,7 @@ __global__ void rows_fwd_kernel(RowParams P, const float* __restrict__ u, const 
   const int n2 = g.ny >> 1;
   const size_t plane = (size_t)g.nx * g.ny;
   const int b = blockIdx.y;
-  u += b * plane; v += b * plane; spec += (size_t)b * g.nx * n2;
+  u += b * plane; v += b * plane; spec += (size_t)b * g.nx * P.sp;
   const int i0 = blockIdx.x * P.rows_per_cta;
   const int i1 = min(i0 + P.rows_per_cta, g.nx);
   for (int i = i0; i < i1; ++i) {
@@ -124,11 +125,15 @@ __global__ void rows_fwd_kernel(RowParams P, const float* __restrict__ u, const 
     __syncthreads();
     fft_forward(P.pl, buf, 1, 0, P.tw, 2);
     // untangle the packed real transform and store the half spectrum (DC.im carries Nyquist)
-    float2* out = spec + (size_t)i * n2;
+    float2* out = spec + (size_t)i * P.sp;
     for (int k = threadIdx.x; k <= n2 / 2; k += blockDim.x) {
       if (k == 0) {
         float2 z = buf[padi(P.pos[0])];
-        out[0] = make_float2(z.x + z.y, z.x - z.y);
+        // DC and Nyquist are both real; they are kept as separate columns: packing them into one
+        // complex column would tie the noise floor of the (most amplified) DC column to the size
+        // of the Nyquist column
+        out[0] = make_float2(z.x + z.y, 0.0f);
+        out[n2] = make_float2(z.x - z.y, 0.0f);
       } else {
         const int km = n2 - k;
         float2 zk = buf[padi(P.pos[k])], zm = cconj(buf[padi(P.pos[km])]);
@@ -153,7 +158,7 @@ __global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, co
   const int pitch = padi(n2) + 1;
   const size_t plane = (size_t)g.nx * g.ny;
   const int b = blockIdx.y;
-  spec += (size_t)b * g.nx * n2;
+  spec += (size_t)b * g.nx * P.sp;
   if (PROJECT) { u += b * plane; v += b * plane; p += b * plane; u_out += b * plane; v_out += b * plane; }
   p_out += b * plane;
   const int i0 = blockIdx.x * P.rows_per_cta;
@@ -162,11 +167,11 @@ __global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, co
   for (int ii = i0; ii <= last; ++ii) {
     const int i = ii >= g.nx ? ii - g.nx : ii;
     float2* cur = smem + ((ii - i0) & 1) * pitch;
-    const float2* in = spec + (size_t)i * n2;
+    const float2* in = spec + (size_t)i * P.sp;
     for (int k = threadIdx.x; k <= n2 / 2; k += blockDim.x) {
       if (k == 0) {
-        float2 x = in[0];  // (X[0], X[ny/2]) both real
-        cur[padi(P.pos[0])] = make_float2(0.5f * (x.x + x.y), 0.5f * (x.x - x.y));
+        const float x0 = in[0].x, xn = in[n2].x;  // X[0], X[ny/2]: both real
+        cur[padi(P.pos[0])] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
       } else {
         const int km = n2 - k;
         float2 xk = in[k], xm = cconj(in[km]);
@@ -214,7 +219,7 @@ __global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, co
 
 // ---- K5 -------------------------------------------------------------------------------------------
 struct ColParams {
-  int nx, n2, ncols;      // spectrum is [nx][n2]; ncols = number of stored columns (n2)
+  int nx, sp, ncols;      // spectrum is [nx][sp]; ncols = number of stored columns
   FftPlan pl;
   const float2* tw;
   const int* pos;
@@ -222,7 +227,6 @@ struct ColParams {
   const double* lam_y;
   int cols_per_cta;
   int packed_all;         // channel: every stored column is a pair of real (DCT) columns
-  int nyq;                // periodic: index of the Nyquist eigenvalue paired with column 0
 };
 
 __device__ __forceinline__ float inv_eig(double lx, double ly) {
@@ -234,20 +238,20 @@ __global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
   extern __shared__ float2 buf[];
   const int nx = P.nx;
   const int pitch = padi(nx) + 1;
-  spec += (size_t)blockIdx.y * nx * P.n2;
+  spec += (size_t)blockIdx.y * nx * P.sp;
   const int c0 = blockIdx.x * P.cols_per_cta;
   const int nc = min(P.cols_per_cta, P.ncols - c0);
   const int total = nx * nc;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     int i = e / nc, c = e - i * nc;
-    buf[c * pitch + padi(i)] = spec[(size_t)i * P.n2 + c0 + c];
+    buf[c * pitch + padi(i)] = spec[(size_t)i * P.sp + c0 + c];
   }
   __syncthreads();
   fft_forward(P.pl, buf, nc, pitch, P.tw, 1);
   for (int c = 0; c < nc; ++c) {
     float2* col = buf + c * pitch;
     const int ky = c0 + c;
-    const bool packed = P.packed_all || ky == 0;
+    const bool packed = P.packed_all;
     if (!packed) {
       const double ly = P.lam_y[ky];
       for (int q = threadIdx.x; q < nx; q += blockDim.x) {
@@ -257,8 +261,8 @@ __global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
     } else {
       // column holds A + iB with A, B the transforms of two REAL sequences a (eigenvalue ly_a) and
       // b (ly_b): A[k] = (Z[k] + conj Z[-k])/2, B[k] = (Z[k] - conj Z[-k])/(2i)
-      const double lya = P.packed_all ? P.lam_y[2 * ky] : P.lam_y[0];
-      const double lyb = P.packed_all ? P.lam_y[2 * ky + 1] : P.lam_y[P.nyq];
+      const double lya = P.lam_y[2 * ky];
+      const double lyb = P.lam_y[2 * ky + 1];
       for (int k = threadIdx.x; k <= nx / 2; k += blockDim.x) {
         const int km = k == 0 ? 0 : nx - k;
         const int p1 = P.pos[k], p2 = P.pos[km];
@@ -276,7 +280,7 @@ __global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
   fft_inverse(P.pl, buf, nc, pitch, P.tw, 1);
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     int i = e / nc, c = e - i * nc;
-    spec[(size_t)i * P.n2 + c0 + c] = buf[c * pitch + padi(i)];
+    spec[(size_t)i * P.sp + c0 + c] = buf[c * pitch + padi(i)];
   }
 }
 
@@ -284,7 +288,7 @@ __global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
 
 const GridF& plan_grid(const jaxib_plan* plan) { return plan->gf; }
 size_t spectrum_floats(const jaxib_plan* plan) {
-  return (size_t)plan->gf.batch * plan->gf.nx * plan->gf.ny;  // [nx][ny/2] complex
+  return (size_t)plan->gf.batch * plan->gf.nx * (plan->gf.ny + 8);  // [nx][ny/2 + 4] complex
 }
 
 int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
@@ -293,6 +297,7 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   const int n2 = g.ny / 2;
   RowParams rp;
   rp.g = g; rp.pl = pl->row; rp.tw = pl->tw_row; rp.pos = pl->row_pos; rp.rows_per_cta = pl->rows_per_cta;
+  rp.sp = n2 + 4;
   rp.scale = (float)(1.0 / ((double)g.nx * (double)n2));
   float2* spec = reinterpret_cast<float2*>(spectrum);
   dim3 rgrid((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
@@ -301,10 +306,10 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);
   ColParams cp;
-  cp.nx = g.nx; cp.n2 = n2; cp.ncols = n2; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
+  cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
   cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
-  cp.packed_all = g.bc == JAXIB_BC_CHANNEL; cp.nyq = n2;
-  dim3 cgrid((n2 + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
+  cp.packed_all = g.bc == JAXIB_BC_CHANNEL;
+  dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
   cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
   rc = check_launch("cols_kernel");
   if (rc) return rc;

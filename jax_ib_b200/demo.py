@@ -7,9 +7,10 @@ import torch
 
 from . import boundaries, configs, engine, grids, kinematics, ops, particle_class
 
-DISPLACEMENT = {"harmonic": kinematics.displacement, "fourier": kinematics.Displacement_Foil_Fourier_Dotted_Mutliple}
+DISPLACEMENT = {"harmonic": kinematics.displacement, "harmonic_multi": kinematics.displacement_multiple, "fourier": kinematics.Displacement_Foil_Fourier_Dotted_Mutliple}
 ROTATION = {
     "harmonic": kinematics.rotation,
+    "harmonic_multi": kinematics.rotation_multiple,
     "fourier": kinematics.rotation_Foil_Fourier_Dotted_Mutliple,
     "fourier_normalized": kinematics.rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED,
 }

@@ -123,3 +123,19 @@ def body_schedule(particles, t0: float, dt: float, nsteps: int):
         table[:, b, 4:6] = U_b
         table[:, b, 6] = om
     return table, times, centers
+
+
+# ---- multi-body harmonic laws (extension: the reference's `displacement` / `rotation` accept one
+# body only -- `list(*parameters)` -- so grids with several flapping bodies need a vectorised form)
+def displacement_multiple(parameters, t):
+    """[2, B]: per body [A0/2 cos(2 pi f t), 0] with parameters = [[A0, f], ...]."""
+    A0 = torch.stack([_as(x, t).reshape(()) for x in _col(parameters, 0)])
+    f = torch.stack([_as(x, t).reshape(()) for x in _col(parameters, 1)])
+    x = A0 / 2 * torch.cos(_TWO_PI * f * t)
+    return torch.stack([x, torch.zeros_like(x)])
+
+
+def rotation_multiple(parameters, t):
+    """[B]: alpha0 + beta sin(2 pi f t + phi) with parameters = [[alpha0, beta, f, phi], ...]."""
+    a0, beta, f, phi = (torch.stack([_as(x, t).reshape(()) for x in _col(parameters, i)]) for i in range(4))
+    return a0 + beta * torch.sin(_TWO_PI * f * t + phi)

@@ -139,3 +139,38 @@ ROTATION = {
     "fourier": (rotation_fourier, rotation_fourier_dot),
     "fourier_normalized": (rotation_fourier_normalized, rotation_fourier_normalized_dot),
 }
+
+
+# ---- multi-body harmonic laws (vectorised form of `displacement` / `rotation`; the reference's own
+# versions take a single body).  Used by the multi-body synthetic workloads.
+def displacement_multi(parameters, t, dtype=_F):
+    cols = _unpack(parameters, 2, dtype)
+    A0, f = cols
+    t = _t(t, dtype)
+    x = A0 / _t(2, dtype) * np.cos(_t(2 * np.pi, dtype) * f * t)
+    return np.array([x, np.zeros_like(x)], dtype=dtype)
+
+
+def displacement_multi_dot(parameters, t, dtype=_F):
+    A0, f = _unpack(parameters, 2, dtype)
+    t = _t(t, dtype)
+    two_pi = _t(2 * np.pi, dtype)
+    x = -(A0 / _t(2, dtype)) * np.sin(two_pi * f * t) * (two_pi * f)
+    return np.array([x, np.zeros_like(x)], dtype=dtype)
+
+
+def rotation_multi(parameters, t, dtype=_F):
+    a0, beta, f, phi = _unpack(parameters, 4, dtype)
+    t = _t(t, dtype)
+    return a0 + beta * np.sin(_t(2 * np.pi, dtype) * f * t + phi)
+
+
+def rotation_multi_dot(parameters, t, dtype=_F):
+    a0, beta, f, phi = _unpack(parameters, 4, dtype)
+    t = _t(t, dtype)
+    two_pi = _t(2 * np.pi, dtype)
+    return beta * np.cos(two_pi * f * t + phi) * (two_pi * f)
+
+
+DISPLACEMENT["harmonic_multi"] = (displacement_multi, displacement_multi_dot)
+ROTATION["harmonic_multi"] = (rotation_multi, rotation_multi_dot)

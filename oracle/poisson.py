@@ -24,6 +24,7 @@ from __future__ import annotations
 import functools
 
 import numpy as np
+import scipy.fft
 import scipy.linalg
 
 from .field import Var, DIRICHLET, NEUMANN, PERIODIC, all_periodic, pressure_bc_from_velocity
@@ -86,8 +87,12 @@ def pseudoinverse(operators, dtype, circulant: bool, implementation=None):
         diag = diag.astype(cdtype)
 
         def apply(rhs):
+            # scipy.fft keeps single precision for float32 input (pocketfft templated on float), as
+            # jnp.fft / XLA do; numpy.fft would silently transform complex64 in double (measured:
+            # rel-L2 2.5e-8 vs 1.1e-7 at n = 1024), which is NOT what the reference computes.
             axes = tuple(range(rhs.ndim))
-            return np.fft.irfftn(diag * np.fft.rfftn(rhs.astype(dtype)), s=rhs.shape, axes=axes).astype(dtype)
+            spec = scipy.fft.rfftn(rhs.astype(dtype), axes=axes)
+            return scipy.fft.irfftn((diag * spec).astype(cdtype), s=rhs.shape, axes=axes).astype(dtype)
 
         return apply
     if implementation == "matmul":

@@ -53,6 +53,15 @@ def main(only=None):
         for _ in range(steps):
             st = step(st)
         data = summarize(st, crop)
+        # float32 round-off floor of this trajectory: the same oracle in float64 against float32
+        # (what two correct float32 implementations may legitimately differ by)
+        st64 = oracle_state(cfg, np.float64)
+        for _ in range(steps):
+            st64 = step(st64)
+        for key, a, b in (("u", st.velocity[0], st64.velocity[0]), ("v", st.velocity[1], st64.velocity[1]),
+                          ("p", st.pressure, st64.pressure)):
+            d = b.data[crop]
+            data[key + "_noise"] = np.float64(np.linalg.norm(a.data[crop] - d) / max(np.linalg.norm(d), 1e-300))
         data["crop"] = np.array([crop[0].start, crop[0].stop, crop[1].start, crop[1].stop])
         data["steps"] = np.int64(steps)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
