@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libjaxib_b200.so")
 STAMP = os.path.join(OUT_DIR, "build.stamp")
-SOURCES = ["capi.cu", "stencil.cu", "ib.cu", "poisson.cu", "tracer.cu", "slab.cu"]
-HEADERS = ["common.cuh", "fft.cuh", os.path.join("..", "..", "include", "jaxib_b200.h")]
+SOURCES = ["capi.cu", "stencil.cu", "stencil_fast.cu", "ib.cu", "poisson.cu", "poisson_fast.cu", "tracer.cu", "slab.cu"]
+HEADERS = ["common.cuh", "fft.cuh", "poisson_fast.cuh", os.path.join("..", "..", "include", "jaxib_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "fft.cuh"
+#include "poisson_fast.cuh"
 
 struct jaxib_plan {
   jaxib_grid grid;
@@ -39,6 +40,11 @@ struct jaxib_plan {
   double* lam_y;       // ly_l, l <= ny/2
   int row_threads, col_threads, cols_per_cta, rows_per_cta;
   size_t row_smem, col_smem;
+  // power-of-two fast paths (poisson_fast.cu)
+  bool fast_rows, fast_cols;
+  int fast_rows_per_group;
+  float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
+  float* lam_y_f;
 };
 
 namespace jaxib {
@@ -144,6 +150,7 @@ __global__ void rows_fwd_kernel(RowParams P, const float* __restrict__ u, const 
         if (km != k) out[km] = cconj(csub(e, t));
       }
     }
+    if (threadIdx.x < 3) out[n2 + 1 + threadIdx.x] = make_float2(0.0f, 0.0f);  // padding columns stay finite
     __syncthreads();
   }
 }
@@ -301,27 +308,46 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   rp.scale = (float)(1.0 / ((double)g.nx * (double)n2));
   float2* spec = reinterpret_cast<float2*>(spectrum);
   dim3 rgrid((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
-  rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
-  int rc = check_launch("rows_fwd_kernel");
+  FastRowParams frp;
+  frp.g = g; frp.tw = pl->tw_row; frp.sp = rp.sp; frp.rows_per_group = pl->fast_rows_per_group; frp.scale = rp.scale;
+  int rc;
+  if (pl->fast_rows) {
+    rc = launch_rows_fwd_fast(s, frp, u, v, spec);
+  } else {
+    rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
+    rc = check_launch("rows_fwd_kernel");
+  }
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);
-  ColParams cp;
-  cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
-  cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
-  cp.packed_all = g.bc == JAXIB_BC_CHANNEL;
-  dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
-  cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
-  rc = check_launch("cols_kernel");
+  if (pl->fast_cols) {
+    FastColParams fcp;
+    fcp.nx = g.nx; fcp.sp = rp.sp; fcp.ncols = n2 + 1; fcp.tw = pl->tw_col;
+    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f;
+    rc = launch_cols_fast(s, fcp, g.batch, spec);
+  } else {
+    ColParams cp;
+    cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
+    cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
+    cp.packed_all = g.bc == JAXIB_BC_CHANNEL;
+    dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
+    cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
+    rc = check_launch("cols_kernel");
+  }
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[1], s);
-  if (q_only) {
-    rows_inv_kernel<false><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, nullptr, nullptr, nullptr,
-                                                                           nullptr, nullptr, q_only);
+  if (pl->fast_rows) {
+    rc = launch_rows_inv_fast(s, frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
   } else {
-    rows_inv_kernel<true><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, u, v, p, u_out, v_out, p_out);
+    if (q_only) {
+      rows_inv_kernel<false><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, nullptr, nullptr, nullptr,
+                                                                             nullptr, nullptr, q_only);
+    } else {
+      rows_inv_kernel<true><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, u, v, p, u_out, v_out, p_out);
+    }
+    rc = check_launch("rows_inv_kernel");
   }
   if (hook) cudaEventRecord(hook->ev[2], s);
-  return check_launch("rows_inv_kernel");
+  return rc;
 }
 
 }  // namespace jaxib
@@ -348,6 +374,17 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     delete pl;
     return JAXIB_ERR_UNSUPPORTED;
   }
+  // power-of-two sizes use the register-resident kernels of poisson_fast.cu; the column plan must
+  // then carry the radix triple those kernels are instantiated with (it defines the digit-reversed
+  // positions of the eigenvalue table)
+  const bool aligned = (ny % 4) == 0;
+  pl->fast_rows = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_size_supported(n2) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
+  pl->fast_cols = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_size_supported(nx) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
+  if (pl->fast_cols) {
+    pl->col.n = nx;
+    pl->col.nstages = 3;
+    fast_radices(nx, pl->col.radix);
+  }
   const double two_pi = 6.283185307179586476925286766559;
   std::vector<float2> twr(ny), twc(nx);
   for (int k = 0; k < ny; ++k) twr[k] = make_float2((float)cos(two_pi * k / ny), (float)-sin(two_pi * k / ny));
@@ -365,6 +402,13 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   if (!rc) rc = upload(&pl->col_pos, cpos);
   if (!rc) rc = upload(&pl->lam_x_pos, lxp);
   if (!rc) rc = upload(&pl->lam_y, ly);
+  {
+    std::vector<float> lxf(nx), lyf(n2 + 4, 1.0f);
+    for (int k = 0; k < nx; ++k) lxf[k] = (float)lxp[k];
+    for (int l = 0; l <= n2; ++l) lyf[l] = (float)ly[l];
+    if (!rc) rc = upload(&pl->lam_x_pos_f, lxf);
+    if (!rc) rc = upload(&pl->lam_y_f, lyf);
+  }
   if (rc) { set_error("plan_create: device allocation failed"); jaxib_plan_destroy(pl); return rc; }
 
   int dev = 0, sms = 148, max_smem = 227 * 1024;
@@ -380,6 +424,11 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   long long rows_total = (long long)nx * pl->gf.batch;
   int rpc = (int)(rows_total / (3LL * sms));
   pl->rows_per_cta = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
+  {  // fast row kernels: one row group per CTA; aim at >= 4 CTAs per SM, at most 8 rows each
+    const char* e = getenv("JAXIB_ROWS_PER_GROUP");
+    int rpg = e ? atoi(e) : (int)(rows_total / (4LL * sms));
+    pl->fast_rows_per_group = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
+  }
   const size_t col_bytes = (size_t)(padi(nx) + 1) * sizeof(float2);
   int cpc = 4;
   while (cpc > 1 && cpc * col_bytes > (size_t)max_smem) cpc /= 2;
@@ -403,7 +452,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
 extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
   if (!pl) return JAXIB_OK;
   cudaFree(pl->tw_row); cudaFree(pl->tw_col); cudaFree(pl->row_pos); cudaFree(pl->col_pos);
-  cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y);
+  cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y); cudaFree(pl->lam_x_pos_f); cudaFree(pl->lam_y_f);
   delete pl;
   return JAXIB_OK;
 }

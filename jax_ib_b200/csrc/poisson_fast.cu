@@ -1,0 +1,471 @@
+// Power-of-two fast paths of the Poisson kernels (N = R1*R2*R3 with radices 8/16, i.e. 512..4096).
+//
+// Same mathematics as poisson.cu (forward DIF, diagonal in digit-reversed positions, exact inverse),
+// re-organised so that the FIRST forward pass reads straight from global memory into registers and
+// the LAST inverse pass writes straight from registers to global memory; only the two inner passes
+// go through shared memory, with compile-time strides (no div/mod) and the innermost pass fused
+// with the diagonal multiply:   [pass3 fwd] * D * [pass3 inv]  in registers.
+//
+//   cols_fast  (K5): a CTA owns 4 adjacent ky columns = two float4 "column pairs"; every global
+//                    access is a 16-byte load/store and each 32-byte sector of the [nx][sp] spectrum
+//                    is used completely by the two threads that share it.
+//   rows_fwd_fast (K4) / rows_inv_fast (K6): one 64..256-thread group per row, several rows per CTA
+//                    in sequence; the untangle of the packed real transform reads the digit-reversed
+//                    positions with shifts and masks.
+#include "fft.cuh"
+#include "poisson_fast.cuh"
+
+namespace jaxib {
+
+namespace {
+
+constexpr float kCutoffF = 10.0f * 1.1920928955078125e-07f;
+
+__device__ __forceinline__ int padq(int p) { return p + (p >> 3); }  // float4 (two-column) arrays
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_dir(float2* v) {
+  if (INV) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = cswap(v[r]);
+  }
+  Dft<R>::run(v);
+  if (INV) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = cswap(v[r]);
+  }
+}
+
+__device__ __forceinline__ float inv_eig_f(float l) { return fabsf(l) > kCutoffF ? __frcp_rn(l) : 0.0f; }
+
+// ---------------------------------------------------------------------------------------------- K5
+template <int R1, int R2, int R3>
+__global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
+  constexpr int N = R1 * R2 * R3;
+  constexpr int S1 = N / R1;   // threads per column pair; stride of pass 1
+  constexpr int L2 = R2 * R3;  // block length of pass 2
+  constexpr int PITCH = N + N / 8 + 1;
+  extern __shared__ float4 smq[];
+  const int pair = threadIdx.x / S1, b = threadIdx.x - pair * S1;
+  const int c = blockIdx.x * 4 + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
+  float4* col = smq + pair * PITCH;
+  float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + c);
+  const size_t rs = (size_t)P.sp / 2;  // row stride in float4 units
+  const float2* __restrict__ tw = P.tw;
+
+  {  // pass 1 forward: global -> registers -> shared
+    float2 va[R1], vb[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      float4 x = g4[(size_t)(b + r * S1) * rs];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+    }
+    Dft<R1>::run(va);
+    Dft<R1>::run(vb);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      if (r > 0) {
+        const float2 w = __ldg(tw + b * r);
+        va[r] = cmul(va[r], w);
+        vb[r] = cmul(vb[r], w);
+      }
+      col[padq(b + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
+  }
+  __syncthreads();
+  // pass 2 forward
+#pragma unroll
+  for (int m = 0; m < R1 / R2; ++m) {
+    const int t = b + m * S1;
+    const int blk = t / R3, b2 = t - blk * R3;
+    const int p0 = blk * L2 + b2;
+    float2 va[R2], vb[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      float4 x = col[padq(p0 + r * R3)];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+    }
+    Dft<R2>::run(va);
+    Dft<R2>::run(vb);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      if (r > 0) {
+        const float2 w = __ldg(tw + b2 * r * R1);
+        va[r] = cmul(va[r], w);
+        vb[r] = cmul(vb[r], w);
+      }
+      col[padq(p0 + r * R3)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
+  }
+  __syncthreads();
+  // pass 3 forward, diagonal, pass 3 inverse -- all in registers
+  {
+    const float lya = P.lam_y[c], lyb = P.lam_y[c + 1];
+#pragma unroll
+    for (int m = 0; m < R1 / R3; ++m) {
+      const int p0 = (b + m * S1) * R3;
+      float2 va[R3], vb[R3];
+#pragma unroll
+      for (int r = 0; r < R3; ++r) {
+        float4 x = col[padq(p0 + r)];
+        va[r] = make_float2(x.x, x.y);
+        vb[r] = make_float2(x.z, x.w);
+      }
+      Dft<R3>::run(va);
+      Dft<R3>::run(vb);
+#pragma unroll
+      for (int r = 0; r < R3; ++r) {
+        const float lx = __ldg(P.lam_x_pos + p0 + r);
+        va[r] = cscale(va[r], inv_eig_f(lx + lya));
+        vb[r] = cscale(vb[r], inv_eig_f(lx + lyb));
+      }
+      dft_dir<R3, true>(va);
+      dft_dir<R3, true>(vb);
+#pragma unroll
+      for (int r = 0; r < R3; ++r) col[padq(p0 + r)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
+  }
+  __syncthreads();
+  // pass 2 inverse
+#pragma unroll
+  for (int m = 0; m < R1 / R2; ++m) {
+    const int t = b + m * S1;
+    const int blk = t / R3, b2 = t - blk * R3;
+    const int p0 = blk * L2 + b2;
+    float2 va[R2], vb[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      float4 x = col[padq(p0 + r * R3)];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+      if (r > 0) {
+        const float2 w = __ldg(tw + b2 * r * R1);
+        va[r] = cmulc(va[r], w);
+        vb[r] = cmulc(vb[r], w);
+      }
+    }
+    dft_dir<R2, true>(va);
+    dft_dir<R2, true>(vb);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) col[padq(p0 + r * R3)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+  }
+  __syncthreads();
+  {  // pass 1 inverse: shared -> registers -> global
+    float2 va[R1], vb[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      float4 x = col[padq(b + r * S1)];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+      if (r > 0) {
+        const float2 w = __ldg(tw + b * r);
+        va[r] = cmulc(va[r], w);
+        vb[r] = cmulc(vb[r], w);
+      }
+    }
+    dft_dir<R1, true>(va);
+    dft_dir<R1, true>(vb);
+#pragma unroll
+    for (int r = 0; r < R1; ++r)
+      g4[(size_t)(b + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- rows
+template <int R1, int R2, int R3>
+struct RowGeom {
+  static constexpr int N = R1 * R2 * R3;  // complex length ny/2
+  static constexpr int S1 = N / R1;       // threads per row group
+  static constexpr int L2 = R2 * R3;
+  static constexpr int PITCH = N + N / 16 + 1;
+  // position of frequency k after the forward DIF (digit reversal of the radix triple)
+  __device__ static __forceinline__ int pos(int k) {
+    return (k % R1) * L2 + ((k / R1) % R2) * R3 + k / (R1 * R2);
+  }
+};
+
+// inner passes (2 and 3) of the row transform on one shared-memory row; G = threads of the group
+template <int R1, int R2, int R3, bool INV>
+__device__ __forceinline__ void row_inner_passes(float2* row, const float2* __restrict__ tw, int b) {
+  using Gm = RowGeom<R1, R2, R3>;
+  auto pass2 = [&]() {
+#pragma unroll
+    for (int m = 0; m < R1 / R2; ++m) {
+      const int t = b + m * Gm::S1;
+      const int blk = t / R3, b2 = t - blk * R3;
+      const int p0 = blk * Gm::L2 + b2;
+      float2 v[R2];
+#pragma unroll
+      for (int r = 0; r < R2; ++r) v[r] = row[padi(p0 + r * R3)];
+      if (!INV) {
+        Dft<R2>::run(v);
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], __ldg(tw + 2 * b2 * r * R1));
+      } else {
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], __ldg(tw + 2 * b2 * r * R1));
+        dft_dir<R2, true>(v);
+      }
+#pragma unroll
+      for (int r = 0; r < R2; ++r) row[padi(p0 + r * R3)] = v[r];
+    }
+  };
+  auto pass3 = [&]() {
+#pragma unroll
+    for (int m = 0; m < R1 / R3; ++m) {
+      const int p0 = (b + m * Gm::S1) * R3;
+      float2 v[R3];
+#pragma unroll
+      for (int r = 0; r < R3; ++r) v[r] = row[padi(p0 + r)];
+      dft_dir<R3, INV>(v);
+#pragma unroll
+      for (int r = 0; r < R3; ++r) row[padi(p0 + r)] = v[r];
+    }
+  };
+  if (!INV) {
+    pass2();
+    __syncthreads();
+    pass3();
+    __syncthreads();
+  } else {
+    pass3();
+    __syncthreads();
+    pass2();
+    __syncthreads();
+  }
+}
+
+// K4: divergence + forward packed-real FFT of one row per iteration; the CTA is ONE row group.
+template <int R1, int R2, int R3>
+__global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P, const float* __restrict__ u,
+                                                                const float* __restrict__ v,
+                                                                float2* __restrict__ spec) {
+  using Gm = RowGeom<R1, R2, R3>;
+  constexpr int N = Gm::N, S1 = Gm::S1;
+  extern __shared__ float2 row[];  // Gm::PITCH values
+  const GridF& g = P.g;
+  const int ny = g.ny;
+  const size_t plane = (size_t)g.nx * ny;
+  u += blockIdx.y * plane;
+  v += blockIdx.y * plane;
+  spec += (size_t)blockIdx.y * g.nx * P.sp;
+  const int b = threadIdx.x;
+  const int i0 = blockIdx.x * P.rows_per_group;
+  const int i1 = min(i0 + P.rows_per_group, g.nx);
+  const float2* __restrict__ tw = P.tw;
+  for (int i = i0; i < i1; ++i) {
+    const float2* ur = reinterpret_cast<const float2*>(u + (size_t)i * ny);
+    const float2* um = reinterpret_cast<const float2*>(u + (size_t)(i == 0 ? g.nx - 1 : i - 1) * ny);
+    const float* vrow = v + (size_t)i * ny;
+    const float2* vr = reinterpret_cast<const float2*>(vrow);
+    float2 z[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const int n = b + r * S1;
+      const float2 a = ur[n], c = um[n], d = vr[n];
+      const float vm = vrow[n > 0 ? 2 * n - 1 : ny - 1];
+      z[r] = make_float2((a.x - c.x) * g.inv_dx + (d.x - vm) * g.inv_dy, (a.y - c.y) * g.inv_dx + (d.y - d.x) * g.inv_dy);
+    }
+    Dft<R1>::run(z);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      if (r > 0) z[r] = cmul(z[r], __ldg(tw + 2 * b * r));
+      row[padi(b + r * S1)] = z[r];
+    }
+    __syncthreads();
+    row_inner_passes<R1, R2, R3, false>(row, tw, b);
+    // untangle: X[k] = E + W^k O, X[N-k] = conj(E - W^k O)
+    float2* out = spec + (size_t)i * P.sp;
+    for (int k = b; k <= N / 2; k += S1) {
+      if (k == 0) {
+        const float2 zz = row[padi(0)];
+        out[0] = make_float2(zz.x + zz.y, 0.0f);
+        out[N] = make_float2(zz.x - zz.y, 0.0f);
+      } else {
+        const int km = N - k;
+        const float2 zk = row[padi(Gm::pos(k))], zm = cconj(row[padi(Gm::pos(km))]);
+        const float2 e = cscale(cadd(zk, zm), 0.5f);
+        const float2 o = cscale(mul_mi(csub(zk, zm)), 0.5f);
+        const float2 t = cmul(__ldg(tw + k), o);
+        out[k] = cadd(e, t);
+        if (km != k) out[km] = cconj(csub(e, t));
+      }
+    }
+    if (b < 3) out[N + 1 + b] = make_float2(0.0f, 0.0f);  // padding columns feed cols_fast: keep them finite
+    __syncthreads();
+  }
+}
+
+// K6: inverse packed-real FFT fused with gradient, velocity correction and pressure update.
+template <int R1, int R2, int R3, bool PROJECT>
+__global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P, const float2* __restrict__ spec,
+                                                                const float* u, const float* v, const float* p,
+                                                                float* u_out, float* v_out, float* p_out) {
+  using Gm = RowGeom<R1, R2, R3>;
+  constexpr int N = Gm::N, S1 = Gm::S1;
+  extern __shared__ float2 rows_sm[];  // two rows of Gm::PITCH values
+  float2* const rows[2] = {rows_sm, rows_sm + Gm::PITCH};
+  const GridF& g = P.g;
+  const int ny = g.ny;
+  const size_t plane = (size_t)g.nx * ny;
+  spec += (size_t)blockIdx.y * g.nx * P.sp;
+  if (PROJECT) { u += blockIdx.y * plane; v += blockIdx.y * plane; p += blockIdx.y * plane; u_out += blockIdx.y * plane; v_out += blockIdx.y * plane; }
+  p_out += blockIdx.y * plane;
+  const int b = threadIdx.x;
+  const int i0 = blockIdx.x * P.rows_per_group;
+  const int i1 = min(i0 + P.rows_per_group, g.nx);
+  const int last = PROJECT ? i1 : i1 - 1;
+  const float2* __restrict__ tw = P.tw;
+  float2 zprev[R1];
+  for (int ii = i0; ii <= last; ++ii) {
+    const int i = ii >= g.nx ? ii - g.nx : ii;
+    float2* cur = rows[(ii - i0) & 1];
+    const float2* in = spec + (size_t)i * P.sp;
+    for (int k = b; k <= N / 2; k += S1) {
+      if (k == 0) {
+        const float x0 = in[0].x, xn = in[N].x;
+        cur[padi(0)] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
+      } else {
+        const int km = N - k;
+        const float2 xk = in[k], xm = cconj(in[km]);
+        const float2 e = cscale(cadd(xk, xm), 0.5f);
+        const float2 o = cmulc(cscale(csub(xk, xm), 0.5f), __ldg(tw + k));
+        cur[padi(Gm::pos(k))] = cadd(e, mul_pi(o));
+        if (km != k) cur[padi(Gm::pos(km))] = cadd(cconj(e), mul_pi(cconj(o)));
+      }
+    }
+    __syncthreads();
+    row_inner_passes<R1, R2, R3, true>(cur, tw, b);
+    float2 z[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      z[r] = cur[padi(b + r * S1)];
+      if (r > 0) z[r] = cmulc(z[r], __ldg(tw + 2 * b * r));
+    }
+    dft_dir<R1, true>(z);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) z[r] = cscale(z[r], P.scale);  // q[i][2n], q[i][2n+1], n = b + r*S1
+    if (!PROJECT) {
+      float2* qo = reinterpret_cast<float2*>(p_out + (size_t)i * ny);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) qo[b + r * S1] = z[r];
+    } else {
+      // publish this row's q in natural order for the y-neighbour lookup of the NEXT iteration
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < R1; ++r) cur[b + r * S1] = z[r];
+      if (ii > i0) {
+        const float2* prv = rows[(ii - 1 - i0) & 1];
+        const size_t ro = (size_t)(ii - 1) * ny;
+        const float2* u2 = reinterpret_cast<const float2*>(u + ro);
+        const float2* v2 = reinterpret_cast<const float2*>(v + ro);
+        const float2* p2 = reinterpret_cast<const float2*>(p + ro);
+        float2* uo = reinterpret_cast<float2*>(u_out + ro);
+        float2* vo = reinterpret_cast<float2*>(v_out + ro);
+        float2* po = reinterpret_cast<float2*>(p_out + ro);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int n = b + r * S1;
+          const float2 q0 = zprev[r], q1 = z[r];
+          const float qn = prv[n + 1 < N ? n + 1 : 0].x;  // q[i-1][2n+2] (periodic)
+          float2 uu = u2[n], vv = v2[n];
+          const float2 pp = p2[n];
+          uu.x -= (q1.x - q0.x) * g.inv_dx;
+          uu.y -= (q1.y - q0.y) * g.inv_dx;
+          vv.x -= (q0.y - q0.x) * g.inv_dy;
+          vv.y -= (qn - q0.y) * g.inv_dy;
+          uo[n] = uu;
+          vo[n] = vv;
+          po[n] = make_float2(q0.x + pp.x, q0.y + pp.y);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R1; ++r) zprev[r] = z[r];
+    }
+    __syncthreads();
+  }
+}
+
+template <int R1, int R2, int R3>
+int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+  constexpr int N = R1 * R2 * R3;
+  const size_t smem = 2 * (size_t)(N + N / 8 + 1) * sizeof(float4);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid((P.ncols + 3) / 4, batch);
+  cols_fast_kernel<R1, R2, R3><<<grid, 2 * (N / R1), smem, s>>>(P, spec);
+  return check_launch("cols_fast_kernel");
+}
+
+template <int R1, int R2, int R3>
+int launch_rows_fwd_t(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
+  dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
+  const size_t smem = RowGeom<R1, R2, R3>::PITCH * sizeof(float2);
+  rows_fwd_fast_kernel<R1, R2, R3><<<grid, R2 * R3, smem, s>>>(P, u, v, spec);
+  return check_launch("rows_fwd_fast_kernel");
+}
+
+template <int R1, int R2, int R3>
+int launch_rows_inv_t(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
+                      const float* p, float* uo, float* vo, float* po, bool project) {
+  dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
+  const size_t smem = 2 * RowGeom<R1, R2, R3>::PITCH * sizeof(float2);
+  if (smem > 48 * 1024) {  // ny = 8192: opt in to > 48 KB dynamic shared memory (idempotent)
+    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if (project)
+    rows_inv_fast_kernel<R1, R2, R3, true><<<grid, R2 * R3, smem, s>>>(P, spec, u, v, p, uo, vo, po);
+  else
+    rows_inv_fast_kernel<R1, R2, R3, false><<<grid, R2 * R3, smem, s>>>(P, spec, u, v, p, uo, vo, po);
+  return check_launch("rows_inv_fast_kernel");
+}
+
+}  // namespace
+
+bool fast_size_supported(int n) { return n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+void fast_radices(int n, int* r) {
+  switch (n) {
+    case 512: r[0] = 8; r[1] = 8; r[2] = 8; break;
+    case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
+    case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break;
+    case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+    default: r[0] = r[1] = r[2] = 0;
+  }
+}
+
+#define JAXIB_DISPATCH_N(n, CALL)             \
+  switch (n) {                                \
+    case 512: return CALL(8, 8, 8);           \
+    case 1024: return CALL(16, 8, 8);         \
+    case 2048: return CALL(16, 16, 8);        \
+    case 4096: return CALL(16, 16, 16);       \
+    default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
+  }
+
+int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+#define CALL_COLS(a, b, c) launch_cols_t<a, b, c>(s, P, batch, spec)
+  JAXIB_DISPATCH_N(P.nx, CALL_COLS)
+#undef CALL_COLS
+}
+
+int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
+#define CALL_RF(a, b, c) launch_rows_fwd_t<a, b, c>(s, P, u, v, spec)
+  JAXIB_DISPATCH_N(P.g.ny / 2, CALL_RF)
+#undef CALL_RF
+}
+
+int launch_rows_inv_fast(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
+                         const float* p, float* uo, float* vo, float* po, bool project) {
+#define CALL_RI(a, b, c) launch_rows_inv_t<a, b, c>(s, P, spec, u, v, p, uo, vo, po, project)
+  JAXIB_DISPATCH_N(P.g.ny / 2, CALL_RI)
+#undef CALL_RI
+}
+
+}  // namespace jaxib

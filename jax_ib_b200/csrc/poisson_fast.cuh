@@ -1,0 +1,29 @@
+// Interface of the power-of-two fast Poisson kernels (poisson_fast.cu).
+#pragma once
+#include "common.cuh"
+
+namespace jaxib {
+
+struct FastColParams {
+  int nx, sp, ncols;
+  const float2* tw;         // W_nx^k
+  const float* lam_x_pos;   // float32(lx[freq(p)]) in digit-reversed position order
+  const float* lam_y;       // float32(ly_l), padded to sp entries
+};
+
+struct FastRowParams {
+  GridF g;
+  const float2* tw;  // W_ny^k
+  int sp;            // spectrum row pitch (complex values)
+  int rows_per_group;
+  float scale;       // 1 / (nx * ny/2)
+};
+
+bool fast_size_supported(int n);
+void fast_radices(int n, int* radix3);
+int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec);
+int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec);
+int launch_rows_inv_fast(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
+                         const float* p, float* uo, float* vo, float* po, bool project);
+
+}  // namespace jaxib

@@ -271,6 +271,8 @@ int launch_explicit(cudaStream_t s, const GridF& g, const float* u, const float*
     set_error("grid %dx%d too small for the radius-2 stencil", g.nx, g.ny);
     return JAXIB_ERR_UNSUPPORTED;
   }
+  int rc = JAXIB_OK;
+  if (launch_explicit_fast(s, g, u, v, p, perm, out_u, out_v, predictor, &rc)) return rc;
   return predictor ? launch_scheme<true>(s, g, u, v, p, perm, out_u, out_v)
                    : launch_scheme<false>(s, g, u, v, p, perm, out_u, out_v);
 }

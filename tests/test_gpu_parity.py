@@ -174,7 +174,9 @@ def test_ib_force_fused_matches_oracle(cfg_name):
 
 
 # ------------------------------------------------------------------------------------------------ K4-K6
-@pytest.mark.parametrize("shape", [(64, 64), (60, 100), (128, 64), (30, 36), (256, 512), (600, 600), (1024, 256)])
+@pytest.mark.parametrize("shape", [(64, 64), (60, 100), (128, 64), (30, 36), (256, 512), (600, 600), (1024, 256),
+                                   # power-of-two fast paths (poisson_fast.cu): every radix triple, rows and columns
+                                   (512, 1024), (1024, 2048), (2048, 4096), (4096, 1024), (512, 8192)])
 def test_pressure_solve_and_projection_periodic(shape):
     cfg = make_cfg(shape, "periodic", "upwind")
     u, v, p = random_fields(shape, 21)
