@@ -30,6 +30,53 @@ def grid_spec_from(grid: grids.Grid, dt, viscosity, density, bc_kind, convect, v
         u_wall=u_wall, v_wall=v_wall, force=force, ib_window=ib_window, batch=batch)
 
 
+def cuda_device(device=None) -> torch.device:
+    """The CUDA device work runs on: the tensor's own device if it is a CUDA tensor, else the current one."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("jax_ib_b200 needs a CUDA device: there is no CPU fallback")
+    if device is not None and torch.device(device).type == "cuda":
+        return torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(t, device=None) -> torch.Tensor:
+    """float32, contiguous, on the GPU (a no-op for tensors that already are)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t, dtype=np.float32))
+    return t.to(cuda_device(t.device if device is None else device), dtype=torch.float32).contiguous()
+
+
+_PLANS = {}
+_BODIES = {}
+
+
+def get_plan(spec: ops.GridSpec, n_markers: int = 0) -> ops.Plan:
+    """Plans (FFT tables + scratch) are cached per (grid spec, device)."""
+    dev = cuda_device()
+    key = (spec.nx, spec.ny, spec.batch, spec.lower, spec.step, spec.bc, spec.u_wall, spec.v_wall, dev.index)
+    plan = _PLANS.get(key)
+    if plan is None or plan.n_markers < n_markers:
+        plan = ops.Plan(spec, n_markers, dev)
+        _PLANS[key] = plan
+    return plan
+
+
+def get_bodies(particles, device) -> ops.DeviceBodies:
+    dev = cuda_device(device)
+    key = (id(particles.shape), tuple(np.asarray(particles.geometry_param, dtype=np.float64).ravel()), dev.index)
+    b = _BODIES.get(key)
+    if b is None:
+        x0s, y0s = [], []
+        grid_p = particles.generate_grid()
+        for gp in particles.geometry_param:
+            x0, y0 = particles.shape(gp, grid_p)
+            x0s.append(np.asarray(x0, dtype=np.float32))
+            y0s.append(np.asarray(y0, dtype=np.float32))
+        b = ops.DeviceBodies(x0s, y0s, dev)
+        _BODIES[key] = b
+    return b
+
+
 def bc_kind_of(v) -> str:
     if boundaries.has_all_periodic_boundary_conditions(*v):
         return "periodic"
@@ -47,15 +94,7 @@ class FusedStepper:
         self.spec = spec
         self.device = torch.device(device)
         self.particles_template = particles
-        self.bodies = None
-        if particles is not None:
-            x0s, y0s = [], []
-            grid_p = particles.generate_grid()
-            for gp in particles.geometry_param:
-                x0, y0 = particles.shape(gp, grid_p)
-                x0s.append(np.asarray(x0, dtype=np.float32))
-                y0s.append(np.asarray(y0, dtype=np.float32))
-            self.bodies = ops.DeviceBodies(x0s, y0s, self.device)
+        self.bodies = get_bodies(particles, self.device) if particles is not None else None
         self.plan = ops.Plan(spec, self.bodies.n_markers if self.bodies else 0, self.device)
         self.perm = perm
         self.incremental_pressure = incremental_pressure
@@ -68,7 +107,7 @@ class FusedStepper:
         self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure)
 
     # -- All_Variables-level --------------------------------------------------------------------
-    def advance(self, all_variables, nsteps: int):
+    def advance(self, all_variables, nsteps: int, move_bodies: bool = True):
         vel = all_variables.velocity
         dev = self.device
         in_dev = vel[0].data.device
@@ -91,10 +130,11 @@ class FusedStepper:
                 md = self.md_step(self._view(all_variables, u, v, p, times[n + 1], particles, md))
             state = dataclasses.replace(state, MD_var=md)
         new_particles = particles
-        if particles is not None:
+        if particles is not None and move_bodies:
             new_particles = dataclasses.replace(particles, particle_center=_like(particles.particle_center, centers[-1]))
         out = self._view(state, u.to(in_dev), v.to(in_dev), p.to(in_dev), times[-1], new_particles, state.MD_var)
-        return dataclasses.replace(out, Step_count=all_variables.Step_count + nsteps)
+        # particle_motion.py:59: the step counter lives in the position update
+        return dataclasses.replace(out, Step_count=all_variables.Step_count + (nsteps if move_bodies else 0))
 
     def _schedule(self, particles, t0, dt, nsteps):
         f32 = np.float32
@@ -102,7 +142,7 @@ class FusedStepper:
             times = np.add.accumulate(np.concatenate([[f32(t0)], np.full(nsteps, f32(dt), f32)]).astype(f32), dtype=f32)
             return None, times, None
         table, times, centers = kinematics.body_schedule(particles, t0, dt, nsteps)
-        table = np.ascontiguousarray(np.broadcast_to(table[:, None], (nsteps, self.spec.batch) + table.shape[1:]))
+        table = np.broadcast_to(table[:, None], (nsteps, self.spec.batch) + table.shape[1:]).copy()
         return torch.from_numpy(table).to(self.device, non_blocking=True), times, centers
 
     def _view(self, all_variables, u, v, p, t, particles, md):
