@@ -45,6 +45,7 @@ struct jaxib_plan {
   int fast_rows_per_group;
   float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
   float* lam_y_f;
+  float2* tw_dct;      // channel: exp(-i pi k / (2 ny))
 };
 
 namespace jaxib {
@@ -224,6 +225,101 @@ __global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, co
   }
 }
 
+// ---- channel rows: DCT-II / DCT-III along y (Neumann pressure) --------------------------------------
+// pressure.py:111-130 diagonalises the Neumann Laplacian (array_utils.py:175-182) with eigh; its
+// eigenvectors are the DCT-II basis, lambda_l = (2cos(pi l/Ny) - 2)/dy^2.  Makhoul's algorithm:
+//   v[n] = x[2n], v[N-1-n] = x[2n+1];  V = FFT_N(v);  C[k] = Re(w_k V[k]),  w_k = exp(-i pi k / 2N)
+// and back:  V[k] = conj(w_k) (C[k] - i C[N-k]),  v = IFFT_N(V).  The real coefficients are stored
+// [Nx][Ny] (pitch 2*sp floats); the column kernel treats adjacent coefficient pairs as one complex
+// column (packed_all).  The forward/inverse pair is exact, so no orthonormal scaling is needed.
+struct DctParams {
+  GridF g;
+  FftPlan pl;          // complex length ny
+  const float2* tw;    // W_ny^k
+  const float2* twd;   // w_k = exp(-i pi k / (2 ny)), k < ny
+  const int* pos;      // digit-reversed position of frequency k (length ny)
+  int rows_per_cta;
+  int sp;              // spectrum pitch in complex units (real pitch = 2 sp)
+  float scale;         // 1 / (nx * ny)
+};
+
+__global__ void rows_fwd_dct_kernel(DctParams P, const float* __restrict__ u, const float* __restrict__ v,
+                                    float* __restrict__ spec) {
+  extern __shared__ float2 buf[];
+  const GridF& g = P.g;
+  const int N = g.ny;
+  const size_t plane = (size_t)g.nx * N;
+  u += blockIdx.y * plane; v += blockIdx.y * plane; spec += (size_t)blockIdx.y * g.nx * 2 * P.sp;
+  const int i0 = blockIdx.x * P.rows_per_cta, i1 = min(i0 + P.rows_per_cta, g.nx);
+  for (int i = i0; i < i1; ++i) {
+    const float* ur = u + (size_t)i * N;
+    const float* um = u + (size_t)wrapi(i - 1, g.nx) * N;
+    const float* vr = v + (size_t)i * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      // divergence with the channel ghost rule: v(i,-1) is the lower wall value (boundaries.py:205-220)
+      const float vm = j > 0 ? vr[j - 1] : g.vw_lo;
+      const float r = (ur[j] - um[j]) * g.inv_dx + (vr[j] - vm) * g.inv_dy;
+      const int n = (j & 1) ? N - 1 - (j >> 1) : (j >> 1);
+      buf[padi(n)] = make_float2(r, 0.0f);
+    }
+    __syncthreads();
+    fft_forward(P.pl, buf, 1, 0, P.tw, 1);
+    float* out = spec + (size_t)i * 2 * P.sp;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) out[k] = cmul(__ldg(P.twd + k), buf[padi(P.pos[k])]).x;
+    __syncthreads();
+  }
+}
+
+template <bool PROJECT>
+__global__ void rows_inv_dct_kernel(DctParams P, const float* __restrict__ spec, const float* u, const float* v,
+                                    const float* p, float* u_out, float* v_out, float* p_out) {
+  extern __shared__ float2 smem[];
+  const GridF& g = P.g;
+  const int N = g.ny;
+  const int pitch = padi(N) + 1;
+  float2* buf = smem;
+  float* qrow[2] = {reinterpret_cast<float*>(smem + pitch), reinterpret_cast<float*>(smem + pitch) + N};
+  const size_t plane = (size_t)g.nx * N;
+  spec += (size_t)blockIdx.y * g.nx * 2 * P.sp;
+  if (PROJECT) { u += blockIdx.y * plane; v += blockIdx.y * plane; p += blockIdx.y * plane; u_out += blockIdx.y * plane; v_out += blockIdx.y * plane; }
+  p_out += blockIdx.y * plane;
+  const int i0 = blockIdx.x * P.rows_per_cta, i1 = min(i0 + P.rows_per_cta, g.nx);
+  const int last = PROJECT ? i1 : i1 - 1;
+  for (int ii = i0; ii <= last; ++ii) {
+    const int i = ii >= g.nx ? ii - g.nx : ii;
+    const float* in = spec + (size_t)i * 2 * P.sp;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const float ck = in[k], cm = k > 0 ? in[N - k] : 0.0f;
+      buf[padi(P.pos[k])] = k > 0 ? cmulc(make_float2(ck, -cm), __ldg(P.twd + k)) : make_float2(ck, 0.0f);
+    }
+    __syncthreads();
+    fft_inverse(P.pl, buf, 1, 0, P.tw, 1);
+    float* cur = qrow[(ii - i0) & 1];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const int n = (j & 1) ? N - 1 - (j >> 1) : (j >> 1);
+      cur[j] = buf[padi(n)].x * P.scale;
+    }
+    __syncthreads();
+    if (!PROJECT) {
+      float* qo = p_out + (size_t)i * N;
+      for (int j = threadIdx.x; j < N; j += blockDim.x) qo[j] = cur[j];
+    } else if (ii > i0) {
+      const float* prv = qrow[(ii - 1 - i0) & 1];
+      const size_t ro = (size_t)(ii - 1) * N;
+      for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float q0 = prv[j], q1 = cur[j];
+        const float qn = j + 1 < N ? prv[j + 1] : q0;  // homogeneous Neumann ghost = edge (boundaries.py:247-269)
+        float vv = v[ro + j] - (qn - q0) * g.inv_dy;
+        if (j + 1 == N) vv = g.vw_hi;                  // impose_bc: the last v row lies on the wall (boundaries.py:405-419)
+        u_out[ro + j] = u[ro + j] - (q1 - q0) * g.inv_dx;
+        v_out[ro + j] = vv;
+        p_out[ro + j] = q0 + p[ro + j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- K5 -------------------------------------------------------------------------------------------
 struct ColParams {
   int nx, sp, ncols;      // spectrum is [nx][sp]; ncols = number of stored columns
@@ -311,7 +407,15 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   FastRowParams frp;
   frp.g = g; frp.tw = pl->tw_row; frp.sp = rp.sp; frp.rows_per_group = pl->fast_rows_per_group; frp.scale = rp.scale;
   int rc;
-  if (pl->fast_rows) {
+  const bool channel = g.bc == JAXIB_BC_CHANNEL;
+  DctParams dp;
+  if (channel) {
+    dp.g = g; dp.pl = pl->row; dp.tw = pl->tw_row; dp.twd = pl->tw_dct; dp.pos = pl->row_pos;
+    dp.rows_per_cta = pl->rows_per_cta; dp.sp = rp.sp;
+    dp.scale = (float)(1.0 / ((double)g.nx * (double)g.ny));
+    rows_fwd_dct_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(dp, u, v, spectrum);
+    rc = check_launch("rows_fwd_dct_kernel");
+  } else if (pl->fast_rows) {
     rc = launch_rows_fwd_fast(s, frp, u, v, spec);
   } else {
     rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
@@ -326,16 +430,26 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
     rc = launch_cols_fast(s, fcp, g.batch, spec);
   } else {
     ColParams cp;
-    cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col; cp.pos = pl->col_pos;
+    // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
+    cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = channel ? n2 : n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col;
+    cp.pos = pl->col_pos;
     cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
-    cp.packed_all = g.bc == JAXIB_BC_CHANNEL;
+    cp.packed_all = channel;
     dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
     cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
     rc = check_launch("cols_kernel");
   }
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[1], s);
-  if (pl->fast_rows) {
+  if (channel) {
+    const size_t smem = pl->row_smem + 2 * (size_t)g.ny * sizeof(float);
+    if (q_only)
+      rows_inv_dct_kernel<false><<<rgrid, pl->row_threads, smem, s>>>(dp, spectrum, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr, q_only);
+    else
+      rows_inv_dct_kernel<true><<<rgrid, pl->row_threads, smem, s>>>(dp, spectrum, u, v, p, u_out, v_out, p_out);
+    rc = check_launch("rows_inv_dct_kernel");
+  } else if (pl->fast_rows) {
     rc = launch_rows_inv_fast(s, frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
   } else {
     if (q_only) {
@@ -359,17 +473,15 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   *out = nullptr;
   int rc = check_grid(grid);
   if (rc) return rc;
-  if (grid->bc == JAXIB_BC_CHANNEL) {
-    set_error("channel (DCT) Poisson plan is not implemented yet");
-    return JAXIB_ERR_UNSUPPORTED;
-  }
   if (grid->ny % 2) { set_error("ny=%d must be even for the packed real FFT", grid->ny); return JAXIB_ERR_UNSUPPORTED; }
   jaxib_plan* pl = new jaxib_plan();
   memset(pl, 0, sizeof(*pl));
   pl->grid = *grid;
   pl->gf = make_gridf(*grid);
   const int nx = grid->nx, ny = grid->ny, n2 = ny / 2;
-  if (!factor_plan(n2, &pl->row) || !factor_plan(nx, &pl->col)) {
+  const bool channel = grid->bc == JAXIB_BC_CHANNEL;
+  const int nrow = channel ? ny : n2;  // complex length of the row transform (DCT via a length-ny FFT)
+  if (!factor_plan(nrow, &pl->row) || !factor_plan(nx, &pl->col)) {
     set_error("grid %dx%d: sizes must factor into 2, 3 and 5", nx, ny);
     delete pl;
     return JAXIB_ERR_UNSUPPORTED;
@@ -389,14 +501,22 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   std::vector<float2> twr(ny), twc(nx);
   for (int k = 0; k < ny; ++k) twr[k] = make_float2((float)cos(two_pi * k / ny), (float)-sin(two_pi * k / ny));
   for (int k = 0; k < nx; ++k) twc[k] = make_float2((float)cos(two_pi * k / nx), (float)-sin(two_pi * k / nx));
-  std::vector<int> rpos(n2), cpos(nx);
-  for (int k = 0; k < n2; ++k) rpos[k] = pos_of_freq(pl->row, k);
+  std::vector<int> rpos(nrow), cpos(nx);
+  for (int k = 0; k < nrow; ++k) rpos[k] = pos_of_freq(pl->row, k);
   for (int k = 0; k < nx; ++k) cpos[k] = pos_of_freq(pl->col, k);
   // eigenvalues of the circulant 1-D Laplacians (array_utils.py:168-173), float64
-  std::vector<double> lxp(nx), ly(n2 + 1);
+  std::vector<double> lxp(nx), ly(channel ? ny : n2 + 1);
   for (int k = 0; k < nx; ++k) lxp[cpos[k]] = (2.0 * cos(two_pi * k / nx) - 2.0) / (grid->dx * grid->dx);
-  for (int l = 0; l <= n2; ++l) ly[l] = (2.0 * cos(two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
-  rc = upload(&pl->tw_row, twr);
+  if (channel) {  // eigenvalues of laplacian_matrix_neumann (array_utils.py:175-182): DCT-II basis
+    for (int l = 0; l < ny; ++l) ly[l] = (2.0 * cos(0.5 * two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
+    std::vector<float2> twd(ny);
+    for (int k = 0; k < ny; ++k)
+      twd[k] = make_float2((float)cos(0.25 * two_pi * k / ny), (float)-sin(0.25 * two_pi * k / ny));
+    rc = upload(&pl->tw_dct, twd);
+  } else {
+    for (int l = 0; l <= n2; ++l) ly[l] = (2.0 * cos(two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
+  }
+  if (!rc) rc = upload(&pl->tw_row, twr);
   if (!rc) rc = upload(&pl->tw_col, twc);
   if (!rc) rc = upload(&pl->row_pos, rpos);
   if (!rc) rc = upload(&pl->col_pos, cpos);
@@ -405,7 +525,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   {
     std::vector<float> lxf(nx), lyf(n2 + 4, 1.0f);
     for (int k = 0; k < nx; ++k) lxf[k] = (float)lxp[k];
-    for (int l = 0; l <= n2; ++l) lyf[l] = (float)ly[l];
+    for (int l = 0; l <= n2 && l < (int)ly.size(); ++l) lyf[l] = (float)ly[l];
     if (!rc) rc = upload(&pl->lam_x_pos_f, lxf);
     if (!rc) rc = upload(&pl->lam_y_f, lyf);
   }
@@ -419,8 +539,8 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     int t = ((n / 8 + 31) / 32) * 32;
     return t < 64 ? 64 : (t > 256 ? 256 : t);
   };
-  pl->row_threads = pick_threads(n2);
-  pl->row_smem = (size_t)(padi(n2) + 1) * sizeof(float2);
+  pl->row_threads = pick_threads(nrow);
+  pl->row_smem = (size_t)(padi(nrow) + 1) * sizeof(float2);
   long long rows_total = (long long)nx * pl->gf.batch;
   int rpc = (int)(rows_total / (3LL * sms));
   pl->rows_per_cta = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
@@ -444,6 +564,12 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   cudaFuncSetAttribute(rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
   cudaFuncSetAttribute(rows_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
   cudaFuncSetAttribute(rows_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
+  if (channel) {
+    const int dsm = (int)(pl->row_smem + 2 * (size_t)ny * sizeof(float));
+    cudaFuncSetAttribute(rows_fwd_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
+    cudaFuncSetAttribute(rows_inv_dct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);
+    cudaFuncSetAttribute(rows_inv_dct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);
+  }
   cudaGetLastError();
   *out = pl;
   return JAXIB_OK;
@@ -453,6 +579,7 @@ extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
   if (!pl) return JAXIB_OK;
   cudaFree(pl->tw_row); cudaFree(pl->tw_col); cudaFree(pl->row_pos); cudaFree(pl->col_pos);
   cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y); cudaFree(pl->lam_x_pos_f); cudaFree(pl->lam_y_f);
+  cudaFree(pl->tw_dct);
   delete pl;
   return JAXIB_OK;
 }

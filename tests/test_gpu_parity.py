@@ -209,6 +209,61 @@ def test_pressure_solve_and_projection_periodic(shape):
     assert np.abs(stencils.divergence(pv)).max() < 2e-5 * div0
 
 
+@pytest.mark.parametrize("shape", [(64, 64), (96, 80), (60, 100), (256, 128), (1024, 256)])
+def test_pressure_solve_and_projection_channel(shape):
+    """pressure.py:111-130 (eigh + tensordot in the reference) against the FFT x DCT-II kernels."""
+    cfg = make_cfg(shape, "channel", "van_leer", wall_u=(0.2, -0.1), wall_v=(0.0, 0.0))
+    u, v, p = random_fields(shape, 23)
+    v[:, -1] = 0.0
+    st = oracle_state(cfg, fields=(u, v, p))
+    st64 = oracle_state(cfg, np.float64, (u, v, p))
+    zm = lambda x: x - x.mean()
+    q64 = zm(poisson.solve_fast_diag_moving_wall(st64.velocity))
+    q32 = poisson.solve_fast_diag_moving_wall(st.velocity)
+    bar = max(5e-6, 2.5 * rel_l2(zm(q32), q64))
+    plan = ops.Plan(demo.make_spec(cfg))
+    q = host(plan.pressure_solve(dev(u), dev(v)))
+    assert abs(q.mean()) < 1e-5 * np.abs(q).max()
+    assert rel_l2(zm(q), q64) < bar, (rel_l2(zm(q), q64), bar)
+    new_v, new_p = poisson.projection_and_update_pressure(st.velocity, st.pressure, "channel")
+    uo, vo, po = plan.project(dev(u), dev(v), dev(p))
+    assert rel_l2(host(uo), new_v[0].data) < bar
+    assert rel_l2(host(vo), new_v[1].data) < bar
+    assert rel_l2(zm(host(po)), zm(new_p.data)) < 2 * bar
+    np.testing.assert_array_equal(host(vo)[:, -1], np.zeros(shape[0], F))  # impose_bc re-stamps the wall row
+
+
+@pytest.mark.parametrize("convect", ["van_leer", "upwind", "van_leer_limiters"])
+def test_full_step_channel_vs_oracle(convect):
+    cfg = dict(configs.channel((64, 48), ((0.0, 2.0), (0.0, 1.0))), convect=convect)
+    steps = 20
+    st, st64 = oracle_state(cfg), oracle_state(cfg, np.float64)
+    step = oracle_step(cfg)
+    for _ in range(steps):
+        st, st64 = step(st), step(st64)
+    out = _run_product(cfg, steps)
+    zm = lambda x: x - x.mean()
+    assert rel_l2(host(out.velocity[0].data), st.velocity[0].data) < 1e-5
+    assert rel_l2(host(out.velocity[1].data), st.velocity[1].data) < 1e-5
+    # |p| << |u| here, so the pressure's float32 round-off floor (oracle32 vs oracle64) sets the bar
+    floor = rel_l2(zm(st.pressure.data), zm(st64.pressure.data))
+    assert rel_l2(zm(host(out.pressure.data)), zm(st.pressure.data)) < max(1e-5, 2.0 * floor), floor
+    assert np.float32(out.velocity[0].bc.time_stamp) == np.float32(st.velocity[0].bc.time_stamp)
+
+
+def test_golden_channel_trajectory():
+    gold = np.load(os.path.join(GOLD, "channel1024x256_5.npz"))
+    out = _run_product(configs.channel(), int(gold["steps"]))
+    a, b, c, d = (int(x) for x in gold["crop"])
+    zm = lambda x: x - x.mean()
+    for key, var in (("u", out.velocity[0]), ("v", out.velocity[1])):
+        bar = max(1e-5, 2.0 * float(gold[key + "_noise"]))
+        assert rel_l2(host(var.data)[a:b, c:d], gold[key + "_crop"]) < bar, key
+    # the pressure of a channel is defined up to a constant; its float64 oracle value is arbitrary
+    pc = host(out.pressure.data)[a:b, c:d]
+    assert rel_l2(zm(pc), zm(gold["p_crop"])) < 1e-4
+
+
 def test_pressure_solve_recovers_known_potential():
     shape = (96, 80)
     cfg = make_cfg(shape, "periodic", "upwind")
