@@ -406,6 +406,7 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   dim3 rgrid((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
   FastRowParams frp;
   frp.g = g; frp.tw = pl->tw_row; frp.sp = rp.sp; frp.rows_per_group = pl->fast_rows_per_group; frp.scale = rp.scale;
+  { const char* e = getenv("JAXIB_DBG"); frp.dbg = e ? atoi(e) : 0; }
   int rc;
   const bool channel = g.bc == JAXIB_BC_CHANNEL;
   DctParams dp;

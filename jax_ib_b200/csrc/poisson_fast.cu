@@ -36,6 +36,23 @@ __device__ __forceinline__ void dft_dir(float2* v) {
   }
 }
 
+// ---- cp.async (LDGSTS) staging: global -> shared without passing through registers ---------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING));
+}
+// cooperative copy of `bytes` (multiple of 16, both sides 16-byte aligned) by `nthreads` threads
+__device__ __forceinline__ void copy_async(void* dst, const void* src, int bytes, int tid, int nthreads) {
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  for (int o = tid * 16; o < bytes; o += nthreads * 16) cp_async16(d + o, s + o);
+}
+
 __device__ __forceinline__ float inv_eig_f(float l) { return fabsf(l) > kCutoffF ? __frcp_rn(l) : 0.0f; }
 
 // ---------------------------------------------------------------------------------------------- K5
@@ -47,11 +64,15 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
   constexpr int PITCH = N + N / 8 + 1;
   extern __shared__ float4 smq[];
   const int pair = threadIdx.x / S1, b = threadIdx.x - pair * S1;
-  const int c = blockIdx.x * 4 + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
+  const int c = blockIdx.x * 2 * (blockDim.x / S1) + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
   float4* col = smq + pair * PITCH;
   float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + c);
   const size_t rs = (size_t)P.sp / 2;  // row stride in float4 units
   const float2* __restrict__ tw = P.tw;
+  // twiddle tables in shared memory (coalesced fill): W_N^m for pass 1, W_N^(b2 r R1) for pass 2.
+  // Reading them from global with a lane stride of r*8 bytes costs up to 32 L1 wavefronts per load.
+  float2* const tws = reinterpret_cast<float2*>(smq + (blockDim.x / S1) * PITCH);
+  float2* const tw2 = tws + N;
 
   {  // pass 1 forward: global -> registers -> shared
     float2 va[R1], vb[R1];
@@ -61,12 +82,16 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
     }
+    // fill the tables while the column loads are in flight
+    for (int e = threadIdx.x; e < N; e += blockDim.x) tws[e] = __ldg(tw + e);
+    for (int e = threadIdx.x; e < R3 * R2; e += blockDim.x) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
+    __syncthreads();
     Dft<R1>::run(va);
     Dft<R1>::run(vb);
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       if (r > 0) {
-        const float2 w = __ldg(tw + b * r);
+        const float2 w = tws[b * r];
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
@@ -92,7 +117,7 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
       if (r > 0) {
-        const float2 w = __ldg(tw + b2 * r * R1);
+        const float2 w = tw2[b2 * (R2 + 1) + r];
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
@@ -141,7 +166,7 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
       if (r > 0) {
-        const float2 w = __ldg(tw + b2 * r * R1);
+        const float2 w = tw2[b2 * (R2 + 1) + r];
         va[r] = cmulc(va[r], w);
         vb[r] = cmulc(vb[r], w);
       }
@@ -160,7 +185,7 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
       if (r > 0) {
-        const float2 w = __ldg(tw + b * r);
+        const float2 w = tws[b * r];
         va[r] = cmulc(va[r], w);
         vb[r] = cmulc(vb[r], w);
       }
@@ -188,12 +213,16 @@ struct RowGeom {
 
 // inner passes (2 and 3) of the row transform on one shared-memory row; G = threads of the group
 template <int R1, int R2, int R3, bool INV>
-__device__ __forceinline__ void row_inner_passes(float2* row, const float2* __restrict__ tw, int b) {
+__device__ __forceinline__ void row_inner_passes(float2* row, const float2* tw2, int b) {
   using Gm = RowGeom<R1, R2, R3>;
+  // N/R2 (N/R3) butterflies are shared by the S1 = N/R1 threads: each thread runs ceil(R1/R2) of them
+  // (when R1 < R2 only the first N/R2 threads have one)
+  constexpr int TRIPS2 = (R1 + R2 - 1) / R2, TRIPS3 = (R1 + R3 - 1) / R3;
   auto pass2 = [&]() {
 #pragma unroll
-    for (int m = 0; m < R1 / R2; ++m) {
+    for (int m = 0; m < TRIPS2; ++m) {
       const int t = b + m * Gm::S1;
+      if (t >= Gm::N / R2) continue;
       const int blk = t / R3, b2 = t - blk * R3;
       const int p0 = blk * Gm::L2 + b2;
       float2 v[R2];
@@ -202,10 +231,10 @@ __device__ __forceinline__ void row_inner_passes(float2* row, const float2* __re
       if (!INV) {
         Dft<R2>::run(v);
 #pragma unroll
-        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], __ldg(tw + 2 * b2 * r * R1));
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], tw2[b2 * (R2 + 1) + r]);
       } else {
 #pragma unroll
-        for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], __ldg(tw + 2 * b2 * r * R1));
+        for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], tw2[b2 * (R2 + 1) + r]);
         dft_dir<R2, true>(v);
       }
 #pragma unroll
@@ -214,7 +243,8 @@ __device__ __forceinline__ void row_inner_passes(float2* row, const float2* __re
   };
   auto pass3 = [&]() {
 #pragma unroll
-    for (int m = 0; m < R1 / R3; ++m) {
+    for (int m = 0; m < TRIPS3; ++m) {
+      if (b + m * Gm::S1 >= Gm::N / R3) continue;
       const int p0 = (b + m * Gm::S1) * R3;
       float2 v[R3];
 #pragma unroll
@@ -244,9 +274,13 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
                                                                 float2* __restrict__ spec) {
   using Gm = RowGeom<R1, R2, R3>;
   constexpr int N = Gm::N, S1 = Gm::S1;
-  extern __shared__ float2 row[];  // Gm::PITCH values
+  // shared memory: FFT row (Gm::PITCH float2) | u rows i-1 / i (2 x ny floats, rotating) | v row i (ny floats)
+  extern __shared__ float2 row[];
   const GridF& g = P.g;
   const int ny = g.ny;
+  float* const stage = reinterpret_cast<float*>(row + Gm::PITCH + 1);
+  float* const ubuf[2] = {stage, stage + ny};
+  float* const vbuf = stage + 2 * ny;
   const size_t plane = (size_t)g.nx * ny;
   u += blockIdx.y * plane;
   v += blockIdx.y * plane;
@@ -255,30 +289,55 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
   const int i0 = blockIdx.x * P.rows_per_group;
   const int i1 = min(i0 + P.rows_per_group, g.nx);
   const float2* __restrict__ tw = P.tw;
+  const int row_bytes = ny * (int)sizeof(float);
+  // twiddles are row-independent: pass-1 factors W^(b r) live in registers, the small pass-2 table
+  // W^(b2 r R1) in shared memory.  (Fetching them per row through L1 with a lane stride of r*8 bytes
+  // costs up to 32 wavefronts per load and saturated the L1tex pipe.)
+  float2* const tw2 = reinterpret_cast<float2*>(stage + 3 * ny);
+  for (int e = b; e < R3 * R2; e += S1) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + 2 * (e / R2) * (e % R2) * R1);
+  float2 tw1[R1];
+#pragma unroll
+  for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
+  // cp.async pipeline: the rows of step i+1 stream into shared memory while row i is transformed
+  copy_async(ubuf[0], u + (size_t)(i0 == 0 ? g.nx - 1 : i0 - 1) * ny, row_bytes, b, S1);
+  copy_async(ubuf[1], u + (size_t)i0 * ny, row_bytes, b, S1);
+  copy_async(vbuf, v + (size_t)i0 * ny, row_bytes, b, S1);
+  cp_async_commit();
   for (int i = i0; i < i1; ++i) {
-    const float2* ur = reinterpret_cast<const float2*>(u + (size_t)i * ny);
-    const float2* um = reinterpret_cast<const float2*>(u + (size_t)(i == 0 ? g.nx - 1 : i - 1) * ny);
-    const float* vrow = v + (size_t)i * ny;
-    const float2* vr = reinterpret_cast<const float2*>(vrow);
+    const int kk = i - i0;
+    const float2* ur = reinterpret_cast<const float2*>(ubuf[(kk + 1) & 1]);
+    const float2* um = reinterpret_cast<const float2*>(ubuf[kk & 1]);
+    const float2* vr = reinterpret_cast<const float2*>(vbuf);
+    cp_async_wait<0>();
+    __syncthreads();
     float2 z[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       const int n = b + r * S1;
       const float2 a = ur[n], c = um[n], d = vr[n];
-      const float vm = vrow[n > 0 ? 2 * n - 1 : ny - 1];
+      const float vm = vbuf[n > 0 ? 2 * n - 1 : ny - 1];
       z[r] = make_float2((a.x - c.x) * g.inv_dx + (d.x - vm) * g.inv_dy, (a.y - c.y) * g.inv_dx + (d.y - d.x) * g.inv_dy);
     }
+    __syncthreads();  // everyone has consumed u[i-1] and v[i]: their slots can be refilled
+    if (i + 1 < i1) {
+      copy_async(ubuf[kk & 1], u + (size_t)(i + 1) * ny, row_bytes, b, S1);
+      copy_async(vbuf, v + (size_t)(i + 1) * ny, row_bytes, b, S1);
+    }
+    cp_async_commit();
     Dft<R1>::run(z);
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      if (r > 0) z[r] = cmul(z[r], __ldg(tw + 2 * b * r));
+      if (r > 0) z[r] = cmul(z[r], tw1[r]);
       row[padi(b + r * S1)] = z[r];
     }
     __syncthreads();
-    row_inner_passes<R1, R2, R3, false>(row, tw, b);
+    row_inner_passes<R1, R2, R3, false>(row, tw2, b);
     // untangle: X[k] = E + W^k O, X[N-k] = conj(E - W^k O)
     float2* out = spec + (size_t)i * P.sp;
-    for (int k = b; k <= N / 2; k += S1) {
+#pragma unroll
+    for (int m = 0; m <= (N / 2) / S1; ++m) {  // k = 0 .. N/2 (the last trip only carries k = N/2)
+      const int k = b + m * S1;
+      if (k > N / 2) continue;
       if (k == 0) {
         const float2 zz = row[padi(0)];
         out[0] = make_float2(zz.x + zz.y, 0.0f);
@@ -305,8 +364,10 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
                                                                 float* u_out, float* v_out, float* p_out) {
   using Gm = RowGeom<R1, R2, R3>;
   constexpr int N = Gm::N, S1 = Gm::S1;
-  extern __shared__ float2 rows_sm[];  // two rows of Gm::PITCH values
+  // shared memory (float2 units): two FFT rows | staged spectrum row (N + 4)
+  extern __shared__ float2 rows_sm[];
   float2* const rows[2] = {rows_sm, rows_sm + Gm::PITCH};
+  float2* const spec_s = rows_sm + 2 * Gm::PITCH;  // 16-byte aligned: 2 * PITCH float2 = multiple of 16 B
   const GridF& g = P.g;
   const int ny = g.ny;
   const size_t plane = (size_t)g.nx * ny;
@@ -318,12 +379,26 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   const int i1 = min(i0 + P.rows_per_group, g.nx);
   const int last = PROJECT ? i1 : i1 - 1;
   const float2* __restrict__ tw = P.tw;
+  const int spec_bytes = (N + 4) * (int)sizeof(float2);
+  float2* const tw2 = spec_s + N + 4;  // pass-2 twiddle table, see rows_fwd_fast_kernel
+  for (int e = b; e < R3 * R2; e += S1) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + 2 * (e / R2) * (e % R2) * R1);
+  float2 tw1[R1];
+#pragma unroll
+  for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
   float2 zprev[R1];
+  // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes
+  copy_async(spec_s, spec + (size_t)i0 * P.sp, spec_bytes, b, S1);
+  cp_async_commit();
   for (int ii = i0; ii <= last; ++ii) {
     const int i = ii >= g.nx ? ii - g.nx : ii;
     float2* cur = rows[(ii - i0) & 1];
-    const float2* in = spec + (size_t)i * P.sp;
-    for (int k = b; k <= N / 2; k += S1) {
+    cp_async_wait<0>();  // the spectrum row issued one iteration ago has landed
+    __syncthreads();
+    const float2* in = spec_s;
+#pragma unroll
+    for (int m = 0; m <= (N / 2) / S1; ++m) {
+      const int k = b + m * S1;
+      if (k > N / 2) continue;
       if (k == 0) {
         const float x0 = in[0].x, xn = in[N].x;
         cur[padi(0)] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
@@ -337,14 +412,19 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
       }
     }
     __syncthreads();
-    row_inner_passes<R1, R2, R3, true>(cur, tw, b);
+    if (ii < last) {  // the staged spectrum row is consumed: prefetch the next one behind the FFT passes
+      const int inext = ii + 1 >= g.nx ? ii + 1 - g.nx : ii + 1;
+      copy_async(spec_s, spec + (size_t)inext * P.sp, spec_bytes, b, S1);
+    }
+    cp_async_commit();
+    if (!(P.dbg & 1)) row_inner_passes<R1, R2, R3, true>(cur, tw2, b);
     float2 z[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       z[r] = cur[padi(b + r * S1)];
-      if (r > 0) z[r] = cmulc(z[r], __ldg(tw + 2 * b * r));
+      if (r > 0) z[r] = cmulc(z[r], tw1[r]);
     }
-    dft_dir<R1, true>(z);
+    if (!(P.dbg & 1)) dft_dir<R1, true>(z);
 #pragma unroll
     for (int r = 0; r < R1; ++r) z[r] = cscale(z[r], P.scale);  // q[i][2n], q[i][2n+1], n = b + r*S1
     if (!PROJECT) {
@@ -356,7 +436,8 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < R1; ++r) cur[b + r * S1] = z[r];
-      if (ii > i0) {
+      __syncthreads();
+      if (ii > i0 && !(P.dbg & 2)) {
         const float2* prv = rows[(ii - 1 - i0) & 1];
         const size_t ro = (size_t)(ii - 1) * ny;
         const float2* u2 = reinterpret_cast<const float2*>(u + ro);
@@ -365,13 +446,23 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
         float2* uo = reinterpret_cast<float2*>(u_out + ro);
         float2* vo = reinterpret_cast<float2*>(v_out + ro);
         float2* po = reinterpret_cast<float2*>(p_out + ro);
+        // all loads first: the outputs may alias the inputs (in-place projection), so the compiler
+        // cannot hoist a load above an earlier store -- interleaving them costs R1 round trips per row
+        float2 ua[R1], va[R1], pa[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int n = b + r * S1;
+          ua[r] = u2[n];
+          va[r] = v2[n];
+          pa[r] = p2[n];
+        }
 #pragma unroll
         for (int r = 0; r < R1; ++r) {
           const int n = b + r * S1;
           const float2 q0 = zprev[r], q1 = z[r];
           const float qn = prv[n + 1 < N ? n + 1 : 0].x;  // q[i-1][2n+2] (periodic)
-          float2 uu = u2[n], vv = v2[n];
-          const float2 pp = p2[n];
+          float2 uu = ua[r], vv = va[r];
+          const float2 pp = pa[r];
           uu.x -= (q1.x - q0.x) * g.inv_dx;
           uu.y -= (q1.y - q0.y) * g.inv_dx;
           vv.x -= (q0.y - q0.x) * g.inv_dy;
@@ -391,21 +482,26 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
 template <int R1, int R2, int R3>
 int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
   constexpr int N = R1 * R2 * R3;
+  const size_t tables = (size_t)(N + R3 * (R2 + 1)) * sizeof(float2);
   const size_t smem = 2 * (size_t)(N + N / 8 + 1) * sizeof(float4);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + tables));
     configured = true;
   }
-  dim3 grid((P.ncols + 3) / 4, batch);
-  cols_fast_kernel<R1, R2, R3><<<grid, 2 * (N / R1), smem, s>>>(P, spec);
+  const char* e = getenv("JAXIB_COL_PAIRS");
+  const int pairs = (e && atoi(e) == 1) ? 1 : 2;  // column pairs (float4) per CTA
+  dim3 grid((P.ncols + 2 * pairs - 1) / (2 * pairs), batch);
+  cols_fast_kernel<R1, R2, R3><<<grid, pairs * (N / R1), smem * pairs / 2 + tables, s>>>(P, spec);
   return check_launch("cols_fast_kernel");
 }
 
 template <int R1, int R2, int R3>
 int launch_rows_fwd_t(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
   dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
-  const size_t smem = RowGeom<R1, R2, R3>::PITCH * sizeof(float2);
+  const size_t smem = (RowGeom<R1, R2, R3>::PITCH + 1 + R3 * (R2 + 1)) * sizeof(float2) + 3 * (size_t)P.g.ny * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(rows_fwd_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   rows_fwd_fast_kernel<R1, R2, R3><<<grid, R2 * R3, smem, s>>>(P, u, v, spec);
   return check_launch("rows_fwd_fast_kernel");
 }
@@ -414,8 +510,8 @@ template <int R1, int R2, int R3>
 int launch_rows_inv_t(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
                       const float* p, float* uo, float* vo, float* po, bool project) {
   dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
-  const size_t smem = 2 * RowGeom<R1, R2, R3>::PITCH * sizeof(float2);
-  if (smem > 48 * 1024) {  // ny = 8192: opt in to > 48 KB dynamic shared memory (idempotent)
+  const size_t smem = (2 * RowGeom<R1, R2, R3>::PITCH + R1 * R2 * R3 + 4 + R3 * (R2 + 1)) * sizeof(float2);
+  if (smem > 48 * 1024) {  // opt in to > 48 KB dynamic shared memory (idempotent)
     cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
@@ -455,16 +551,26 @@ int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* 
 #undef CALL_COLS
 }
 
+// rows: first radix 8 where possible = twice the threads per row (the row kernels are latency bound)
+#define JAXIB_DISPATCH_ROWS(n, CALL)          \
+  switch (n) {                                \
+    case 512: return CALL(8, 8, 8);           \
+    case 1024: return CALL(8, 16, 8);         \
+    case 2048: return CALL(8, 16, 16);        \
+    case 4096: return CALL(16, 16, 16);       \
+    default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
+  }
+
 int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
 #define CALL_RF(a, b, c) launch_rows_fwd_t<a, b, c>(s, P, u, v, spec)
-  JAXIB_DISPATCH_N(P.g.ny / 2, CALL_RF)
+  JAXIB_DISPATCH_ROWS(P.g.ny / 2, CALL_RF)
 #undef CALL_RF
 }
 
 int launch_rows_inv_fast(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
                          const float* p, float* uo, float* vo, float* po, bool project) {
 #define CALL_RI(a, b, c) launch_rows_inv_t<a, b, c>(s, P, spec, u, v, p, uo, vo, po, project)
-  JAXIB_DISPATCH_N(P.g.ny / 2, CALL_RI)
+  JAXIB_DISPATCH_ROWS(P.g.ny / 2, CALL_RI)
 #undef CALL_RI
 }
 

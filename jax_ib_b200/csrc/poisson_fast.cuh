@@ -16,6 +16,7 @@ struct FastRowParams {
   const float2* tw;  // W_ny^k
   int sp;            // spectrum row pitch (complex values)
   int rows_per_group;
+  int dbg;           // timing experiments only (JAXIB_DBG): bit0 skip FFT passes, bit1 skip finalize
   float scale;       // 1 / (nx * ny/2)
 };
 
