@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
 }
 
 // ---------------------------------------------------------------------------------------------- rows
+// Bank swizzle of a row buffer (8-byte elements: the low 4 index bits select the bank pair).  Besides
+// contiguous runs the row kernels access it with stride R3 (innermost pass), stride L2 = R2*R3 in the
+// fastest lanes (the digit-reversed scatter/gather of the real-FFT untangle) and b2 + L2*blk (pass 2);
+// XOR-ing index bits 4-6 and 7-9 into bits 0-2 and bit 7 into bit 3 spreads all of them over the 16
+// bank pairs (plain padding left the untangle 8-way conflicted: half of all shared wavefronts).
+__device__ __forceinline__ int rswz(int p) {
+  return p ^ (((p >> 4) ^ (p >> 7)) & 7) ^ (((p >> 7) & 1) << 3);
+}
+
 template <int R1, int R2, int R3>
 struct RowGeom {
   static constexpr int N = R1 * R2 * R3;  // complex length ny/2
@@ -227,7 +236,7 @@ __device__ __forceinline__ void row_inner_passes(float2* row, const float2* tw2,
       const int p0 = blk * Gm::L2 + b2;
       float2 v[R2];
 #pragma unroll
-      for (int r = 0; r < R2; ++r) v[r] = row[padi(p0 + r * R3)];
+      for (int r = 0; r < R2; ++r) v[r] = row[rswz(p0 + r * R3)];
       if (!INV) {
         Dft<R2>::run(v);
 #pragma unroll
@@ -238,7 +247,7 @@ __device__ __forceinline__ void row_inner_passes(float2* row, const float2* tw2,
         dft_dir<R2, true>(v);
       }
 #pragma unroll
-      for (int r = 0; r < R2; ++r) row[padi(p0 + r * R3)] = v[r];
+      for (int r = 0; r < R2; ++r) row[rswz(p0 + r * R3)] = v[r];
     }
   };
   auto pass3 = [&]() {
@@ -248,10 +257,10 @@ __device__ __forceinline__ void row_inner_passes(float2* row, const float2* tw2,
       const int p0 = (b + m * Gm::S1) * R3;
       float2 v[R3];
 #pragma unroll
-      for (int r = 0; r < R3; ++r) v[r] = row[padi(p0 + r)];
+      for (int r = 0; r < R3; ++r) v[r] = row[rswz(p0 + r)];
       dft_dir<R3, INV>(v);
 #pragma unroll
-      for (int r = 0; r < R3; ++r) row[padi(p0 + r)] = v[r];
+      for (int r = 0; r < R3; ++r) row[rswz(p0 + r)] = v[r];
     }
   };
   if (!INV) {
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       if (r > 0) z[r] = cmul(z[r], tw1[r]);
-      row[padi(b + r * S1)] = z[r];
+      row[rswz(b + r * S1)] = z[r];
     }
     __syncthreads();
     row_inner_passes<R1, R2, R3, false>(row, tw2, b);
@@ -339,12 +348,12 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
       const int k = b + m * S1;
       if (k > N / 2) continue;
       if (k == 0) {
-        const float2 zz = row[padi(0)];
+        const float2 zz = row[rswz(0)];
         out[0] = make_float2(zz.x + zz.y, 0.0f);
         out[N] = make_float2(zz.x - zz.y, 0.0f);
       } else {
         const int km = N - k;
-        const float2 zk = row[padi(Gm::pos(k))], zm = cconj(row[padi(Gm::pos(km))]);
+        const float2 zk = row[rswz(Gm::pos(k))], zm = cconj(row[rswz(Gm::pos(km))]);
         const float2 e = cscale(cadd(zk, zm), 0.5f);
         const float2 o = cscale(mul_mi(csub(zk, zm)), 0.5f);
         const float2 t = cmul(__ldg(tw + k), o);
@@ -366,7 +375,6 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   constexpr int N = Gm::N, S1 = Gm::S1;
   // shared memory (float2 units): two FFT rows | staged spectrum row (N + 4)
   extern __shared__ float2 rows_sm[];
-  float2* const rows[2] = {rows_sm, rows_sm + Gm::PITCH};
   float2* const spec_s = rows_sm + 2 * Gm::PITCH;  // 16-byte aligned: 2 * PITCH float2 = multiple of 16 B
   const GridF& g = P.g;
   const int ny = g.ny;
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   cp_async_commit();
   for (int ii = i0; ii <= last; ++ii) {
     const int i = ii >= g.nx ? ii - g.nx : ii;
-    float2* cur = rows[(ii - i0) & 1];
+    float2* cur = rows_sm + ((ii - i0) & 1) * Gm::PITCH;
     cp_async_wait<0>();  // the spectrum row issued one iteration ago has landed
     __syncthreads();
     const float2* in = spec_s;
@@ -401,14 +409,14 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
       if (k > N / 2) continue;
       if (k == 0) {
         const float x0 = in[0].x, xn = in[N].x;
-        cur[padi(0)] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
+        cur[rswz(0)] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
       } else {
         const int km = N - k;
         const float2 xk = in[k], xm = cconj(in[km]);
         const float2 e = cscale(cadd(xk, xm), 0.5f);
         const float2 o = cmulc(cscale(csub(xk, xm), 0.5f), __ldg(tw + k));
-        cur[padi(Gm::pos(k))] = cadd(e, mul_pi(o));
-        if (km != k) cur[padi(Gm::pos(km))] = cadd(cconj(e), mul_pi(cconj(o)));
+        cur[rswz(Gm::pos(k))] = cadd(e, mul_pi(o));
+        if (km != k) cur[rswz(Gm::pos(km))] = cadd(cconj(e), mul_pi(cconj(o)));
       }
     }
     __syncthreads();
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
     float2 z[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      z[r] = cur[padi(b + r * S1)];
+      z[r] = cur[rswz(b + r * S1)];
       if (r > 0) z[r] = cmulc(z[r], tw1[r]);
     }
     if (!(P.dbg & 1)) dft_dir<R1, true>(z);
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
       for (int r = 0; r < R1; ++r) cur[b + r * S1] = z[r];
       __syncthreads();
       if (ii > i0 && !(P.dbg & 2)) {
-        const float2* prv = rows[(ii - 1 - i0) & 1];
+        const float2* prv = rows_sm + ((ii - 1 - i0) & 1) * Gm::PITCH;
         const size_t ro = (size_t)(ii - 1) * ny;
         const float2* u2 = reinterpret_cast<const float2*>(u + ro);
         const float2* v2 = reinterpret_cast<const float2*>(v + ro);

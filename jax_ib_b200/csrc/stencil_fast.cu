@@ -52,6 +52,42 @@ __device__ __forceinline__ Row5 load_row5(const float* __restrict__ f, int i, in
   return r;
 }
 
+// Prefetch stage: the raw 16-byte column load plus the two warp-edge halo values.  The neighbour
+// shuffles are deferred to `finish_row6/5` one iteration later -- doing them here would make the warp
+// wait for the load it has just issued (ncu: 60 % long-scoreboard stalls on the SHFLs).
+struct Raw6 {
+  float4 c;
+  float left, right;
+};
+__device__ __forceinline__ Raw6 fetch_row(const float* __restrict__ f, int i, int j, int ny, bool active, int lane) {
+  const float* row = f + (size_t)i * ny;
+  Raw6 r;
+  r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.left = r.right = 0.f;
+  if (active) {
+    r.c = *reinterpret_cast<const float4*>(row + j);
+    if (lane == 0) r.left = row[j == 0 ? ny - 1 : j - 1];
+    if (lane == 31 || j + 4 >= ny) r.right = row[j + 4 >= ny ? j + 4 - ny : j + 4];
+  }
+  return r;
+}
+__device__ __forceinline__ Row6 finish_row6(const Raw6& w, int j, int ny, bool active, int lane) {
+  float left = __shfl_up_sync(FULLM, w.c.w, 1);
+  float right = __shfl_down_sync(FULLM, w.c.x, 1);
+  if (lane == 0) left = w.left;
+  if (lane == 31 || j + 4 >= ny) right = w.right;
+  Row6 r;
+  r.a[0] = left; r.a[1] = w.c.x; r.a[2] = w.c.y; r.a[3] = w.c.z; r.a[4] = w.c.w; r.a[5] = right;
+  return r;
+}
+__device__ __forceinline__ Row5 finish_row5(const Raw6& w, int j, int ny, bool active, int lane) {
+  float right = __shfl_down_sync(FULLM, w.c.x, 1);
+  if (lane == 31 || j + 4 >= ny) right = w.right;
+  Row5 r;
+  r.a[0] = w.c.x; r.a[1] = w.c.y; r.a[2] = w.c.z; r.a[3] = w.c.w; r.a[4] = right;
+  return r;
+}
+
 __device__ __forceinline__ float upw(float w, float c0, float cp) { return (w > 0.0f ? c0 : cp) * w; }
 
 template <bool PREDICT>
@@ -95,12 +131,12 @@ __global__ void __launch_bounds__(FT) explicit_upwind_periodic_kernel(GridF g, i
   }
 
   for (int i = i0; i < i1; ++i) {
-    // prefetch row i+2 (the next iteration's row i+1)
+    // prefetch row i+2 (the next iteration's row i+1): loads only, no dependent instruction
     const int ip2 = wrap1(wrap1(i + 2, nx), nx);
-    Row6 unn = load_row6(u, ip2, j, ny, active, lane);
-    Row6 vnn = load_row6(v, ip2, j, ny, active, lane);
-    Row5 pnn;
-    if (PREDICT && p) pnn = load_row5(p, ip2, j, ny, active, lane);
+    const Raw6 uraw = fetch_row(u, ip2, j, ny, active, lane);
+    const Raw6 vraw = fetch_row(v, ip2, j, ny, active, lane);
+    Raw6 praw;
+    if (PREDICT && p) praw = fetch_row(p, ip2, j, ny, active, lane);
 
     // y-face fluxes of row i through faces k = 0..4 (face k sits between columns j-1+k and j+k)
     float fyu[5], fyv[5];
@@ -154,9 +190,9 @@ __global__ void __launch_bounds__(FT) explicit_upwind_periodic_kernel(GridF g, i
       *reinterpret_cast<float4*>(out_u + idx) = make_float4(ou[0], ou[1], ou[2], ou[3]);
       *reinterpret_cast<float4*>(out_v + idx) = make_float4(ov[0], ov[1], ov[2], ov[3]);
     }
-    um = uc; uc = un; un = unn;
-    vm = vc; vc = vn; vn = vnn;
-    if (PREDICT && p) { pc = pn; pn = pnn; }
+    um = uc; uc = un; un = finish_row6(uraw, j, ny, active, lane);
+    vm = vc; vc = vn; vn = finish_row6(vraw, j, ny, active, lane);
+    if (PREDICT && p) { pc = pn; pn = finish_row5(praw, j, ny, active, lane); }
   }
 }
 
