@@ -67,6 +67,12 @@ typedef struct {
   double v_wall[2];    /* channel: v at the lower / upper y wall                                */
   double force[2];     /* constant body force (forcing(v) of the Taylor demo), per component    */
   int32_t ib_window;   /* Gaussian truncation radius R in cells (window 2R x 2R); default 6     */
+  /* Slab decomposition along x (0 / 0 / 0 for a full grid): the arrays hold global rows
+   * [row0, row0 + nx) (halo rows included); immersed-boundary forces are computed only for markers
+   * whose owning u-cell row lies in [own_lo, own_hi) and are zero otherwise (the caller sums the
+   * per-slab force arrays), while spreading writes every local row.                              */
+  int32_t row0;
+  int32_t own_lo, own_hi;
   int32_t reserved;
 } jaxib_grid;
 

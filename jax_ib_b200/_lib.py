@@ -23,7 +23,8 @@ class Grid(C.Structure):
         ("dt", C.c_double), ("nu", C.c_double), ("density", C.c_double),
         ("bc", C.c_int32), ("convect", C.c_int32),
         ("u_wall", C.c_double * 2), ("v_wall", C.c_double * 2), ("force", C.c_double * 2),
-        ("ib_window", C.c_int32), ("reserved", C.c_int32),
+        ("ib_window", C.c_int32), ("row0", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -26,6 +26,7 @@ struct GridF {
   int bc, convect;
   float uw_lo, uw_hi, vw_lo, vw_hi;
   int R;                 // IB window radius
+  int row0, own_lo, own_hi;  // slab decomposition (see jaxib_grid)
 };
 
 inline GridF make_gridf(const jaxib_grid& g) {
@@ -46,6 +47,7 @@ inline GridF make_gridf(const jaxib_grid& g) {
   f.uw_lo = (float)g.u_wall[0]; f.uw_hi = (float)g.u_wall[1];
   f.vw_lo = (float)g.v_wall[0]; f.vw_hi = (float)g.v_wall[1];
   f.R = g.ib_window > 0 ? g.ib_window : 6;
+  f.row0 = g.row0; f.own_lo = g.own_lo; f.own_hi = g.own_hi;
   return f;
 }
 

@@ -52,6 +52,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 struct Mesh {
   float lower_x, lower_y, dx, dy, off_x, off_y, pref_x, pref_y;
   int nx, ny, R;
+  int row0;  // global row of local row 0: indices are LOCAL, coordinates use local + row0
 };
 
 __device__ __forceinline__ Mesh make_mesh(const GridF& g, float off_x, float off_y) {
@@ -61,26 +62,30 @@ __device__ __forceinline__ Mesh make_mesh(const GridF& g, float off_x, float off
   const float s2pi = sqrtf(6.283185307179586f);
   m.pref_x = __fdiv_rn(1.0f, __fmul_rn(g.dx, s2pi));
   m.pref_y = __fdiv_rn(1.0f, __fmul_rn(g.dy, s2pi));
-  m.nx = g.nx; m.ny = g.ny; m.R = g.R;
+  m.nx = g.nx; m.ny = g.ny; m.R = g.R; m.row0 = g.row0;
   return m;
 }
 
 // Window sum for one marker, executed by a full warp.  Returns the sum in every lane.
-__device__ float interp_marker(const Mesh& m, const float* __restrict__ field, float xp, float yp, int* ik_out,
-                               int* jk_out) {
+// RT > 0 fixes the window radius at compile time: the window loop is unrolled and its loads issue together.
+template <int RT>
+__device__ __forceinline__ float interp_marker(const Mesh& m, const float* __restrict__ field, float xp, float yp,
+                                               int* ik_out, int* jk_out) {
   const int lane = threadIdx.x & 31;
-  const int W = 2 * m.R;
-  const int ik = cell_index(xp, m.dx, m.off_x), jk = cell_index(yp, m.dy, m.off_y);
-  if (ik_out) { *ik_out = ik; *jk_out = jk; }
-  const int ia = ik - m.R + 1, ja = jk - m.R + 1;
+  const int R = RT > 0 ? RT : m.R;
+  const int W = 2 * R;
+  const int ik = cell_index(xp, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.dy, m.off_y);
+  if (ik_out) { *ik_out = ik + m.row0; *jk_out = jk; }
+  const int ia = ik - R + 1, ja = jk - R + 1;
   float gx = 0.0f, gy = 0.0f;
   if (lane < W) {
-    gx = gauss(xp, mesh_coord(m.lower_x, ia + lane, m.off_x, m.dx), m.dx, m.pref_x);
+    gx = gauss(xp, mesh_coord(m.lower_x, ia + lane + m.row0, m.off_x, m.dx), m.dx, m.pref_x);
     gy = gauss(yp, mesh_coord(m.lower_y, ja + lane, m.off_y, m.dy), m.dy, m.pref_y);
   }
   float acc = 0.0f;
   const int cells = W * W;
-  for (int base = 0; base < cells; base += 32) {
+#pragma unroll
+  for (int base = 0; base < (RT > 0 ? 4 * RT * RT : cells); base += 32) {
     int e = base + lane;
     int wi = e / W, wj = e - wi * W;
     bool in = e < cells;
@@ -104,7 +109,7 @@ __global__ void interp_points_kernel(GridF g, float off_x, float off_y, const fl
   if (k >= n) return;
   Mesh m = make_mesh(g, off_x, off_y);
   int ik, jk;
-  float s = interp_marker(m, field, xp[k], yp[k], &ik, &jk);
+  float s = interp_marker<0>(m, field, xp[k], yp[k], &ik, &jk);
   if ((threadIdx.x & 31) == 0) {
     out[k] = s;
     if (ci) { ci[k] = ik; cj[k] = jk; }
@@ -113,11 +118,14 @@ __global__ void interp_points_kernel(GridF g, float off_x, float off_y, const fl
 
 // ---- fused marker kinematics + interpolation + direct forcing --------------------------------
 // scratch layout: [5][batch][n_markers] = xp, yp, dS, Fx, Fy
+template <int RT>
 __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                                     const float* __restrict__ x0, const float* __restrict__ y0,
                                     const float* __restrict__ body_state, const float* __restrict__ u_star,
                                     const float* __restrict__ v_star, float* __restrict__ markers) {
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int gw = wid >> 1, comp = wid & 1;
   const int total = g.batch * n_markers;
   if (gw >= total) return;
   const int s = gw / n_markers, k = gw - s * n_markers;
@@ -133,22 +141,28 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
   const float xq = __fadd_rn(__fsub_rn(__fmul_rn(bx, c), __fmul_rn(by, sn)), xc);
   const float yq = __fadd_rn(__fadd_rn(__fmul_rn(bx, sn), __fmul_rn(by, c)), yc);
   const size_t plane = (size_t)g.nx * g.ny;
-  Mesh mu = make_mesh(g, 1.0f, 0.5f), mv = make_mesh(g, 0.5f, 1.0f);
-  const float Uu = interp_marker(mu, u_star + s * plane, xp, yp, nullptr, nullptr);
-  const float Uv = interp_marker(mv, v_star + s * plane, xp, yp, nullptr, nullptr);
+  const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
+  const float U = interp_marker<RT>(m, (comp == 0 ? u_star : v_star) + s * plane, xp, yp, nullptr, nullptr);
   if ((threadIdx.x & 31) == 0) {
-    const float rx = -(__fsub_rn(yp, yc));
-    const float ry = __fsub_rn(xp, xc);
-    const float UPx = __fadd_rn(U0x, __fmul_rn(om, rx));
-    const float UPy = __fadd_rn(U0y, __fmul_rn(om, ry));
-    const float dxl = __fsub_rn(xq, xp), dyl = __fsub_rn(yq, yp);
     const size_t stride = (size_t)total;
     float* mk = markers + gw;
-    mk[0] = xp;
-    mk[stride] = yp;
-    mk[2 * stride] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
-    mk[3 * stride] = __fdiv_rn(__fsub_rn(UPx, Uu), g.dt);
-    mk[4 * stride] = __fdiv_rn(__fsub_rn(UPy, Uv), g.dt);
+    // slab decomposition: only the slab that owns the marker's u-cell row reports its force
+    const int iku = cell_index(xp, g.dx, 1.0f);
+    // (the first / last slab pass own_lo = INT_MIN / own_hi = INT_MAX: markers may lie off the grid)
+    const bool owner = g.own_hi <= g.own_lo || (iku >= g.own_lo && iku < g.own_hi);
+    if (comp == 0) {
+      const float rx = -(__fsub_rn(yp, yc));
+      const float UPx = __fadd_rn(U0x, __fmul_rn(om, rx));
+      const float dxl = __fsub_rn(xq, xp), dyl = __fsub_rn(yq, yp);
+      mk[0] = xp;
+      mk[stride] = yp;
+      mk[2 * stride] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
+      mk[3 * stride] = owner ? __fdiv_rn(__fsub_rn(UPx, U), g.dt) : 0.0f;
+    } else {
+      const float ry = __fsub_rn(xp, xc);
+      const float UPy = __fadd_rn(U0y, __fmul_rn(om, ry));
+      mk[4 * stride] = owner ? __fdiv_rn(__fsub_rn(UPy, U), g.dt) : 0.0f;
+    }
   }
 }
 
@@ -170,7 +184,7 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int slice = tid / (TS * TS);  // which quarter of the culled list this thread sums
-  const float X = mesh_coord(m.lower_x, i, m.off_x, m.dx);
+  const float X = mesh_coord(m.lower_x, i + m.row0, m.off_x, m.dx);
   const float Y = mesh_coord(m.lower_y, j, m.off_y, m.dy);
   const float mhalf_inv_w2 = -0.5f / (m.dx * m.dx);
   float acc = 0.0f;
@@ -183,7 +197,7 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
       xp = mxp[k]; yp = myp[k];
       // IBM_Force.py:67: F * delta(r, 0, dx) * dS -- the marker's constant factor F * pref * dS
       c = mF[k] * m.pref_x * mdS[k];
-      ik = cell_index(xp, m.dx, m.off_x);
+      ik = cell_index(xp, m.dx, m.off_x) - m.row0;
       jk = cell_index(yp, m.dy, m.off_y);
       keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
     }
@@ -224,7 +238,7 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
 }
 
 __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic, int& jc) {
-  ic = cell_index(st[2], m.dx, m.off_x);
+  ic = cell_index(st[2], m.dx, m.off_x) - m.row0;
   jc = cell_index(st[3], m.dy, m.off_y);
 }
 
@@ -279,7 +293,7 @@ __global__ void bbox_kernel(GridF g, float off_x, float off_y, const float* __re
                             const float* __restrict__ yp, int n, int* __restrict__ box) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  int ik = cell_index(xp[k], g.dx, off_x), jk = cell_index(yp[k], g.dy, off_y);
+  int ik = cell_index(xp[k], g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.dy, off_y);
   atomicMin(box + 0, ik); atomicMax(box + 1, ik);
   atomicMin(box + 2, jk); atomicMax(box + 3, jk);
 }
@@ -325,9 +339,14 @@ int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const int threads = 128;
-  const long long total = (long long)g.batch * b.n_markers * 32;
-  interp_force_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-      g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state, u_star, v_star, markers);
+  const long long total = (long long)g.batch * b.n_markers * 2 * 32;
+  const unsigned nblk = (unsigned)((total + threads - 1) / threads);
+  if (g.R == 6)
+    interp_force_kernel<6><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
+                                                     u_star, v_star, markers);
+  else
+    interp_force_kernel<0><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
+                                                     u_star, v_star, markers);
   int rc = check_launch("interp_force_kernel");
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);

@@ -427,7 +427,7 @@ int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const f
   if (pl->fast_cols) {
     FastColParams fcp;
     fcp.nx = g.nx; fcp.sp = rp.sp; fcp.ncols = n2 + 1; fcp.tw = pl->tw_col;
-    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f;
+    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f; fcp.dbg = frp.dbg;
     rc = launch_cols_fast(s, fcp, g.batch, spec);
   } else {
     ColParams cp;
@@ -547,7 +547,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   pl->rows_per_cta = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
   {  // fast row kernels: one row group per CTA; aim at >= 4 CTAs per SM, at most 8 rows each
     const char* e = getenv("JAXIB_ROWS_PER_GROUP");
-    int rpg = e ? atoi(e) : (int)(rows_total / (4LL * sms));
+    int rpg = e ? atoi(e) : (int)((rows_total + 3LL * sms - 1) / (3LL * sms));
     pl->fast_rows_per_group = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
   }
   const size_t col_bytes = (size_t)(padi(nx) + 1) * sizeof(float2);

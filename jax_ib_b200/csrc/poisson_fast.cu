@@ -56,29 +56,49 @@ __device__ __forceinline__ void copy_async(void* dst, const void* src, int bytes
 __device__ __forceinline__ float inv_eig_f(float l) { return fabsf(l) > kCutoffF ? __frcp_rn(l) : 0.0f; }
 
 // ---------------------------------------------------------------------------------------------- K5
-template <int R1, int R2, int R3>
-__global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
+// float4 = two adjacent ky columns at one kx.  Bank swizzle of the [N] float4 column-pair buffer:
+// XOR index bits 4-6 into bits 0-2 so that the stride-R3 accesses of the innermost pass spread over the
+// eight 16-byte bank groups (contiguous runs stay contiguous inside aligned blocks of 16).
+__device__ __forceinline__ int qswz(int p) { return p ^ ((p >> 4) & 7); }
+
+// Thread mapping: the global (first / last) pass moves float4 = both columns of a pair with S1 = N/R1
+// threads per pair (R1 = 8 keeps it light in registers); the two inner passes run ONE column per
+// thread (8-byte shared accesses), so a radix-16 butterfly costs 32 data registers instead of 64 and
+// every thread has work in every pass.
+template <int R1, int R2, int R3, int NP>
+__global__ void __launch_bounds__(NP * R2 * R3, (NP * R2 * R3 <= 512 ? 2 : 1))
+cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   constexpr int N = R1 * R2 * R3;
   constexpr int S1 = N / R1;   // threads per column pair; stride of pass 1
   constexpr int L2 = R2 * R3;  // block length of pass 2
-  constexpr int PITCH = N + N / 8 + 1;
   extern __shared__ float4 smq[];
+  constexpr int npairs = NP;  // column pairs per CTA: 4 pairs = 64 contiguous bytes per spectrum row
+  // inner passes: thread -> (pair, b) blocked, so that a warp stays inside one pair's buffer
   const int pair = threadIdx.x / S1, b = threadIdx.x - pair * S1;
-  const int c = blockIdx.x * 2 * (blockDim.x / S1) + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
-  float4* col = smq + pair * PITCH;
-  float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + c);
+  const int c = blockIdx.x * 2 * npairs + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
+  float4* col = smq + pair * N;
+  float2* col2 = reinterpret_cast<float2*>(col);
+  // global passes: thread -> (b, pair) with the pair index FASTEST, so that adjacent lanes cover the
+  // adjacent 16-byte halves of one 32-byte sector of a spectrum row (a warp-wide load then fetches
+  // every sector once; with the blocked mapping each sector was fetched by two different warps)
+  const int gpair = threadIdx.x % npairs, gb = threadIdx.x / npairs;
+  float4* gcol = smq + gpair * N;
+  const int gc = blockIdx.x * 2 * npairs + 2 * gpair;  // first column of this thread's global pair
+  const bool gvalid = gc + 1 < P.sp;                   // the last CTA may overhang the row pitch
+  float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + gc);
   const size_t rs = (size_t)P.sp / 2;  // row stride in float4 units
   const float2* __restrict__ tw = P.tw;
-  // twiddle tables in shared memory (coalesced fill): W_N^m for pass 1, W_N^(b2 r R1) for pass 2.
+  // twiddle tables in shared memory (coalesced fill): W_N^m for the outer pass, W_N^(b2 r R1) for pass 2.
   // Reading them from global with a lane stride of r*8 bytes costs up to 32 L1 wavefronts per load.
-  float2* const tws = reinterpret_cast<float2*>(smq + (blockDim.x / S1) * PITCH);
+  float2* const tws = reinterpret_cast<float2*>(smq + npairs * N);
   float2* const tw2 = tws + N;
 
   {  // pass 1 forward: global -> registers -> shared
     float2 va[R1], vb[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      float4 x = g4[(size_t)(b + r * S1) * rs];
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gvalid && !(P.dbg & 16)) x = g4[(size_t)(gb + r * S1) * rs];
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
     }
@@ -91,110 +111,96 @@ __global__ void __launch_bounds__(2 * R2 * R3, (R1 * R2 * R3 <= 2048 ? 2 : 1)) c
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       if (r > 0) {
-        const float2 w = tws[b * r];
+        const float2 w = tws[gb * r];
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
-      col[padq(b + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+      gcol[qswz(gb + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
     }
   }
   __syncthreads();
-  // pass 2 forward
+  if (!(P.dbg & 4)) {
+  // pass 2 forward, one column per thread
 #pragma unroll
-  for (int m = 0; m < R1 / R2; ++m) {
-    const int t = b + m * S1;
-    const int blk = t / R3, b2 = t - blk * R3;
+  for (int m = 0; m < (2 * R1 + R2 - 1) / R2; ++m) {
+    const int w = b + m * S1;
+    if (w >= 2 * (N / R2)) continue;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / R3, b2 = bf - blk * R3;
     const int p0 = blk * L2 + b2;
-    float2 va[R2], vb[R2];
+    float2 v[R2];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      float4 x = col[padq(p0 + r * R3)];
-      va[r] = make_float2(x.x, x.y);
-      vb[r] = make_float2(x.z, x.w);
-    }
-    Dft<R2>::run(va);
-    Dft<R2>::run(vb);
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * R3) + cc];
+    Dft<R2>::run(v);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      if (r > 0) {
-        const float2 w = tw2[b2 * (R2 + 1) + r];
-        va[r] = cmul(va[r], w);
-        vb[r] = cmul(vb[r], w);
-      }
-      col[padq(p0 + r * R3)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
-    }
+    for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], tw2[b2 * (R2 + 1) + r]);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * R3) + cc] = v[r];
   }
   __syncthreads();
-  // pass 3 forward, diagonal, pass 3 inverse -- all in registers
-  {
-    const float lya = P.lam_y[c], lyb = P.lam_y[c + 1];
+  // pass 3 forward, diagonal, pass 3 inverse -- in registers, one column per thread
 #pragma unroll
-    for (int m = 0; m < R1 / R3; ++m) {
-      const int p0 = (b + m * S1) * R3;
-      float2 va[R3], vb[R3];
+  for (int m = 0; m < (2 * R1 + R3 - 1) / R3; ++m) {
+    const int w = b + m * S1;
+    if (w >= 2 * (N / R3)) continue;
+    const int cc = w & 1, p0 = (w >> 1) * R3;
+    const float ly = P.lam_y[c + cc];
+    float lx[R3];
 #pragma unroll
-      for (int r = 0; r < R3; ++r) {
-        float4 x = col[padq(p0 + r)];
-        va[r] = make_float2(x.x, x.y);
-        vb[r] = make_float2(x.z, x.w);
-      }
-      Dft<R3>::run(va);
-      Dft<R3>::run(vb);
-#pragma unroll
-      for (int r = 0; r < R3; ++r) {
-        const float lx = __ldg(P.lam_x_pos + p0 + r);
-        va[r] = cscale(va[r], inv_eig_f(lx + lya));
-        vb[r] = cscale(vb[r], inv_eig_f(lx + lyb));
-      }
-      dft_dir<R3, true>(va);
-      dft_dir<R3, true>(vb);
-#pragma unroll
-      for (int r = 0; r < R3; ++r) col[padq(p0 + r)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    for (int r = 0; r < R3; r += 4) {
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(P.lam_x_pos + p0 + r));
+      lx[r] = l4.x; lx[r + 1] = l4.y; lx[r + 2] = l4.z; lx[r + 3] = l4.w;
     }
+    float2 v[R3];
+#pragma unroll
+    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r) + cc];
+    Dft<R3>::run(v);
+#pragma unroll
+    for (int r = 0; r < R3; ++r) v[r] = cscale(v[r], inv_eig_f(lx[r] + ly));
+    dft_dir<R3, true>(v);
+#pragma unroll
+    for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r) + cc] = v[r];
   }
   __syncthreads();
   // pass 2 inverse
 #pragma unroll
-  for (int m = 0; m < R1 / R2; ++m) {
-    const int t = b + m * S1;
-    const int blk = t / R3, b2 = t - blk * R3;
+  for (int m = 0; m < (2 * R1 + R2 - 1) / R2; ++m) {
+    const int w = b + m * S1;
+    if (w >= 2 * (N / R2)) continue;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / R3, b2 = bf - blk * R3;
     const int p0 = blk * L2 + b2;
-    float2 va[R2], vb[R2];
+    float2 v[R2];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) {
-      float4 x = col[padq(p0 + r * R3)];
-      va[r] = make_float2(x.x, x.y);
-      vb[r] = make_float2(x.z, x.w);
-      if (r > 0) {
-        const float2 w = tw2[b2 * (R2 + 1) + r];
-        va[r] = cmulc(va[r], w);
-        vb[r] = cmulc(vb[r], w);
-      }
-    }
-    dft_dir<R2, true>(va);
-    dft_dir<R2, true>(vb);
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * R3) + cc];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) col[padq(p0 + r * R3)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], tw2[b2 * (R2 + 1) + r]);
+    dft_dir<R2, true>(v);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * R3) + cc] = v[r];
   }
+  }  // dbg
   __syncthreads();
   {  // pass 1 inverse: shared -> registers -> global
     float2 va[R1], vb[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      float4 x = col[padq(b + r * S1)];
+      float4 x = gcol[qswz(gb + r * S1)];
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
       if (r > 0) {
-        const float2 w = tws[b * r];
+        const float2 w = tws[gb * r];
         va[r] = cmulc(va[r], w);
         vb[r] = cmulc(vb[r], w);
       }
     }
     dft_dir<R1, true>(va);
     dft_dir<R1, true>(vb);
+    if (gvalid && !(P.dbg & 8)) {
 #pragma unroll
-    for (int r = 0; r < R1; ++r)
-      g4[(size_t)(b + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+      for (int r = 0; r < R1; ++r)
+        g4[(size_t)(gb + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
   }
 }
 
@@ -491,16 +497,29 @@ template <int R1, int R2, int R3>
 int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
   constexpr int N = R1 * R2 * R3;
   const size_t tables = (size_t)(N + R3 * (R2 + 1)) * sizeof(float2);
-  const size_t smem = 2 * (size_t)(N + N / 8 + 1) * sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + tables));
-    configured = true;
-  }
   const char* e = getenv("JAXIB_COL_PAIRS");
-  const int pairs = (e && atoi(e) == 1) ? 1 : 2;  // column pairs (float4) per CTA
+  int pairs = e ? atoi(e) : 4;  // column pairs (float4) per CTA
+  if (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024) pairs = 2;
+  if (pairs != 1 && pairs != 2 && pairs != 4) pairs = 2;
+  const size_t smem = pairs * (size_t)N * sizeof(float4) + tables;
   dim3 grid((P.ncols + 2 * pairs - 1) / (2 * pairs), batch);
-  cols_fast_kernel<R1, R2, R3><<<grid, pairs * (N / R1), smem * pairs / 2 + tables, s>>>(P, spec);
+  // the opt-in for > 48 KB dynamic shared memory is set once per instantiation (idempotent; a
+  // driver call on every launch costs several microseconds of host time on the critical path)
+  static bool configured[5] = {false, false, false, false, false};
+  if (!configured[pairs]) {
+    const int cap = 220 * 1024;
+    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    cudaFuncSetAttribute(cols_fast_kernel<R1, R2, R3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    configured[pairs] = true;
+  }
+  if (pairs == 4) {
+    cols_fast_kernel<R1, R2, R3, 4><<<grid, 4 * (N / R1), smem, s>>>(P, spec);
+  } else if (pairs == 2) {
+    cols_fast_kernel<R1, R2, R3, 2><<<grid, 2 * (N / R1), smem, s>>>(P, spec);
+  } else {
+    cols_fast_kernel<R1, R2, R3, 1><<<grid, N / R1, smem, s>>>(P, spec);
+  }
   return check_launch("cols_fast_kernel");
 }
 
@@ -508,8 +527,11 @@ template <int R1, int R2, int R3>
 int launch_rows_fwd_t(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
   dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
   const size_t smem = (RowGeom<R1, R2, R3>::PITCH + 1 + R3 * (R2 + 1)) * sizeof(float2) + 3 * (size_t)P.g.ny * sizeof(float);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(rows_fwd_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(rows_fwd_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
   rows_fwd_fast_kernel<R1, R2, R3><<<grid, R2 * R3, smem, s>>>(P, u, v, spec);
   return check_launch("rows_fwd_fast_kernel");
 }
@@ -519,9 +541,11 @@ int launch_rows_inv_t(cudaStream_t s, const FastRowParams& P, const float2* spec
                       const float* p, float* uo, float* vo, float* po, bool project) {
   dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
   const size_t smem = (2 * RowGeom<R1, R2, R3>::PITCH + R1 * R2 * R3 + 4 + R3 * (R2 + 1)) * sizeof(float2);
-  if (smem > 48 * 1024) {  // opt in to > 48 KB dynamic shared memory (idempotent)
-    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;
+  if (!configured) {  // opt in to > 48 KB dynamic shared memory once (idempotent)
+    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
   }
   if (project)
     rows_inv_fast_kernel<R1, R2, R3, true><<<grid, R2 * R3, smem, s>>>(P, spec, u, v, p, uo, vo, po);
@@ -537,25 +561,26 @@ bool fast_size_supported(int n) { return n == 512 || n == 1024 || n == 2048 || n
 void fast_radices(int n, int* r) {
   switch (n) {
     case 512: r[0] = 8; r[1] = 8; r[2] = 8; break;
-    case 1024: r[0] = 16; r[1] = 8; r[2] = 8; break;
-    case 2048: r[0] = 16; r[1] = 16; r[2] = 8; break;
+    case 1024: r[0] = 8; r[1] = 8; r[2] = 16; break;
+    case 2048: r[0] = 8; r[1] = 16; r[2] = 16; break;
     case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
     default: r[0] = r[1] = r[2] = 0;
   }
 }
 
-#define JAXIB_DISPATCH_N(n, CALL)             \
+// columns: must agree with fast_radices() (the eigenvalue table is stored in this digit order)
+#define JAXIB_DISPATCH_COLS(n, CALL)          \
   switch (n) {                                \
     case 512: return CALL(8, 8, 8);           \
-    case 1024: return CALL(16, 8, 8);         \
-    case 2048: return CALL(16, 16, 8);        \
+    case 1024: return CALL(8, 8, 16);         \
+    case 2048: return CALL(8, 16, 16);        \
     case 4096: return CALL(16, 16, 16);       \
     default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
   }
 
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
 #define CALL_COLS(a, b, c) launch_cols_t<a, b, c>(s, P, batch, spec)
-  JAXIB_DISPATCH_N(P.nx, CALL_COLS)
+  JAXIB_DISPATCH_COLS(P.nx, CALL_COLS)
 #undef CALL_COLS
 }
 

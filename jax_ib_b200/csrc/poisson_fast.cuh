@@ -9,6 +9,7 @@ struct FastColParams {
   const float2* tw;         // W_nx^k
   const float* lam_x_pos;   // float32(lx[freq(p)]) in digit-reversed position order
   const float* lam_y;       // float32(ly_l), padded to sp entries
+  int dbg;                  // timing experiments only (JAXIB_DBG)
 };
 
 struct FastRowParams {

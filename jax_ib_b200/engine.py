@@ -132,7 +132,13 @@ class FusedStepper:
         new_particles = particles
         if particles is not None and move_bodies:
             new_particles = dataclasses.replace(particles, particle_center=_like(particles.particle_center, centers[-1]))
-        out = self._view(state, u.to(in_dev), v.to(in_dev), p.to(in_dev), times[-1], new_particles, state.MD_var)
+        if in_dev.type == "cpu":  # host buffers in, host buffers out: pinned staging + one sync
+            outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (u, v, p)]
+            for o, t in zip(outs, (u, v, p)):
+                o.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            u, v, p = outs
+        out = self._view(state, u, v, p, times[-1], new_particles, state.MD_var)
         # particle_motion.py:59: the step counter lives in the position update
         return dataclasses.replace(out, Step_count=all_variables.Step_count + (nsteps if move_bodies else 0))
 

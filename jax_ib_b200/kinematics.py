@@ -111,15 +111,37 @@ def body_schedule(particles, t0: float, dt: float, nsteps: int):
         inc = f32(dt) * U_all[1:, a, :]  # float32 product, then sequential float32 accumulation
         centers[:, :, a] = np.add.accumulate(np.concatenate([centers0[None, :, a], inc], axis=0), axis=0, dtype=f32)
     table = np.zeros((nsteps, B, 8), dtype=f32)
+    table[:, :, 2:4] = centers[:nsteps]
+    # The reference evaluates the laws body by body (`[param_b]`, IBM_Force.py:99-104).  The multi-body
+    # laws are element-wise over bodies, so one vectorised evaluation of all bodies gives the same
+    # numbers at a fraction of the host cost; single-body laws (`displacement`, `rotation`) take the
+    # per-body path.
+    th_all = om_all = None
+    if B > 1:
+        try:
+            th_v, om_v = _values_and_rates(rot, list(rparams), tt[:nsteps])
+            if th_v.reshape(nsteps, -1).shape[1] == B and U_all.shape[2] == B:
+                th_all = th_v.reshape(nsteps, B).numpy().astype(f32)
+                om_all = om_v.reshape(nsteps, B).numpy().astype(f32)
+        except Exception:
+            th_all = None
+    if th_all is not None:
+        table[:, :, 0] = np.cos(th_all)
+        table[:, :, 1] = np.sin(th_all)
+        table[:, :, 4:6] = np.transpose(U_all[:nsteps], (0, 2, 1))
+        table[:, :, 6] = om_all
+        return table, times, centers
     for b in range(B):
-        _, U_b = _values_and_rates(disp, [dparams[b]], tt[:nsteps])
+        if B == 1:
+            U_b = U_all[:nsteps, :, 0]
+        else:
+            _, U_b = _values_and_rates(disp, [dparams[b]], tt[:nsteps])
+            U_b = U_b.reshape(nsteps, 2, -1).numpy().astype(f32)[:, :, 0]
         th_b, om_b = _values_and_rates(rot, [rparams[b]], tt[:nsteps])
-        U_b = U_b.reshape(nsteps, 2, -1).numpy().astype(f32)[:, :, 0]
         th = th_b.reshape(nsteps, -1).numpy().astype(f32)[:, 0]
         om = om_b.reshape(nsteps, -1).numpy().astype(f32)[:, 0]
         table[:, b, 0] = np.cos(th)
         table[:, b, 1] = np.sin(th)
-        table[:, b, 2:4] = centers[:nsteps, b, :]
         table[:, b, 4:6] = U_b
         table[:, b, 6] = om
     return table, times, centers
