@@ -70,10 +70,13 @@ typedef struct {
   /* Slab decomposition along x (0 / 0 / 0 for a full grid): the arrays hold global rows
    * [row0, row0 + nx) (halo rows included); immersed-boundary forces are computed only for markers
    * whose owning u-cell row lies in [own_lo, own_hi) and are zero otherwise (the caller sums the
-   * per-slab force arrays), while spreading writes every local row.                              */
+   * per-slab force arrays), while spreading writes every local row.  nx_global > 0 marks a slab
+   * for the Poisson row stages (jaxib_poisson_rows_fwd / _rows_inv): the nx local rows are "open" --
+   * row -1 of u and spectrum row nx are read from the memory next to the arrays (the caller's halo)
+   * instead of wrapping -- and transforms are normalised with nx_global.                           */
   int32_t row0;
   int32_t own_lo, own_hi;
-  int32_t reserved;
+  int32_t nx_global;
 } jaxib_grid;
 
 /* Rigid bodies of ONE simulation (identical marker topology across the batch).
@@ -148,6 +151,32 @@ int jaxib_pressure_solve(jaxib_stream_t stream, const jaxib_plan* plan, const fl
  * (u,v) - forward_difference(q) [+ impose_bc for channel].  Outputs may alias the inputs.     */
 int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v, const float* p,
                   float* u_out, float* v_out, float* p_out, void* scratch, size_t scratch_bytes);
+
+/* ---- stage-level entry points for the slab decomposition -------------------------------------- */
+/* New capability (the reference only shards MARKERS with jax.pmap, grid replicated:
+ * IBM_Force.py:77-87, convolution_functions.py:28-35; no grid decomposition exists there).  A
+ * slab rank calls the stages of one step separately and places its own exchange between them
+ * (jax_ib_b200/slab.py): marker forces are summed over ranks between the two IB halves, and the
+ * spectrum is transposed (all-to-all) on either side of the column transform.
+ *
+ * jaxib_ib_force split in two.  `markers`: [5][batch][n_markers] floats (xp, yp, dS, Fx, Fy);
+ * Fx, Fy are zero for markers this slab does not own (grid->own_lo / own_hi).                  */
+int jaxib_ib_marker_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
+                          const float* body_state, const float* u_star, const float* v_star, float* markers);
+int jaxib_ib_spread_bodies(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
+                           const float* body_state, const float* markers, float* u_star, float* v_star);
+/* jaxib_project split in three.  `spectrum` is [plan nx (+1 in slab mode for rows_inv)][sp] complex
+ * float32; sp = row pitch in complex values (0 = ny/2 + 4; otherwise a multiple of 4, >= ny/2 + 4).
+ * rows_fwd: divergence of (u, v) + real row FFT.  cols: in-place column FFT, division by the
+ * eigenvalues (pressure.py:94-130), inverse column FFT for `ncols` columns holding the y-wavenumbers
+ * col0 .. col0+ncols-1 (the plan's nx is the GLOBAL row count).  rows_inv: inverse row FFT fused
+ * with p_out = p + q, (u, v)_out = (u, v) - grad q; it reads spectrum row i+1 for row i.        */
+int jaxib_poisson_rows_fwd(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v,
+                           float* spectrum, int32_t sp);
+int jaxib_poisson_cols(jaxib_stream_t stream, const jaxib_plan* plan, float* spectrum, int32_t sp, int32_t ncols,
+                       int32_t col0);
+int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const float* spectrum, int32_t sp,
+                           const float* u, const float* v, const float* p, float* u_out, float* v_out, float* p_out);
 
 /* ---- fused step ------------------------------------------------------------------------------ */
 /* time_stepping.py:144-255 step_fn, `nsteps` times, in place on (u, v, p):

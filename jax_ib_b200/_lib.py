@@ -24,7 +24,7 @@ class Grid(C.Structure):
         ("bc", C.c_int32), ("convect", C.c_int32),
         ("u_wall", C.c_double * 2), ("v_wall", C.c_double * 2), ("force", C.c_double * 2),
         ("ib_window", C.c_int32), ("row0", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32),
-        ("reserved", C.c_int32),
+        ("nx_global", C.c_int32),
     ]
 
 
@@ -56,6 +56,11 @@ _SIGNATURES = {
     "jaxib_ib_spread": (C.c_int, [_P, C.POINTER(Grid), C.c_double, C.c_double, _P, _P, _P, _P, C.c_int32,
                                   C.c_double, _P, _P, C.c_size_t]),
     "jaxib_ib_force": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(Bodies), _P, _P, _P, _P, C.c_size_t]),
+    "jaxib_ib_marker_force": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(Bodies), _P, _P, _P, _P]),
+    "jaxib_ib_spread_bodies": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(Bodies), _P, _P, _P, _P]),
+    "jaxib_poisson_rows_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32]),
+    "jaxib_poisson_cols": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "jaxib_poisson_rows_inv": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "jaxib_pressure_solve": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_project": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_size_t]),

@@ -174,6 +174,65 @@ int jaxib_ib_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bo
   return launch_ib_force((cudaStream_t)stream, g, *bodies, body_state, u_star, v_star, reinterpret_cast<float*>(a));
 }
 
+int jaxib_ib_marker_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
+                          const float* body_state, const float* u_star, const float* v_star, float* markers) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if ((rc = check_bodies(bodies))) return rc;
+  if ((rc = check_ptrs("ib_marker_force", {body_state, u_star, v_star, markers}))) return rc;
+  return launch_ib_marker_force((cudaStream_t)stream, make_gridf(*grid), *bodies, body_state, u_star, v_star, markers);
+}
+
+int jaxib_ib_spread_bodies(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
+                           const float* body_state, const float* markers, float* u_star, float* v_star) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if ((rc = check_bodies(bodies))) return rc;
+  if ((rc = check_ptrs("ib_spread_bodies", {body_state, markers, u_star, v_star}))) return rc;
+  return launch_ib_spread_bodies((cudaStream_t)stream, make_gridf(*grid), *bodies, body_state, markers, u_star, v_star);
+}
+
+static int check_pitch(const char* what, const jaxib_plan* plan, int32_t sp) {
+  const GridF& g = plan_grid(plan);
+  if (sp != 0 && (sp < g.ny / 2 + 4 || sp % 4 != 0)) {
+    set_error("%s: spectrum pitch %d must be 0 or a multiple of 4 that is >= ny/2 + 4 = %d", what, sp, g.ny / 2 + 4);
+    return JAXIB_ERR_INVALID;
+  }
+  return JAXIB_OK;
+}
+
+int jaxib_poisson_rows_fwd(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v,
+                           float* spectrum, int32_t sp) {
+  if (!plan) { set_error("poisson_rows_fwd: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("poisson_rows_fwd", {u, v, spectrum});
+  if (rc) return rc;
+  if ((rc = check_pitch("poisson_rows_fwd", plan, sp))) return rc;
+  return launch_rows_fwd((cudaStream_t)stream, plan, u, v, spectrum, sp);
+}
+
+int jaxib_poisson_cols(jaxib_stream_t stream, const jaxib_plan* plan, float* spectrum, int32_t sp, int32_t ncols,
+                       int32_t col0) {
+  if (!plan) { set_error("poisson_cols: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("poisson_cols", {spectrum});
+  if (rc) return rc;
+  const GridF& g = plan_grid(plan);
+  if (sp < 0 || ncols < 0 || col0 < 0 || (sp > 0 && (sp % 2 != 0 || ncols > sp)) ||
+      col0 + ncols > g.ny / 2 + 4 + 1024) {
+    set_error("poisson_cols: bad column range (sp=%d ncols=%d col0=%d)", sp, ncols, col0);
+    return JAXIB_ERR_INVALID;
+  }
+  return launch_cols((cudaStream_t)stream, plan, spectrum, sp, ncols, col0);
+}
+
+int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const float* spectrum, int32_t sp,
+                           const float* u, const float* v, const float* p, float* u_out, float* v_out, float* p_out) {
+  if (!plan) { set_error("poisson_rows_inv: plan is null"); return JAXIB_ERR_INVALID; }
+  int rc = check_ptrs("poisson_rows_inv", {spectrum, u, v, p, u_out, v_out, p_out});
+  if (rc) return rc;
+  if ((rc = check_pitch("poisson_rows_inv", plan, sp))) return rc;
+  return launch_rows_inv((cudaStream_t)stream, plan, spectrum, sp, u, v, p, u_out, v_out, p_out, nullptr);
+}
+
 int jaxib_pressure_solve(jaxib_stream_t stream, const jaxib_plan* plan, const float* u, const float* v, float* q,
                          void* scratch, size_t scratch_bytes) {
   if (!plan) { set_error("pressure_solve: plan is null"); return JAXIB_ERR_INVALID; }

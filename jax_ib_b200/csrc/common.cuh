@@ -26,7 +26,7 @@ struct GridF {
   int bc, convect;
   float uw_lo, uw_hi, vw_lo, vw_hi;
   int R;                 // IB window radius
-  int row0, own_lo, own_hi;  // slab decomposition (see jaxib_grid)
+  int row0, own_lo, own_hi, nx_global;  // slab decomposition (see jaxib_grid)
 };
 
 inline GridF make_gridf(const jaxib_grid& g) {
@@ -47,7 +47,7 @@ inline GridF make_gridf(const jaxib_grid& g) {
   f.uw_lo = (float)g.u_wall[0]; f.uw_hi = (float)g.u_wall[1];
   f.vw_lo = (float)g.v_wall[0]; f.vw_hi = (float)g.v_wall[1];
   f.R = g.ib_window > 0 ? g.ib_window : 6;
-  f.row0 = g.row0; f.own_lo = g.own_lo; f.own_hi = g.own_hi;
+  f.row0 = g.row0; f.own_lo = g.own_lo; f.own_hi = g.own_hi; f.nx_global = g.nx_global;
   return f;
 }
 
@@ -72,6 +72,10 @@ struct StageHook {
 };
 int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                     float* u_star, float* v_star, float* marker_scratch, const StageHook* hook = nullptr);
+int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
+                           const float* u_star, const float* v_star, float* markers);
+int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
+                            const float* markers, float* u_star, float* v_star);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                           const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
@@ -82,6 +86,11 @@ int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, c
 int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
                    float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
                    const StageHook* hook = nullptr);
+// Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
+int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp);
+int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0);
+int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
+                    const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only);
 size_t spectrum_floats(const jaxib_plan* plan);
 const GridF& plan_grid(const jaxib_plan* plan);
 

@@ -334,8 +334,8 @@ int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, c
   return check_launch("interp_points_kernel");
 }
 
-int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state, float* u_star,
-                    float* v_star, float* markers, const StageHook* hook) {
+int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
+                           const float* u_star, const float* v_star, float* markers) {
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const int threads = 128;
@@ -347,17 +347,30 @@ int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const
   else
     interp_force_kernel<0><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
                                                      u_star, v_star, markers);
-  int rc = check_launch("interp_force_kernel");
-  if (rc) return rc;
-  if (hook) cudaEventRecord(hook->ev[0], s);
+  return check_launch("interp_force_kernel");
+}
+
+int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
+                            const float* markers, float* u_star, float* v_star) {
+  if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
+  if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const float hmin = g.dx < g.dy ? g.dx : g.dy;
   const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
   const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
   dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
   spread_bodies_kernel<<<grid, block, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
                                               half_extent, tiles, u_star, v_star);
-  if (hook) cudaEventRecord(hook->ev[1], s);
   return check_launch("spread_bodies_kernel");
+}
+
+int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state, float* u_star,
+                    float* v_star, float* markers, const StageHook* hook) {
+  int rc = launch_ib_marker_force(s, g, b, body_state, u_star, v_star, markers);
+  if (rc) return rc;
+  if (hook) cudaEventRecord(hook->ev[0], s);
+  rc = launch_ib_spread_bodies(s, g, b, body_state, markers, u_star, v_star);
+  if (hook) cudaEventRecord(hook->ev[1], s);
+  return rc;
 }
 
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F, const float* xp,

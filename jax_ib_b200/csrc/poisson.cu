@@ -52,6 +52,7 @@ namespace jaxib {
 namespace {
 
 constexpr double kCutoff = 10.0 * 1.1920928955078125e-07;  // 10 * finfo(float32).eps
+constexpr int kLamPad = 1024;  // eigenvalue tables are padded with 1.0: slab ranks hold padded column ranges
 
 bool factor_plan(int n, FftPlan* pl) {
   pl->n = n;
@@ -116,7 +117,7 @@ __global__ void rows_fwd_kernel(RowParams P, const float* __restrict__ u, const 
   const int i1 = min(i0 + P.rows_per_cta, g.nx);
   for (int i = i0; i < i1; ++i) {
     const float2* ur = reinterpret_cast<const float2*>(u + (size_t)i * g.ny);
-    const float2* um = reinterpret_cast<const float2*>(u + (size_t)wrapi(i - 1, g.nx) * g.ny);
+    const float2* um = reinterpret_cast<const float2*>(u + (ptrdiff_t)(g.nx_global ? i - 1 : wrapi(i - 1, g.nx)) * g.ny);
     const float* vrow = v + (size_t)i * g.ny;
     const float2* vr = reinterpret_cast<const float2*>(vrow);
     for (int n = threadIdx.x; n < n2; n += blockDim.x) {
@@ -173,7 +174,7 @@ __global__ void rows_inv_kernel(RowParams P, const float2* __restrict__ spec, co
   const int i1 = min(i0 + P.rows_per_cta, g.nx);
   const int last = PROJECT ? i1 : i1 - 1;  // projection needs q of the row after the last owned one
   for (int ii = i0; ii <= last; ++ii) {
-    const int i = ii >= g.nx ? ii - g.nx : ii;
+    const int i = (ii >= g.nx && g.nx_global == 0) ? ii - g.nx : ii;  // slab mode: spectrum row nx exists (halo)
     float2* cur = smem + ((ii - i0) & 1) * pitch;
     const float2* in = spec + (size_t)i * P.sp;
     for (int k = threadIdx.x; k <= n2 / 2; k += blockDim.x) {
@@ -394,73 +395,113 @@ size_t spectrum_floats(const jaxib_plan* plan) {
   return (size_t)plan->gf.batch * plan->gf.nx * (plan->gf.ny + 8);  // [nx][ny/2 + 4] complex
 }
 
-int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
-                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook) {
+namespace {
+
+struct StageParams {
+  RowParams rp;
+  FastRowParams frp;
+  DctParams dp;
+  dim3 rgrid;
+  bool channel;
+};
+
+// sp = spectrum row pitch in complex values (0 = the default ny/2 + 4)
+StageParams stage_params(const jaxib_plan* pl, int sp) {
+  StageParams S;
   const GridF& g = pl->gf;
   const int n2 = g.ny / 2;
-  RowParams rp;
-  rp.g = g; rp.pl = pl->row; rp.tw = pl->tw_row; rp.pos = pl->row_pos; rp.rows_per_cta = pl->rows_per_cta;
-  rp.sp = n2 + 4;
-  rp.scale = (float)(1.0 / ((double)g.nx * (double)n2));
-  float2* spec = reinterpret_cast<float2*>(spectrum);
-  dim3 rgrid((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
-  FastRowParams frp;
-  frp.g = g; frp.tw = pl->tw_row; frp.sp = rp.sp; frp.rows_per_group = pl->fast_rows_per_group; frp.scale = rp.scale;
-  { const char* e = getenv("JAXIB_DBG"); frp.dbg = e ? atoi(e) : 0; }
-  int rc;
-  const bool channel = g.bc == JAXIB_BC_CHANNEL;
-  DctParams dp;
-  if (channel) {
-    dp.g = g; dp.pl = pl->row; dp.tw = pl->tw_row; dp.twd = pl->tw_dct; dp.pos = pl->row_pos;
-    dp.rows_per_cta = pl->rows_per_cta; dp.sp = rp.sp;
-    dp.scale = (float)(1.0 / ((double)g.nx * (double)g.ny));
-    rows_fwd_dct_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(dp, u, v, spectrum);
-    rc = check_launch("rows_fwd_dct_kernel");
-  } else if (pl->fast_rows) {
-    rc = launch_rows_fwd_fast(s, frp, u, v, spec);
-  } else {
-    rows_fwd_kernel<<<rgrid, pl->row_threads, pl->row_smem, s>>>(rp, u, v, spec);
-    rc = check_launch("rows_fwd_kernel");
+  const double nxg = g.nx_global > 0 ? g.nx_global : g.nx;  // slab: normalise with the global length
+  S.channel = g.bc == JAXIB_BC_CHANNEL;
+  S.rp.g = g; S.rp.pl = pl->row; S.rp.tw = pl->tw_row; S.rp.pos = pl->row_pos; S.rp.rows_per_cta = pl->rows_per_cta;
+  S.rp.sp = sp > 0 ? sp : n2 + 4;
+  S.rp.scale = (float)(1.0 / (nxg * (double)n2));
+  S.rgrid = dim3((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
+  S.frp.g = g; S.frp.tw = pl->tw_row; S.frp.sp = S.rp.sp; S.frp.rows_per_group = pl->fast_rows_per_group;
+  S.frp.scale = S.rp.scale;
+  { const char* e = getenv("JAXIB_DBG"); S.frp.dbg = e ? atoi(e) : 0; }  // timing experiments only
+  if (S.channel) {
+    S.dp.g = g; S.dp.pl = pl->row; S.dp.tw = pl->tw_row; S.dp.twd = pl->tw_dct; S.dp.pos = pl->row_pos;
+    S.dp.rows_per_cta = pl->rows_per_cta; S.dp.sp = S.rp.sp;
+    S.dp.scale = (float)(1.0 / (nxg * (double)g.ny));
   }
-  if (rc) return rc;
-  if (hook) cudaEventRecord(hook->ev[0], s);
+  return S;
+}
+
+}  // namespace
+
+// K4: divergence of (u, v) + forward row transform -> spectrum [nx][sp]
+int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, float* spectrum, int sp) {
+  const StageParams S = stage_params(pl, sp);
+  float2* spec = reinterpret_cast<float2*>(spectrum);
+  if (S.channel) {
+    rows_fwd_dct_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.dp, u, v, spectrum);
+    return check_launch("rows_fwd_dct_kernel");
+  }
+  if (pl->fast_rows) return launch_rows_fwd_fast(s, S.frp, u, v, spec);
+  rows_fwd_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.rp, u, v, spec);
+  return check_launch("rows_fwd_kernel");
+}
+
+// K5: column transform, division by the eigenvalues, inverse column transform, in place, for the
+// `ncols` stored columns whose y-wavenumbers start at col0 (a slab rank holds a column range)
+int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0) {
+  const GridF& g = pl->gf;
+  const int n2 = g.ny / 2;
+  const bool channel = g.bc == JAXIB_BC_CHANNEL;
+  if (sp <= 0) sp = n2 + 4;
+  float2* spec = reinterpret_cast<float2*>(spectrum);
   if (pl->fast_cols) {
     FastColParams fcp;
-    fcp.nx = g.nx; fcp.sp = rp.sp; fcp.ncols = n2 + 1; fcp.tw = pl->tw_col;
-    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f; fcp.dbg = frp.dbg;
-    rc = launch_cols_fast(s, fcp, g.batch, spec);
-  } else {
-    ColParams cp;
-    // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
-    cp.nx = g.nx; cp.sp = rp.sp; cp.ncols = channel ? n2 : n2 + 1; cp.pl = pl->col; cp.tw = pl->tw_col;
-    cp.pos = pl->col_pos;
-    cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y; cp.cols_per_cta = pl->cols_per_cta;
-    cp.packed_all = channel;
-    dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
-    cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
-    rc = check_launch("cols_kernel");
+    fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
+    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0;
+    { const char* e = getenv("JAXIB_DBG"); fcp.dbg = e ? atoi(e) : 0; }
+    return launch_cols_fast(s, fcp, g.batch, spec);
   }
-  if (rc) return rc;
-  if (hook) cudaEventRecord(hook->ev[1], s);
-  if (channel) {
+  ColParams cp;
+  // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
+  cp.nx = g.nx; cp.sp = sp; cp.ncols = ncols > 0 ? ncols : (channel ? n2 : n2 + 1); cp.pl = pl->col; cp.tw = pl->tw_col;
+  cp.pos = pl->col_pos;
+  cp.lam_x_pos = pl->lam_x_pos; cp.lam_y = pl->lam_y + (channel ? 2 * col0 : col0); cp.cols_per_cta = pl->cols_per_cta;
+  cp.packed_all = channel;
+  dim3 cgrid((cp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
+  cols_kernel<<<cgrid, pl->col_threads, pl->col_smem, s>>>(cp, spec);
+  return check_launch("cols_kernel");
+}
+
+// K6: inverse row transform (+ projection and pressure update unless q_only)
+int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum, int sp, const float* u, const float* v,
+                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only) {
+  const StageParams S = stage_params(pl, sp);
+  const GridF& g = pl->gf;
+  const float2* spec = reinterpret_cast<const float2*>(spectrum);
+  if (S.channel) {
     const size_t smem = pl->row_smem + 2 * (size_t)g.ny * sizeof(float);
     if (q_only)
-      rows_inv_dct_kernel<false><<<rgrid, pl->row_threads, smem, s>>>(dp, spectrum, nullptr, nullptr, nullptr, nullptr,
-                                                                      nullptr, q_only);
+      rows_inv_dct_kernel<false><<<S.rgrid, pl->row_threads, smem, s>>>(S.dp, spectrum, nullptr, nullptr, nullptr,
+                                                                        nullptr, nullptr, q_only);
     else
-      rows_inv_dct_kernel<true><<<rgrid, pl->row_threads, smem, s>>>(dp, spectrum, u, v, p, u_out, v_out, p_out);
-    rc = check_launch("rows_inv_dct_kernel");
-  } else if (pl->fast_rows) {
-    rc = launch_rows_inv_fast(s, frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
-  } else {
-    if (q_only) {
-      rows_inv_kernel<false><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, nullptr, nullptr, nullptr,
-                                                                             nullptr, nullptr, q_only);
-    } else {
-      rows_inv_kernel<true><<<rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(rp, spec, u, v, p, u_out, v_out, p_out);
-    }
-    rc = check_launch("rows_inv_kernel");
+      rows_inv_dct_kernel<true><<<S.rgrid, pl->row_threads, smem, s>>>(S.dp, spectrum, u, v, p, u_out, v_out, p_out);
+    return check_launch("rows_inv_dct_kernel");
   }
+  if (pl->fast_rows)
+    return launch_rows_inv_fast(s, S.frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
+  if (q_only)
+    rows_inv_kernel<false><<<S.rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(S.rp, spec, nullptr, nullptr, nullptr,
+                                                                             nullptr, nullptr, q_only);
+  else
+    rows_inv_kernel<true><<<S.rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(S.rp, spec, u, v, p, u_out, v_out, p_out);
+  return check_launch("rows_inv_kernel");
+}
+
+int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
+                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook) {
+  int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0);
+  if (rc) return rc;
+  if (hook) cudaEventRecord(hook->ev[0], s);
+  rc = launch_cols(s, pl, spectrum, 0, 0, 0);
+  if (rc) return rc;
+  if (hook) cudaEventRecord(hook->ev[1], s);
+  rc = launch_rows_inv(s, pl, spectrum, 0, u, v, p, u_out, v_out, p_out, q_only);
   if (hook) cudaEventRecord(hook->ev[2], s);
   return rc;
 }
@@ -506,7 +547,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   for (int k = 0; k < nrow; ++k) rpos[k] = pos_of_freq(pl->row, k);
   for (int k = 0; k < nx; ++k) cpos[k] = pos_of_freq(pl->col, k);
   // eigenvalues of the circulant 1-D Laplacians (array_utils.py:168-173), float64
-  std::vector<double> lxp(nx), ly(channel ? ny : n2 + 1);
+  std::vector<double> lxp(nx), ly((channel ? ny : n2 + 1) + kLamPad, 1.0);
   for (int k = 0; k < nx; ++k) lxp[cpos[k]] = (2.0 * cos(two_pi * k / nx) - 2.0) / (grid->dx * grid->dx);
   if (channel) {  // eigenvalues of laplacian_matrix_neumann (array_utils.py:175-182): DCT-II basis
     for (int l = 0; l < ny; ++l) ly[l] = (2.0 * cos(0.5 * two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
@@ -524,9 +565,9 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   if (!rc) rc = upload(&pl->lam_x_pos, lxp);
   if (!rc) rc = upload(&pl->lam_y, ly);
   {
-    std::vector<float> lxf(nx), lyf(n2 + 4, 1.0f);
+    std::vector<float> lxf(nx), lyf(n2 + 4 + kLamPad, 1.0f);
     for (int k = 0; k < nx; ++k) lxf[k] = (float)lxp[k];
-    for (int l = 0; l <= n2 && l < (int)ly.size(); ++l) lyf[l] = (float)ly[l];
+    for (int l = 0; l <= n2 && !channel; ++l) lyf[l] = (float)ly[l];
     if (!rc) rc = upload(&pl->lam_x_pos_f, lxf);
     if (!rc) rc = upload(&pl->lam_y_f, lyf);
   }

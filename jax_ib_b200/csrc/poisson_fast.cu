@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
 #pragma unroll
   for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
   // cp.async pipeline: the rows of step i+1 stream into shared memory while row i is transformed
-  copy_async(ubuf[0], u + (size_t)(i0 == 0 ? g.nx - 1 : i0 - 1) * ny, row_bytes, b, S1);
+  // slab mode (nx_global > 0): the rows are open -- u row -1 / spectrum row nx sit next to the arrays (halo)
+  const ptrdiff_t im1 = (i0 == 0 && g.nx_global == 0) ? g.nx - 1 : i0 - 1;
+  copy_async(ubuf[0], u + im1 * ny, row_bytes, b, S1);
   copy_async(ubuf[1], u + (size_t)i0 * ny, row_bytes, b, S1);
   copy_async(vbuf, v + (size_t)i0 * ny, row_bytes, b, S1);
   cp_async_commit();
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   copy_async(spec_s, spec + (size_t)i0 * P.sp, spec_bytes, b, S1);
   cp_async_commit();
   for (int ii = i0; ii <= last; ++ii) {
-    const int i = ii >= g.nx ? ii - g.nx : ii;
+    const int i = (ii >= g.nx && g.nx_global == 0) ? ii - g.nx : ii;
     float2* cur = rows_sm + ((ii - i0) & 1) * Gm::PITCH;
     cp_async_wait<0>();  // the spectrum row issued one iteration ago has landed
     __syncthreads();
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
     }
     __syncthreads();
     if (ii < last) {  // the staged spectrum row is consumed: prefetch the next one behind the FFT passes
-      const int inext = ii + 1 >= g.nx ? ii + 1 - g.nx : ii + 1;
+      const int inext = (ii + 1 >= g.nx && g.nx_global == 0) ? ii + 1 - g.nx : ii + 1;
       copy_async(spec_s, spec + (size_t)inext * P.sp, spec_bytes, b, S1);
     }
     cp_async_commit();

@@ -57,6 +57,11 @@ class GridSpec:
     force: Tuple[float, float] = (0.0, 0.0)
     ib_window: int = 6
     batch: int = 1
+    # slab decomposition (see the header): global row of local row 0, marker ownership range, global nx
+    row0: int = 0
+    own_lo: int = 0
+    own_hi: int = 0
+    nx_global: int = 0
 
     def c_struct(self) -> _lib.Grid:
         g = _lib.Grid()
@@ -72,6 +77,7 @@ class GridSpec:
         g.v_wall[0], g.v_wall[1] = (float(x) for x in self.v_wall)
         g.force[0], g.force[1] = (float(x) for x in self.force)
         g.ib_window = int(self.ib_window)
+        g.row0, g.own_lo, g.own_hi, g.nx_global = int(self.row0), int(self.own_lo), int(self.own_hi), int(self.nx_global)
         return g
 
     @property
@@ -99,10 +105,10 @@ def explicit_terms(spec: GridSpec, u, v, perm=None):
     return du, dv
 
 
-def explicit_predict(spec: GridSpec, u, v, p=None, perm=None):
+def explicit_predict(spec: GridSpec, u, v, p=None, perm=None, out=None):
     """time_stepping.py:191-208: (u*, v*) = (u, v) + dt*F(u, v) - grad(p)."""
     _check_field(spec, u, "u"); _check_field(spec, v, "v")
-    us, vs = torch.empty_like(u), torch.empty_like(v)
+    us, vs = (torch.empty_like(u), torch.empty_like(v)) if out is None else out
     g = spec.c_struct()
     _lib.check(_lib.load().jaxib_explicit_predict(_stream(), C.byref(g), _ptr(u), _ptr(v), _ptr(p), _ptr(perm),
                                                   _ptr(us), _ptr(vs)), "explicit_predict")
@@ -174,10 +180,30 @@ def ib_force(spec: GridSpec, bodies: DeviceBodies, body_state, u_star, v_star):
     return scratch[skip:skip + 5 * spec.batch * bodies.n_markers * 4].view(torch.float32).view(5, spec.batch, bodies.n_markers)
 
 
+def ib_marker_force(spec: GridSpec, bodies: DeviceBodies, body_state, u_star, v_star, markers):
+    """First half of ib_force: fills markers [5, batch, n_markers] = xp, yp, dS, Fx, Fy (F = 0 for markers
+    outside spec.own_lo .. own_hi when that range is set)."""
+    _check_field(spec, u_star, "u_star"); _check_field(spec, v_star, "v_star")
+    if markers.numel() < 5 * spec.batch * bodies.n_markers:
+        raise _lib.JaxibError("markers buffer too small")
+    g, b = spec.c_struct(), bodies.c_struct()
+    _lib.check(_lib.load().jaxib_ib_marker_force(_stream(), C.byref(g), C.byref(b), _ptr(_f32(body_state)), _ptr(u_star),
+                                                 _ptr(v_star), _ptr(_f32(markers))), "ib_marker_force")
+    return markers
+
+
+def ib_spread_bodies(spec: GridSpec, bodies: DeviceBodies, body_state, markers, u_star, v_star):
+    """Second half of ib_force: (u*, v*) += dt * spread(markers), in place."""
+    _check_field(spec, u_star, "u_star"); _check_field(spec, v_star, "v_star")
+    g, b = spec.c_struct(), bodies.c_struct()
+    _lib.check(_lib.load().jaxib_ib_spread_bodies(_stream(), C.byref(g), C.byref(b), _ptr(_f32(body_state)),
+                                                  _ptr(_f32(markers)), _ptr(u_star), _ptr(v_star)), "ib_spread_bodies")
+
+
 class Plan:
     """jaxib_plan + a scratch buffer sized for the fused step."""
 
-    def __init__(self, spec: GridSpec, n_markers: int = 0, device="cuda"):
+    def __init__(self, spec: GridSpec, n_markers: int = 0, device="cuda", alloc_scratch: bool = True):
         self.spec = spec
         self.device = torch.device(device)
         self._lib = _lib.load()
@@ -187,7 +213,8 @@ class Plan:
             _lib.check(self._lib.jaxib_plan_create(C.byref(g), C.byref(self._h)), "plan_create")
         self.n_markers = n_markers
         self.scratch_bytes = int(self._lib.jaxib_scratch_bytes(self._h, n_markers))
-        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=self.device)
+        # stage-level users (slab.py) bring their own buffers
+        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=self.device) if alloc_scratch else None
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -214,6 +241,20 @@ class Plan:
         _lib.check(self._lib.jaxib_project(_stream(), self._h, _ptr(u), _ptr(v), _ptr(p), _ptr(uo), _ptr(vo), _ptr(po),
                                            _ptr(self.scratch), self.scratch_bytes), "project")
         return uo, vo, po
+
+    # -- stage-level (slab decomposition: the caller exchanges data between the stages) ----------
+    def rows_fwd(self, u, v, spectrum, sp=0):
+        """divergence + row FFT of the plan's nx rows starting at u / v (slab mode reads u row -1 in place)."""
+        _lib.check(self._lib.jaxib_poisson_rows_fwd(_stream(), self._h, _ptr(u), _ptr(v), _ptr(spectrum), int(sp)),
+                   "poisson_rows_fwd")
+
+    def cols(self, spectrum, sp=0, ncols=0, col0=0):
+        _lib.check(self._lib.jaxib_poisson_cols(_stream(), self._h, _ptr(spectrum), int(sp), int(ncols), int(col0)),
+                   "poisson_cols")
+
+    def rows_inv(self, spectrum, u, v, p, u_out, v_out, p_out, sp=0):
+        _lib.check(self._lib.jaxib_poisson_rows_inv(_stream(), self._h, _ptr(spectrum), int(sp), _ptr(u), _ptr(v), _ptr(p),
+                                                    _ptr(u_out), _ptr(v_out), _ptr(p_out)), "poisson_rows_inv")
 
     def step(self, u, v, p, nsteps=1, bodies: Optional[DeviceBodies] = None, body_table=None, perm=None,
              incremental_pressure=True):

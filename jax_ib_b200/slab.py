@@ -1,0 +1,343 @@
+"""Slab decomposition of ONE large grid over several GPUs (BASELINE config 4).
+
+New capability: the reference only shards markers with `jax.pmap` and replicates the grid
+(IBM_Force.py:77-87, convolution_functions.py:28-35).  Here the x axis (rows; y stays contiguous) is
+split into `world` slabs of `nx / world` rows.  Every rank keeps its rows plus `halo` rows of its
+neighbours on either side, so that one step needs exactly four exchanges:
+
+    K1 predictor on the extended slab (the halo absorbs the stencil; the local array is treated as a
+       periodic grid of its own, garbage stays inside the outermost two halo rows)
+    K2 marker forces for the markers whose u-cell row this slab owns (zero for the others)
+  X1 all-reduce(sum) of the [2, M] force arrays: every marker has exactly one non-zero contributor,
+       so the sum is exact and every rank ends up with the single-GPU forces bit for bit
+    K3 spreading onto the local rows (all markers, culled per tile as on one GPU)
+    K4 divergence + row FFT of the owned rows -> spectrum [nloc][world * cpr]
+  X2 all-to-all: rank r receives the columns [r * cpr, (r+1) * cpr) of every row
+    K5 column FFT x eigenvalues x inverse over all nx rows of the local columns
+  X3 all-to-all back; every destination also gets the first row of the NEXT slab (K6 differences q
+       forward in x), so no separate halo pass is needed for q
+    K6 inverse row FFT + projection + pressure update on the owned rows
+  X4 halo exchange of the new u, v, p rows with the two neighbours (periodic ring)
+
+Cells next to the periodic seam: the reference takes no periodic image of a marker (raw xp - X), so
+the IB kernels see the local array as un-wrapped segments -- the rows whose global index lies in
+[0, nx) -- plus, on the first slab, the single wrapped row nx-1 that K4's backward difference reads.
+
+The per-rank compute (`SlabRank`) is separated from the exchanges (`DistComm`: torch.distributed,
+NCCL over NVLink on GPUs, gloo in the CPU tests of the exchange logic; `LocalComm`: several virtual
+slabs inside one process on one GPU), so the decomposition is tested against the single-GPU step on
+one GPU and the collectives on real multi-GPU boxes.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import kinematics, ops
+
+INT_MAX = 2 ** 31 - 1
+
+
+@dataclasses.dataclass(frozen=True)
+class Segment:
+    """Local rows [start, start + rows) hold the global rows [global0, global0 + rows), un-wrapped."""
+    start: int
+    rows: int
+    global0: int
+
+
+class SlabLayout:
+    """Pure index arithmetic of one rank's slab (host only; covered by the CPU tests)."""
+
+    def __init__(self, nx: int, ny: int, world: int, rank: int, halo: int):
+        if nx % world:
+            raise ValueError(f"nx={nx} is not divisible by the number of slabs {world}")
+        if ny % 2:
+            raise ValueError("ny must be even")
+        self.nx, self.ny, self.world, self.rank, self.halo = nx, ny, world, rank, halo
+        self.nloc = nx // world
+        if halo > self.nloc:
+            raise ValueError(f"halo {halo} exceeds the slab height {self.nloc}")
+        self.own_lo = rank * self.nloc
+        self.own_hi = self.own_lo + self.nloc
+        self.nxl = self.nloc + 2 * halo
+        self.row0 = self.own_lo - halo  # global row of local row 0 (may be negative: wrapped)
+        n2 = ny // 2
+        # columns per rank: the n2 + 1 wavenumbers (+3 padding columns the row kernels write), rounded to 8
+        per_rank = -(-(n2 + 4) // world)
+        self.cpr = -(-per_rank // 8) * 8
+        self.sp = world * self.cpr
+
+    # marker ownership: the first / last slab also own markers that lie off the grid
+    @property
+    def marker_lo(self) -> int:
+        return -INT_MAX if self.rank == 0 else self.own_lo
+
+    @property
+    def marker_hi(self) -> int:
+        return INT_MAX if self.rank == self.world - 1 else self.own_hi
+
+    def main_segment(self) -> Segment:
+        a = max(0, -self.row0)
+        b = min(self.nxl, self.nx - self.row0)
+        return Segment(a, b - a, self.row0 + a)
+
+    def seam_row(self) -> Optional[Segment]:
+        """The wrapped row below the first owned row (global nx-1 on the first slab), else None."""
+        if self.own_lo == 0:
+            return Segment(self.halo - 1, 1, self.nx - 1)
+        return None
+
+    def inverse_row_index(self) -> np.ndarray:
+        """Rows of the [nx][cpr] column buffer sent back to each destination: its nloc rows + the next one."""
+        idx = (np.arange(self.world)[:, None] * self.nloc + np.arange(self.nloc + 1)[None, :]) % self.nx
+        return idx.reshape(-1).astype(np.int64)
+
+    def global_rows(self) -> np.ndarray:
+        """Global (wrapped) row of every local row."""
+        return (self.row0 + np.arange(self.nxl)) % self.nx
+
+
+# ------------------------------------------------------------------------------------------------
+# exchanges
+class DistComm:
+    """torch.distributed exchanges for ONE local rank (lists of length 1)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def sum_forces(self, forces: Sequence[torch.Tensor]):
+        dist.all_reduce(forces[0], op=dist.ReduceOp.SUM, group=self.group)
+
+    def transpose(self, send: Sequence[torch.Tensor], recv: Sequence[torch.Tensor]):
+        dist.all_to_all_single(recv[0], send[0], group=self.group)
+
+    def halos(self, lo_send, hi_send, lo_recv, hi_recv):
+        """lo_send[0] / hi_send[0]: lists of contiguous tensors (first / last owned rows of u, v, p);
+        lo_recv / hi_recv: the halo views they land in on the neighbours."""
+        prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        if self.group is not None:
+            prev, nxt = dist.get_global_rank(self.group, prev), dist.get_global_rank(self.group, nxt)
+        ops_ = []
+        # message order per peer pair is the same on both sides (first rows up, last rows down)
+        for t in lo_send[0]:
+            ops_.append(dist.P2POp(dist.isend, t, prev, self.group))
+        for t in hi_send[0]:
+            ops_.append(dist.P2POp(dist.isend, t, nxt, self.group))
+        for t in hi_recv[0]:
+            ops_.append(dist.P2POp(dist.irecv, t, nxt, self.group))
+        for t in lo_recv[0]:
+            ops_.append(dist.P2POp(dist.irecv, t, prev, self.group))
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+
+
+class LocalComm:
+    """The same exchanges between `world` virtual slabs living in one process (one GPU)."""
+
+    def __init__(self, world: int):
+        self.world = world
+
+    def sum_forces(self, forces):
+        total = forces[0].clone()
+        for f in forces[1:]:
+            total += f
+        for f in forces:
+            f.copy_(total)
+
+    def transpose(self, send, recv):
+        # send[r][d] goes to recv[d][r]
+        for r in range(self.world):
+            for d in range(self.world):
+                recv[d][r].copy_(send[r][d])
+
+    def halos(self, lo_send, hi_send, lo_recv, hi_recv):
+        for r in range(self.world):
+            prev, nxt = (r - 1) % self.world, (r + 1) % self.world
+            for src, dst in zip(lo_send[r], hi_recv[prev]):
+                dst.copy_(src)
+            for src, dst in zip(hi_send[r], lo_recv[nxt]):
+                dst.copy_(src)
+
+
+# ------------------------------------------------------------------------------------------------
+class SlabRank:
+    """Device state and kernels of one slab."""
+
+    def __init__(self, spec: ops.GridSpec, layout: SlabLayout, bodies: Optional[ops.DeviceBodies], device):
+        if spec.bc != "periodic":
+            raise NotImplementedError("slab decomposition: periodic grids only")
+        if spec.batch != 1:
+            raise NotImplementedError("slab decomposition: batch = 1")
+        self.spec, self.lay, self.bodies, self.device = spec, layout, bodies, torch.device(device)
+        L = layout
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.u, self.v, self.p = (torch.zeros(L.nxl, L.ny, **f32) for _ in range(3))
+        self.us, self.vs = torch.zeros(L.nxl, L.ny, **f32), torch.zeros(L.nxl, L.ny, **f32)
+        self.spec_ext = spec.replace(nx=L.nxl, row0=L.row0)
+        seg = L.main_segment()
+        self.seg = seg
+        self.spec_ib = spec.replace(nx=seg.rows, row0=seg.global0, own_lo=L.marker_lo, own_hi=L.marker_hi)
+        seam = L.seam_row()
+        self.seam = seam
+        self.spec_seam = None if seam is None else spec.replace(nx=1, row0=seam.global0)
+        self.plan_rows = ops.Plan(spec.replace(nx=L.nloc, nx_global=L.nx), 0, self.device, alloc_scratch=False)
+        self.plan_cols = ops.Plan(spec.replace(nx=L.nx), 0, self.device, alloc_scratch=False)
+        M = bodies.n_markers if bodies is not None else 0
+        self.markers = torch.zeros(5, 1, max(M, 1), **f32)
+        # spectrum buffers (complex as trailing [2] float32)
+        self.spectrum = torch.zeros(L.nloc + 1, L.world, L.cpr, 2, **f32)
+        self.send = torch.zeros(L.world, L.nloc, L.cpr, 2, **f32)
+        self.recv = torch.zeros(L.world, L.nloc, L.cpr, 2, **f32)        # == [nx][cpr] complex
+        self.send2 = torch.zeros(L.world, L.nloc + 1, L.cpr, 2, **f32)
+        self.recv2 = torch.zeros(L.world, L.nloc + 1, L.cpr, 2, **f32)
+        self.inv_idx = torch.from_numpy(L.inverse_row_index()).to(self.device)
+
+    # -- data movement helpers ---------------------------------------------------------------------
+    def load_global(self, u, v, p):
+        """Takes this slab's rows (+ halos) out of full [nx, ny] arrays (any device)."""
+        rows = torch.from_numpy(self.lay.global_rows()).to(u.device)
+        for dst, src in ((self.u, u), (self.v, v), (self.p, p)):
+            dst.copy_(src.index_select(0, rows).to(self.device, dtype=torch.float32))
+
+    def owned(self, t: torch.Tensor) -> torch.Tensor:
+        h = self.lay.halo
+        return t[h:h + self.lay.nloc]
+
+    def _rows(self, t, seg: Segment):
+        return t[seg.start:seg.start + seg.rows]
+
+    # -- phases ------------------------------------------------------------------------------------
+    def phase_a(self, body_state: Optional[torch.Tensor]):
+        """K1 + K2.  body_state: [1, B, 8] float32 (device) for this step."""
+        ops.explicit_predict(self.spec_ext, self.u, self.v, self.p, out=(self.us, self.vs))
+        if self.bodies is not None:
+            ops.ib_marker_force(self.spec_ib, self.bodies, body_state, self._rows(self.us, self.seg),
+                                self._rows(self.vs, self.seg), self.markers)
+
+    def forces(self) -> torch.Tensor:
+        return self.markers[3:5]
+
+    def phase_b(self, body_state: Optional[torch.Tensor]):
+        """K3 + K4 + pack."""
+        if self.bodies is not None:
+            ops.ib_spread_bodies(self.spec_ib, self.bodies, body_state, self.markers, self._rows(self.us, self.seg),
+                                 self._rows(self.vs, self.seg))
+            if self.seam is not None:
+                ops.ib_spread_bodies(self.spec_seam, self.bodies, body_state, self.markers,
+                                     self._rows(self.us, self.seam), self._rows(self.vs, self.seam))
+        L = self.lay
+        self.plan_rows.rows_fwd(self.owned(self.us), self.owned(self.vs), self.spectrum, sp=L.sp)
+        self.send.copy_(self.spectrum[:L.nloc].permute(1, 0, 2, 3))
+
+    def phase_c(self):
+        """K5 on the local columns + pack for the way back."""
+        L = self.lay
+        self.plan_cols.cols(self.recv, sp=L.cpr, ncols=L.cpr, col0=L.rank * L.cpr)
+        torch.index_select(self.recv.view(L.nx, L.cpr * 2), 0, self.inv_idx,
+                           out=self.send2.view(L.world * (L.nloc + 1), L.cpr * 2))
+
+    def phase_d(self):
+        """unpack + K6 (writes the owned rows of u, v, p in place)."""
+        L = self.lay
+        self.spectrum.copy_(self.recv2.permute(1, 0, 2, 3))
+        uo, vo, po = self.owned(self.u), self.owned(self.v), self.owned(self.p)
+        self.plan_rows.rows_inv(self.spectrum, self.owned(self.us), self.owned(self.vs), po, uo, vo, po, sp=L.sp)
+
+    def halo_views(self):
+        h, n = self.lay.halo, self.lay.nloc
+        fields = (self.u, self.v, self.p)
+        lo_send = [t[h:2 * h] for t in fields]          # first owned rows -> previous slab's upper halo
+        hi_send = [t[n:n + h] for t in fields]          # last owned rows  -> next slab's lower halo
+        lo_recv = [t[0:h] for t in fields]
+        hi_recv = [t[h + n:h + n + h] for t in fields]
+        return lo_send, hi_send, lo_recv, hi_recv
+
+
+def _step(ranks: List[SlabRank], comm, body_state):
+    for r in ranks:
+        r.phase_a(body_state)
+    if ranks[0].bodies is not None:
+        comm.sum_forces([r.forces() for r in ranks])
+    for r in ranks:
+        r.phase_b(body_state)
+    comm.transpose([r.send for r in ranks], [r.recv for r in ranks])
+    for r in ranks:
+        r.phase_c()
+    comm.transpose([r.send2 for r in ranks], [r.recv2 for r in ranks])
+    for r in ranks:
+        r.phase_d()
+    views = [r.halo_views() for r in ranks]
+    comm.halos(*[[v[k] for v in views] for k in range(4)])
+
+
+class SlabStepper:
+    """One simulation on `world` slabs.  `virtual=True` keeps all slabs in this process (one GPU, tests
+    and single-GPU comparison); otherwise this process is one rank of the torch.distributed group."""
+
+    def __init__(self, spec: ops.GridSpec, particles=None, world: Optional[int] = None, halo: Optional[int] = None,
+                 device="cuda", virtual: bool = False, group=None):
+        from . import engine  # local import: engine imports ops as well
+        if not torch.cuda.is_available():
+            raise RuntimeError("jax_ib_b200 needs a CUDA device: there is no CPU fallback")
+        self.spec = spec
+        self.device = torch.device(device)
+        self.particles = particles
+        self.halo = spec.ib_window + 4 if halo is None else halo
+        if self.halo < spec.ib_window + 3:
+            raise ValueError(f"halo {self.halo} < ib_window + 3: marker windows would leave the slab")
+        bodies = engine.get_bodies(particles, self.device) if particles is not None else None
+        if virtual:
+            self.world = int(world or 1)
+            self.comm = LocalComm(self.world)
+            my = range(self.world)
+        else:
+            self.comm = DistComm(group) if dist.is_initialized() else LocalComm(1)
+            self.world = self.comm.world
+            my = [self.comm.rank] if dist.is_initialized() else [0]
+        self.ranks = [SlabRank(spec, SlabLayout(spec.nx, spec.ny, self.world, r, self.halo), bodies, self.device)
+                      for r in my]
+        self.time = np.float32(0.0)
+
+    def load(self, u, v, p, t0=0.0):
+        for r in self.ranks:
+            r.load_global(u, v, p)
+        self.time = np.float32(t0)
+
+    def advance(self, nsteps: int):
+        """`nsteps` steps in place; returns the body centres after the block (host, float32) or None."""
+        table = centers = None
+        if self.particles is not None:
+            tab, times, centers = kinematics.body_schedule(self.particles, float(self.time), self.spec.dt, nsteps)
+            table = torch.from_numpy(np.ascontiguousarray(tab[:, None])).to(self.device)  # [nsteps, 1, B, 8]
+            self.time = times[-1]
+            self.particles = dataclasses.replace(self.particles, particle_center=centers[-1])
+        else:
+            for _ in range(nsteps):
+                self.time = np.float32(self.time + np.float32(self.spec.dt))
+        for n in range(nsteps):
+            _step(self.ranks, self.comm, None if table is None else table[n])
+        return None if centers is None else centers[-1]
+
+    def owned_fields(self):
+        """[(own_lo, u_rows, v_rows, p_rows)] for the slabs held by this process."""
+        return [(r.lay.own_lo, r.owned(r.u), r.owned(r.v), r.owned(r.p)) for r in self.ranks]
+
+    def gather(self):
+        """Full (u, v, p) on every rank (tests / output; not part of the timed path)."""
+        parts = self.owned_fields()
+        if isinstance(self.comm, LocalComm):
+            return tuple(torch.cat([q[k] for q in parts], dim=0) for k in (1, 2, 3))
+        outs = []
+        for k in (1, 2, 3):
+            mine = parts[0][k].contiguous()
+            bufs = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(bufs, mine, group=self.comm.group)
+            outs.append(torch.cat(bufs, dim=0))
+        return tuple(outs)

@@ -1,0 +1,194 @@
+"""Slab decomposition: index arithmetic and exchanges on CPU (incl. world_size-2 gloo),
+and on the GPU the decomposed step against the single-GPU step -- bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from jax_ib_b200 import slab  # noqa: E402
+
+
+# ---- CPU: layout --------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny,world,halo", [(64, 64, 1, 10), (64, 32, 2, 10), (256, 128, 4, 10), (8192, 8192, 8, 10)])
+def test_layout_covers_every_row_once(nx, ny, world, halo):
+    owned = []
+    for r in range(world):
+        L = slab.SlabLayout(nx, ny, world, r, halo)
+        assert L.nxl == L.nloc + 2 * halo
+        g = L.global_rows()
+        assert list(g[halo:halo + L.nloc]) == list(range(L.own_lo, L.own_hi))
+        assert g[0] == (L.own_lo - halo) % nx and g[-1] == (L.own_hi + halo - 1) % nx
+        owned += list(range(L.own_lo, L.own_hi))
+        seg = L.main_segment()
+        # the main segment is exactly the un-wrapped part of the local array
+        un = [(L.row0 + i) for i in range(L.nxl) if 0 <= L.row0 + i < nx]
+        assert seg.rows == len(un) and seg.global0 == un[0] and L.row0 + seg.start == un[0]
+        seam = L.seam_row()
+        assert (seam is not None) == (r == 0)
+        if seam is not None:
+            assert g[seam.start] == nx - 1 == seam.global0
+        # column ranges tile the padded spectrum pitch and cover the ny/2 + 4 columns the row kernels write
+        assert L.cpr % 8 == 0 and L.sp == world * L.cpr >= ny // 2 + 4
+        idx = L.inverse_row_index().reshape(world, L.nloc + 1)
+        for d in range(world):
+            assert list(idx[d]) == [(d * L.nloc + i) % nx for i in range(L.nloc + 1)]
+    assert owned == list(range(nx))
+    assert slab.SlabLayout(nx, ny, world, 0, halo).marker_lo < -10 ** 9
+    assert slab.SlabLayout(nx, ny, world, world - 1, halo).marker_hi > 10 ** 9
+
+
+def test_layout_rejects_bad_splits():
+    with pytest.raises(ValueError):
+        slab.SlabLayout(100, 64, 3, 0, 10)
+    with pytest.raises(ValueError):
+        slab.SlabLayout(64, 64, 8, 0, 10)  # halo deeper than the slab
+
+
+def _fake_exchange_buffers(world, nloc, cpr, halo, ny, seed=0):
+    """Per rank: send [world, nloc, cpr, 2], force [2, M], fields [nloc + 2 halo, ny] x 3."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in range(world):
+        out.append(dict(
+            send=torch.from_numpy(rng.standard_normal((world, nloc, cpr, 2)).astype(np.float32)),
+            force=torch.from_numpy(rng.standard_normal((2, 7)).astype(np.float32)),
+            fields=[torch.from_numpy(rng.standard_normal((nloc + 2 * halo, ny)).astype(np.float32)) for _ in range(3)],
+        ))
+    return out
+
+
+def _halo_views(fields, halo, nloc):
+    return ([t[halo:2 * halo] for t in fields], [t[nloc:nloc + halo] for t in fields],
+            [t[0:halo] for t in fields], [t[halo + nloc:] for t in fields])
+
+
+def _local_reference(world, nloc, cpr, halo, ny):
+    bufs = _fake_exchange_buffers(world, nloc, cpr, halo, ny)
+    comm = slab.LocalComm(world)
+    recv = [torch.zeros_like(b["send"]) for b in bufs]
+    comm.transpose([b["send"] for b in bufs], recv)
+    comm.sum_forces([b["force"] for b in bufs])
+    views = [_halo_views(b["fields"], halo, nloc) for b in bufs]
+    comm.halos(*[[v[k] for v in views] for k in range(4)])
+    return bufs, recv
+
+
+def test_local_comm_semantics():
+    world, nloc, cpr, halo, ny = 3, 4, 8, 2, 6
+    orig = _fake_exchange_buffers(world, nloc, cpr, halo, ny)
+    bufs, recv = _local_reference(world, nloc, cpr, halo, ny)
+    for d in range(world):
+        for r in range(world):
+            assert torch.equal(recv[d][r], orig[r]["send"][d])
+    total = sum(o["force"] for o in orig)
+    for b in bufs:
+        assert torch.allclose(b["force"], total)
+    for r in range(world):
+        nxt, prev = (r + 1) % world, (r - 1) % world
+        for k in range(3):
+            # upper halo = first owned rows of the next slab, lower halo = last owned rows of the previous one
+            assert torch.equal(bufs[r]["fields"][k][halo + nloc:], orig[nxt]["fields"][k][halo:2 * halo])
+            assert torch.equal(bufs[r]["fields"][k][:halo], orig[prev]["fields"][k][nloc:nloc + halo])
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nloc, cpr, halo, ny = 4, 8, 2, 6
+        mine = _fake_exchange_buffers(world, nloc, cpr, halo, ny)[rank]
+        comm = slab.DistComm()
+        recv = torch.zeros_like(mine["send"])
+        comm.transpose([mine["send"]], [recv])
+        comm.sum_forces([mine["force"]])
+        views = _halo_views(mine["fields"], halo, nloc)
+        comm.halos(*[[v] for v in views])
+        q.put((rank, recv.numpy(), mine["force"].numpy(), [f.numpy() for f in mine["fields"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dist_comm_matches_local_comm_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, recv, force, fields = q.get(timeout=120)
+        got[r] = (recv, force, fields)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bufs, recv_ref = _local_reference(world, 4, 8, 2, 6)
+    for r in range(world):
+        np.testing.assert_array_equal(got[r][0], recv_ref[r].numpy())
+        np.testing.assert_allclose(got[r][1], bufs[r]["force"].numpy(), rtol=1e-6)
+        for k in range(3):
+            np.testing.assert_array_equal(got[r][2][k], bufs[r]["fields"][k].numpy())
+
+
+# ---- GPU: decomposed step == single-GPU step ------------------------------------------------------
+def _seam_cfg(n):
+    """Bodies on the periodic seam (markers off the grid), on a slab boundary and in a slab's interior."""
+    from jax_ib_b200 import configs
+    cfg = configs.ib_periodic(n, 2, dx=0.025)
+    L = n * 0.025
+    cfg["bodies"]["centers"] = [[0.004 * L, 0.3 * L], [0.5 * L, 0.55 * L], [0.985 * L, 0.7 * L], [0.27 * L, 0.8 * L]]
+    return cfg
+
+
+def _single_gpu(cfg, steps):
+    from jax_ib_b200 import configs, demo, kinematics
+    stp = demo.make_stepper(cfg)
+    u, v, p = (torch.from_numpy(a).cuda() for a in configs.initial_fields(cfg))
+    table = None
+    if cfg["bodies"] is not None:
+        tab, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], steps)
+        table = torch.from_numpy(np.ascontiguousarray(tab[:, None])).cuda()
+    stp.run_block(u, v, p, steps, table)
+    return u, v, p
+
+
+def _virtual(cfg, steps, world, chunks=(None,)):
+    from jax_ib_b200 import configs, demo
+    st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), world=world, virtual=True)
+    st.load(*(torch.from_numpy(a) for a in configs.initial_fields(cfg)))
+    done = 0
+    for c in chunks:
+        k = steps - done if c is None else c
+        st.advance(k)
+        done += k
+    assert done == steps
+    return st.gather()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,world", [(256, 1), (256, 2), (256, 4), (1024, 2), (1024, 8)])
+def test_virtual_slabs_match_single_gpu_bitwise(n, world):
+    cfg = _seam_cfg(n)
+    steps = 6
+    ref = _single_gpu(cfg, steps)
+    got = _virtual(cfg, steps, world, chunks=(2, None))
+    for name, a, b in zip("uvp", got, ref):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+
+
+@pytest.mark.gpu
+def test_virtual_slabs_without_bodies():
+    from jax_ib_b200 import configs
+    cfg = configs.small_periodic(64, bodies=False)
+    ref = _single_gpu(cfg, 5)
+    got = _virtual(cfg, 5, 2)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
