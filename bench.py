@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ib2048")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="skip the 8192^2 slab-decomposed measurement")
     return ap.parse_args()
 
 
@@ -58,6 +59,9 @@ def workload_cfg(name):
         return configs.ib_periodic(1024, 1)
     if name == "flap600":
         return configs.flap600()
+    if name.startswith("slab"):  # slab8192 = G4 `multi8192`: (n/2048)^2 flapping ellipses on an n^2 grid
+        n = int(name[4:])
+        return configs.ib_periodic(n, max(1, n // 2048))
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -173,6 +177,64 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ slab arm
+def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
+    """ONE simulation of the `name` grid on `world` GPUs (strong scaling): slab decomposition along x,
+    NCCL all-to-all FFT transpose + halo exchange (jax_ib_b200/slab.py).  At world == 1 the single-GPU
+    fused step runs the same grid.  Returns a dict for the JSON line."""
+    import numpy as np
+    import torch
+
+    from jax_ib_b200 import configs, demo, kinematics, slab
+
+    cfg = workload_cfg(name)
+    nx, ny = cfg["shape"]
+    cells = nx * ny
+    fields = configs.initial_fields(cfg)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = None
+    if world == 1:
+        stepper = demo.make_stepper(cfg, device=device)
+        u, v, p = (torch.from_numpy(a).to(device) for a in fields)
+        tab, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], W + K)
+        tab = torch.from_numpy(np.ascontiguousarray(tab[:, None])).to(device)
+        stepper.run_block(u, v, p, W, tab[:W])
+        barrier()
+        e0.record()
+        stepper.run_block(u, v, p, K, tab[W:])
+        e1.record()
+        barrier()
+        finite = bool(torch.isfinite(u).all().item())
+        how = "single-GPU fused step (jaxib_step)"
+    else:
+        st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device)
+        st.load(*(torch.from_numpy(a) for a in fields))
+        st.advance(W)
+        barrier()
+        st.advance(K, profile=True)
+        phases = {k: round(max_over_ranks(v) / K * 1e3, 1) for k, v in st.last_profile.items()}
+        barrier()
+        # the timed block: as at one GPU, the kinematic table of the block is on the device before it starts
+        table, _ = st.schedule(K)
+        barrier()
+        e0.record()
+        st.run(table, K)
+        e1.record()
+        barrier()
+        finite = bool(torch.isfinite(st.ranks[0].u).all().item())
+        L = st.ranks[0].lay
+        how = (f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; per step: all-reduce of marker forces, 2 all-to-all "
+               f"spectrum transposes ({L.cpr} columns per rank), 1 halo exchange (NCCL)")
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out = {"workload": name, "grid": [nx, ny], "bodies": len(cfg["bodies"]["centers"]), "n_gpus": world,
+           "scaling": "strong", "steps": K, "ms_per_step": ms / K, "value": cells * K / (ms * 1e-3) / 1e6,
+           "unit": UNIT, "finite": finite, "how": how,
+           "l2": "state (5 fields + spectrum buffers) per GPU exceeds the 126 MB L2; steps run back to back"}
+    if phases:
+        out["phase_us_max_over_ranks"] = phases
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ own arm
 def run_b200(args, rank, world, local_rank):
     import numpy as np
@@ -185,6 +247,34 @@ def run_b200(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.workload.startswith("slab"):
+        res = measure_slab(args.workload, args.steps, args.warmup, rank, world, device, barrier, max_over_ranks)
+        if rank == 0:
+            hbm_peak, peak_src = peaks()
+            gbs = STEP_BYTES * res["value"] * 1e6 / 1e9
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": res,
+                    "step_roofline": {"algorithmic_bytes_per_cell_step": STEP_BYTES, "achieved_gbs": gbs,
+                                      "frac_of_aggregate_peak": gbs / (hbm_peak * world), "peak_source": peak_src}}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cfg = workload_cfg(args.workload)
     if world > 1:  # ensemble sweep: every rank gets its own kinematic phase
         b = dict(cfg["bodies"])
@@ -201,19 +291,6 @@ def run_b200(args, rank, world, local_rank):
     table, times, centers = kinematics.body_schedule(particles, 0.0, cfg["dt"], W + K + K)
     table = torch.from_numpy(np.ascontiguousarray(table[:, None])).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # 256 MiB > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     u, v, p = u0.clone(), v0.clone(), p0.clone()
     stepper.run_block(u, v, p, W, table[:W])  # warm-up (untimed)
@@ -249,7 +326,15 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
 
+    # second partitioning: one 8192^2 grid slab-decomposed over the same GPUs (strong scaling)
+    slab_res = None
+    if args.workload == "ib2048" and not args.no_slab:
+        del flush
+        torch.cuda.empty_cache()
+        slab_res = measure_slab("slab8192", max(5, min(K, 30)), 3, rank, world, device, barrier, max_over_ranks)
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     hbm_peak, peak_src = peaks()
     value = world * cells * K / (ms_flushed * 1e-3) / 1e6
@@ -289,6 +374,8 @@ def run_b200(args, rank, world, local_rank):
             "sample": (f"{steps_cpu} steps of a 512^2 tile of the same workload (same dx, dt, upwind, FFT Poisson, one "
                        f"298-marker ellipse, dense O(M*Nx*Ny) IB sums as the reference) with the single-threaded NumPy "
                        f"float32 oracle: {wall:.1f} s on 1 of {os.cpu_count()} host cores")}
+    if slab_res is not None:
+        line["slab"] = slab_res
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -139,6 +139,34 @@ struct Dft<16> {
   }
 };
 
+template <>
+struct Dft<32> {
+  __device__ static __forceinline__ void run(float2* v) {
+    // even / odd split: X[k] = E[k] + W32^k O[k], X[k + 16] = E[k] - W32^k O[k]
+    float2 a[16], b[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) { a[n] = v[2 * n]; b[n] = v[2 * n + 1]; }
+    Dft<16>::run(a);
+    Dft<16>::run(b);
+    const float c[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                         0.19509032201612826785f, 0.0f, -0.19509032201612826785f, -0.38268343236508977173f,
+                         -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                         -0.92387953251128675613f, -0.98078528040323044913f};
+    const float sn[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                          0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                          0.98078528040323044913f, 1.0f, 0.98078528040323044913f, 0.92387953251128675613f,
+                          0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                          0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float2 t = k == 0 ? b[0] : cmul(b[k], make_float2(c[k], -sn[k]));
+      v[k] = cadd(a[k], t);
+      v[k + 16] = csub(a[k], t);
+    }
+  }
+};
+
 // One radix-R pass over `ntr` independent length-n transforms stored at buf + tr*pitch (padded).
 // L is the current block length; tw is the table of W_N^m with N = n * tw_stride.
 template <int R, bool INV>

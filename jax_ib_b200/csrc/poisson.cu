@@ -533,7 +533,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   // positions of the eigenvalue table)
   const bool aligned = (ny % 4) == 0;
   pl->fast_rows = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_size_supported(n2) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
-  pl->fast_cols = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_size_supported(nx) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
+  pl->fast_cols = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_cols_supported(nx) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
   if (pl->fast_cols) {
     pl->col.n = nx;
     pl->col.nstages = 3;

@@ -66,7 +66,7 @@ __device__ __forceinline__ int qswz(int p) { return p ^ ((p >> 4) & 7); }
 // thread (8-byte shared accesses), so a radix-16 butterfly costs 32 data registers instead of 64 and
 // every thread has work in every pass.
 template <int R1, int R2, int R3, int NP>
-__global__ void __launch_bounds__(NP * R2 * R3, (NP * R2 * R3 <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(NP * R2 * R3, (NP * R2 * R3 <= 512 && R1 * R2 * R3 <= 4096 ? 2 : 1))
 cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   constexpr int N = R1 * R2 * R3;
   constexpr int S1 = N / R1;   // threads per column pair; stride of pass 1
@@ -501,8 +501,8 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
   const size_t tables = (size_t)(N + R3 * (R2 + 1)) * sizeof(float2);
   const char* e = getenv("JAXIB_COL_PAIRS");
   int pairs = e ? atoi(e) : 4;  // column pairs (float4) per CTA
-  if (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024) pairs = 2;
-  if (pairs != 1 && pairs != 2 && pairs != 4) pairs = 2;
+  if (pairs != 1 && pairs != 2 && pairs != 4) pairs = 4;
+  while (pairs > 1 && (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024)) pairs /= 2;
   const size_t smem = pairs * (size_t)N * sizeof(float4) + tables;
   dim3 grid((P.ncols + 2 * pairs - 1) / (2 * pairs), batch);
   // the opt-in for > 48 KB dynamic shared memory is set once per instantiation (idempotent; a
@@ -559,6 +559,7 @@ int launch_rows_inv_t(cudaStream_t s, const FastRowParams& P, const float2* spec
 }  // namespace
 
 bool fast_size_supported(int n) { return n == 512 || n == 1024 || n == 2048 || n == 4096; }
+bool fast_cols_supported(int n) { return fast_size_supported(n) || n == 8192; }
 
 void fast_radices(int n, int* r) {
   switch (n) {
@@ -566,6 +567,7 @@ void fast_radices(int n, int* r) {
     case 1024: r[0] = 8; r[1] = 8; r[2] = 16; break;
     case 2048: r[0] = 8; r[1] = 16; r[2] = 16; break;
     case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+    case 8192: r[0] = 16; r[1] = 32; r[2] = 16; break;  // columns only
     default: r[0] = r[1] = r[2] = 0;
   }
 }
@@ -577,6 +579,7 @@ void fast_radices(int n, int* r) {
     case 1024: return CALL(8, 8, 16);         \
     case 2048: return CALL(8, 16, 16);        \
     case 4096: return CALL(16, 16, 16);       \
+    case 8192: return CALL(16, 32, 16);       \
     default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
   }
 

@@ -260,21 +260,35 @@ class SlabRank:
         return lo_send, hi_send, lo_recv, hi_recv
 
 
-def _step(ranks: List[SlabRank], comm, body_state):
+PHASES = ("predict_force", "x_forces", "spread_rows_fwd", "x_transpose_fwd", "cols", "x_transpose_inv",
+          "rows_inv", "x_halos")
+
+
+def _step(ranks: List[SlabRank], comm, body_state, mark=None):
+    """One time step.  `mark(k)` (measurement only) is called after phase k of PHASES has been enqueued."""
+    mark = mark or (lambda k: None)
     for r in ranks:
         r.phase_a(body_state)
+    mark(0)
     if ranks[0].bodies is not None:
         comm.sum_forces([r.forces() for r in ranks])
+    mark(1)
     for r in ranks:
         r.phase_b(body_state)
+    mark(2)
     comm.transpose([r.send for r in ranks], [r.recv for r in ranks])
+    mark(3)
     for r in ranks:
         r.phase_c()
+    mark(4)
     comm.transpose([r.send2 for r in ranks], [r.recv2 for r in ranks])
+    mark(5)
     for r in ranks:
         r.phase_d()
+    mark(6)
     views = [r.halo_views() for r in ranks]
     comm.halos(*[[v[k] for v in views] for k in range(4)])
+    mark(7)
 
 
 class SlabStepper:
@@ -310,8 +324,16 @@ class SlabStepper:
             r.load_global(u, v, p)
         self.time = np.float32(t0)
 
-    def advance(self, nsteps: int):
-        """`nsteps` steps in place; returns the body centres after the block (host, float32) or None."""
+    def advance(self, nsteps: int, profile: bool = False):
+        """`nsteps` steps in place; returns the body centres after the block (host, float32) or None.
+        profile=True brackets every phase with CUDA events (summed ms in self.last_profile; synchronises)."""
+        table, centers = self.schedule(nsteps)
+        self.run(table, nsteps, profile)
+        return None if centers is None else centers[-1]
+
+    def schedule(self, nsteps: int):
+        """Host part of a block (as engine.FusedStepper._schedule): evaluates the kinematic laws for the
+        next `nsteps` steps, uploads the [nsteps, 1, B, 8] table and advances the clock / body centres."""
         table = centers = None
         if self.particles is not None:
             tab, times, centers = kinematics.body_schedule(self.particles, float(self.time), self.spec.dt, nsteps)
@@ -321,9 +343,25 @@ class SlabStepper:
         else:
             for _ in range(nsteps):
                 self.time = np.float32(self.time + np.float32(self.spec.dt))
+        return table, centers
+
+    def run(self, table, nsteps: int, profile: bool = False):
+        """Device part of a block: enqueues `nsteps` steps on the current stream."""
+        prof = None
+        if profile:
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(PHASES) + 1)] for _ in range(nsteps)]
         for n in range(nsteps):
-            _step(self.ranks, self.comm, None if table is None else table[n])
-        return None if centers is None else centers[-1]
+            state = None if table is None else table[n]
+            if profile:
+                evs[n][0].record()
+                _step(self.ranks, self.comm, state, mark=lambda k, e=evs[n]: e[k + 1].record())
+            else:
+                _step(self.ranks, self.comm, state)
+        if profile:
+            torch.cuda.synchronize()
+            prof = {name: sum(e[k].elapsed_time(e[k + 1]) for e in evs) for k, name in enumerate(PHASES)}
+            prof["step"] = sum(e[0].elapsed_time(e[-1]) for e in evs)
+        self.last_profile = prof
 
     def owned_fields(self):
         """[(own_lo, u_rows, v_rows, p_rows)] for the slabs held by this process."""

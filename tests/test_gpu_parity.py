@@ -176,7 +176,8 @@ def test_ib_force_fused_matches_oracle(cfg_name):
 # ------------------------------------------------------------------------------------------------ K4-K6
 @pytest.mark.parametrize("shape", [(64, 64), (60, 100), (128, 64), (30, 36), (256, 512), (600, 600), (1024, 256),
                                    # power-of-two fast paths (poisson_fast.cu): every radix triple, rows and columns
-                                   (512, 1024), (1024, 2048), (2048, 4096), (4096, 1024), (512, 8192)])
+                                   (512, 1024), (1024, 2048), (2048, 4096), (4096, 1024), (512, 8192),
+                                   (8192, 64)])  # columns-only radix (16, 32, 16)
 def test_pressure_solve_and_projection_periodic(shape):
     cfg = make_cfg(shape, "periodic", "upwind")
     u, v, p = random_fields(shape, 21)

@@ -192,3 +192,20 @@ def test_virtual_slabs_without_bodies():
     got = _virtual(cfg, 5, 2)
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_slabs_over_nccl_match_single_gpu():
+    """Real exchanges (NCCL over NVLink): needs >= 2 GPUs on the box, one rank per GPU."""
+    import subprocess
+    n_gpus = torch.cuda.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 4 if n_gpus >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29100 + os.getpid() % 500), os.path.join(root, "tools", "slab_check.py"),
+           "--size", "1024", "--steps", "6"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "SLAB_CHECK OK" in res.stdout
