@@ -207,31 +207,49 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
         finite = bool(torch.isfinite(u).all().item())
         how = "single-GPU fused step (jaxib_step)"
     else:
+        def timed(st):
+            st.load(*(torch.from_numpy(a) for a in fields))
+            st.advance(W)
+            table, _ = st.schedule(K)  # as at one GPU: the kinematic table of the block is on the device first
+            barrier()
+            e0.record()
+            st.run(table, K)
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1))
+
+        # baseline: the same kernels with NCCL collectives between them (all-reduce, 2 all-to-all, send/recv)
         st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device)
-        st.load(*(torch.from_numpy(a) for a in fields))
-        st.advance(W)
-        barrier()
+        ms_nccl = timed(st)
         st.advance(K, profile=True)
         phases = {k: round(max_over_ranks(v) / K * 1e3, 1) for k, v in st.last_profile.items()}
-        barrier()
-        # the timed block: as at one GPU, the kinematic table of the block is on the device before it starts
-        table, _ = st.schedule(K)
-        barrier()
-        e0.record()
-        st.run(table, K)
-        e1.record()
-        barrier()
-        finite = bool(torch.isfinite(st.ranks[0].u).all().item())
         L = st.ranks[0].lay
-        how = (f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; per step: all-reduce of marker forces, 2 all-to-all "
-               f"spectrum transposes ({L.cpr} columns per rank), 1 halo exchange (NCCL)")
-    ms = max_over_ranks(e0.elapsed_time(e1))
+        del st
+        torch.cuda.empty_cache()
+        # product: exchanges fused into the kernels as NVLink stores to peer-mapped memory + flag barriers
+        mode, ms_peer = "peer-memory", None
+        try:
+            st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device, peer=True)
+            ms_peer = timed(st)
+            if st.ranks[0].barrier_timed_out():
+                raise RuntimeError("a flag barrier timed out")
+            finite = bool(torch.isfinite(st.ranks[0].u).all().item())
+        except Exception as e:  # noqa: BLE001  (no peer mapping on this box: report the NCCL path)
+            mode, ms_peer = f"nccl (peer-memory mode unavailable: {type(e).__name__}: {e})"[:200], None
+            finite = True
+        how = (f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}: marker forces, both spectrum transposes "
+               f"({L.cpr} columns per slab) and the halo rows are stored by the kernels into the consuming GPU's memory "
+               f"over NVLink, 4 flag barriers per step" if ms_peer is not None else
+               f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}")
+        e_ms = ms_peer if ms_peer is not None else ms_nccl
+    ms = max_over_ranks(e0.elapsed_time(e1)) if world == 1 else e_ms
     out = {"workload": name, "grid": [nx, ny], "bodies": len(cfg["bodies"]["centers"]), "n_gpus": world,
            "scaling": "strong", "steps": K, "ms_per_step": ms / K, "value": cells * K / (ms * 1e-3) / 1e6,
            "unit": UNIT, "finite": finite, "how": how,
            "l2": "state (5 fields + spectrum buffers) per GPU exceeds the 126 MB L2; steps run back to back"}
     if phases:
-        out["phase_us_max_over_ranks"] = phases
+        out["nccl_path"] = {"ms_per_step": ms_nccl / K, "value": cells * K / (ms_nccl * 1e-3) / 1e6,
+                            "phase_us_max_over_ranks": phases}
     return out
 
 

@@ -96,6 +96,7 @@ typedef struct {
  *   [cos(theta), sin(theta), xc, yc, U0x, U0y, Omega, 0]
  * laid out [step][batch][n_bodies][8]. */
 #define JAXIB_BODY_STATE_STRIDE 8
+#define JAXIB_MAX_PEERS 16
 
 typedef struct jaxib_plan jaxib_plan; /* opaque: FFT twiddles, Laplacian eigenvalues, radix plan */
 
@@ -177,6 +178,37 @@ int jaxib_poisson_cols(jaxib_stream_t stream, const jaxib_plan* plan, float* spe
                        int32_t col0);
 int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const float* spectrum, int32_t sp,
                            const float* u, const float* v, const float* p, float* u_out, float* v_out, float* p_out);
+
+/* ---- slab-decomposed step over peer-mapped memory ---------------------------------------------- */
+/* One simulation on `world` GPUs (one process each), x split into slabs of nloc = nx / world rows.
+ * The buffers below exist on every slab at the same sizes and are mapped into every process (CUDA
+ * VMM / IPC peer mappings made by the host side; jax_ib_b200/slab.py uses torch symmetric memory);
+ * entry [d] is slab d's buffer as addressed from THIS process, entry [rank] is the local one.
+ * The kernels of a step store straight into the buffer of the slab that consumes the data (NVLink
+ * stores: marker forces, both spectrum transposes, halo rows), with a flag barrier between the four
+ * phases -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
+typedef struct {
+  int32_t world, rank;
+  int32_t halo;                      /* halo rows on either side, in [ib_window + 3, nloc]           */
+  int32_t cpr;                       /* spectrum columns per slab: multiple of 8, world*cpr >= ny/2+4 */
+  float* u[JAXIB_MAX_PEERS];         /* [nloc + 2 halo][ny], owned rows in the middle                */
+  float* v[JAXIB_MAX_PEERS];
+  float* p[JAXIB_MAX_PEERS];
+  float* markers[JAXIB_MAX_PEERS];   /* [5][n_markers]: xp, yp, dS, Fx, Fy (NULL without bodies)     */
+  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised                          */
+  float* specbuf[JAXIB_MAX_PEERS];   /* [nloc + 1][world * cpr] complex                              */
+  uint32_t* flags[JAXIB_MAX_PEERS];  /* 128 words, zero-initialised: barrier flags + error word [64] */
+} jaxib_slab;
+/* `nsteps` steps of slab `slab->rank`, in place on its u, v, p.  plan_rows: plan of the slab grid
+ * (nx = nloc, nx_global = nx); plan_cols: plan of the global grid; grid: the GLOBAL grid.
+ * body_table: [nsteps][n_bodies][8].  u_star, v_star: local scratch, [nloc + 2 halo][ny] each.
+ * *epoch (host): barrier generation counter, starts at 0, advanced by nsteps; must be identical on all
+ * slabs.  phase_lo..phase_hi (0..3) and barriers = 0 let a test run several slabs of ONE GPU in
+ * lockstep from one process; production use is phases 0..3 with barriers = 1.                     */
+int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const jaxib_plan* plan_cols,
+                    const jaxib_grid* grid, const jaxib_slab* slab, const jaxib_bodies* bodies,
+                    const float* body_table, int32_t nsteps, int32_t phase_lo, int32_t phase_hi, int32_t barriers,
+                    uint32_t* epoch, float* u_star, float* v_star);
 
 /* ---- fused step ------------------------------------------------------------------------------ */
 /* time_stepping.py:144-255 step_fn, `nsteps` times, in place on (u, v, p):

@@ -38,6 +38,16 @@ class Bodies(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class Slab(C.Structure):
+    """struct jaxib_slab."""
+
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("halo", C.c_int32), ("cpr", C.c_int32)] + [
+        (name, C.c_void_p * MAX_PEERS) for name in ("u", "v", "p", "markers", "colbuf", "specbuf", "flags")]
+
+
 BC = {"periodic": 0, "channel": 1}
 CONVECT = {"upwind": 0, "van_leer": 1, "van_leer_limiters": 2, "none": 3}
 BODY_STATE_STRIDE = 8
@@ -61,6 +71,8 @@ _SIGNATURES = {
     "jaxib_poisson_rows_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32]),
     "jaxib_poisson_cols": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32]),
     "jaxib_poisson_rows_inv": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "jaxib_slab_step": (C.c_int, [_P, _P, _P, C.POINTER(Grid), C.POINTER(Slab), C.POINTER(Bodies), _P, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), _P, _P]),
     "jaxib_pressure_solve": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_project": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_size_t]),

@@ -51,6 +51,43 @@ inline GridF make_gridf(const jaxib_grid& g) {
   return f;
 }
 
+// ---- peer-memory slab mode (slab.cu): kernels store their results straight into the buffers of
+// the slab that consumes them (NVLink stores through peer mappings) instead of handing them to a
+// separate exchange.  cpr / world == 0 selects the ordinary single-GPU addressing.
+constexpr int kMaxPeers = JAXIB_MAX_PEERS;
+
+struct SpecScatter {          // K4 output: column block d of every spectrum row -> slab d's column buffer
+  float2* base[kMaxPeers];    // [nx_global][cpr] complex on every slab
+  int cpr;                    // columns per slab (0: plain [nx][sp] spectrum)
+  unsigned magic;             // ceil(2^32 / cpr): k / cpr == umulhi(k, magic) for the k used here
+  int row_offset;             // global row of this slab's first owned row
+};
+
+struct ColScatter {           // K5 output: row R of the local columns -> slab R / nloc's spectrum buffer
+  float2* base[kMaxPeers];    // [nloc + 1][sp_out] complex on every slab
+  int world;                  // 0: write back in place
+  int nloc;
+  unsigned magic;             // ceil(2^32 / nloc)
+  int sp_out;                 // row pitch of the destination spectrum (complex values)
+  int col_offset;             // first destination column of this slab's column block
+};
+
+struct HaloOut {              // K6 output: owned boundary rows are also stored into the neighbours' halos
+  float* lo[3];               // previous slab: its upper halo rows of u, v, p (row i of my block -> + i * ny)
+  float* hi[3];               // next slab: its lower halo rows (row i -> + (i - (nx - halo)) * ny)
+  int halo;                   // 0: off
+};
+
+struct ForceScatter {         // K2 output: the owner of a marker stores its force on every slab
+  float* markers[kMaxPeers];  // [5][n_markers] marker buffers
+  int world;                  // 0: off (write locally, zero when not the owner)
+};
+
+__device__ __forceinline__ float2* spec_addr(const SpecScatter& S, int i, int k) {
+  const unsigned d = __umulhi((unsigned)k, S.magic);
+  return S.base[d] + (size_t)(S.row_offset + i) * S.cpr + (k - (int)d * S.cpr);
+}
+
 void set_error(const char* fmt, ...);
 int check_grid(const jaxib_grid* g);
 int check_launch(const char* what);
@@ -73,7 +110,8 @@ struct StageHook {
 int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                     float* u_star, float* v_star, float* marker_scratch, const StageHook* hook = nullptr);
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers);
+                           const float* u_star, const float* v_star, float* markers,
+                           const ForceScatter* fs = nullptr);
 int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                             const float* markers, float* u_star, float* v_star);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
@@ -87,10 +125,15 @@ int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const
                    float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
                    const StageHook* hook = nullptr);
 // Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
-int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp);
-int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0);
+int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp,
+                    const SpecScatter* sc = nullptr);
+int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0,
+                const ColScatter* cs = nullptr);
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
-                    const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only);
+                    const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only,
+                    const HaloOut* ho = nullptr);
+bool plan_fast_rows(const jaxib_plan* plan);
+bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);
 const GridF& plan_grid(const jaxib_plan* plan);
 

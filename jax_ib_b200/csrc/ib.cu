@@ -21,6 +21,8 @@
 // memory) and every cell sums its contributions in marker order.  No float atomics anywhere.
 // Marker coordinates and cell indices use explicitly rounded (non-contracted) float ops so that
 // they match a NumPy float32 evaluation bit for bit.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace jaxib {
@@ -122,7 +124,7 @@ template <int RT>
 __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                                     const float* __restrict__ x0, const float* __restrict__ y0,
                                     const float* __restrict__ body_state, const float* __restrict__ u_star,
-                                    const float* __restrict__ v_star, float* __restrict__ markers) {
+                                    const float* __restrict__ v_star, float* __restrict__ markers, ForceScatter fs) {
   // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gw = wid >> 1, comp = wid & 1;
@@ -157,11 +159,17 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
       mk[0] = xp;
       mk[stride] = yp;
       mk[2 * stride] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
-      mk[3 * stride] = owner ? __fdiv_rn(__fsub_rn(UPx, U), g.dt) : 0.0f;
+      const float F = __fdiv_rn(__fsub_rn(UPx, U), g.dt);
+      if (fs.world == 0) mk[3 * stride] = owner ? F : 0.0f;
+      else if (owner)  // peer-memory slab mode: the owner publishes the force on every slab (NVLink stores)
+        for (int d = 0; d < fs.world; ++d) fs.markers[d][3 * stride + gw] = F;
     } else {
       const float ry = __fsub_rn(xp, xc);
       const float UPy = __fadd_rn(U0y, __fmul_rn(om, ry));
-      mk[4 * stride] = owner ? __fdiv_rn(__fsub_rn(UPy, U), g.dt) : 0.0f;
+      const float F = __fdiv_rn(__fsub_rn(UPy, U), g.dt);
+      if (fs.world == 0) mk[4 * stride] = owner ? F : 0.0f;
+      else if (owner)
+        for (int d = 0; d < fs.world; ++d) fs.markers[d][4 * stride + gw] = F;
     }
   }
 }
@@ -335,7 +343,10 @@ int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, c
 }
 
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers) {
+                           const float* u_star, const float* v_star, float* markers, const ForceScatter* fsp) {
+  ForceScatter fs;
+  memset(&fs, 0, sizeof(fs));
+  if (fsp) fs = *fsp;
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const int threads = 128;
@@ -343,10 +354,10 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
   if (g.R == 6)
     interp_force_kernel<6><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers);
+                                                     u_star, v_star, markers, fs);
   else
     interp_force_kernel<0><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers);
+                                                     u_star, v_star, markers, fs);
   return check_launch("interp_force_kernel");
 }
 

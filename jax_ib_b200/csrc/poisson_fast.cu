@@ -196,7 +196,24 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
     }
     dft_dir<R1, true>(va);
     dft_dir<R1, true>(vb);
-    if (gvalid && !(P.dbg & 8)) {
+    if (gvalid && P.cs.world > 0) {
+      // slab mode: row R belongs to slab R / nloc; its first row is also the row after the last one of the
+      // previous slab (K6 differences q forward in x), so that row is stored twice
+      const ColScatter& C = P.cs;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int R = gb + r * S1;
+        const int d = (int)__umulhi((unsigned)R, C.magic);
+        const int l = R - d * C.nloc;
+        const float4 val = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+        const size_t co = (size_t)C.col_offset + gc;
+        *reinterpret_cast<float4*>(C.base[d] + (size_t)l * C.sp_out + co) = val;
+        if (l == 0) {
+          const int dp = d == 0 ? C.world - 1 : d - 1;
+          *reinterpret_cast<float4*>(C.base[dp] + (size_t)C.nloc * C.sp_out + co) = val;
+        }
+      }
+    } else if (gvalid && !(P.dbg & 8)) {
 #pragma unroll
       for (int r = 0; r < R1; ++r)
         g4[(size_t)(gb + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
@@ -351,25 +368,30 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
     row_inner_passes<R1, R2, R3, false>(row, tw2, b);
     // untangle: X[k] = E + W^k O, X[N-k] = conj(E - W^k O)
     float2* out = spec + (size_t)i * P.sp;
+    const bool scatter = P.sc.cpr != 0;  // slab mode: column k lives in the buffer of the slab that owns it
+    auto put = [&](int k, float2 val) {
+      if (scatter) *spec_addr(P.sc, i, k) = val;
+      else out[k] = val;
+    };
 #pragma unroll
     for (int m = 0; m <= (N / 2) / S1; ++m) {  // k = 0 .. N/2 (the last trip only carries k = N/2)
       const int k = b + m * S1;
       if (k > N / 2) continue;
       if (k == 0) {
         const float2 zz = row[rswz(0)];
-        out[0] = make_float2(zz.x + zz.y, 0.0f);
-        out[N] = make_float2(zz.x - zz.y, 0.0f);
+        put(0, make_float2(zz.x + zz.y, 0.0f));
+        put(N, make_float2(zz.x - zz.y, 0.0f));
       } else {
         const int km = N - k;
         const float2 zk = row[rswz(Gm::pos(k))], zm = cconj(row[rswz(Gm::pos(km))]);
         const float2 e = cscale(cadd(zk, zm), 0.5f);
         const float2 o = cscale(mul_mi(csub(zk, zm)), 0.5f);
         const float2 t = cmul(__ldg(tw + k), o);
-        out[k] = cadd(e, t);
-        if (km != k) out[km] = cconj(csub(e, t));
+        put(k, cadd(e, t));
+        if (km != k) put(km, cconj(csub(e, t)));
       }
     }
-    if (b < 3) out[N + 1 + b] = make_float2(0.0f, 0.0f);  // padding columns feed cols_fast: keep them finite
+    if (b < 3) put(N + 1 + b, make_float2(0.0f, 0.0f));  // padding columns feed cols_fast: keep them finite
     __syncthreads();
   }
 }
@@ -483,9 +505,25 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
           uu.y -= (q1.y - q0.y) * g.inv_dx;
           vv.x -= (q0.y - q0.x) * g.inv_dy;
           vv.y -= (qn - q0.y) * g.inv_dy;
+          const float2 pn = make_float2(q0.x + pp.x, q0.y + pp.y);
           uo[n] = uu;
           vo[n] = vv;
-          po[n] = make_float2(q0.x + pp.x, q0.y + pp.y);
+          po[n] = pn;
+          if (P.ho.halo) {  // slab mode: boundary rows are also the neighbours' halo rows (NVLink stores)
+            const int im = ii - 1;
+            if (im < P.ho.halo) {
+              const size_t o = (size_t)im * ny;
+              reinterpret_cast<float2*>(P.ho.lo[0] + o)[n] = uu;
+              reinterpret_cast<float2*>(P.ho.lo[1] + o)[n] = vv;
+              reinterpret_cast<float2*>(P.ho.lo[2] + o)[n] = pn;
+            }
+            if (im >= g.nx - P.ho.halo) {
+              const size_t o = (size_t)(im - (g.nx - P.ho.halo)) * ny;
+              reinterpret_cast<float2*>(P.ho.hi[0] + o)[n] = uu;
+              reinterpret_cast<float2*>(P.ho.hi[1] + o)[n] = vv;
+              reinterpret_cast<float2*>(P.ho.hi[2] + o)[n] = pn;
+            }
+          }
         }
       }
 #pragma unroll

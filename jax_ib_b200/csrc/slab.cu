@@ -1,0 +1,197 @@
+// Slab-decomposed step over peer-mapped GPU memory (jaxib_slab_step, see include/jaxib_b200.h).
+//
+// One simulation, `world` GPUs, one process per GPU.  Every slab keeps nloc = nx / world rows (+ halo
+// rows of its neighbours) and the buffers every OTHER slab writes into are mapped into each process
+// (CUDA VMM peer mappings, made by the host side: jax_ib_b200/slab.py uses torch symmetric memory).
+// The kernels of a step store their results where the NEXT kernel will read them -- on whichever GPU
+// that is -- so the "collectives" of the decomposition are NVLink stores issued tile by tile from inside
+// the compute kernels, and all that is left between the phases is a flag barrier:
+//
+//   phase 0  K1 predictor on the extended slab;  K2 marker forces: the owner of a marker stores its
+//            force into every slab's marker buffer                                   | barrier 0
+//   phase 1  K3 spreading;  K4 divergence + row FFT: spectrum column block d of every row is stored
+//            into slab d's column buffer (the all-to-all transpose)                  | barrier 1
+//   phase 2  K5 column FFT x 1/lambda x inverse on the local columns: row R of the result is stored
+//            into the spectrum buffer of slab R / nloc (the transpose back; the first row of every
+//            slab also goes to the previous slab, K6 needs q of the next row)        | barrier 2
+//   phase 3  K6 inverse row FFT + projection + pressure update: owned rows in place, boundary rows
+//            also into the neighbours' halo rows (the halo exchange)                 | barrier 3
+//
+// Barrier = one tiny kernel per GPU: a system-scope release store of the step number into every peer's
+// flag word, then an acquire spin on the own flag words (bounded: a lost peer sets an error word
+// instead of hanging the GPU).  Reuse hazards: a buffer written in phase k of step n+1 was last read
+// in phase k+1 of step n, and every slab passes barrier k+1.. of step n only after that read finished.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace jaxib {
+namespace {
+
+struct BarrierArgs {
+  uint32_t* flags[kMaxPeers];
+  int world, rank, slot;
+  uint32_t epoch;
+  long long timeout_cycles;
+};
+
+__global__ void slab_barrier_kernel(BarrierArgs a) {
+  const int t = threadIdx.x;
+  if (t >= a.world) return;
+  // everything this GPU stored before (earlier kernels of the stream, local or over NVLink) becomes
+  // visible system-wide before the flag does
+  __threadfence_system();
+  uint32_t* remote = a.flags[t] + a.slot * kMaxPeers + a.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(a.epoch) : "memory");
+  const uint32_t* mine = a.flags[a.rank] + a.slot * kMaxPeers + t;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - a.epoch) >= 0) break;
+    if (clock64() - t0 > a.timeout_cycles) {  // a peer never arrived: record it and let the stream drain
+      a.flags[a.rank][4 * kMaxPeers] = a.epoch;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epoch) {
+  BarrierArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int d = 0; d < sl.world; ++d) a.flags[d] = sl.flags[d];
+  a.world = sl.world; a.rank = sl.rank; a.slot = slot; a.epoch = epoch;
+  a.timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
+  slab_barrier_kernel<<<1, 32, 0, s>>>(a);
+  return check_launch("slab_barrier_kernel");
+}
+
+unsigned magic_of(int d) { return (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
+
+}  // namespace
+}  // namespace jaxib
+
+using namespace jaxib;
+
+extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const jaxib_plan* plan_cols,
+                               const jaxib_grid* grid, const jaxib_slab* slab, const jaxib_bodies* bodies,
+                               const float* body_table, int32_t nsteps, int32_t phase_lo, int32_t phase_hi,
+                               int32_t barriers, uint32_t* epoch, float* u_star, float* v_star) {
+  int rc = check_grid(grid);
+  if (rc) return rc;
+  if (!plan_rows || !plan_cols || !slab || !epoch || !u_star || !v_star) {
+    set_error("slab_step: null argument");
+    return JAXIB_ERR_INVALID;
+  }
+  const jaxib_slab& sl = *slab;
+  const int W = sl.world, me = sl.rank;
+  if (W < 1 || W > JAXIB_MAX_PEERS || me < 0 || me >= W) { set_error("slab_step: bad world/rank %d/%d", W, me); return JAXIB_ERR_INVALID; }
+  if (grid->bc != JAXIB_BC_PERIODIC || grid->batch != 1) {
+    set_error("slab_step: periodic grids with batch = 1 only");
+    return JAXIB_ERR_UNSUPPORTED;
+  }
+  const int nx = grid->nx, ny = grid->ny, n2 = ny / 2;
+  if (nx % W) { set_error("slab_step: nx=%d not divisible by %d slabs", nx, W); return JAXIB_ERR_INVALID; }
+  const int nloc = nx / W, halo = sl.halo, cpr = sl.cpr, sp = W * cpr;
+  const int R = grid->ib_window > 0 ? grid->ib_window : 6;
+  if (halo < R + 3 || halo > nloc) { set_error("slab_step: halo=%d must lie in [ib_window + 3, nx / world]", halo); return JAXIB_ERR_INVALID; }
+  if (cpr <= 0 || cpr % 8 || sp < n2 + 4) { set_error("slab_step: cpr=%d must be a multiple of 8 with world * cpr >= ny/2 + 4", cpr); return JAXIB_ERR_INVALID; }
+  const GridF& gr = plan_grid(plan_rows);
+  const GridF& gc = plan_grid(plan_cols);
+  if (gr.nx != nloc || gr.ny != ny || gr.nx_global != nx || gc.nx != nx || gc.ny != ny) {
+    set_error("slab_step: plans do not match the decomposition (rows plan %dx%d nx_global=%d, cols plan %dx%d)", gr.nx,
+              gr.ny, gr.nx_global, gc.nx, gc.ny);
+    return JAXIB_ERR_INVALID;
+  }
+  if (!plan_fast_rows(plan_rows) || !plan_fast_cols(plan_cols)) {
+    set_error("slab_step: needs ny/2 in {512..4096} and nx in {512..8192} (powers of two)");
+    return JAXIB_ERR_UNSUPPORTED;
+  }
+  const bool has_ib = bodies && bodies->n_markers > 0;
+  if (has_ib && !body_table) { set_error("slab_step: bodies given without body_table"); return JAXIB_ERR_INVALID; }
+  for (int d = 0; d < W; ++d)
+    if (!sl.u[d] || !sl.v[d] || !sl.p[d] || !sl.colbuf[d] || !sl.specbuf[d] || !sl.flags[d] || (has_ib && !sl.markers[d])) {
+      set_error("slab_step: null buffer for slab %d", d);
+      return JAXIB_ERR_INVALID;
+    }
+  if (phase_lo < 0 || phase_hi > 3 || phase_lo > phase_hi || nsteps < 0) { set_error("slab_step: bad phase range / nsteps"); return JAXIB_ERR_INVALID; }
+
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nxl = nloc + 2 * halo, own_lo = me * nloc, row0 = own_lo - halo;
+  // K1 sees the extended slab as a periodic grid of its own
+  jaxib_grid g_ext = *grid;
+  g_ext.nx = nxl; g_ext.row0 = row0; g_ext.own_lo = g_ext.own_hi = 0; g_ext.nx_global = 0;
+  const GridF gf_ext = make_gridf(g_ext);
+  // the IB kernels see the un-wrapped rows (no periodic image of a marker: raw xp - X in the reference)
+  const int seg_a = row0 < 0 ? -row0 : 0;
+  const int seg_b = nx - row0 < nxl ? nx - row0 : nxl;
+  jaxib_grid g_ib = *grid;
+  g_ib.nx = seg_b - seg_a; g_ib.row0 = row0 + seg_a; g_ib.nx_global = 0;
+  g_ib.own_lo = me == 0 ? -2147483647 : own_lo;
+  g_ib.own_hi = me == W - 1 ? 2147483647 : own_lo + nloc;
+  const GridF gf_ib = make_gridf(g_ib);
+  jaxib_grid g_seam = *grid;  // first slab: the wrapped row nx-1 below its first owned row (K4 reads it)
+  g_seam.nx = 1; g_seam.row0 = nx - 1; g_seam.own_lo = g_seam.own_hi = 0; g_seam.nx_global = 0;
+  const GridF gf_seam = make_gridf(g_seam);
+
+  float* u = sl.u[me]; float* v = sl.v[me]; float* p = sl.p[me];
+  const size_t own_off = (size_t)halo * ny;
+  ForceScatter fs; memset(&fs, 0, sizeof(fs));
+  SpecScatter sc; memset(&sc, 0, sizeof(sc));
+  ColScatter cs; memset(&cs, 0, sizeof(cs));
+  HaloOut ho; memset(&ho, 0, sizeof(ho));
+  fs.world = W;
+  sc.cpr = cpr; sc.magic = magic_of(cpr); sc.row_offset = own_lo;
+  cs.world = W; cs.nloc = nloc; cs.magic = magic_of(nloc); cs.sp_out = sp; cs.col_offset = me * cpr;
+  for (int d = 0; d < W; ++d) {
+    fs.markers[d] = sl.markers[d];
+    sc.base[d] = reinterpret_cast<float2*>(sl.colbuf[d]);
+    cs.base[d] = reinterpret_cast<float2*>(sl.specbuf[d]);
+  }
+  const int prev = (me + W - 1) % W, next = (me + 1) % W;
+  ho.halo = halo;
+  float* const* fields[3] = {sl.u, sl.v, sl.p};
+  for (int f = 0; f < 3; ++f) {
+    ho.lo[f] = fields[f][prev] + (size_t)(halo + nloc) * ny;  // previous slab's upper halo
+    ho.hi[f] = fields[f][next];                               // next slab's lower halo
+  }
+  const size_t state_stride = has_ib ? (size_t)bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
+
+  for (int n = 0; n < nsteps; ++n) {
+    const uint32_t ep = ++(*epoch);
+    const float* state = has_ib ? body_table + n * state_stride : nullptr;
+    for (int ph = phase_lo; ph <= phase_hi; ++ph) {
+      switch (ph) {
+        case 0:
+          if ((rc = launch_explicit(s, gf_ext, u, v, p, nullptr, u_star, v_star, true))) return rc;
+          if (has_ib && (rc = launch_ib_marker_force(s, gf_ib, *bodies, state, u_star + (size_t)seg_a * ny,
+                                                     v_star + (size_t)seg_a * ny, sl.markers[me], &fs)))
+            return rc;
+          break;
+        case 1:
+          if (has_ib) {
+            if ((rc = launch_ib_spread_bodies(s, gf_ib, *bodies, state, sl.markers[me], u_star + (size_t)seg_a * ny,
+                                              v_star + (size_t)seg_a * ny)))
+              return rc;
+            if (own_lo == 0 && (rc = launch_ib_spread_bodies(s, gf_seam, *bodies, state, sl.markers[me],
+                                                             u_star + (size_t)(halo - 1) * ny,
+                                                             v_star + (size_t)(halo - 1) * ny)))
+              return rc;
+          }
+          if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
+          break;
+        case 2:
+          if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr, &cs))) return rc;
+          break;
+        case 3:
+          if ((rc = launch_rows_inv(s, plan_rows, sl.specbuf[me], sp, u_star + own_off, v_star + own_off, p + own_off,
+                                    u + own_off, v + own_off, p + own_off, nullptr, &ho)))
+            return rc;
+          break;
+      }
+      if (barriers && (ph != 0 || has_ib) && (rc = enqueue_barrier(s, sl, ph, ep))) return rc;
+    }
+  }
+  return JAXIB_OK;
+}

@@ -291,12 +291,117 @@ def _step(ranks: List[SlabRank], comm, body_state, mark=None):
     mark(7)
 
 
+# ------------------------------------------------------------------------------------------------
+# peer-memory mode: the kernels store into the consuming slab's buffers over NVLink (csrc/slab.cu)
+def _align(n: int, a: int = 256) -> int:
+    return -(-n // a) * a
+
+
+class PeerBlock:
+    """Byte layout of one slab's symmetric allocation (identical on every slab): the buffers of
+    struct jaxib_slab, each 256-byte aligned."""
+
+    FLAG_WORDS = 128
+
+    def __init__(self, layout: SlabLayout, n_markers: int):
+        L = layout
+        sizes = [("u", L.nxl * L.ny * 4), ("v", L.nxl * L.ny * 4), ("p", L.nxl * L.ny * 4),
+                 ("markers", 5 * max(n_markers, 1) * 4), ("colbuf", L.nx * L.cpr * 8),
+                 ("specbuf", (L.nloc + 1) * L.sp * 8), ("flags", self.FLAG_WORDS * 4)]
+        self.offset, off = {}, 0
+        for name, nbytes in sizes:
+            self.offset[name] = off
+            off += _align(nbytes)
+        self.nbytes = off
+        self.size = dict(sizes)
+
+
+class PeerRank:
+    """One slab in peer-memory mode: views into its own block + the jaxib_slab pointer table."""
+
+    def __init__(self, spec: ops.GridSpec, layout: SlabLayout, bodies, device, block: PeerBlock, local: torch.Tensor,
+                 base_ptrs: Sequence[int]):
+        import ctypes as C
+
+        from . import _lib
+        if spec.bc != "periodic" or spec.batch != 1:
+            raise NotImplementedError("slab decomposition: periodic grids, batch = 1")
+        self.spec, self.lay, self.bodies, self.device = spec, layout, bodies, torch.device(device)
+        L = layout
+        self.block, self.local = block, local
+        M = bodies.n_markers if bodies is not None else 0
+
+        def view(name, shape):
+            o = block.offset[name]
+            n = int(np.prod(shape)) * 4
+            return local[o:o + n].view(torch.float32).view(*shape)
+
+        self.u, self.v, self.p = (view(k, (L.nxl, L.ny)) for k in "uvp")
+        self.markers = view("markers", (5, 1, max(M, 1)))
+        self.colbuf = view("colbuf", (L.nx, L.cpr, 2))
+        self.specbuf = view("specbuf", (L.nloc + 1, L.sp, 2))
+        self.flags = local[block.offset["flags"]:block.offset["flags"] + 4 * PeerBlock.FLAG_WORDS].view(torch.int32)
+        self.us = torch.zeros(L.nxl, L.ny, dtype=torch.float32, device=self.device)
+        self.vs = torch.zeros(L.nxl, L.ny, dtype=torch.float32, device=self.device)
+        self.plan_rows = ops.Plan(spec.replace(nx=L.nloc, nx_global=L.nx), 0, self.device, alloc_scratch=False)
+        self.plan_cols = ops.Plan(spec.replace(nx=L.nx), 0, self.device, alloc_scratch=False)
+        sl = _lib.Slab()
+        sl.world, sl.rank, sl.halo, sl.cpr = L.world, L.rank, L.halo, L.cpr
+        for d, base in enumerate(base_ptrs):
+            for name in ("u", "v", "p", "colbuf", "specbuf", "flags"):
+                getattr(sl, name)[d] = base + block.offset[name]
+            sl.markers[d] = base + block.offset["markers"] if M else None
+        self.c_slab = sl
+        self.c_grid = spec.c_struct()  # the GLOBAL grid
+        self.epoch = C.c_uint32(0)
+        self._lib = _lib
+
+    load_global = SlabRank.load_global
+    owned = SlabRank.owned
+
+    def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True):
+        import ctypes as C
+        b = self.bodies.c_struct() if self.bodies is not None else None
+        lib = self._lib
+        lib.check(lib.load().jaxib_slab_step(
+            ops._stream(), self.plan_rows._h, self.plan_cols._h, C.byref(self.c_grid), C.byref(self.c_slab),
+            C.byref(b) if b is not None else None, ops._ptr(table), int(nsteps), int(phase_lo), int(phase_hi),
+            1 if barriers else 0, C.byref(self.epoch), ops._ptr(self.us), ops._ptr(self.vs)), "slab_step")
+
+    def barrier_timed_out(self) -> bool:
+        """True if a barrier of this slab ever gave up waiting for a peer (the results are then invalid)."""
+        return bool(self.flags[64].item() != 0)
+
+
+def _peer_ranks(spec, particles_bodies, world, halo, device, virtual, group):
+    """Allocates the symmetric blocks and returns (ranks, handle)."""
+    bodies = particles_bodies
+    M = bodies.n_markers if bodies is not None else 0
+    if virtual:
+        lays = [SlabLayout(spec.nx, spec.ny, world, r, halo) for r in range(world)]
+        block = PeerBlock(lays[0], M)
+        locals_ = [torch.zeros(block.nbytes, dtype=torch.uint8, device=device) for _ in range(world)]
+        ptrs = [t.data_ptr() for t in locals_]
+        return [PeerRank(spec, lays[r], bodies, device, block, locals_[r], ptrs) for r in range(world)], None
+    import torch.distributed._symmetric_memory as symm_mem
+    grp = group if group is not None else dist.group.WORLD
+    rank = dist.get_rank(grp)
+    lay = SlabLayout(spec.nx, spec.ny, world, rank, halo)
+    block = PeerBlock(lay, M)
+    local = symm_mem.empty(block.nbytes, dtype=torch.uint8, device=device)
+    hdl = symm_mem.rendezvous(local, grp)
+    local.zero_()
+    torch.cuda.synchronize(device)
+    dist.barrier(group=grp)  # every block is zeroed (flags!) before anyone stores into a peer
+    return [PeerRank(spec, lay, bodies, device, block, local, [int(p) for p in hdl.buffer_ptrs])], hdl
+
+
 class SlabStepper:
     """One simulation on `world` slabs.  `virtual=True` keeps all slabs in this process (one GPU, tests
     and single-GPU comparison); otherwise this process is one rank of the torch.distributed group."""
 
     def __init__(self, spec: ops.GridSpec, particles=None, world: Optional[int] = None, halo: Optional[int] = None,
-                 device="cuda", virtual: bool = False, group=None):
+                 device="cuda", virtual: bool = False, group=None, peer: bool = False):
         from . import engine  # local import: engine imports ops as well
         if not torch.cuda.is_available():
             raise RuntimeError("jax_ib_b200 needs a CUDA device: there is no CPU fallback")
@@ -307,16 +412,22 @@ class SlabStepper:
         if self.halo < spec.ib_window + 3:
             raise ValueError(f"halo {self.halo} < ib_window + 3: marker windows would leave the slab")
         bodies = engine.get_bodies(particles, self.device) if particles is not None else None
-        if virtual:
+        self.peer = bool(peer)
+        self.virtual = bool(virtual) or not dist.is_initialized()
+        if self.virtual:
             self.world = int(world or 1)
             self.comm = LocalComm(self.world)
             my = range(self.world)
         else:
-            self.comm = DistComm(group) if dist.is_initialized() else LocalComm(1)
+            self.comm = DistComm(group)
             self.world = self.comm.world
-            my = [self.comm.rank] if dist.is_initialized() else [0]
-        self.ranks = [SlabRank(spec, SlabLayout(spec.nx, spec.ny, self.world, r, self.halo), bodies, self.device)
-                      for r in my]
+            my = [self.comm.rank]
+        if self.peer:
+            # peer-memory mode (csrc/slab.cu): the exchanges are NVLink stores inside the kernels
+            self.ranks, self._symm = _peer_ranks(spec, bodies, self.world, self.halo, self.device, self.virtual, group)
+        else:
+            self.ranks = [SlabRank(spec, SlabLayout(spec.nx, spec.ny, self.world, r, self.halo), bodies, self.device)
+                          for r in my]
         self.time = np.float32(0.0)
 
     def load(self, u, v, p, t0=0.0):
@@ -347,6 +458,17 @@ class SlabStepper:
 
     def run(self, table, nsteps: int, profile: bool = False):
         """Device part of a block: enqueues `nsteps` steps on the current stream."""
+        if self.peer:
+            tab = None if table is None else table.view(nsteps, -1, 8)
+            if not self.virtual:
+                self.ranks[0].run(tab, nsteps)  # one C call: 4 phases x nsteps with flag barriers
+            else:  # several slabs of one GPU: lockstep, phase by phase (a flag barrier would deadlock here)
+                for n in range(nsteps):
+                    for ph in range(4):
+                        for r in self.ranks:
+                            r.run(None if tab is None else tab[n:n + 1], 1, ph, ph, barriers=False)
+            self.last_profile = None
+            return
         prof = None
         if profile:
             evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(PHASES) + 1)] for _ in range(nsteps)]

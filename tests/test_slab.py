@@ -159,9 +159,9 @@ def _single_gpu(cfg, steps):
     return u, v, p
 
 
-def _virtual(cfg, steps, world, chunks=(None,)):
+def _virtual(cfg, steps, world, chunks=(None,), peer=False):
     from jax_ib_b200 import configs, demo
-    st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), world=world, virtual=True)
+    st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), world=world, virtual=True, peer=peer)
     st.load(*(torch.from_numpy(a) for a in configs.initial_fields(cfg)))
     done = 0
     for c in chunks:
@@ -185,6 +185,38 @@ def test_virtual_slabs_match_single_gpu_bitwise(n, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,world", [(1024, 1), (1024, 2), (1024, 4), (1024, 8), (2048, 4)])
+def test_peer_memory_slabs_match_single_gpu_bitwise(n, world):
+    """csrc/slab.cu: the kernels scatter into the consuming slab's buffers (here: all on one GPU, phases in
+    lockstep without the flag barrier).  Same arithmetic per cell as on one GPU => identical bits."""
+    cfg = _seam_cfg(n)
+    steps = 6
+    ref = _single_gpu(cfg, steps)
+    got = _virtual(cfg, steps, world, chunks=(2, None), peer=True)
+    for name, a, b in zip("uvp", got, ref):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+
+
+@pytest.mark.gpu
+def test_peer_memory_slabs_without_bodies():
+    from jax_ib_b200 import configs
+    cfg = dict(configs.ib_periodic(1024, 1), bodies=None)
+    ref = _single_gpu(cfg, 4)
+    got = _virtual(cfg, 4, 4, peer=True)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_peer_memory_mode_rejects_unsupported_sizes():
+    from jax_ib_b200 import _lib, configs
+    cfg = configs.small_periodic(64)
+    with pytest.raises(_lib.JaxibError):
+        _virtual(cfg, 1, 2, peer=True)
+
+
+@pytest.mark.gpu
 def test_virtual_slabs_without_bodies():
     from jax_ib_b200 import configs
     cfg = configs.small_periodic(64, bodies=False)
@@ -195,8 +227,10 @@ def test_virtual_slabs_without_bodies():
 
 
 @pytest.mark.gpu
-def test_slabs_over_nccl_match_single_gpu():
-    """Real exchanges (NCCL over NVLink): needs >= 2 GPUs on the box, one rank per GPU."""
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_slabs_on_several_gpus_match_single_gpu(mode):
+    """Real exchanges: NCCL collectives, or NVLink stores from the kernels + flag barriers (peer mode).
+    Needs >= 2 GPUs on the box, one rank per GPU."""
     import subprocess
     n_gpus = torch.cuda.device_count()
     if n_gpus < 2:
@@ -205,7 +239,7 @@ def test_slabs_over_nccl_match_single_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(29100 + os.getpid() % 500), os.path.join(root, "tools", "slab_check.py"),
-           "--size", "1024", "--steps", "6"]
+           "--size", "1024", "--steps", "6"] + (["--peer"] if mode == "peer" else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "SLAB_CHECK OK" in res.stdout
