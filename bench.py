@@ -227,10 +227,12 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
         del st
         torch.cuda.empty_cache()
         # product: exchanges fused into the kernels as NVLink stores to peer-mapped memory + flag barriers
-        mode, ms_peer = "peer-memory", None
+        mode, ms_peer, peer_phases = "peer-memory", None, None
         try:
             st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device, peer=True)
             ms_peer = timed(st)
+            st.advance(K, profile=True)
+            peer_phases = {k: round(max_over_ranks(v) / K * 1e3, 1) for k, v in st.last_profile.items()}
             if st.ranks[0].barrier_timed_out():
                 raise RuntimeError("a flag barrier timed out")
             finite = bool(torch.isfinite(st.ranks[0].u).all().item())
@@ -248,6 +250,8 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
            "unit": UNIT, "finite": finite, "how": how,
            "l2": "state (5 fields + spectrum buffers) per GPU exceeds the 126 MB L2; steps run back to back"}
     if phases:
+        if peer_phases:
+            out["phase_us_max_over_ranks"] = peer_phases
         out["nccl_path"] = {"ms_per_step": ms_nccl / K, "value": cells * K / (ms_nccl * 1e-3) / 1e6,
                             "phase_us_max_over_ranks": phases}
     return out

@@ -460,6 +460,18 @@ class SlabStepper:
         """Device part of a block: enqueues `nsteps` steps on the current stream."""
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
+            if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
+                names = ("predict_force+barrier", "spread_rows_fwd+barrier", "cols+barrier", "rows_inv+barrier")
+                evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsteps)]
+                for n in range(nsteps):
+                    evs[n][0].record()
+                    for ph in range(4):
+                        self.ranks[0].run(None if tab is None else tab[n:n + 1], 1, ph, ph)
+                        evs[n][ph + 1].record()
+                torch.cuda.synchronize()
+                self.last_profile = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in evs) for k, nm in enumerate(names)}
+                self.last_profile["step"] = sum(e[0].elapsed_time(e[4]) for e in evs)
+                return
             if not self.virtual:
                 self.ranks[0].run(tab, nsteps)  # one C call: 4 phases x nsteps with flag barriers
             else:  # several slabs of one GPU: lockstep, phase by phase (a flag barrier would deadlock here)
