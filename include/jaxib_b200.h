@@ -184,9 +184,10 @@ int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const 
  * The buffers below exist on every slab at the same sizes and are mapped into every process (CUDA
  * VMM / IPC peer mappings made by the host side; jax_ib_b200/slab.py uses torch symmetric memory);
  * entry [d] is slab d's buffer as addressed from THIS process, entry [rank] is the local one.
- * The kernels of a step store straight into the buffer of the slab that consumes the data (NVLink
- * stores: marker forces, both spectrum transposes, halo rows), with a flag barrier between the four
- * phases -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
+ * The kernels of a step move the data themselves over NVLink: marker forces, the forward spectrum
+ * transpose and the halo rows are stored into the consuming slab's buffers, the transpose back is
+ * pulled row chunk by row chunk by the inverse row kernel; a flag barrier separates the four phases
+ * -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
 typedef struct {
   int32_t world, rank;
   int32_t halo;                      /* halo rows on either side, in [ib_window + 3, nloc]           */
@@ -195,8 +196,7 @@ typedef struct {
   float* v[JAXIB_MAX_PEERS];
   float* p[JAXIB_MAX_PEERS];
   float* markers[JAXIB_MAX_PEERS];   /* [5][n_markers]: xp, yp, dS, Fx, Fy (NULL without bodies)     */
-  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised                          */
-  float* specbuf[JAXIB_MAX_PEERS];   /* [nloc + 1][world * cpr] complex                              */
+  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised: this slab's spectrum columns */
   uint32_t* flags[JAXIB_MAX_PEERS];  /* 128 words, zero-initialised: barrier flags + error word [64] */
 } jaxib_slab;
 /* `nsteps` steps of slab `slab->rank`, in place on its u, v, p.  plan_rows: plan of the slab grid

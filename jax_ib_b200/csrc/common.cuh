@@ -63,13 +63,12 @@ struct SpecScatter {          // K4 output: column block d of every spectrum row
   int row_offset;             // global row of this slab's first owned row
 };
 
-struct ColScatter {           // K5 output: row R of the local columns -> slab R / nloc's spectrum buffer
-  float2* base[kMaxPeers];    // [nloc + 1][sp_out] complex on every slab
-  int world;                  // 0: write back in place
-  int nloc;
-  unsigned magic;             // ceil(2^32 / nloc)
-  int sp_out;                 // row pitch of the destination spectrum (complex values)
-  int col_offset;             // first destination column of this slab's column block
+struct SpecGather {           // K6 input: column block d of a spectrum row is PULLED from slab d's column buffer
+  const float2* base[kMaxPeers];  // (16-byte stores of K5's strided last pass would waste NVLink packets;
+  int cpr;                        //  warp-contiguous 16-byte cp.async reads of whole row chunks do not)
+  unsigned magic;             // ceil(2^32 / cpr)
+  int row_offset;             // global row of this slab's first owned row
+  int nx_global;              // rows wrap here (row nloc of the last slab is global row 0)
 };
 
 struct HaloOut {              // K6 output: owned boundary rows are also stored into the neighbours' halos
@@ -127,11 +126,10 @@ int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const
 // Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp,
                     const SpecScatter* sc = nullptr);
-int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0,
-                const ColScatter* cs = nullptr);
+int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0);
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
                     const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only,
-                    const HaloOut* ho = nullptr);
+                    const SpecGather* sg = nullptr, const HaloOut* ho = nullptr);
 bool plan_fast_rows(const jaxib_plan* plan);
 bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);

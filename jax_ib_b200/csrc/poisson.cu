@@ -419,6 +419,7 @@ StageParams stage_params(const jaxib_plan* pl, int sp) {
   S.frp.g = g; S.frp.tw = pl->tw_row; S.frp.sp = S.rp.sp; S.frp.rows_per_group = pl->fast_rows_per_group;
   S.frp.scale = S.rp.scale;
   memset(&S.frp.sc, 0, sizeof(S.frp.sc));
+  memset(&S.frp.sg, 0, sizeof(S.frp.sg));
   memset(&S.frp.ho, 0, sizeof(S.frp.ho));
   { const char* e = getenv("JAXIB_DBG"); S.frp.dbg = e ? atoi(e) : 0; }  // timing experiments only
   if (S.channel) {
@@ -454,8 +455,7 @@ int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const 
 bool plan_fast_rows(const jaxib_plan* pl) { return pl->fast_rows; }
 bool plan_fast_cols(const jaxib_plan* pl) { return pl->fast_cols; }
 
-int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0,
-                const ColScatter* cs) {
+int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0) {
   const GridF& g = pl->gf;
   const int n2 = g.ny / 2;
   const bool channel = g.bc == JAXIB_BC_CHANNEL;
@@ -466,11 +466,8 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
     fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
     fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0;
     { const char* e = getenv("JAXIB_DBG"); fcp.dbg = e ? atoi(e) : 0; }
-    memset(&fcp.cs, 0, sizeof(fcp.cs));
-    if (cs && cs->world) fcp.cs = *cs;
     return launch_cols_fast(s, fcp, g.batch, spec);
   }
-  if (cs && cs->world) { set_error("peer-memory slab mode needs nx in {512, ..., 8192}"); return JAXIB_ERR_UNSUPPORTED; }
   ColParams cp;
   // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
   cp.nx = g.nx; cp.sp = sp; cp.ncols = ncols > 0 ? ncols : (channel ? n2 : n2 + 1); cp.pl = pl->col; cp.tw = pl->tw_col;
@@ -484,11 +481,13 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
 
 // K6: inverse row transform (+ projection and pressure update unless q_only)
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum, int sp, const float* u, const float* v,
-                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const HaloOut* ho) {
+                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const SpecGather* sg,
+                    const HaloOut* ho) {
   StageParams S = stage_params(pl, sp);
-  if (ho && ho->halo) {
+  if ((ho && ho->halo) || (sg && sg->cpr)) {
     if (!pl->fast_rows) { set_error("peer-memory slab mode needs ny/2 in {512, 1024, 2048, 4096}"); return JAXIB_ERR_UNSUPPORTED; }
-    S.frp.ho = *ho;
+    if (ho) S.frp.ho = *ho;
+    if (sg) S.frp.sg = *sg;
   }
   const GridF& g = pl->gf;
   const float2* spec = reinterpret_cast<const float2*>(spectrum);

@@ -196,24 +196,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
     }
     dft_dir<R1, true>(va);
     dft_dir<R1, true>(vb);
-    if (gvalid && P.cs.world > 0) {
-      // slab mode: row R belongs to slab R / nloc; its first row is also the row after the last one of the
-      // previous slab (K6 differences q forward in x), so that row is stored twice
-      const ColScatter& C = P.cs;
-#pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        const int R = gb + r * S1;
-        const int d = (int)__umulhi((unsigned)R, C.magic);
-        const int l = R - d * C.nloc;
-        const float4 val = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
-        const size_t co = (size_t)C.col_offset + gc;
-        *reinterpret_cast<float4*>(C.base[d] + (size_t)l * C.sp_out + co) = val;
-        if (l == 0) {
-          const int dp = d == 0 ? C.world - 1 : d - 1;
-          *reinterpret_cast<float4*>(C.base[dp] + (size_t)C.nloc * C.sp_out + co) = val;
-        }
-      }
-    } else if (gvalid && !(P.dbg & 8)) {
+    if (gvalid && !(P.dbg & 8)) {
 #pragma unroll
       for (int r = 0; r < R1; ++r)
         g4[(size_t)(gb + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
@@ -424,8 +407,22 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
 #pragma unroll
   for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
   float2 zprev[R1];
-  // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes
-  copy_async(spec_s, spec + (size_t)i0 * P.sp, spec_bytes, b, S1);
+  // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes.
+  // Slab mode: column block d of a row is pulled from slab d's column buffer (NVLink reads, whole
+  // contiguous chunks of cpr columns; the row after the last owned one is the next slab's first).
+  auto stage_row = [&](int irow) {
+    if (P.sg.cpr == 0) {
+      copy_async(spec_s, spec + (size_t)irow * P.sp, spec_bytes, b, S1);
+    } else {
+      int grow = P.sg.row_offset + irow;
+      if (grow >= P.sg.nx_global) grow -= P.sg.nx_global;
+      for (int o = 2 * b; o < N + 4; o += 2 * S1) {  // 16-byte pieces; cpr is a multiple of 8
+        const unsigned d = __umulhi((unsigned)o, P.sg.magic);
+        cp_async16(spec_s + o, P.sg.base[d] + (size_t)grow * P.sg.cpr + (o - (int)d * P.sg.cpr));
+      }
+    }
+  };
+  stage_row(i0);
   cp_async_commit();
   for (int ii = i0; ii <= last; ++ii) {
     const int i = (ii >= g.nx && g.nx_global == 0) ? ii - g.nx : ii;
@@ -452,7 +449,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
     __syncthreads();
     if (ii < last) {  // the staged spectrum row is consumed: prefetch the next one behind the FFT passes
       const int inext = (ii + 1 >= g.nx && g.nx_global == 0) ? ii + 1 - g.nx : ii + 1;
-      copy_async(spec_s, spec + (size_t)inext * P.sp, spec_bytes, b, S1);
+      stage_row(inext);
     }
     cp_async_commit();
     if (!(P.dbg & 1)) row_inner_passes<R1, R2, R3, true>(cur, tw2, b);

@@ -10,7 +10,6 @@ struct FastColParams {
   const float* lam_x_pos;   // float32(lx[freq(p)]) in digit-reversed position order
   const float* lam_y;       // float32(ly_l), padded to sp entries
   int dbg;                  // timing experiments only (JAXIB_DBG)
-  ColScatter cs;            // slab mode: results go to the row owners' spectrum buffers
 };
 
 struct FastRowParams {
@@ -21,6 +20,7 @@ struct FastRowParams {
   int dbg;           // timing experiments only (JAXIB_DBG): bit0 skip FFT passes, bit1 skip finalize
   float scale;       // 1 / (nx * ny/2)
   SpecScatter sc;    // rows_fwd, slab mode: spectrum columns go to the column owners
+  SpecGather sg;     // rows_inv, slab mode: spectrum rows are pulled from the column owners
   HaloOut ho;        // rows_inv, slab mode: boundary rows also go to the neighbours' halos
 };
 

@@ -11,11 +11,12 @@
 //            force into every slab's marker buffer                                   | barrier 0
 //   phase 1  K3 spreading;  K4 divergence + row FFT: spectrum column block d of every row is stored
 //            into slab d's column buffer (the all-to-all transpose)                  | barrier 1
-//   phase 2  K5 column FFT x 1/lambda x inverse on the local columns: row R of the result is stored
-//            into the spectrum buffer of slab R / nloc (the transpose back; the first row of every
-//            slab also goes to the previous slab, K6 needs q of the next row)        | barrier 2
-//   phase 3  K6 inverse row FFT + projection + pressure update: owned rows in place, boundary rows
-//            also into the neighbours' halo rows (the halo exchange)                 | barrier 3
+//   phase 2  K5 column FFT x 1/lambda x inverse on the local columns, in place         | barrier 2
+//   phase 3  K6 inverse row FFT + projection + pressure update: every spectrum row is PULLED chunk by
+//            chunk from the column owners (the transpose back; cp.async reads over NVLink, prefetched
+//            one row ahead -- K5's strided 16-byte stores would waste NVLink packets, whole 4 KB row
+//            chunks do not); owned rows are updated in place, boundary rows are also stored into the
+//            neighbours' halo rows (the halo exchange)                               | barrier 3
 //
 // Barrier = one tiny kernel per GPU: a system-scope release store of the step number into every peer's
 // flag word, then an acquire spin on the own flag words (bounded: a lost peer sets an error word
@@ -111,7 +112,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   const bool has_ib = bodies && bodies->n_markers > 0;
   if (has_ib && !body_table) { set_error("slab_step: bodies given without body_table"); return JAXIB_ERR_INVALID; }
   for (int d = 0; d < W; ++d)
-    if (!sl.u[d] || !sl.v[d] || !sl.p[d] || !sl.colbuf[d] || !sl.specbuf[d] || !sl.flags[d] || (has_ib && !sl.markers[d])) {
+    if (!sl.u[d] || !sl.v[d] || !sl.p[d] || !sl.colbuf[d] || !sl.flags[d] || (has_ib && !sl.markers[d])) {
       set_error("slab_step: null buffer for slab %d", d);
       return JAXIB_ERR_INVALID;
     }
@@ -139,15 +140,15 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   const size_t own_off = (size_t)halo * ny;
   ForceScatter fs; memset(&fs, 0, sizeof(fs));
   SpecScatter sc; memset(&sc, 0, sizeof(sc));
-  ColScatter cs; memset(&cs, 0, sizeof(cs));
+  SpecGather sg; memset(&sg, 0, sizeof(sg));
   HaloOut ho; memset(&ho, 0, sizeof(ho));
   fs.world = W;
   sc.cpr = cpr; sc.magic = magic_of(cpr); sc.row_offset = own_lo;
-  cs.world = W; cs.nloc = nloc; cs.magic = magic_of(nloc); cs.sp_out = sp; cs.col_offset = me * cpr;
+  sg.cpr = cpr; sg.magic = magic_of(cpr); sg.row_offset = own_lo; sg.nx_global = nx;
   for (int d = 0; d < W; ++d) {
     fs.markers[d] = sl.markers[d];
     sc.base[d] = reinterpret_cast<float2*>(sl.colbuf[d]);
-    cs.base[d] = reinterpret_cast<float2*>(sl.specbuf[d]);
+    sg.base[d] = reinterpret_cast<const float2*>(sl.colbuf[d]);
   }
   const int prev = (me + W - 1) % W, next = (me + 1) % W;
   ho.halo = halo;
@@ -179,14 +180,14 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
                                                              v_star + (size_t)(halo - 1) * ny)))
               return rc;
           }
-          if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
+          if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.colbuf[me], sp, &sc))) return rc;
           break;
         case 2:
-          if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr, &cs))) return rc;
+          if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr))) return rc;
           break;
         case 3:
-          if ((rc = launch_rows_inv(s, plan_rows, sl.specbuf[me], sp, u_star + own_off, v_star + own_off, p + own_off,
-                                    u + own_off, v + own_off, p + own_off, nullptr, &ho)))
+          if ((rc = launch_rows_inv(s, plan_rows, sl.colbuf[me], sp, u_star + own_off, v_star + own_off, p + own_off,
+                                    u + own_off, v + own_off, p + own_off, nullptr, &sg, &ho)))
             return rc;
           break;
       }

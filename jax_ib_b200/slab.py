@@ -307,7 +307,7 @@ class PeerBlock:
         L = layout
         sizes = [("u", L.nxl * L.ny * 4), ("v", L.nxl * L.ny * 4), ("p", L.nxl * L.ny * 4),
                  ("markers", 5 * max(n_markers, 1) * 4), ("colbuf", L.nx * L.cpr * 8),
-                 ("specbuf", (L.nloc + 1) * L.sp * 8), ("flags", self.FLAG_WORDS * 4)]
+                 ("flags", self.FLAG_WORDS * 4)]
         self.offset, off = {}, 0
         for name, nbytes in sizes:
             self.offset[name] = off
@@ -339,7 +339,6 @@ class PeerRank:
         self.u, self.v, self.p = (view(k, (L.nxl, L.ny)) for k in "uvp")
         self.markers = view("markers", (5, 1, max(M, 1)))
         self.colbuf = view("colbuf", (L.nx, L.cpr, 2))
-        self.specbuf = view("specbuf", (L.nloc + 1, L.sp, 2))
         self.flags = local[block.offset["flags"]:block.offset["flags"] + 4 * PeerBlock.FLAG_WORDS].view(torch.int32)
         self.us = torch.zeros(L.nxl, L.ny, dtype=torch.float32, device=self.device)
         self.vs = torch.zeros(L.nxl, L.ny, dtype=torch.float32, device=self.device)
@@ -348,7 +347,7 @@ class PeerRank:
         sl = _lib.Slab()
         sl.world, sl.rank, sl.halo, sl.cpr = L.world, L.rank, L.halo, L.cpr
         for d, base in enumerate(base_ptrs):
-            for name in ("u", "v", "p", "colbuf", "specbuf", "flags"):
+            for name in ("u", "v", "p", "colbuf", "flags"):
                 getattr(sl, name)[d] = base + block.offset[name]
             sl.markers[d] = base + block.offset["markers"] if M else None
         self.c_slab = sl
