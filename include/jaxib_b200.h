@@ -67,13 +67,13 @@ typedef struct {
   double v_wall[2];    /* channel: v at the lower / upper y wall                                */
   double force[2];     /* constant body force (forcing(v) of the Taylor demo), per component    */
   int32_t ib_window;   /* Gaussian truncation radius R in cells (window 2R x 2R); default 6     */
-  /* Slab decomposition along x (0 / 0 / 0 for a full grid): the arrays hold global rows
-   * [row0, row0 + nx) (halo rows included); immersed-boundary forces are computed only for markers
-   * whose owning u-cell row lies in [own_lo, own_hi) and are zero otherwise (the caller sums the
-   * per-slab force arrays), while spreading writes every local row.  nx_global > 0 marks a slab
-   * for the Poisson row stages (jaxib_poisson_rows_fwd / _rows_inv): the nx local rows are "open" --
-   * row -1 of u and spectrum row nx are read from the memory next to the arrays (the caller's halo)
-   * instead of wrapping -- and transforms are normalised with nx_global.                           */
+  /* Slab decomposition along x (all zero for a full grid): the arrays hold global rows
+   * [row0, row0 + nx) (halo rows included).  jaxib_ib_marker_force computes forces only for markers
+   * whose u-cell row floor(xp/dx - 1) lies in [own_lo, own_hi) and leaves the entries of the others
+   * untouched (own_hi <= own_lo: all markers); spreading writes every local row.  nx_global > 0
+   * marks a slab for the Poisson row stages (jaxib_poisson_rows_fwd / _rows_inv): the nx local rows
+   * are "open" -- row -1 of u and spectrum row nx are read from the memory next to the arrays (the
+   * caller's halo) instead of wrapping -- and transforms are normalised with nx_global.            */
   int32_t row0;
   int32_t own_lo, own_hi;
   int32_t nx_global;
@@ -157,11 +157,12 @@ int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u,
 /* New capability (the reference only shards MARKERS with jax.pmap, grid replicated:
  * IBM_Force.py:77-87, convolution_functions.py:28-35; no grid decomposition exists there).  A
  * slab rank calls the stages of one step separately and places its own exchange between them
- * (jax_ib_b200/slab.py): marker forces are summed over ranks between the two IB halves, and the
- * spectrum is transposed (all-to-all) on either side of the column transform.
+ * (jax_ib_b200/slab.py): the spectrum is transposed (all-to-all) on either side of the column
+ * transform and halo rows are refreshed after the projection.  Marker forces need no exchange:
+ * with 2 * ib_window + 4 halo rows every slab computes the forces of the markers near it itself.
  *
  * jaxib_ib_force split in two.  `markers`: [5][batch][n_markers] floats (xp, yp, dS, Fx, Fy);
- * Fx, Fy are zero for markers this slab does not own (grid->own_lo / own_hi).                  */
+ * Fx, Fy are written only for the markers selected by grid->own_lo / own_hi.                   */
 int jaxib_ib_marker_force(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
                           const float* body_state, const float* u_star, const float* v_star, float* markers);
 int jaxib_ib_spread_bodies(jaxib_stream_t stream, const jaxib_grid* grid, const jaxib_bodies* bodies,
@@ -184,19 +185,19 @@ int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const 
  * The buffers below exist on every slab at the same sizes and are mapped into every process (CUDA
  * VMM / IPC peer mappings made by the host side; jax_ib_b200/slab.py uses torch symmetric memory);
  * entry [d] is slab d's buffer as addressed from THIS process, entry [rank] is the local one.
- * The kernels of a step move the data themselves over NVLink: marker forces, the forward spectrum
- * transpose and the halo rows are stored into the consuming slab's buffers, the transpose back is
- * pulled row chunk by row chunk by the inverse row kernel; a flag barrier separates the four phases
- * -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
+ * The kernels of a step store straight into the buffer of the slab that consumes the data (NVLink
+ * stores: both spectrum transposes and the halo rows), with a flag barrier after each of the three
+ * exchanging phases -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
 typedef struct {
   int32_t world, rank;
-  int32_t halo;                      /* halo rows on either side, in [ib_window + 3, nloc]           */
+  int32_t halo;                      /* halo rows on either side, in [2 * ib_window + 4, nloc]       */
   int32_t cpr;                       /* spectrum columns per slab: multiple of 8, world*cpr >= ny/2+4 */
   float* u[JAXIB_MAX_PEERS];         /* [nloc + 2 halo][ny], owned rows in the middle                */
   float* v[JAXIB_MAX_PEERS];
   float* p[JAXIB_MAX_PEERS];
   float* markers[JAXIB_MAX_PEERS];   /* [5][n_markers]: xp, yp, dS, Fx, Fy (NULL without bodies)     */
-  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised: this slab's spectrum columns */
+  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised                          */
+  float* specbuf[JAXIB_MAX_PEERS];   /* [nloc + 1][world * cpr] complex                              */
   uint32_t* flags[JAXIB_MAX_PEERS];  /* 128 words, zero-initialised: barrier flags + error word [64] */
 } jaxib_slab;
 /* `nsteps` steps of slab `slab->rank`, in place on its u, v, p.  plan_rows: plan of the slab grid

@@ -45,7 +45,7 @@ class Slab(C.Structure):
     """struct jaxib_slab."""
 
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("halo", C.c_int32), ("cpr", C.c_int32)] + [
-        (name, C.c_void_p * MAX_PEERS) for name in ("u", "v", "p", "markers", "colbuf", "flags")]
+        (name, C.c_void_p * MAX_PEERS) for name in ("u", "v", "p", "markers", "colbuf", "specbuf", "flags")]
 
 
 BC = {"periodic": 0, "channel": 1}

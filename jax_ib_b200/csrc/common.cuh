@@ -63,23 +63,10 @@ struct SpecScatter {          // K4 output: column block d of every spectrum row
   int row_offset;             // global row of this slab's first owned row
 };
 
-struct SpecGather {           // K6 input: column block d of a spectrum row is PULLED from slab d's column buffer
-  const float2* base[kMaxPeers];  // (16-byte stores of K5's strided last pass would waste NVLink packets;
-  int cpr;                        //  warp-contiguous 16-byte cp.async reads of whole row chunks do not)
-  unsigned magic;             // ceil(2^32 / cpr)
-  int row_offset;             // global row of this slab's first owned row
-  int nx_global;              // rows wrap here (row nloc of the last slab is global row 0)
-};
-
 struct HaloOut {              // K6 output: owned boundary rows are also stored into the neighbours' halos
   float* lo[3];               // previous slab: its upper halo rows of u, v, p (row i of my block -> + i * ny)
   float* hi[3];               // next slab: its lower halo rows (row i -> + (i - (nx - halo)) * ny)
   int halo;                   // 0: off
-};
-
-struct ForceScatter {         // K2 output: the owner of a marker stores its force on every slab
-  float* markers[kMaxPeers];  // [5][n_markers] marker buffers
-  int world;                  // 0: off (write locally, zero when not the owner)
 };
 
 __device__ __forceinline__ float2* spec_addr(const SpecScatter& S, int i, int k) {
@@ -109,8 +96,7 @@ struct StageHook {
 int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                     float* u_star, float* v_star, float* marker_scratch, const StageHook* hook = nullptr);
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers,
-                           const ForceScatter* fs = nullptr);
+                           const float* u_star, const float* v_star, float* markers);
 int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                             const float* markers, float* u_star, float* v_star);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
@@ -129,7 +115,7 @@ int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, cons
 int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0);
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
                     const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only,
-                    const SpecGather* sg = nullptr, const HaloOut* ho = nullptr);
+                    const HaloOut* ho = nullptr);
 bool plan_fast_rows(const jaxib_plan* plan);
 bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);

@@ -124,7 +124,7 @@ template <int RT>
 __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                                     const float* __restrict__ x0, const float* __restrict__ y0,
                                     const float* __restrict__ body_state, const float* __restrict__ u_star,
-                                    const float* __restrict__ v_star, float* __restrict__ markers, ForceScatter fs) {
+                                    const float* __restrict__ v_star, float* __restrict__ markers) {
   // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gw = wid >> 1, comp = wid & 1;
@@ -144,14 +144,16 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
   const float yq = __fadd_rn(__fadd_rn(__fmul_rn(bx, sn), __fmul_rn(by, c)), yc);
   const size_t plane = (size_t)g.nx * g.ny;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
-  const float U = interp_marker<RT>(m, (comp == 0 ? u_star : v_star) + s * plane, xp, yp, nullptr, nullptr);
+  // slab decomposition: a slab only needs the forces of the markers near its rows (u-cell row in
+  // [own_lo, own_hi)); the entries of the others are left untouched -- no cell of the slab sees them --
+  // and their window sums are skipped (warp-uniform)
+  const int iku = cell_index(xp, g.dx, 1.0f);
+  const bool wanted = g.own_hi <= g.own_lo || (iku >= g.own_lo && iku < g.own_hi);
+  float U = 0.0f;
+  if (wanted) U = interp_marker<RT>(m, (comp == 0 ? u_star : v_star) + s * plane, xp, yp, nullptr, nullptr);
   if ((threadIdx.x & 31) == 0) {
     const size_t stride = (size_t)total;
     float* mk = markers + gw;
-    // slab decomposition: only the slab that owns the marker's u-cell row reports its force
-    const int iku = cell_index(xp, g.dx, 1.0f);
-    // (the first / last slab pass own_lo = INT_MIN / own_hi = INT_MAX: markers may lie off the grid)
-    const bool owner = g.own_hi <= g.own_lo || (iku >= g.own_lo && iku < g.own_hi);
     if (comp == 0) {
       const float rx = -(__fsub_rn(yp, yc));
       const float UPx = __fadd_rn(U0x, __fmul_rn(om, rx));
@@ -159,17 +161,11 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
       mk[0] = xp;
       mk[stride] = yp;
       mk[2 * stride] = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
-      const float F = __fdiv_rn(__fsub_rn(UPx, U), g.dt);
-      if (fs.world == 0) mk[3 * stride] = owner ? F : 0.0f;
-      else if (owner)  // peer-memory slab mode: the owner publishes the force on every slab (NVLink stores)
-        for (int d = 0; d < fs.world; ++d) fs.markers[d][3 * stride + gw] = F;
+      if (wanted) mk[3 * stride] = __fdiv_rn(__fsub_rn(UPx, U), g.dt);
     } else {
       const float ry = __fsub_rn(xp, xc);
       const float UPy = __fadd_rn(U0y, __fmul_rn(om, ry));
-      const float F = __fdiv_rn(__fsub_rn(UPy, U), g.dt);
-      if (fs.world == 0) mk[4 * stride] = owner ? F : 0.0f;
-      else if (owner)
-        for (int d = 0; d < fs.world; ++d) fs.markers[d][4 * stride + gw] = F;
+      if (wanted) mk[4 * stride] = __fdiv_rn(__fsub_rn(UPy, U), g.dt);
     }
   }
 }
@@ -343,10 +339,7 @@ int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, c
 }
 
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers, const ForceScatter* fsp) {
-  ForceScatter fs;
-  memset(&fs, 0, sizeof(fs));
-  if (fsp) fs = *fsp;
+                           const float* u_star, const float* v_star, float* markers) {
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const int threads = 128;
@@ -354,10 +347,10 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
   if (g.R == 6)
     interp_force_kernel<6><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers, fs);
+                                                     u_star, v_star, markers);
   else
     interp_force_kernel<0><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers, fs);
+                                                     u_star, v_star, markers);
   return check_launch("interp_force_kernel");
 }
 

@@ -419,7 +419,6 @@ StageParams stage_params(const jaxib_plan* pl, int sp) {
   S.frp.g = g; S.frp.tw = pl->tw_row; S.frp.sp = S.rp.sp; S.frp.rows_per_group = pl->fast_rows_per_group;
   S.frp.scale = S.rp.scale;
   memset(&S.frp.sc, 0, sizeof(S.frp.sc));
-  memset(&S.frp.sg, 0, sizeof(S.frp.sg));
   memset(&S.frp.ho, 0, sizeof(S.frp.ho));
   { const char* e = getenv("JAXIB_DBG"); S.frp.dbg = e ? atoi(e) : 0; }  // timing experiments only
   if (S.channel) {
@@ -481,13 +480,11 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
 
 // K6: inverse row transform (+ projection and pressure update unless q_only)
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum, int sp, const float* u, const float* v,
-                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const SpecGather* sg,
-                    const HaloOut* ho) {
+                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const HaloOut* ho) {
   StageParams S = stage_params(pl, sp);
-  if ((ho && ho->halo) || (sg && sg->cpr)) {
+  if (ho && ho->halo) {
     if (!pl->fast_rows) { set_error("peer-memory slab mode needs ny/2 in {512, 1024, 2048, 4096}"); return JAXIB_ERR_UNSUPPORTED; }
-    if (ho) S.frp.ho = *ho;
-    if (sg) S.frp.sg = *sg;
+    S.frp.ho = *ho;
   }
   const GridF& g = pl->gf;
   const float2* spec = reinterpret_cast<const float2*>(spectrum);

@@ -407,22 +407,8 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
 #pragma unroll
   for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
   float2 zprev[R1];
-  // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes.
-  // Slab mode: column block d of a row is pulled from slab d's column buffer (NVLink reads, whole
-  // contiguous chunks of cpr columns; the row after the last owned one is the next slab's first).
-  auto stage_row = [&](int irow) {
-    if (P.sg.cpr == 0) {
-      copy_async(spec_s, spec + (size_t)irow * P.sp, spec_bytes, b, S1);
-    } else {
-      int grow = P.sg.row_offset + irow;
-      if (grow >= P.sg.nx_global) grow -= P.sg.nx_global;
-      for (int o = 2 * b; o < N + 4; o += 2 * S1) {  // 16-byte pieces; cpr is a multiple of 8
-        const unsigned d = __umulhi((unsigned)o, P.sg.magic);
-        cp_async16(spec_s + o, P.sg.base[d] + (size_t)grow * P.sg.cpr + (o - (int)d * P.sg.cpr));
-      }
-    }
-  };
-  stage_row(i0);
+  // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes
+  copy_async(spec_s, spec + (size_t)i0 * P.sp, spec_bytes, b, S1);
   cp_async_commit();
   for (int ii = i0; ii <= last; ++ii) {
     const int i = (ii >= g.nx && g.nx_global == 0) ? ii - g.nx : ii;
@@ -449,7 +435,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
     __syncthreads();
     if (ii < last) {  // the staged spectrum row is consumed: prefetch the next one behind the FFT passes
       const int inext = (ii + 1 >= g.nx && g.nx_global == 0) ? ii + 1 - g.nx : ii + 1;
-      stage_row(inext);
+      copy_async(spec_s, spec + (size_t)inext * P.sp, spec_bytes, b, S1);
     }
     cp_async_commit();
     if (!(P.dbg & 1)) row_inner_passes<R1, R2, R3, true>(cur, tw2, b);

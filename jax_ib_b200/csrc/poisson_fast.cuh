@@ -20,7 +20,6 @@ struct FastRowParams {
   int dbg;           // timing experiments only (JAXIB_DBG): bit0 skip FFT passes, bit1 skip finalize
   float scale;       // 1 / (nx * ny/2)
   SpecScatter sc;    // rows_fwd, slab mode: spectrum columns go to the column owners
-  SpecGather sg;     // rows_inv, slab mode: spectrum rows are pulled from the column owners
   HaloOut ho;        // rows_inv, slab mode: boundary rows also go to the neighbours' halos
 };
 

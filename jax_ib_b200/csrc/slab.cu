@@ -7,16 +7,16 @@
 // that is -- so the "collectives" of the decomposition are NVLink stores issued tile by tile from inside
 // the compute kernels, and all that is left between the phases is a flag barrier:
 //
-//   phase 0  K1 predictor on the extended slab;  K2 marker forces: the owner of a marker stores its
-//            force into every slab's marker buffer                                   | barrier 0
+//   phase 0  K1 predictor on the extended slab;  K2 forces of the markers near the slab (the halo is
+//            2R + 4 rows deep, so their interpolation windows are local: no exchange)  | --
 //   phase 1  K3 spreading;  K4 divergence + row FFT: spectrum column block d of every row is stored
 //            into slab d's column buffer (the all-to-all transpose)                  | barrier 1
-//   phase 2  K5 column FFT x 1/lambda x inverse on the local columns, in place         | barrier 2
-//   phase 3  K6 inverse row FFT + projection + pressure update: every spectrum row is PULLED chunk by
-//            chunk from the column owners (the transpose back; cp.async reads over NVLink, prefetched
-//            one row ahead -- K5's strided 16-byte stores would waste NVLink packets, whole 4 KB row
-//            chunks do not); owned rows are updated in place, boundary rows are also stored into the
-//            neighbours' halo rows (the halo exchange)                               | barrier 3
+//   phase 2  K5 column FFT x 1/lambda x inverse on the local columns, in place; a push kernel then
+//            stores row R of the result into the spectrum buffer of slab R / nloc in whole row chunks
+//            (the transpose back; the first row of every slab also goes to the previous slab: K6
+//            needs q of the next row)                                                | barrier 2
+//   phase 3  K6 inverse row FFT + projection + pressure update: owned rows in place, boundary rows
+//            also into the neighbours' halo rows (the halo exchange)                 | barrier 3
 //
 // Barrier = one tiny kernel per GPU: a system-scope release store of the step number into every peer's
 // flag word, then an acquire spin on the own flag words (bounded: a lost peer sets an error word
@@ -70,6 +70,52 @@ int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epo
 
 unsigned magic_of(int d) { return (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
 
+// The transpose back: row R of this slab's solved columns [nx][cpr] goes to the spectrum buffer
+// [nloc + 1][sp] of slab R / nloc at column offset rank * cpr; the first row of every slab is also the
+// row after the last one of the previous slab (K6 differences q forward in x).  One warp moves one row
+// chunk (cpr * 8 bytes, contiguous on both sides) with 16-byte accesses, all loads before the stores:
+// whole chunks make full-size NVLink write packets (K5's own last pass stores 16 bytes per row, and a
+// pull by K6 was measured 2-3x slower: NVLink reads are latency-bound, posted writes are not).
+struct PushArgs {
+  float2* spec[kMaxPeers];
+  const float2* cols;
+  int world, nloc, nx, cpr, sp, col_offset;
+  unsigned magic;
+};
+
+constexpr int kPushMaxVec = 12;  // float4 per lane per row chunk: cpr <= 2 * 32 * 12 = 768 columns per pass
+
+__global__ void __launch_bounds__(256) slab_push_kernel(PushArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = a.cpr >> 1;  // float4 per row chunk
+  for (int R = warp; R < a.nx; R += nwarps) {
+    const int d = (int)__umulhi((unsigned)R, a.magic);
+    const int l = R - d * a.nloc;
+    const float4* src = reinterpret_cast<const float4*>(a.cols + (size_t)R * a.cpr);
+    float4* dst = reinterpret_cast<float4*>(a.spec[d] + (size_t)l * a.sp + a.col_offset);
+    float4* dst2 = nullptr;
+    if (l == 0) dst2 = reinterpret_cast<float4*>(a.spec[d == 0 ? a.world - 1 : d - 1] + (size_t)a.nloc * a.sp + a.col_offset);
+    for (int base = 0; base < nvec; base += 32 * kPushMaxVec) {
+      float4 v[kPushMaxVec];
+#pragma unroll
+      for (int k = 0; k < kPushMaxVec; ++k) {
+        const int e = base + lane + 32 * k;
+        if (e < nvec) v[k] = __ldcs(src + e);
+      }
+#pragma unroll
+      for (int k = 0; k < kPushMaxVec; ++k) {
+        const int e = base + lane + 32 * k;
+        if (e < nvec) {
+          dst[e] = v[k];
+          if (dst2) dst2[e] = v[k];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace jaxib
 
@@ -96,7 +142,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   if (nx % W) { set_error("slab_step: nx=%d not divisible by %d slabs", nx, W); return JAXIB_ERR_INVALID; }
   const int nloc = nx / W, halo = sl.halo, cpr = sl.cpr, sp = W * cpr;
   const int R = grid->ib_window > 0 ? grid->ib_window : 6;
-  if (halo < R + 3 || halo > nloc) { set_error("slab_step: halo=%d must lie in [ib_window + 3, nx / world]", halo); return JAXIB_ERR_INVALID; }
+  if (halo < 2 * R + 4 || halo > nloc) { set_error("slab_step: halo=%d must lie in [2 * ib_window + 4, nx / world]", halo); return JAXIB_ERR_INVALID; }
   if (cpr <= 0 || cpr % 8 || sp < n2 + 4) { set_error("slab_step: cpr=%d must be a multiple of 8 with world * cpr >= ny/2 + 4", cpr); return JAXIB_ERR_INVALID; }
   const GridF& gr = plan_grid(plan_rows);
   const GridF& gc = plan_grid(plan_cols);
@@ -112,7 +158,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   const bool has_ib = bodies && bodies->n_markers > 0;
   if (has_ib && !body_table) { set_error("slab_step: bodies given without body_table"); return JAXIB_ERR_INVALID; }
   for (int d = 0; d < W; ++d)
-    if (!sl.u[d] || !sl.v[d] || !sl.p[d] || !sl.colbuf[d] || !sl.flags[d] || (has_ib && !sl.markers[d])) {
+    if (!sl.u[d] || !sl.v[d] || !sl.p[d] || !sl.colbuf[d] || !sl.specbuf[d] || !sl.flags[d] || (has_ib && !sl.markers[d])) {
       set_error("slab_step: null buffer for slab %d", d);
       return JAXIB_ERR_INVALID;
     }
@@ -129,8 +175,17 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   const int seg_b = nx - row0 < nxl ? nx - row0 : nxl;
   jaxib_grid g_ib = *grid;
   g_ib.nx = seg_b - seg_a; g_ib.row0 = row0 + seg_a; g_ib.nx_global = 0;
-  g_ib.own_lo = me == 0 ? -2147483647 : own_lo;
-  g_ib.own_hi = me == W - 1 ? 2147483647 : own_lo + nloc;
+  // forces are needed for every marker whose window touches u** rows [own_lo-1, own_hi) or v** rows
+  // [own_lo, own_hi): u-cell row in [own_lo - R - 2, own_hi + R); their interpolation windows stay inside
+  // the 2R + 4 halo rows, so every slab computes the forces it needs itself -- no exchange of forces
+  g_ib.own_lo = me == 0 ? -2147483647 : own_lo - R - 2;
+  g_ib.own_hi = me == W - 1 ? 2147483647 : own_lo + nloc + R;
+  // first slab of several: the seam row nx-1 is fed by markers near the TOP of the domain; their windows
+  // lie in the wrapped lower halo (global rows nx - halo .. nx - 1)
+  jaxib_grid g_top = *grid;
+  g_top.nx = halo; g_top.row0 = nx - halo; g_top.nx_global = 0;
+  g_top.own_lo = nx - R - 3; g_top.own_hi = 2147483647;
+  const GridF gf_top = make_gridf(g_top);
   const GridF gf_ib = make_gridf(g_ib);
   jaxib_grid g_seam = *grid;  // first slab: the wrapped row nx-1 below its first owned row (K4 reads it)
   g_seam.nx = 1; g_seam.row0 = nx - 1; g_seam.own_lo = g_seam.own_hi = 0; g_seam.nx_global = 0;
@@ -138,17 +193,15 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
 
   float* u = sl.u[me]; float* v = sl.v[me]; float* p = sl.p[me];
   const size_t own_off = (size_t)halo * ny;
-  ForceScatter fs; memset(&fs, 0, sizeof(fs));
   SpecScatter sc; memset(&sc, 0, sizeof(sc));
-  SpecGather sg; memset(&sg, 0, sizeof(sg));
+  PushArgs pa; memset(&pa, 0, sizeof(pa));
   HaloOut ho; memset(&ho, 0, sizeof(ho));
-  fs.world = W;
   sc.cpr = cpr; sc.magic = magic_of(cpr); sc.row_offset = own_lo;
-  sg.cpr = cpr; sg.magic = magic_of(cpr); sg.row_offset = own_lo; sg.nx_global = nx;
+  pa.cols = reinterpret_cast<const float2*>(sl.colbuf[me]);
+  pa.world = W; pa.nloc = nloc; pa.nx = nx; pa.cpr = cpr; pa.sp = sp; pa.col_offset = me * cpr; pa.magic = magic_of(nloc);
   for (int d = 0; d < W; ++d) {
-    fs.markers[d] = sl.markers[d];
     sc.base[d] = reinterpret_cast<float2*>(sl.colbuf[d]);
-    sg.base[d] = reinterpret_cast<const float2*>(sl.colbuf[d]);
+    pa.spec[d] = reinterpret_cast<float2*>(sl.specbuf[d]);
   }
   const int prev = (me + W - 1) % W, next = (me + 1) % W;
   ho.halo = halo;
@@ -157,6 +210,10 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
     ho.lo[f] = fields[f][prev] + (size_t)(halo + nloc) * ny;  // previous slab's upper halo
     ho.hi[f] = fields[f][next];                               // next slab's lower halo
   }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int push_ctas = 4 * sms;
   const size_t state_stride = has_ib ? (size_t)bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
 
   for (int n = 0; n < nsteps; ++n) {
@@ -167,7 +224,10 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
         case 0:
           if ((rc = launch_explicit(s, gf_ext, u, v, p, nullptr, u_star, v_star, true))) return rc;
           if (has_ib && (rc = launch_ib_marker_force(s, gf_ib, *bodies, state, u_star + (size_t)seg_a * ny,
-                                                     v_star + (size_t)seg_a * ny, sl.markers[me], &fs)))
+                                                     v_star + (size_t)seg_a * ny, sl.markers[me])))
+            return rc;
+          if (has_ib && own_lo == 0 && W > 1 &&
+              (rc = launch_ib_marker_force(s, gf_top, *bodies, state, u_star, v_star, sl.markers[me])))
             return rc;
           break;
         case 1:
@@ -180,18 +240,20 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
                                                              v_star + (size_t)(halo - 1) * ny)))
               return rc;
           }
-          if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.colbuf[me], sp, &sc))) return rc;
+          if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
           break;
         case 2:
           if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr))) return rc;
+          slab_push_kernel<<<push_ctas, 256, 0, s>>>(pa);
+          if ((rc = check_launch("slab_push_kernel"))) return rc;
           break;
         case 3:
-          if ((rc = launch_rows_inv(s, plan_rows, sl.colbuf[me], sp, u_star + own_off, v_star + own_off, p + own_off,
-                                    u + own_off, v + own_off, p + own_off, nullptr, &sg, &ho)))
+          if ((rc = launch_rows_inv(s, plan_rows, sl.specbuf[me], sp, u_star + own_off, v_star + own_off, p + own_off,
+                                    u + own_off, v + own_off, p + own_off, nullptr, &ho)))
             return rc;
           break;
       }
-      if (barriers && (ph != 0 || has_ib) && (rc = enqueue_barrier(s, sl, ph, ep))) return rc;
+      if (barriers && ph != 0 && (rc = enqueue_barrier(s, sl, ph, ep))) return rc;
     }
   }
   return JAXIB_OK;

@@ -2,22 +2,21 @@
 
 New capability: the reference only shards markers with `jax.pmap` and replicates the grid
 (IBM_Force.py:77-87, convolution_functions.py:28-35).  Here the x axis (rows; y stays contiguous) is
-split into `world` slabs of `nx / world` rows.  Every rank keeps its rows plus `halo` rows of its
-neighbours on either side, so that one step needs exactly four exchanges:
+split into `world` slabs of `nx / world` rows.  Every rank keeps its rows plus `halo` = 2R + 4 rows of
+its neighbours on either side, so that one step needs exactly three exchanges:
 
     K1 predictor on the extended slab (the halo absorbs the stencil; the local array is treated as a
        periodic grid of its own, garbage stays inside the outermost two halo rows)
-    K2 marker forces for the markers whose u-cell row this slab owns (zero for the others)
-  X1 all-reduce(sum) of the [2, M] force arrays: every marker has exactly one non-zero contributor,
-       so the sum is exact and every rank ends up with the single-GPU forces bit for bit
+    K2 forces of the markers whose spreading window touches the slab; their interpolation windows lie
+       inside the halo, so every slab computes them itself, bit for bit as one GPU would -- no exchange
     K3 spreading onto the local rows (all markers, culled per tile as on one GPU)
     K4 divergence + row FFT of the owned rows -> spectrum [nloc][world * cpr]
-  X2 all-to-all: rank r receives the columns [r * cpr, (r+1) * cpr) of every row
+  X1 all-to-all: rank r receives the columns [r * cpr, (r+1) * cpr) of every row
     K5 column FFT x eigenvalues x inverse over all nx rows of the local columns
-  X3 all-to-all back; every destination also gets the first row of the NEXT slab (K6 differences q
+  X2 all-to-all back; every destination also gets the first row of the NEXT slab (K6 differences q
        forward in x), so no separate halo pass is needed for q
     K6 inverse row FFT + projection + pressure update on the owned rows
-  X4 halo exchange of the new u, v, p rows with the two neighbours (periodic ring)
+  X3 halo exchange of the new u, v, p rows with the two neighbours (periodic ring)
 
 Cells next to the periodic seam: the reference takes no periodic image of a marker (raw xp - X), so
 the IB kernels see the local array as un-wrapped segments -- the rows whose global index lies in
@@ -72,14 +71,22 @@ class SlabLayout:
         self.cpr = -(-per_rank // 8) * 8
         self.sp = world * self.cpr
 
-    # marker ownership: the first / last slab also own markers that lie off the grid
-    @property
-    def marker_lo(self) -> int:
-        return -INT_MAX if self.rank == 0 else self.own_lo
+    # Markers a slab needs the force of: every marker whose spreading window touches the u** rows
+    # [own_lo - 1, own_hi) or the v** rows [own_lo, own_hi), i.e. u-cell row in [own_lo - R - 2, own_hi + R).
+    # Their interpolation windows reach 2R + 2 rows past the owned block, so with a halo of 2R + 4 rows
+    # (2 more for the predictor's stencil) every slab computes these forces itself: nothing is exchanged.
+    # The first / last slab also take the markers that lie off the grid.
+    def marker_range(self, R: int):
+        lo = -INT_MAX if self.rank == 0 else self.own_lo - R - 2
+        hi = INT_MAX if self.rank == self.world - 1 else self.own_hi + R
+        return lo, hi
 
-    @property
-    def marker_hi(self) -> int:
-        return INT_MAX if self.rank == self.world - 1 else self.own_hi
+    def top_segment(self, R: int):
+        """First slab of several: the seam row nx-1 is fed by markers near the TOP of the domain, whose
+        windows lie in the wrapped lower halo.  Returns (Segment, marker_lo, marker_hi) or None."""
+        if self.rank == 0 and self.world > 1:
+            return Segment(0, self.halo, self.nx - self.halo), self.nx - R - 3, INT_MAX
+        return None
 
     def main_segment(self) -> Segment:
         a = max(0, -self.row0)
@@ -112,9 +119,6 @@ class DistComm:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def sum_forces(self, forces: Sequence[torch.Tensor]):
-        dist.all_reduce(forces[0], op=dist.ReduceOp.SUM, group=self.group)
-
     def transpose(self, send: Sequence[torch.Tensor], recv: Sequence[torch.Tensor]):
         dist.all_to_all_single(recv[0], send[0], group=self.group)
 
@@ -143,13 +147,6 @@ class LocalComm:
 
     def __init__(self, world: int):
         self.world = world
-
-    def sum_forces(self, forces):
-        total = forces[0].clone()
-        for f in forces[1:]:
-            total += f
-        for f in forces:
-            f.copy_(total)
 
     def transpose(self, send, recv):
         # send[r][d] goes to recv[d][r]
@@ -183,7 +180,12 @@ class SlabRank:
         self.spec_ext = spec.replace(nx=L.nxl, row0=L.row0)
         seg = L.main_segment()
         self.seg = seg
-        self.spec_ib = spec.replace(nx=seg.rows, row0=seg.global0, own_lo=L.marker_lo, own_hi=L.marker_hi)
+        mlo, mhi = L.marker_range(spec.ib_window)
+        self.spec_ib = spec.replace(nx=seg.rows, row0=seg.global0, own_lo=mlo, own_hi=mhi)
+        top = L.top_segment(spec.ib_window)
+        self.top = None if top is None else top[0]
+        self.spec_top = None if top is None else spec.replace(nx=top[0].rows, row0=top[0].global0, own_lo=top[1],
+                                                              own_hi=top[2])
         seam = L.seam_row()
         self.seam = seam
         self.spec_seam = None if seam is None else spec.replace(nx=1, row0=seam.global0)
@@ -220,9 +222,9 @@ class SlabRank:
         if self.bodies is not None:
             ops.ib_marker_force(self.spec_ib, self.bodies, body_state, self._rows(self.us, self.seg),
                                 self._rows(self.vs, self.seg), self.markers)
-
-    def forces(self) -> torch.Tensor:
-        return self.markers[3:5]
+            if self.top is not None:  # markers near the top of the domain feed the first slab's seam row
+                ops.ib_marker_force(self.spec_top, self.bodies, body_state, self._rows(self.us, self.top),
+                                    self._rows(self.vs, self.top), self.markers)
 
     def phase_b(self, body_state: Optional[torch.Tensor]):
         """K3 + K4 + pack."""
@@ -260,8 +262,7 @@ class SlabRank:
         return lo_send, hi_send, lo_recv, hi_recv
 
 
-PHASES = ("predict_force", "x_forces", "spread_rows_fwd", "x_transpose_fwd", "cols", "x_transpose_inv",
-          "rows_inv", "x_halos")
+PHASES = ("predict_force", "spread_rows_fwd", "x_transpose_fwd", "cols", "x_transpose_inv", "rows_inv", "x_halos")
 
 
 def _step(ranks: List[SlabRank], comm, body_state, mark=None):
@@ -270,25 +271,22 @@ def _step(ranks: List[SlabRank], comm, body_state, mark=None):
     for r in ranks:
         r.phase_a(body_state)
     mark(0)
-    if ranks[0].bodies is not None:
-        comm.sum_forces([r.forces() for r in ranks])
-    mark(1)
     for r in ranks:
         r.phase_b(body_state)
-    mark(2)
+    mark(1)
     comm.transpose([r.send for r in ranks], [r.recv for r in ranks])
-    mark(3)
+    mark(2)
     for r in ranks:
         r.phase_c()
-    mark(4)
+    mark(3)
     comm.transpose([r.send2 for r in ranks], [r.recv2 for r in ranks])
-    mark(5)
+    mark(4)
     for r in ranks:
         r.phase_d()
-    mark(6)
+    mark(5)
     views = [r.halo_views() for r in ranks]
     comm.halos(*[[v[k] for v in views] for k in range(4)])
-    mark(7)
+    mark(6)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,7 +305,7 @@ class PeerBlock:
         L = layout
         sizes = [("u", L.nxl * L.ny * 4), ("v", L.nxl * L.ny * 4), ("p", L.nxl * L.ny * 4),
                  ("markers", 5 * max(n_markers, 1) * 4), ("colbuf", L.nx * L.cpr * 8),
-                 ("flags", self.FLAG_WORDS * 4)]
+                 ("specbuf", (L.nloc + 1) * L.sp * 8), ("flags", self.FLAG_WORDS * 4)]
         self.offset, off = {}, 0
         for name, nbytes in sizes:
             self.offset[name] = off
@@ -347,7 +345,7 @@ class PeerRank:
         sl = _lib.Slab()
         sl.world, sl.rank, sl.halo, sl.cpr = L.world, L.rank, L.halo, L.cpr
         for d, base in enumerate(base_ptrs):
-            for name in ("u", "v", "p", "colbuf", "flags"):
+            for name in ("u", "v", "p", "colbuf", "specbuf", "flags"):
                 getattr(sl, name)[d] = base + block.offset[name]
             sl.markers[d] = base + block.offset["markers"] if M else None
         self.c_slab = sl
@@ -407,9 +405,9 @@ class SlabStepper:
         self.spec = spec
         self.device = torch.device(device)
         self.particles = particles
-        self.halo = spec.ib_window + 4 if halo is None else halo
-        if self.halo < spec.ib_window + 3:
-            raise ValueError(f"halo {self.halo} < ib_window + 3: marker windows would leave the slab")
+        self.halo = 2 * spec.ib_window + 4 if halo is None else halo
+        if self.halo < 2 * spec.ib_window + 4:
+            raise ValueError(f"halo {self.halo} < 2 * ib_window + 4: marker windows would leave the slab")
         bodies = engine.get_bodies(particles, self.device) if particles is not None else None
         self.peer = bool(peer)
         self.virtual = bool(virtual) or not dist.is_initialized()
@@ -460,7 +458,7 @@ class SlabStepper:
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
-                names = ("predict_force+barrier", "spread_rows_fwd+barrier", "cols+barrier", "rows_inv+barrier")
+                names = ("predict_force", "spread_rows_fwd+barrier", "cols_push+barrier", "rows_inv+barrier")
                 evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsteps)]
                 for n in range(nsteps):
                     evs[n][0].record()

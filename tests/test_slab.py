@@ -15,7 +15,7 @@ from jax_ib_b200 import slab  # noqa: E402
 
 
 # ---- CPU: layout --------------------------------------------------------------------------------
-@pytest.mark.parametrize("nx,ny,world,halo", [(64, 64, 1, 10), (64, 32, 2, 10), (256, 128, 4, 10), (8192, 8192, 8, 10)])
+@pytest.mark.parametrize("nx,ny,world,halo", [(64, 64, 1, 16), (64, 32, 2, 16), (256, 128, 4, 16), (8192, 8192, 8, 16)])
 def test_layout_covers_every_row_once(nx, ny, world, halo):
     owned = []
     for r in range(world):
@@ -39,15 +39,23 @@ def test_layout_covers_every_row_once(nx, ny, world, halo):
         for d in range(world):
             assert list(idx[d]) == [(d * L.nloc + i) % nx for i in range(L.nloc + 1)]
     assert owned == list(range(nx))
-    assert slab.SlabLayout(nx, ny, world, 0, halo).marker_lo < -10 ** 9
-    assert slab.SlabLayout(nx, ny, world, world - 1, halo).marker_hi > 10 ** 9
+    # markers a slab needs: everything within R + 2 rows of its block; the outer slabs take the off-grid ones
+    R = 6
+    first, last = slab.SlabLayout(nx, ny, world, 0, halo), slab.SlabLayout(nx, ny, world, world - 1, halo)
+    assert first.marker_range(R)[0] < -10 ** 9 and last.marker_range(R)[1] > 10 ** 9
+    if world > 1:
+        assert first.marker_range(R)[1] == first.own_hi + R and last.marker_range(R)[0] == last.own_lo - R - 2
+        seg, lo, hi = first.top_segment(R)
+        assert (seg.start, seg.rows, seg.global0) == (0, halo, nx - halo) and lo == nx - R - 3 and hi > 10 ** 9
+    else:
+        assert first.top_segment(R) is None
 
 
 def test_layout_rejects_bad_splits():
     with pytest.raises(ValueError):
         slab.SlabLayout(100, 64, 3, 0, 10)
     with pytest.raises(ValueError):
-        slab.SlabLayout(64, 64, 8, 0, 10)  # halo deeper than the slab
+        slab.SlabLayout(64, 64, 8, 0, 16)  # halo deeper than the slab
 
 
 def _fake_exchange_buffers(world, nloc, cpr, halo, ny, seed=0):
@@ -73,7 +81,6 @@ def _local_reference(world, nloc, cpr, halo, ny):
     comm = slab.LocalComm(world)
     recv = [torch.zeros_like(b["send"]) for b in bufs]
     comm.transpose([b["send"] for b in bufs], recv)
-    comm.sum_forces([b["force"] for b in bufs])
     views = [_halo_views(b["fields"], halo, nloc) for b in bufs]
     comm.halos(*[[v[k] for v in views] for k in range(4)])
     return bufs, recv
@@ -86,9 +93,6 @@ def test_local_comm_semantics():
     for d in range(world):
         for r in range(world):
             assert torch.equal(recv[d][r], orig[r]["send"][d])
-    total = sum(o["force"] for o in orig)
-    for b in bufs:
-        assert torch.allclose(b["force"], total)
     for r in range(world):
         nxt, prev = (r + 1) % world, (r - 1) % world
         for k in range(3):
@@ -106,7 +110,6 @@ def _gloo_worker(rank, world, port, q):
         comm = slab.DistComm()
         recv = torch.zeros_like(mine["send"])
         comm.transpose([mine["send"]], [recv])
-        comm.sum_forces([mine["force"]])
         views = _halo_views(mine["fields"], halo, nloc)
         comm.halos(*[[v] for v in views])
         q.put((rank, recv.numpy(), mine["force"].numpy(), [f.numpy() for f in mine["fields"]]))
@@ -132,7 +135,6 @@ def test_dist_comm_matches_local_comm_gloo():
     bufs, recv_ref = _local_reference(world, 4, 8, 2, 6)
     for r in range(world):
         np.testing.assert_array_equal(got[r][0], recv_ref[r].numpy())
-        np.testing.assert_allclose(got[r][1], bufs[r]["force"].numpy(), rtol=1e-6)
         for k in range(3):
             np.testing.assert_array_equal(got[r][2][k], bufs[r]["fields"][k].numpy())
 
