@@ -363,6 +363,11 @@ def run_b200(args, rank, world, local_rank):
     stage_ms = {k: prof[k] / K for k in ops.STAGES}
     dom = max(ALGO_BYTES, key=lambda k: stage_ms[k])
     achieved = ALGO_BYTES[dom] * cells / (stage_ms[dom] * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (ib2048 only)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if args.workload == "ib2048" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -380,7 +385,7 @@ def run_b200(args, rank, world, local_rank):
                           "frac_back_to_back": STEP_BYTES * cells * K / (ms_warm * 1e-3) / 1e9 / hbm_peak},
         "stage_us": {k: round(v * 1e3, 2) for k, v in stage_ms.items()},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * cells},
         "clocks": clocks,
         "gpu_launches": stepper.launches_per_step * K,
