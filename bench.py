@@ -218,12 +218,14 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
             barrier()
             return max_over_ranks(e0.elapsed_time(e1))
 
-        # baseline: the same kernels with NCCL collectives between them (all-reduce, 2 all-to-all, send/recv)
+        # baseline: the same kernels with NCCL collectives between them (2 all-to-all + pack copies, send/recv)
         st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device)
-        ms_nccl = timed(st)
-        st.advance(K, profile=True)
-        phases = {k: round(max_over_ranks(v) / K * 1e3, 1) for k, v in st.last_profile.items()}
         L = st.ranks[0].lay
+        ms_nccl = None
+        if not os.environ.get("JAXIB_BENCH_SKIP_NCCL"):
+            ms_nccl = timed(st)
+            st.advance(K, profile=True)
+            phases = {k: round(max_over_ranks(v) / K * 1e3, 1) for k, v in st.last_profile.items()}
         del st
         torch.cuda.empty_cache()
         # product: exchanges fused into the kernels as NVLink stores to peer-mapped memory + flag barriers
@@ -249,9 +251,9 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
            "scaling": "strong", "steps": K, "ms_per_step": ms / K, "value": cells * K / (ms * 1e-3) / 1e6,
            "unit": UNIT, "finite": finite, "how": how,
            "l2": "state (5 fields + spectrum buffers) per GPU exceeds the 126 MB L2; steps run back to back"}
+    if world > 1 and peer_phases:
+        out["phase_us_max_over_ranks"] = peer_phases
     if phases:
-        if peer_phases:
-            out["phase_us_max_over_ranks"] = peer_phases
         out["nccl_path"] = {"ms_per_step": ms_nccl / K, "value": cells * K / (ms_nccl * 1e-3) / 1e6,
                             "phase_us_max_over_ranks": phases}
     return out

@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/jaxib_b200.h: argument checking, scratch carving
 // and the fused step driver.  Nothing here synchronises; every call only enqueues on `stream`.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <initializer_list>
@@ -17,6 +18,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled(int kernel_bit) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* m = getenv("JAXIB_PDL_MASK");
+    mask = getenv("JAXIB_NO_PDL") ? 0 : (m ? atoi(m) : 0x7fffffff);
+  }
+  return (mask & kernel_bit) != 0;
 }
 
 int check_launch(const char* what) {

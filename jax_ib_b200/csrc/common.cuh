@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/jaxib_b200.h"
 
@@ -77,6 +78,31 @@ __device__ __forceinline__ float2* spec_addr(const SpecScatter& S, int i, int k)
 void set_error(const char* fmt, ...);
 int check_grid(const jaxib_grid* g);
 int check_launch(const char* what);
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The kernels of a step form a dependency chain on one stream.  Launched with the programmatic
+// stream-serialisation attribute, kernel N+1 may be scheduled while the last wave of kernel N is
+// still running: its CTAs run their prologue (index arithmetic, twiddle tables into registers /
+// shared memory -- nothing kernel N writes) and then block in pdl_wait() until kernel N has
+// completed and flushed.  Every kernel calls pdl_trigger() first thing, and touches no global data
+// of the chain (and writes nothing at all) before pdl_wait().  JAXIB_NO_PDL=1 restores plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled(int kernel_bit);  // JAXIB_PDL_MASK (default all) selects the kernels launched this way
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int kernel_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(kernel_bit) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- FFT plan (poisson.cu) ----------------------------------------------------------------
 constexpr int kMaxStages = 16;

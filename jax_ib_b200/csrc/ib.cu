@@ -126,6 +126,8 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
                                     const float* __restrict__ body_state, const float* __restrict__ u_star,
                                     const float* __restrict__ v_star, float* __restrict__ markers) {
   // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel
+  pdl_trigger();
+  pdl_wait();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gw = wid >> 1, comp = wid & 1;
   const int total = g.batch * n_markers;
@@ -252,6 +254,8 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
                      const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
                      int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star) {
   __shared__ SpreadShared sh;
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
@@ -346,11 +350,11 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   const long long total = (long long)g.batch * b.n_markers * 2 * 32;
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
   if (g.R == 6)
-    interp_force_kernel<6><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers);
+    launch_pdl(2, interp_force_kernel<6>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
+               b.y0, body_state, u_star, v_star, markers);
   else
-    interp_force_kernel<0><<<nblk, threads, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, b.x0, b.y0, body_state,
-                                                     u_star, v_star, markers);
+    launch_pdl(2, interp_force_kernel<0>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
+               b.y0, body_state, u_star, v_star, markers);
   return check_launch("interp_force_kernel");
 }
 
@@ -362,8 +366,8 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
   const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
   const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
   dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
-  spread_bodies_kernel<<<grid, block, 0, s>>>(g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
-                                              half_extent, tiles, u_star, v_star);
+  launch_pdl(4, spread_bodies_kernel, grid, block, 0, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
+             half_extent, tiles, u_star, v_star);
   return check_launch("spread_bodies_kernel");
 }
 

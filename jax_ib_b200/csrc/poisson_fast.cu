@@ -94,6 +94,17 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   float2* const tw2 = tws + N;
 
   {  // pass 1 forward: global -> registers -> shared
+    // prologue (independent of the previous kernel): the twiddle tables; then wait for the spectrum
+    // CTAs of the first wave may start under the tail of the previous kernel: they fill the tables before
+    // waiting for it; later waves fill them while their column loads are in flight
+    pdl_trigger();
+    const bool early = (int)blockIdx.x < P.first_wave;
+    auto fill_tables = [&]() {
+      for (int e = threadIdx.x; e < N; e += blockDim.x) tws[e] = __ldg(tw + e);
+      for (int e = threadIdx.x; e < R3 * R2; e += blockDim.x) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
+    };
+    if (early) fill_tables();
+    pdl_wait();
     float2 va[R1], vb[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
@@ -102,9 +113,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
     }
-    // fill the tables while the column loads are in flight
-    for (int e = threadIdx.x; e < N; e += blockDim.x) tws[e] = __ldg(tw + e);
-    for (int e = threadIdx.x; e < R3 * R2; e += blockDim.x) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
+    if (!early) fill_tables();
     __syncthreads();
     Dft<R1>::run(va);
     Dft<R1>::run(vb);
@@ -291,6 +300,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
   constexpr int N = Gm::N, S1 = Gm::S1;
   // shared memory: FFT row (Gm::PITCH float2) | u rows i-1 / i (2 x ny floats, rotating) | v row i (ny floats)
   extern __shared__ float2 row[];
+  pdl_trigger();
   const GridF& g = P.g;
   const int ny = g.ny;
   float* const stage = reinterpret_cast<float*>(row + Gm::PITCH + 1);
@@ -313,6 +323,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
   float2 tw1[R1];
 #pragma unroll
   for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
+  pdl_wait();  // everything above is independent of the previous kernel (twiddle prologue)
   // cp.async pipeline: the rows of step i+1 stream into shared memory while row i is transformed
   // slab mode (nx_global > 0): the rows are open -- u row -1 / spectrum row nx sit next to the arrays (halo)
   const ptrdiff_t im1 = (i0 == 0 && g.nx_global == 0) ? g.nx - 1 : i0 - 1;
@@ -388,6 +399,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   constexpr int N = Gm::N, S1 = Gm::S1;
   // shared memory (float2 units): two FFT rows | staged spectrum row (N + 4)
   extern __shared__ float2 rows_sm[];
+  pdl_trigger();
   float2* const spec_s = rows_sm + 2 * Gm::PITCH;  // 16-byte aligned: 2 * PITCH float2 = multiple of 16 B
   const GridF& g = P.g;
   const int ny = g.ny;
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
 #pragma unroll
   for (int r = 1; r < R1; ++r) tw1[r] = __ldg(tw + 2 * b * r);
   float2 zprev[R1];
+  pdl_wait();  // twiddle prologue done; the spectrum is the previous kernel's output
   // cp.async pipeline: the next spectrum row streams into shared memory behind the FFT passes
   copy_async(spec_s, spec + (size_t)i0 * P.sp, spec_bytes, b, S1);
   cp_async_commit();
@@ -526,6 +539,13 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
   while (pairs > 1 && (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024)) pairs /= 2;
   const size_t smem = pairs * (size_t)N * sizeof(float4) + tables;
   dim3 grid((P.ncols + 2 * pairs - 1) / (2 * pairs), batch);
+  FastColParams Q = P;
+  {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
+    Q.first_wave = sms * per_sm;
+  }
   // the opt-in for > 48 KB dynamic shared memory is set once per instantiation (idempotent; a
   // driver call on every launch costs several microseconds of host time on the critical path)
   static bool configured[5] = {false, false, false, false, false};
@@ -537,11 +557,11 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
     configured[pairs] = true;
   }
   if (pairs == 4) {
-    cols_fast_kernel<R1, R2, R3, 4><<<grid, 4 * (N / R1), smem, s>>>(P, spec);
+    launch_pdl(16, cols_fast_kernel<R1, R2, R3, 4>, grid, dim3(4 * (N / R1)), smem, s, Q, spec);
   } else if (pairs == 2) {
-    cols_fast_kernel<R1, R2, R3, 2><<<grid, 2 * (N / R1), smem, s>>>(P, spec);
+    launch_pdl(16, cols_fast_kernel<R1, R2, R3, 2>, grid, dim3(2 * (N / R1)), smem, s, Q, spec);
   } else {
-    cols_fast_kernel<R1, R2, R3, 1><<<grid, N / R1, smem, s>>>(P, spec);
+    launch_pdl(16, cols_fast_kernel<R1, R2, R3, 1>, grid, dim3(N / R1), smem, s, Q, spec);
   }
   return check_launch("cols_fast_kernel");
 }
@@ -555,7 +575,7 @@ int launch_rows_fwd_t(cudaStream_t s, const FastRowParams& P, const float* u, co
     cudaFuncSetAttribute(rows_fwd_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  rows_fwd_fast_kernel<R1, R2, R3><<<grid, R2 * R3, smem, s>>>(P, u, v, spec);
+  launch_pdl(8, rows_fwd_fast_kernel<R1, R2, R3>, grid, dim3(R2 * R3), smem, s, P, u, v, spec);
   return check_launch("rows_fwd_fast_kernel");
 }
 
@@ -570,10 +590,13 @@ int launch_rows_inv_t(cudaStream_t s, const FastRowParams& P, const float2* spec
     cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
+  // measured: behind the 8192-row column kernel (one 196 KB CTA per SM) an early-launched K6 costs 5 % of
+  // the step; everywhere else (smaller grids, slab mode: K6 follows the barrier kernel) it gains 1-6 %
+  const int pdl_bit = (P.g.nx_global == 0 && P.g.nx >= 8192) ? 0 : 32;
   if (project)
-    rows_inv_fast_kernel<R1, R2, R3, true><<<grid, R2 * R3, smem, s>>>(P, spec, u, v, p, uo, vo, po);
+    launch_pdl(pdl_bit, rows_inv_fast_kernel<R1, R2, R3, true>, grid, dim3(R2 * R3), smem, s, P, spec, u, v, p, uo, vo, po);
   else
-    rows_inv_fast_kernel<R1, R2, R3, false><<<grid, R2 * R3, smem, s>>>(P, spec, u, v, p, uo, vo, po);
+    launch_pdl(pdl_bit, rows_inv_fast_kernel<R1, R2, R3, false>, grid, dim3(R2 * R3), smem, s, P, spec, u, v, p, uo, vo, po);
   return check_launch("rows_inv_fast_kernel");
 }
 

@@ -10,6 +10,7 @@ struct FastColParams {
   const float* lam_x_pos;   // float32(lx[freq(p)]) in digit-reversed position order
   const float* lam_y;       // float32(ly_l), padded to sp entries
   int dbg;                  // timing experiments only (JAXIB_DBG)
+  int first_wave;           // CTAs that may start early under PDL (set by the launcher)
 };
 
 struct FastRowParams {

@@ -37,6 +37,8 @@ struct BarrierArgs {
 };
 
 __global__ void slab_barrier_kernel(BarrierArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int t = threadIdx.x;
   if (t >= a.world) return;
   // everything this GPU stored before (earlier kernels of the stream, local or over NVLink) becomes
@@ -64,7 +66,7 @@ int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epo
   for (int d = 0; d < sl.world; ++d) a.flags[d] = sl.flags[d];
   a.world = sl.world; a.rank = sl.rank; a.slot = slot; a.epoch = epoch;
   a.timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
-  slab_barrier_kernel<<<1, 32, 0, s>>>(a);
+  launch_pdl(64, slab_barrier_kernel, dim3(1), dim3(32), 0, s, a);
   return check_launch("slab_barrier_kernel");
 }
 
@@ -86,6 +88,8 @@ struct PushArgs {
 constexpr int kPushMaxVec = 12;  // float4 per lane per row chunk: cpr <= 2 * 32 * 12 = 768 columns per pass
 
 __global__ void __launch_bounds__(256) slab_push_kernel(PushArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -244,7 +248,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
           break;
         case 2:
           if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr))) return rc;
-          slab_push_kernel<<<push_ctas, 256, 0, s>>>(pa);
+          launch_pdl(64, slab_push_kernel, dim3(push_ctas), dim3(256), 0, s, pa);
           if ((rc = check_launch("slab_push_kernel"))) return rc;
           break;
         case 3:

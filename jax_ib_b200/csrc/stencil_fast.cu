@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(FT) explicit_upwind_periodic_kernel(GridF g, i
                                                                      const float* __restrict__ perm,
                                                                      float* __restrict__ out_u,
                                                                      float* __restrict__ out_v) {
+  pdl_trigger();
+  pdl_wait();
   const size_t plane = (size_t)g.nx * g.ny;
   const size_t boff = (size_t)blockIdx.z * plane;
   u += boff; v += boff; out_u += boff; out_v += boff;
@@ -216,9 +218,9 @@ bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const 
   rpc = rpc < 4 ? 4 : (rpc > 32 ? 32 : rpc);
   dim3 grid(strips, (g.nx + rpc - 1) / rpc, g.batch);
   if (predictor)
-    explicit_upwind_periodic_kernel<true><<<grid, FT, 0, s>>>(g, rpc, u, v, p, perm, out_u, out_v);
+    launch_pdl(1, explicit_upwind_periodic_kernel<true>, grid, dim3(FT), 0, s, g, rpc, u, v, p, perm, out_u, out_v);
   else
-    explicit_upwind_periodic_kernel<false><<<grid, FT, 0, s>>>(g, rpc, u, v, nullptr, perm, out_u, out_v);
+    launch_pdl(1, explicit_upwind_periodic_kernel<false>, grid, dim3(FT), 0, s, g, rpc, u, v, (const float*)nullptr, perm, out_u, out_v);
   *rc = check_launch("explicit_upwind_periodic_kernel");
   return true;
 }
