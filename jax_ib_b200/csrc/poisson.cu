@@ -42,7 +42,8 @@ struct jaxib_plan {
   size_t row_smem, col_smem;
   // power-of-two fast paths (poisson_fast.cu)
   bool fast_rows, fast_cols;
-  int fast_rows_per_group;
+  int fast_rows_per_group;      // K4
+  int fast_rows_per_group_inv;  // K6 (each group also transforms the row after its last one)
   float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
   float* lam_y_f;
   float2* tw_dct;      // channel: exp(-i pi k / (2 ny))
@@ -416,7 +417,7 @@ StageParams stage_params(const jaxib_plan* pl, int sp) {
   S.rp.sp = sp > 0 ? sp : n2 + 4;
   S.rp.scale = (float)(1.0 / (nxg * (double)n2));
   S.rgrid = dim3((g.nx + pl->rows_per_cta - 1) / pl->rows_per_cta, g.batch);
-  S.frp.g = g; S.frp.tw = pl->tw_row; S.frp.sp = S.rp.sp; S.frp.rows_per_group = pl->fast_rows_per_group;
+  S.frp.g = g; S.frp.tw = pl->tw_row; S.frp.sp = S.rp.sp; S.frp.rows_per_group = pl->fast_rows_per_group;  // launch_rows_inv overrides with the K6 value
   S.frp.scale = S.rp.scale;
   memset(&S.frp.sc, 0, sizeof(S.frp.sc));
   memset(&S.frp.ho, 0, sizeof(S.frp.ho));
@@ -497,8 +498,10 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum,
       rows_inv_dct_kernel<true><<<S.rgrid, pl->row_threads, smem, s>>>(S.dp, spectrum, u, v, p, u_out, v_out, p_out);
     return check_launch("rows_inv_dct_kernel");
   }
-  if (pl->fast_rows)
+  if (pl->fast_rows) {
+    S.frp.rows_per_group = pl->fast_rows_per_group_inv;
     return launch_rows_inv_fast(s, S.frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
+  }
   if (q_only)
     rows_inv_kernel<false><<<S.rgrid, pl->row_threads, 2 * pl->row_smem, s>>>(S.rp, spec, nullptr, nullptr, nullptr,
                                                                              nullptr, nullptr, q_only);
@@ -600,10 +603,31 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   long long rows_total = (long long)nx * pl->gf.batch;
   int rpc = (int)(rows_total / (3LL * sms));
   pl->rows_per_cta = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
-  {  // fast row kernels: one row group per CTA; aim at >= 4 CTAs per SM, at most 8 rows each
+  {  // fast row kernels: one row group per CTA, `rpg` rows in sequence.  Wave-quantisation model, checked
+     // against a sweep on B200 (tools/tune_rows.py): time ~ waves * (rpg + 1 [+ 1 for K6's extra row]),
+     // waves = ceil(groups / resident CTAs).  E.g. a 1024-row slab of 8192 columns: 3 rows/CTA = 342 CTAs =
+     // 3 waves (53 us) vs 7 rows/CTA = 147 CTAs = 1 wave (43 us).
+    auto pick = [&](bool inverse) {
+      const long long slots = (long long)sms * (pl->fast_rows ? fast_rows_ctas_per_sm(ny, inverse) : 1);
+      int best = 1;
+      long long best_cost = -1;
+      for (int rpg = 1; rpg <= 12; ++rpg) {
+        const long long groups = ((nx + rpg - 1) / rpg) * (long long)pl->gf.batch;
+        const long long waves = (groups + slots - 1) / slots;
+        const long long cost = waves * (rpg + 1 + (inverse ? 1 : 0));
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rpg; }
+      }
+      return best;
+    };
     const char* e = getenv("JAXIB_ROWS_PER_GROUP");
-    int rpg = e ? atoi(e) : (int)((rows_total + 3LL * sms - 1) / (3LL * sms));
-    pl->fast_rows_per_group = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
+    pl->fast_rows_per_group = e ? atoi(e) : pick(false);
+    pl->fast_rows_per_group_inv = e ? atoi(e) : pick(true);
+    if (pl->fast_rows_per_group < 1) pl->fast_rows_per_group = 1;
+    if (pl->fast_rows_per_group_inv < 1) pl->fast_rows_per_group_inv = 1;
+    const char* ef = getenv("JAXIB_RPG_FWD");
+    const char* ei = getenv("JAXIB_RPG_INV");
+    if (ef) pl->fast_rows_per_group = atoi(ef);
+    if (ei) pl->fast_rows_per_group_inv = atoi(ei);
   }
   const size_t col_bytes = (size_t)(padi(nx) + 1) * sizeof(float2);
   int cpc = 4;

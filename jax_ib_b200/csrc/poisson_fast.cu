@@ -643,6 +643,32 @@ int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* 
     default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
   }
 
+// resident CTAs per SM of the row kernels for this row length (wave-quantisation model in plan_create)
+template <int R1, int R2, int R3>
+int rows_ctas_per_sm_t(int ny, bool inverse) {
+  int nb = 1;
+  if (inverse) {
+    const size_t smem = (2 * RowGeom<R1, R2, R3>::PITCH + R1 * R2 * R3 + 4 + R3 * (R2 + 1)) * sizeof(float2);
+    cudaFuncSetAttribute(rows_inv_fast_kernel<R1, R2, R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rows_inv_fast_kernel<R1, R2, R3, true>, R2 * R3, smem);
+  } else {
+    const size_t smem = (RowGeom<R1, R2, R3>::PITCH + 1 + R3 * (R2 + 1)) * sizeof(float2) + 3 * (size_t)ny * sizeof(float);
+    cudaFuncSetAttribute(rows_fwd_fast_kernel<R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rows_fwd_fast_kernel<R1, R2, R3>, R2 * R3, smem);
+  }
+  return nb < 1 ? 1 : nb;
+}
+
+int fast_rows_ctas_per_sm(int ny, bool inverse) {
+  switch (ny / 2) {
+    case 512: return rows_ctas_per_sm_t<8, 8, 8>(ny, inverse);
+    case 1024: return rows_ctas_per_sm_t<8, 16, 8>(ny, inverse);
+    case 2048: return rows_ctas_per_sm_t<8, 16, 16>(ny, inverse);
+    case 4096: return rows_ctas_per_sm_t<16, 16, 16>(ny, inverse);
+    default: return 1;
+  }
+}
+
 int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
 #define CALL_RF(a, b, c) launch_rows_fwd_t<a, b, c>(s, P, u, v, spec)
   JAXIB_DISPATCH_ROWS(P.g.ny / 2, CALL_RF)

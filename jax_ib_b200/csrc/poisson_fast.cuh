@@ -27,6 +27,7 @@ struct FastRowParams {
 bool fast_size_supported(int n);
 bool fast_cols_supported(int n);  // the column kernel also handles 8192
 void fast_radices(int n, int* radix3);
+int fast_rows_ctas_per_sm(int ny, bool inverse);
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec);
 int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec);
 int launch_rows_inv_fast(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,
