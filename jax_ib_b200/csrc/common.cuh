@@ -138,7 +138,9 @@ int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const
 // Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp,
                     const SpecScatter* sc = nullptr);
-int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0);
+int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0,
+                int col_begin = 0);
+void plan_cols_geometry(const jaxib_plan* plan, int* cols_per_cta, int* ctas_per_sm);
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
                     const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only,
                     const HaloOut* ho = nullptr);

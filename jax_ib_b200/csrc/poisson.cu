@@ -455,14 +455,22 @@ int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const 
 bool plan_fast_rows(const jaxib_plan* pl) { return pl->fast_rows; }
 bool plan_fast_cols(const jaxib_plan* pl) { return pl->fast_cols; }
 
-int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0) {
+void plan_cols_geometry(const jaxib_plan* pl, int* cols_per_cta, int* ctas_per_sm) {
+  if (pl->fast_cols) fast_cols_geometry(pl->gf.nx, cols_per_cta, ctas_per_sm);
+  else { *cols_per_cta = pl->cols_per_cta; *ctas_per_sm = 1; }
+}
+
+// col_begin: first column (of the `sp` stored per row) to transform; col0: y-wavenumber of stored column 0
+int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0, int col_begin) {
   const GridF& g = pl->gf;
   const int n2 = g.ny / 2;
   const bool channel = g.bc == JAXIB_BC_CHANNEL;
   if (sp <= 0) sp = n2 + 4;
-  float2* spec = reinterpret_cast<float2*>(spectrum);
+  float2* spec = reinterpret_cast<float2*>(spectrum) + col_begin;
+  col0 += col_begin;
   if (pl->fast_cols) {
     FastColParams fcp;
+    fcp.limit = sp - col_begin;
     fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
     fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0;
     { const char* e = getenv("JAXIB_DBG"); fcp.dbg = e ? atoi(e) : 0; }

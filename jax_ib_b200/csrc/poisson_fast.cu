@@ -84,7 +84,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   const int gpair = threadIdx.x % npairs, gb = threadIdx.x / npairs;
   float4* gcol = smq + gpair * N;
   const int gc = blockIdx.x * 2 * npairs + 2 * gpair;  // first column of this thread's global pair
-  const bool gvalid = gc + 1 < P.sp;                   // the last CTA may overhang the row pitch
+  const bool gvalid = gc + 1 < P.limit;                // the last CTA may overhang the columns of the buffer
   float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + gc);
   const size_t rs = (size_t)P.sp / 2;  // row stride in float4 units
   const float2* __restrict__ tw = P.tw;
@@ -529,8 +529,9 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   }
 }
 
+// column pairs per CTA, shared memory per CTA and resident CTAs per SM of the column kernel
 template <int R1, int R2, int R3>
-int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+void cols_geometry_t(int* pairs_out, size_t* smem_out, int* per_sm_out) {
   constexpr int N = R1 * R2 * R3;
   const size_t tables = (size_t)(N + R3 * (R2 + 1)) * sizeof(float2);
   const char* e = getenv("JAXIB_COL_PAIRS");
@@ -538,12 +539,23 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
   if (pairs != 1 && pairs != 2 && pairs != 4) pairs = 4;
   while (pairs > 1 && (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024)) pairs /= 2;
   const size_t smem = pairs * (size_t)N * sizeof(float4) + tables;
+  int per_sm = (int)((220 * 1024) / smem);
+  const int by_threads = 2048 / (pairs * (N / R1));
+  if (per_sm > by_threads) per_sm = by_threads;
+  *pairs_out = pairs; *smem_out = smem; *per_sm_out = per_sm < 1 ? 1 : per_sm;
+}
+
+template <int R1, int R2, int R3>
+int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+  constexpr int N = R1 * R2 * R3;
+  int pairs, per_sm;
+  size_t smem;
+  cols_geometry_t<R1, R2, R3>(&pairs, &smem, &per_sm);
   dim3 grid((P.ncols + 2 * pairs - 1) / (2 * pairs), batch);
   FastColParams Q = P;
   {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
     Q.first_wave = sms * per_sm;
   }
   // the opt-in for > 48 KB dynamic shared memory is set once per instantiation (idempotent; a
@@ -626,6 +638,21 @@ void fast_radices(int n, int* r) {
     case 8192: return CALL(16, 32, 16);       \
     default: set_error("fast FFT path: unsupported size %d", n); return JAXIB_ERR_UNSUPPORTED; \
   }
+
+void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm) {
+  int pairs = 1, per_sm = 1;
+  size_t smem = 0;
+  switch (nx) {
+    case 512: cols_geometry_t<8, 8, 8>(&pairs, &smem, &per_sm); break;
+    case 1024: cols_geometry_t<8, 8, 16>(&pairs, &smem, &per_sm); break;
+    case 2048: cols_geometry_t<8, 16, 16>(&pairs, &smem, &per_sm); break;
+    case 4096: cols_geometry_t<16, 16, 16>(&pairs, &smem, &per_sm); break;
+    case 8192: cols_geometry_t<16, 32, 16>(&pairs, &smem, &per_sm); break;
+    default: break;
+  }
+  *cols_per_cta = 2 * pairs;
+  *ctas_per_sm = per_sm;
+}
 
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
 #define CALL_COLS(a, b, c) launch_cols_t<a, b, c>(s, P, batch, spec)

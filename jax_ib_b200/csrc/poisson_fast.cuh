@@ -11,6 +11,7 @@ struct FastColParams {
   const float* lam_y;       // float32(ly_l), padded to sp entries
   int dbg;                  // timing experiments only (JAXIB_DBG)
   int first_wave;           // CTAs that may start early under PDL (set by the launcher)
+  int limit;                // columns addressable from `spec` (row pitch minus the column offset)
 };
 
 struct FastRowParams {
@@ -28,6 +29,7 @@ bool fast_size_supported(int n);
 bool fast_cols_supported(int n);  // the column kernel also handles 8192
 void fast_radices(int n, int* radix3);
 int fast_rows_ctas_per_sm(int ny, bool inverse);
+void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm);
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec);
 int launch_rows_fwd_fast(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec);
 int launch_rows_inv_fast(cudaStream_t s, const FastRowParams& P, const float2* spec, const float* u, const float* v,

@@ -22,6 +22,7 @@
 // flag word, then an acquire spin on the own flag words (bounded: a lost peer sets an error word
 // instead of hanging the GPU).  Reuse hazards: a buffer written in phase k of step n+1 was last read
 // in phase k+1 of step n, and every slab passes barrier k+1.. of step n only after that read finished.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -70,6 +71,25 @@ int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epo
   return check_launch("slab_barrier_kernel");
 }
 
+// side stream + events for the overlapped push (one per process: one GPU per process)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+};
+SideStream& side_stream() {
+  static SideStream st;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) st.stream = nullptr;
+    if (st.stream && (cudaEventCreateWithFlags(&st.ev_a, cudaEventDisableTiming) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&st.ev_b, cudaEventDisableTiming) != cudaSuccess))
+      st.stream = nullptr;
+    cudaGetLastError();
+  }
+  return st;
+}
+
 unsigned magic_of(int d) { return (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
 
 // The transpose back: row R of this slab's solved columns [nx][cpr] goes to the spectrum buffer
@@ -83,6 +103,7 @@ struct PushArgs {
   const float2* cols;
   int world, nloc, nx, cpr, sp, col_offset;
   unsigned magic;
+  int c_begin, c_end;  // column sub-range of the cpr local columns moved by this launch
 };
 
 constexpr int kPushMaxVec = 12;  // float4 per lane per row chunk: cpr <= 2 * 32 * 12 = 768 columns per pass
@@ -93,14 +114,15 @@ __global__ void __launch_bounds__(256) slab_push_kernel(PushArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nvec = a.cpr >> 1;  // float4 per row chunk
+  const int nvec = (a.c_end - a.c_begin) >> 1;  // float4 per row chunk
   for (int R = warp; R < a.nx; R += nwarps) {
     const int d = (int)__umulhi((unsigned)R, a.magic);
     const int l = R - d * a.nloc;
-    const float4* src = reinterpret_cast<const float4*>(a.cols + (size_t)R * a.cpr);
-    float4* dst = reinterpret_cast<float4*>(a.spec[d] + (size_t)l * a.sp + a.col_offset);
+    const float4* src = reinterpret_cast<const float4*>(a.cols + (size_t)R * a.cpr + a.c_begin);
+    float4* dst = reinterpret_cast<float4*>(a.spec[d] + (size_t)l * a.sp + a.col_offset + a.c_begin);
     float4* dst2 = nullptr;
-    if (l == 0) dst2 = reinterpret_cast<float4*>(a.spec[d == 0 ? a.world - 1 : d - 1] + (size_t)a.nloc * a.sp + a.col_offset);
+    if (l == 0)
+      dst2 = reinterpret_cast<float4*>(a.spec[d == 0 ? a.world - 1 : d - 1] + (size_t)a.nloc * a.sp + a.col_offset + a.c_begin);
     for (int base = 0; base < nvec; base += 32 * kPushMaxVec) {
       float4 v[kPushMaxVec];
 #pragma unroll
@@ -218,6 +240,17 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int push_ctas = 4 * sms;
+  // split of the column transform into two launches of whole waves (0: one launch)
+  int split_cols = 0;
+  SideStream& side = side_stream();
+  if (!getenv("JAXIB_NO_SPLIT") && side.stream) {
+    int cols_per_cta = 2, per_sm = 1;
+    plan_cols_geometry(plan_cols, &cols_per_cta, &per_sm);
+    const int ctas = (cpr + cols_per_cta - 1) / cols_per_cta, slots = sms * per_sm;
+    const int waves = (ctas + slots - 1) / slots;
+    if (waves >= 2) split_cols = ((waves + 1) / 2) * slots * cols_per_cta;
+    if (split_cols >= cpr) split_cols = 0;
+  }
   const size_t state_stride = has_ib ? (size_t)bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
 
   for (int n = 0; n < nsteps; ++n) {
@@ -247,8 +280,24 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
           if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
           break;
         case 2:
-          if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr))) return rc;
-          launch_pdl(64, slab_push_kernel, dim3(push_ctas), dim3(256), 0, s, pa);
+          if (split_cols > 0) {
+            // K5 in two launches of whole waves; the push of the first part runs on a side stream under
+            // the second K5 launch (the push is NVLink-bound and needs few SMs, K5 is latency-bound)
+            if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, split_cols, me * cpr, 0))) return rc;
+            cudaEventRecord(side.ev_a, s);
+            if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr - split_cols, me * cpr, split_cols))) return rc;
+            cudaStreamWaitEvent(side.stream, side.ev_a, 0);
+            pa.c_begin = 0; pa.c_end = split_cols;
+            slab_push_kernel<<<push_ctas, 256, 0, side.stream>>>(pa);
+            cudaEventRecord(side.ev_b, side.stream);
+            pa.c_begin = split_cols; pa.c_end = cpr;
+            launch_pdl(64, slab_push_kernel, dim3(push_ctas), dim3(256), 0, s, pa);
+            cudaStreamWaitEvent(s, side.ev_b, 0);
+          } else {
+            if ((rc = launch_cols(s, plan_cols, sl.colbuf[me], cpr, cpr, me * cpr))) return rc;
+            pa.c_begin = 0; pa.c_end = cpr;
+            launch_pdl(64, slab_push_kernel, dim3(push_ctas), dim3(256), 0, s, pa);
+          }
           if ((rc = check_launch("slab_push_kernel"))) return rc;
           break;
         case 3:

@@ -201,6 +201,25 @@ def test_peer_memory_slabs_match_single_gpu_bitwise(n, world):
 
 
 @pytest.mark.gpu
+def test_peer_memory_slabs_8192_rows_split_column_transform():
+    """Nx = 8192, 520 spectrum columns per slab: the radix 16x32x16 column kernel (one CTA per SM, 260 CTAs)
+    runs in two launches of whole waves and the push of the first part overlaps the second launch on a side
+    stream (csrc/slab.cu phase 2)."""
+    from jax_ib_b200 import configs
+    cfg = configs.ib_periodic(8192, 1, dx=0.025)
+    cfg["shape"] = (8192, 2048)
+    cfg["domain"] = ((0.0, 8192 * 0.025), (0.0, 2048 * 0.025))
+    cfg["bodies"]["centers"] = [[0.5 * 8192 * 0.025, 0.5 * 2048 * 0.025]]  # on the slab boundary
+    assert slab.SlabLayout(8192, 2048, 2, 0, 16).cpr == 520
+    steps = 3
+    ref = _single_gpu(cfg, steps)
+    got = _virtual(cfg, steps, 2, peer=True)
+    for name, a, b in zip("uvp", got, ref):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+
+
+@pytest.mark.gpu
 def test_peer_memory_slabs_without_bodies():
     from jax_ib_b200 import configs
     cfg = dict(configs.ib_periodic(1024, 1), bodies=None)
