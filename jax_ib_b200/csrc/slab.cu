@@ -74,7 +74,7 @@ int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epo
 // side stream + events for the overlapped push (one per process: one GPU per process)
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
 };
 SideStream& side_stream() {
   static SideStream st;
@@ -83,7 +83,9 @@ SideStream& side_stream() {
     tried = true;
     if (cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) st.stream = nullptr;
     if (st.stream && (cudaEventCreateWithFlags(&st.ev_a, cudaEventDisableTiming) != cudaSuccess ||
-                      cudaEventCreateWithFlags(&st.ev_b, cudaEventDisableTiming) != cudaSuccess))
+                      cudaEventCreateWithFlags(&st.ev_b, cudaEventDisableTiming) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&st.ev_c, cudaEventDisableTiming) != cudaSuccess ||
+                      cudaEventCreateWithFlags(&st.ev_d, cudaEventDisableTiming) != cudaSuccess))
       st.stream = nullptr;
     cudaGetLastError();
   }
@@ -260,11 +262,19 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
       switch (ph) {
         case 0:
           if ((rc = launch_explicit(s, gf_ext, u, v, p, nullptr, u_star, v_star, true))) return rc;
+          if (has_ib && own_lo == 0 && W > 1) {
+            // first slab of several: forces of the markers at the top of the domain (disjoint marker set) and,
+            // in phase 1, the seam row they feed -- on the side stream, next to the main IB kernels, so that
+            // slab 0 is not 20 us behind the others at every barrier
+            cudaStream_t st = side.stream ? side.stream : s;
+            if (side.stream) {
+              cudaEventRecord(side.ev_c, s);  // K1 done
+              cudaStreamWaitEvent(side.stream, side.ev_c, 0);
+            }
+            if ((rc = launch_ib_marker_force(st, gf_top, *bodies, state, u_star, v_star, sl.markers[me]))) return rc;
+          }
           if (has_ib && (rc = launch_ib_marker_force(s, gf_ib, *bodies, state, u_star + (size_t)seg_a * ny,
                                                      v_star + (size_t)seg_a * ny, sl.markers[me])))
-            return rc;
-          if (has_ib && own_lo == 0 && W > 1 &&
-              (rc = launch_ib_marker_force(s, gf_top, *bodies, state, u_star, v_star, sl.markers[me])))
             return rc;
           break;
         case 1:
@@ -272,10 +282,16 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
             if ((rc = launch_ib_spread_bodies(s, gf_ib, *bodies, state, sl.markers[me], u_star + (size_t)seg_a * ny,
                                               v_star + (size_t)seg_a * ny)))
               return rc;
-            if (own_lo == 0 && (rc = launch_ib_spread_bodies(s, gf_seam, *bodies, state, sl.markers[me],
-                                                             u_star + (size_t)(halo - 1) * ny,
-                                                             v_star + (size_t)(halo - 1) * ny)))
-              return rc;
+            if (own_lo == 0) {
+              const bool aside = W > 1 && side.stream;  // the seam row only depends on the top-marker forces
+              if ((rc = launch_ib_spread_bodies(aside ? side.stream : s, gf_seam, *bodies, state, sl.markers[me],
+                                                u_star + (size_t)(halo - 1) * ny, v_star + (size_t)(halo - 1) * ny)))
+                return rc;
+              if (aside) {
+                cudaEventRecord(side.ev_d, side.stream);
+                cudaStreamWaitEvent(s, side.ev_d, 0);
+              }
+            }
           }
           if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
           break;
