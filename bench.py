@@ -241,9 +241,9 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
         except Exception as e:  # noqa: BLE001  (no peer mapping on this box: report the NCCL path)
             mode, ms_peer = f"nccl (peer-memory mode unavailable: {type(e).__name__}: {e})"[:200], None
             finite = True
-        how = (f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}: marker forces, both spectrum transposes "
+        how = (f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}: both spectrum transposes "
                f"({L.cpr} columns per slab) and the halo rows are stored by the kernels into the consuming GPU's memory "
-               f"over NVLink, 4 flag barriers per step" if ms_peer is not None else
+               f"over NVLink, 3 flag barriers per step, marker forces computed locally from the halo" if ms_peer is not None else
                f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}")
         e_ms = ms_peer if ms_peer is not None else ms_nccl
     ms = max_over_ranks(e0.elapsed_time(e1)) if world == 1 else e_ms
