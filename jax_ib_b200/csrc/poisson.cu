@@ -421,7 +421,6 @@ StageParams stage_params(const jaxib_plan* pl, int sp) {
   S.frp.scale = S.rp.scale;
   memset(&S.frp.sc, 0, sizeof(S.frp.sc));
   memset(&S.frp.ho, 0, sizeof(S.frp.ho));
-  { const char* e = getenv("JAXIB_DBG"); S.frp.dbg = e ? atoi(e) : 0; }  // timing experiments only
   if (S.channel) {
     S.dp.g = g; S.dp.pl = pl->row; S.dp.tw = pl->tw_row; S.dp.twd = pl->tw_dct; S.dp.pos = pl->row_pos;
     S.dp.rows_per_cta = pl->rows_per_cta; S.dp.sp = S.rp.sp;
@@ -473,7 +472,6 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
     fcp.limit = sp - col_begin;
     fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
     fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0;
-    { const char* e = getenv("JAXIB_DBG"); fcp.dbg = e ? atoi(e) : 0; }
     return launch_cols_fast(s, fcp, g.batch, spec);
   }
   ColParams cp;

@@ -109,7 +109,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gvalid && !(P.dbg & 16)) x = g4[(size_t)(gb + r * S1) * rs];
+      if (gvalid) x = g4[(size_t)(gb + r * S1) * rs];
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
     }
@@ -128,7 +128,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
     }
   }
   __syncthreads();
-  if (!(P.dbg & 4)) {
+  {
   // pass 2 forward, one column per thread
 #pragma unroll
   for (int m = 0; m < (2 * R1 + R2 - 1) / R2; ++m) {
@@ -188,7 +188,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
 #pragma unroll
     for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * R3) + cc] = v[r];
   }
-  }  // dbg
+  }
   __syncthreads();
   {  // pass 1 inverse: shared -> registers -> global
     float2 va[R1], vb[R1];
@@ -205,7 +205,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
     }
     dft_dir<R1, true>(va);
     dft_dir<R1, true>(vb);
-    if (gvalid && !(P.dbg & 8)) {
+    if (gvalid) {
 #pragma unroll
       for (int r = 0; r < R1; ++r)
         g4[(size_t)(gb + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
@@ -451,14 +451,14 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
       copy_async(spec_s, spec + (size_t)inext * P.sp, spec_bytes, b, S1);
     }
     cp_async_commit();
-    if (!(P.dbg & 1)) row_inner_passes<R1, R2, R3, true>(cur, tw2, b);
+    row_inner_passes<R1, R2, R3, true>(cur, tw2, b);
     float2 z[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       z[r] = cur[rswz(b + r * S1)];
       if (r > 0) z[r] = cmulc(z[r], tw1[r]);
     }
-    if (!(P.dbg & 1)) dft_dir<R1, true>(z);
+    dft_dir<R1, true>(z);
 #pragma unroll
     for (int r = 0; r < R1; ++r) z[r] = cscale(z[r], P.scale);  // q[i][2n], q[i][2n+1], n = b + r*S1
     if (!PROJECT) {
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
 #pragma unroll
       for (int r = 0; r < R1; ++r) cur[b + r * S1] = z[r];
       __syncthreads();
-      if (ii > i0 && !(P.dbg & 2)) {
+      if (ii > i0) {
         const float2* prv = rows_sm + ((ii - 1 - i0) & 1) * Gm::PITCH;
         const size_t ro = (size_t)(ii - 1) * ny;
         const float2* u2 = reinterpret_cast<const float2*>(u + ro);

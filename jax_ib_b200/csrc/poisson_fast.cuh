@@ -9,7 +9,6 @@ struct FastColParams {
   const float2* tw;         // W_nx^k
   const float* lam_x_pos;   // float32(lx[freq(p)]) in digit-reversed position order
   const float* lam_y;       // float32(ly_l), padded to sp entries
-  int dbg;                  // timing experiments only (JAXIB_DBG)
   int first_wave;           // CTAs that may start early under PDL (set by the launcher)
   int limit;                // columns addressable from `spec` (row pitch minus the column offset)
 };
@@ -19,7 +18,6 @@ struct FastRowParams {
   const float2* tw;  // W_ny^k
   int sp;            // spectrum row pitch (complex values)
   int rows_per_group;
-  int dbg;           // timing experiments only (JAXIB_DBG): bit0 skip FFT passes, bit1 skip finalize
   float scale;       // 1 / (nx * ny/2)
   SpecScatter sc;    // rows_fwd, slab mode: spectrum columns go to the column owners
   HaloOut ho;        // rows_inv, slab mode: boundary rows also go to the neighbours' halos
