@@ -66,7 +66,7 @@ __device__ __forceinline__ int qswz(int p) { return p ^ ((p >> 4) & 7); }
 // thread (8-byte shared accesses), so a radix-16 butterfly costs 32 data registers instead of 64 and
 // every thread has work in every pass.
 template <int R1, int R2, int R3, int NP>
-__global__ void __launch_bounds__(NP * R2 * R3, (NP * R2 * R3 <= 512 && R1 * R2 * R3 <= 4096 ? 2 : 1))
+__global__ void __launch_bounds__(NP * R2 * R3, (NP * R2 * R3 <= 256 ? 2 : 1))
 cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   constexpr int N = R1 * R2 * R3;
   constexpr int S1 = N / R1;   // threads per column pair; stride of pass 1
@@ -76,13 +76,16 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   // inner passes: thread -> (pair, b) blocked, so that a warp stays inside one pair's buffer
   const int pair = threadIdx.x / S1, b = threadIdx.x - pair * S1;
   const int c = blockIdx.x * 2 * npairs + 2 * pair;  // columns c, c+1 (padding columns hold zeros)
-  float4* col = smq + pair * N;
+  // pair buffers are N + 2 float4 apart: with the pair index fastest across lanes a quarter-warp's 16-byte
+  // accesses (4 pairs x 2 rows) then hit 8 different bank groups instead of 2 (4-way conflict measured)
+  constexpr int PQ = N + 2;
+  float4* col = smq + pair * PQ;
   float2* col2 = reinterpret_cast<float2*>(col);
   // global passes: thread -> (b, pair) with the pair index FASTEST, so that adjacent lanes cover the
   // adjacent 16-byte halves of one 32-byte sector of a spectrum row (a warp-wide load then fetches
   // every sector once; with the blocked mapping each sector was fetched by two different warps)
   const int gpair = threadIdx.x % npairs, gb = threadIdx.x / npairs;
-  float4* gcol = smq + gpair * N;
+  float4* gcol = smq + gpair * PQ;
   const int gc = blockIdx.x * 2 * npairs + 2 * gpair;  // first column of this thread's global pair
   const bool gvalid = gc + 1 < P.limit;                // the last CTA may overhang the columns of the buffer
   float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + gc);
@@ -90,7 +93,7 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   const float2* __restrict__ tw = P.tw;
   // twiddle tables in shared memory (coalesced fill): W_N^m for the outer pass, W_N^(b2 r R1) for pass 2.
   // Reading them from global with a lane stride of r*8 bytes costs up to 32 L1 wavefronts per load.
-  float2* const tws = reinterpret_cast<float2*>(smq + npairs * N);
+  float2* const tws = reinterpret_cast<float2*>(smq + npairs * PQ);
   float2* const tw2 = tws + N;
 
   {  // pass 1 forward: global -> registers -> shared
@@ -154,18 +157,21 @@ cols_fast_kernel(FastColParams P, float2* __restrict__ spec) {
     if (w >= 2 * (N / R3)) continue;
     const int cc = w & 1, p0 = (w >> 1) * R3;
     const float ly = P.lam_y[c + cc];
-    float lx[R3];
-#pragma unroll
-    for (int r = 0; r < R3; r += 4) {
-      const float4 l4 = __ldg(reinterpret_cast<const float4*>(P.lam_x_pos + p0 + r));
-      lx[r] = l4.x; lx[r + 1] = l4.y; lx[r + 2] = l4.z; lx[r + 3] = l4.w;
-    }
     float2 v[R3];
 #pragma unroll
     for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r) + cc];
     Dft<R3>::run(v);
+    // eigenvalues are fetched four at a time right where they are used (L1-resident table): holding all
+    // R3 of them across the butterfly cost 16 registers and pushed the 64-register kernel into spills
+    const float4* lx4 = reinterpret_cast<const float4*>(P.lam_x_pos + p0);
 #pragma unroll
-    for (int r = 0; r < R3; ++r) v[r] = cscale(v[r], inv_eig_f(lx[r] + ly));
+    for (int r = 0; r < R3; r += 4) {
+      const float4 l4 = __ldg(lx4 + r / 4);
+      v[r] = cscale(v[r], inv_eig_f(l4.x + ly));
+      v[r + 1] = cscale(v[r + 1], inv_eig_f(l4.y + ly));
+      v[r + 2] = cscale(v[r + 2], inv_eig_f(l4.z + ly));
+      v[r + 3] = cscale(v[r + 3], inv_eig_f(l4.w + ly));
+    }
     dft_dir<R3, true>(v);
 #pragma unroll
     for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r) + cc] = v[r];
@@ -537,8 +543,8 @@ void cols_geometry_t(int* pairs_out, size_t* smem_out, int* per_sm_out) {
   const char* e = getenv("JAXIB_COL_PAIRS");
   int pairs = e ? atoi(e) : 4;  // column pairs (float4) per CTA
   if (pairs != 1 && pairs != 2 && pairs != 4) pairs = 4;
-  while (pairs > 1 && (pairs * (N / R1) > 1024 || pairs * (size_t)N * sizeof(float4) + tables > 220 * 1024)) pairs /= 2;
-  const size_t smem = pairs * (size_t)N * sizeof(float4) + tables;
+  while (pairs > 1 && (pairs * (N / R1) > 1024 || pairs * (size_t)(N + 2) * sizeof(float4) + tables > 220 * 1024)) pairs /= 2;
+  const size_t smem = pairs * (size_t)(N + 2) * sizeof(float4) + tables;
   int per_sm = (int)((220 * 1024) / smem);
   const int by_threads = 2048 / (pairs * (N / R1));
   if (per_sm > by_threads) per_sm = by_threads;
