@@ -234,7 +234,7 @@ struct RowGeom {
   static constexpr int N = R1 * R2 * R3;  // complex length ny/2
   static constexpr int S1 = N / R1;       // threads per row group
   static constexpr int L2 = R2 * R3;
-  static constexpr int PITCH = N + N / 16 + 1;
+  static constexpr int PITCH = N + 16;  // a multiple of 128 bytes: the cp.async staging buffers behind the rows stay line-aligned
   // position of frequency k after the forward DIF (digit reversal of the radix triple)
   __device__ static __forceinline__ int pos(int k) {
     return (k % R1) * L2 + ((k / R1) % R2) * R3 + k / (R1 * R2);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
   pdl_trigger();
   const GridF& g = P.g;
   const int ny = g.ny;
-  float* const stage = reinterpret_cast<float*>(row + Gm::PITCH + 1);
+  float* const stage = reinterpret_cast<float*>(row + Gm::PITCH);
   float* const ubuf[2] = {stage, stage + ny};
   float* const vbuf = stage + 2 * ny;
   const size_t plane = (size_t)g.nx * ny;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P,
   // shared memory (float2 units): two FFT rows | staged spectrum row (N + 4)
   extern __shared__ float2 rows_sm[];
   pdl_trigger();
-  float2* const spec_s = rows_sm + 2 * Gm::PITCH;  // 16-byte aligned: 2 * PITCH float2 = multiple of 16 B
+  float2* const spec_s = rows_sm + 2 * Gm::PITCH;  // 128-byte aligned
   const GridF& g = P.g;
   const int ny = g.ny;
   const size_t plane = (size_t)g.nx * ny;
