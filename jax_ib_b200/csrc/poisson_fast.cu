@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(R2 * R3) rows_fwd_fast_kernel(FastRowParams P,
 
 // K6: inverse packed-real FFT fused with gradient, velocity correction and pressure update.
 template <int R1, int R2, int R3, bool PROJECT>
-__global__ void __launch_bounds__(R2 * R3) rows_inv_fast_kernel(FastRowParams P, const float2* __restrict__ spec,
+__global__ void __launch_bounds__(R2 * R3, (R2 * R3 <= 128 ? 4 : 1)) rows_inv_fast_kernel(FastRowParams P, const float2* __restrict__ spec,
                                                                 const float* u, const float* v, const float* p,
                                                                 float* u_out, float* v_out, float* p_out) {
   using Gm = RowGeom<R1, R2, R3>;
