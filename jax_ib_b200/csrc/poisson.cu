@@ -559,8 +559,8 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   pl->fast_cols = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_cols_supported(nx) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
   if (pl->fast_cols) {
     pl->col.n = nx;
-    pl->col.nstages = 3;
-    fast_radices(nx, pl->col.radix);
+    fast_radices(nx, pl->col.radix);  // three radices, four for nx = 8192
+    pl->col.nstages = pl->col.radix[3] ? 4 : 3;
   }
   const double two_pi = 6.283185307179586476925286766559;
   std::vector<float2> twr(ny), twc(nx);

@@ -12,6 +12,8 @@
 //   rows_fwd_fast (K4) / rows_inv_fast (K6): one 64..256-thread group per row, several rows per CTA
 //                    in sequence; the untangle of the packed real transform reads the digit-reversed
 //                    positions with shifts and masks.
+#include <stdlib.h>
+
 #include "fft.cuh"
 #include "poisson_fast.cuh"
 
@@ -584,6 +586,197 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
   return check_launch("cols_fast_kernel");
 }
 
+// ---- K5 for Nx = 8192: four passes, 1024 threads ----------------------------------------------------
+// The three-pass instantiation (16, 32, 16) needs 128 registers for its radix-32 pass, i.e. 512 threads
+// and 16 warps per SM (one 196 KB CTA): 0.43 MB/us against 0.74 MB/us of the 2048-row kernel.  With
+// radices (8, 8, 8, 16) every butterfly fits the 64 registers of a 1024-thread CTA, at the price of one
+// more trip through shared memory.  One column pair per CTA (128 KB); the pass-1 twiddles W_N^(gb r)
+// are read from global memory (lane stride r * 8 bytes, r < 8: at most 14 sectors per warp load), the
+// inner passes use small shared tables.  Position of frequency k after the forward passes:
+//   (k % 8) * 1024 + ((k / 8) % 8) * 128 + ((k / 64) % 8) * 16 + k / 512   (= the plan's digit reversal).
+template <int R1, int R2, int R3, int R4>
+__global__ void __launch_bounds__(R2 * R3 * R4, 1) cols4_fast_kernel(FastColParams P, float2* __restrict__ spec) {
+  constexpr int N = R1 * R2 * R3 * R4;
+  constexpr int S1 = N / R1;        // threads per CTA = stride of pass 1
+  constexpr int L2 = N / R1;        // block length of pass 2
+  constexpr int L3 = L2 / R2;       // block length of pass 3 = stride of pass 2
+  constexpr int L4 = L3 / R3;       // = R4: block length of pass 4 = stride of pass 3
+  static_assert(L4 == R4, "radix product");
+  extern __shared__ float4 smq[];
+  float4* const col = smq;
+  float2* const col2 = reinterpret_cast<float2*>(smq);
+  float2* const tw2 = reinterpret_cast<float2*>(smq + N);  // [L3][R2 + 1]: W_N^(b r R1)
+  float2* const tw3 = tw2 + L3 * (R2 + 1);                 // [L4][R3 + 1]: W_N^(b r R1 R2)
+  const int gb = threadIdx.x;
+  const int gc = blockIdx.x * 2;
+  const bool gvalid = gc + 1 < P.limit;
+  float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + gc);
+  const size_t rs = (size_t)P.sp / 2;
+  const float2* __restrict__ tw = P.tw;
+
+  pdl_trigger();
+  for (int e = threadIdx.x; e < L3 * R2; e += S1) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
+  for (int e = threadIdx.x; e < L4 * R3; e += S1) tw3[(e / R3) * (R3 + 1) + e % R3] = __ldg(tw + (e / R3) * (e % R3) * R1 * R2);
+  pdl_wait();
+  {  // pass 1 forward: global -> registers -> shared
+    float2 va[R1], vb[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gvalid) x = g4[(size_t)(gb + r * S1) * rs];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+    }
+    Dft<R1>::run(va);
+    Dft<R1>::run(vb);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      if (r > 0) {
+        const float2 w = __ldg(tw + gb * r);
+        va[r] = cmul(va[r], w);
+        vb[r] = cmul(vb[r], w);
+      }
+      col[qswz(gb + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
+  }
+  __syncthreads();
+  // pass 2 forward (radix R2, stride L3), one column per thread
+#pragma unroll
+  for (int m = 0; m < 2 * (N / R2) / S1; ++m) {
+    const int w = gb + m * S1;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / L3, b = bf - blk * L3;
+    const int p0 = blk * L2 + b;
+    float2 v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * L3) + cc];
+    Dft<R2>::run(v);
+#pragma unroll
+    for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], tw2[b * (R2 + 1) + r]);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * L3) + cc] = v[r];
+  }
+  __syncthreads();
+  // pass 3 forward (radix R3, stride L4)
+#pragma unroll
+  for (int m = 0; m < 2 * (N / R3) / S1; ++m) {
+    const int w = gb + m * S1;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / L4, b = bf - blk * L4;
+    const int p0 = blk * L3 + b;
+    float2 v[R3];
+#pragma unroll
+    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r * L4) + cc];
+    Dft<R3>::run(v);
+#pragma unroll
+    for (int r = 1; r < R3; ++r) v[r] = cmul(v[r], tw3[b * (R3 + 1) + r]);
+#pragma unroll
+    for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r * L4) + cc] = v[r];
+  }
+  __syncthreads();
+  // pass 4 forward, diagonal, pass 4 inverse -- in registers
+#pragma unroll
+  for (int m = 0; m < (2 * (N / R4) + S1 - 1) / S1; ++m) {
+    const int w = gb + m * S1;
+    if (w >= 2 * (N / R4)) continue;
+    const int cc = w & 1, p0 = (w >> 1) * R4;
+    const float ly = P.lam_y[gc + cc];
+    float2 v[R4];
+#pragma unroll
+    for (int r = 0; r < R4; ++r) v[r] = col2[2 * qswz(p0 + r) + cc];
+    Dft<R4>::run(v);
+    const float4* lx4 = reinterpret_cast<const float4*>(P.lam_x_pos + p0);
+#pragma unroll
+    for (int r = 0; r < R4; r += 4) {
+      const float4 l4 = __ldg(lx4 + r / 4);
+      v[r] = cscale(v[r], inv_eig_f(l4.x + ly));
+      v[r + 1] = cscale(v[r + 1], inv_eig_f(l4.y + ly));
+      v[r + 2] = cscale(v[r + 2], inv_eig_f(l4.z + ly));
+      v[r + 3] = cscale(v[r + 3], inv_eig_f(l4.w + ly));
+    }
+    dft_dir<R4, true>(v);
+#pragma unroll
+    for (int r = 0; r < R4; ++r) col2[2 * qswz(p0 + r) + cc] = v[r];
+  }
+  __syncthreads();
+  // pass 3 inverse
+#pragma unroll
+  for (int m = 0; m < 2 * (N / R3) / S1; ++m) {
+    const int w = gb + m * S1;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / L4, b = bf - blk * L4;
+    const int p0 = blk * L3 + b;
+    float2 v[R3];
+#pragma unroll
+    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r * L4) + cc];
+#pragma unroll
+    for (int r = 1; r < R3; ++r) v[r] = cmulc(v[r], tw3[b * (R3 + 1) + r]);
+    dft_dir<R3, true>(v);
+#pragma unroll
+    for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r * L4) + cc] = v[r];
+  }
+  __syncthreads();
+  // pass 2 inverse
+#pragma unroll
+  for (int m = 0; m < 2 * (N / R2) / S1; ++m) {
+    const int w = gb + m * S1;
+    const int cc = w & 1, bf = w >> 1;
+    const int blk = bf / L3, b = bf - blk * L3;
+    const int p0 = blk * L2 + b;
+    float2 v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * L3) + cc];
+#pragma unroll
+    for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], tw2[b * (R2 + 1) + r]);
+    dft_dir<R2, true>(v);
+#pragma unroll
+    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * L3) + cc] = v[r];
+  }
+  __syncthreads();
+  {  // pass 1 inverse: shared -> registers -> global
+    float2 va[R1], vb[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const float4 x = col[qswz(gb + r * S1)];
+      va[r] = make_float2(x.x, x.y);
+      vb[r] = make_float2(x.z, x.w);
+      if (r > 0) {
+        const float2 w = __ldg(tw + gb * r);
+        va[r] = cmulc(va[r], w);
+        vb[r] = cmulc(vb[r], w);
+      }
+    }
+    dft_dir<R1, true>(va);
+    dft_dir<R1, true>(vb);
+    if (gvalid) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r)
+        g4[(size_t)(gb + r * S1) * rs] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+    }
+  }
+}
+
+template <int R1, int R2, int R3, int R4>
+int launch_cols4_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+  constexpr int N = R1 * R2 * R3 * R4;
+  const size_t smem = (size_t)N * sizeof(float4) +
+                      ((size_t)(N / R1 / R2) * (R2 + 1) + (size_t)R4 * (R3 + 1)) * sizeof(float2);
+  dim3 grid((P.ncols + 1) / 2, batch);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(cols4_fast_kernel<R1, R2, R3, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    configured = true;
+  }
+  launch_pdl(16, cols4_fast_kernel<R1, R2, R3, R4>, grid, dim3(N / R1), smem, s, P, spec);
+  return check_launch("cols4_fast_kernel");
+}
+
+static bool four_pass_8192() {
+  static int on = -1;
+  if (on < 0) on = getenv("JAXIB_COLS8192_3PASS") == nullptr ? 1 : 0;  // =1: the 512-thread three-pass kernel (A/B)
+  return on == 1;
+}
+
 template <int R1, int R2, int R3>
 int launch_rows_fwd_t(cudaStream_t s, const FastRowParams& P, const float* u, const float* v, float2* spec) {
   dim3 grid((P.g.nx + P.rows_per_group - 1) / P.rows_per_group, P.g.batch);
@@ -629,9 +822,13 @@ void fast_radices(int n, int* r) {
     case 1024: r[0] = 8; r[1] = 8; r[2] = 16; break;
     case 2048: r[0] = 8; r[1] = 16; r[2] = 16; break;
     case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
-    case 8192: r[0] = 16; r[1] = 32; r[2] = 16; break;  // columns only
+    case 8192:  // columns only
+      if (four_pass_8192()) { r[0] = 8; r[1] = 8; r[2] = 8; r[3] = 16; }
+      else { r[0] = 16; r[1] = 32; r[2] = 16; r[3] = 0; }
+      break;
     default: r[0] = r[1] = r[2] = 0;
   }
+  if (n != 8192) r[3] = 0;
 }
 
 // columns: must agree with fast_radices() (the eigenvalue table is stored in this digit order)
@@ -653,7 +850,7 @@ void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm) {
     case 1024: cols_geometry_t<8, 8, 16>(&pairs, &smem, &per_sm); break;
     case 2048: cols_geometry_t<8, 16, 16>(&pairs, &smem, &per_sm); break;
     case 4096: cols_geometry_t<16, 16, 16>(&pairs, &smem, &per_sm); break;
-    case 8192: cols_geometry_t<16, 32, 16>(&pairs, &smem, &per_sm); break;
+    case 8192: cols_geometry_t<16, 32, 16>(&pairs, &smem, &per_sm); break;  // one pair per CTA, one CTA per SM: both kernels
     default: break;
   }
   *cols_per_cta = 2 * pairs;
@@ -661,6 +858,7 @@ void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm) {
 }
 
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
+  if (P.nx == 8192 && four_pass_8192()) return launch_cols4_t<8, 8, 8, 16>(s, P, batch, spec);
 #define CALL_COLS(a, b, c) launch_cols_t<a, b, c>(s, P, batch, spec)
   JAXIB_DISPATCH_COLS(P.nx, CALL_COLS)
 #undef CALL_COLS
@@ -677,6 +875,7 @@ int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* 
   }
 
 // resident CTAs per SM of the row kernels for this row length (wave-quantisation model in plan_create)
+
 template <int R1, int R2, int R3>
 int rows_ctas_per_sm_t(int ny, bool inverse) {
   int nb = 1;

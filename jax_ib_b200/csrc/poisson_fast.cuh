@@ -25,7 +25,7 @@ struct FastRowParams {
 
 bool fast_size_supported(int n);
 bool fast_cols_supported(int n);  // the column kernel also handles 8192
-void fast_radices(int n, int* radix3);
+void fast_radices(int n, int* radix4);  // radix4[3] == 0: three passes
 int fast_rows_ctas_per_sm(int ny, bool inverse);
 void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm);
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec);
