@@ -112,9 +112,10 @@ class FusedStepper:
         dev = self.device
         in_dev = vel[0].data.device
         # first touch: copy (functional semantics: the caller's arrays are never modified)
-        u = vel[0].data.to(dev, dtype=torch.float32, copy=True).contiguous()
-        v = vel[1].data.to(dev, dtype=torch.float32, copy=True).contiguous()
-        p = all_variables.pressure.data.to(dev, dtype=torch.float32, copy=True).contiguous()
+        # (non_blocking: from pinned host arrays the three uploads overlap the host-side kinematics below)
+        u = vel[0].data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
+        v = vel[1].data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
+        p = all_variables.pressure.data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
         t0 = vel[0].bc.time_stamp
         dt = self.spec.dt
         particles = all_variables.particles
