@@ -594,29 +594,37 @@ int launch_cols_t(cudaStream_t s, const FastColParams& P, int batch, float2* spe
 // are read from global memory (lane stride r * 8 bytes, r < 8: at most 14 sectors per warp load), the
 // inner passes use small shared tables.  Position of frequency k after the forward passes:
 //   (k % 8) * 1024 + ((k / 8) % 8) * 128 + ((k / 64) % 8) * 16 + k / 512   (= the plan's digit reversal).
-template <int R1, int R2, int R3, int R4>
-__global__ void __launch_bounds__(R2 * R3 * R4, 1) cols4_fast_kernel(FastColParams P, float2* __restrict__ spec) {
+template <int SW>
+__device__ __forceinline__ int qswz_t(int p) { return p ^ ((p >> SW) & 7); }  // SW = log2(innermost radix)
+
+template <int R1, int R2, int R3, int R4, int NP>
+__global__ void __launch_bounds__(NP * R2 * R3 * R4, 1) cols4_fast_kernel(FastColParams P, float2* __restrict__ spec) {
   constexpr int N = R1 * R2 * R3 * R4;
-  constexpr int S1 = N / R1;        // threads per CTA = stride of pass 1
+  constexpr int S1 = N / R1;        // threads per column pair = stride of pass 1
   constexpr int L2 = N / R1;        // block length of pass 2
   constexpr int L3 = L2 / R2;       // block length of pass 3 = stride of pass 2
   constexpr int L4 = L3 / R3;       // = R4: block length of pass 4 = stride of pass 3
-  static_assert(L4 == R4, "radix product");
+  constexpr int SW = R4 == 16 ? 4 : 3;
+  constexpr int PQ = N + 2;         // pair pitch (see cols_fast_kernel)
+  static_assert(L4 == R4 && (R4 == 8 || R4 == 16), "radix product");
   extern __shared__ float4 smq[];
-  float4* const col = smq;
-  float2* const col2 = reinterpret_cast<float2*>(smq);
-  float2* const tw2 = reinterpret_cast<float2*>(smq + N);  // [L3][R2 + 1]: W_N^(b r R1)
-  float2* const tw3 = tw2 + L3 * (R2 + 1);                 // [L4][R3 + 1]: W_N^(b r R1 R2)
-  const int gb = threadIdx.x;
-  const int gc = blockIdx.x * 2;
+  // inner passes: thread -> (pair, b) blocked; global passes: pair index fastest (see cols_fast_kernel)
+  const int pair = threadIdx.x / S1, bt = threadIdx.x - pair * S1;
+  const int gpair = threadIdx.x % NP, gb = threadIdx.x / NP;
+  float2* const col2 = reinterpret_cast<float2*>(smq + pair * PQ);
+  float4* const gcol = smq + gpair * PQ;
+  float2* const tw2 = reinterpret_cast<float2*>(smq + NP * PQ);  // [L3][R2 + 1]: W_N^(b r R1)
+  float2* const tw3 = tw2 + L3 * (R2 + 1);                       // [L4][R3 + 1]: W_N^(b r R1 R2)
+  const int c = blockIdx.x * 2 * NP + 2 * pair;
+  const int gc = blockIdx.x * 2 * NP + 2 * gpair;
   const bool gvalid = gc + 1 < P.limit;
   float4* g4 = reinterpret_cast<float4*>(spec + (size_t)blockIdx.y * P.nx * P.sp + gc);
   const size_t rs = (size_t)P.sp / 2;
   const float2* __restrict__ tw = P.tw;
 
   pdl_trigger();
-  for (int e = threadIdx.x; e < L3 * R2; e += S1) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
-  for (int e = threadIdx.x; e < L4 * R3; e += S1) tw3[(e / R3) * (R3 + 1) + e % R3] = __ldg(tw + (e / R3) * (e % R3) * R1 * R2);
+  for (int e = threadIdx.x; e < L3 * R2; e += NP * S1) tw2[(e / R2) * (R2 + 1) + e % R2] = __ldg(tw + (e / R2) * (e % R2) * R1);
+  for (int e = threadIdx.x; e < L4 * R3; e += NP * S1) tw3[(e / R3) * (R3 + 1) + e % R3] = __ldg(tw + (e / R3) * (e % R3) * R1 * R2);
   pdl_wait();
   {  // pass 1 forward: global -> registers -> shared
     float2 va[R1], vb[R1];
@@ -636,54 +644,54 @@ __global__ void __launch_bounds__(R2 * R3 * R4, 1) cols4_fast_kernel(FastColPara
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
-      col[qswz(gb + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
+      gcol[qswz_t<SW>(gb + r * S1)] = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
     }
   }
   __syncthreads();
   // pass 2 forward (radix R2, stride L3), one column per thread
 #pragma unroll
   for (int m = 0; m < 2 * (N / R2) / S1; ++m) {
-    const int w = gb + m * S1;
+    const int w = bt + m * S1;
     const int cc = w & 1, bf = w >> 1;
     const int blk = bf / L3, b = bf - blk * L3;
     const int p0 = blk * L2 + b;
     float2 v[R2];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * L3) + cc];
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz_t<SW>(p0 + r * L3) + cc];
     Dft<R2>::run(v);
 #pragma unroll
     for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], tw2[b * (R2 + 1) + r]);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * L3) + cc] = v[r];
+    for (int r = 0; r < R2; ++r) col2[2 * qswz_t<SW>(p0 + r * L3) + cc] = v[r];
   }
   __syncthreads();
   // pass 3 forward (radix R3, stride L4)
 #pragma unroll
   for (int m = 0; m < 2 * (N / R3) / S1; ++m) {
-    const int w = gb + m * S1;
+    const int w = bt + m * S1;
     const int cc = w & 1, bf = w >> 1;
     const int blk = bf / L4, b = bf - blk * L4;
     const int p0 = blk * L3 + b;
     float2 v[R3];
 #pragma unroll
-    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r * L4) + cc];
+    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz_t<SW>(p0 + r * L4) + cc];
     Dft<R3>::run(v);
 #pragma unroll
     for (int r = 1; r < R3; ++r) v[r] = cmul(v[r], tw3[b * (R3 + 1) + r]);
 #pragma unroll
-    for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r * L4) + cc] = v[r];
+    for (int r = 0; r < R3; ++r) col2[2 * qswz_t<SW>(p0 + r * L4) + cc] = v[r];
   }
   __syncthreads();
   // pass 4 forward, diagonal, pass 4 inverse -- in registers
 #pragma unroll
   for (int m = 0; m < (2 * (N / R4) + S1 - 1) / S1; ++m) {
-    const int w = gb + m * S1;
+    const int w = bt + m * S1;
     if (w >= 2 * (N / R4)) continue;
     const int cc = w & 1, p0 = (w >> 1) * R4;
-    const float ly = P.lam_y[gc + cc];
+    const float ly = P.lam_y[c + cc];
     float2 v[R4];
 #pragma unroll
-    for (int r = 0; r < R4; ++r) v[r] = col2[2 * qswz(p0 + r) + cc];
+    for (int r = 0; r < R4; ++r) v[r] = col2[2 * qswz_t<SW>(p0 + r) + cc];
     Dft<R4>::run(v);
     const float4* lx4 = reinterpret_cast<const float4*>(P.lam_x_pos + p0);
 #pragma unroll
@@ -696,48 +704,48 @@ __global__ void __launch_bounds__(R2 * R3 * R4, 1) cols4_fast_kernel(FastColPara
     }
     dft_dir<R4, true>(v);
 #pragma unroll
-    for (int r = 0; r < R4; ++r) col2[2 * qswz(p0 + r) + cc] = v[r];
+    for (int r = 0; r < R4; ++r) col2[2 * qswz_t<SW>(p0 + r) + cc] = v[r];
   }
   __syncthreads();
   // pass 3 inverse
 #pragma unroll
   for (int m = 0; m < 2 * (N / R3) / S1; ++m) {
-    const int w = gb + m * S1;
+    const int w = bt + m * S1;
     const int cc = w & 1, bf = w >> 1;
     const int blk = bf / L4, b = bf - blk * L4;
     const int p0 = blk * L3 + b;
     float2 v[R3];
 #pragma unroll
-    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz(p0 + r * L4) + cc];
+    for (int r = 0; r < R3; ++r) v[r] = col2[2 * qswz_t<SW>(p0 + r * L4) + cc];
 #pragma unroll
     for (int r = 1; r < R3; ++r) v[r] = cmulc(v[r], tw3[b * (R3 + 1) + r]);
     dft_dir<R3, true>(v);
 #pragma unroll
-    for (int r = 0; r < R3; ++r) col2[2 * qswz(p0 + r * L4) + cc] = v[r];
+    for (int r = 0; r < R3; ++r) col2[2 * qswz_t<SW>(p0 + r * L4) + cc] = v[r];
   }
   __syncthreads();
   // pass 2 inverse
 #pragma unroll
   for (int m = 0; m < 2 * (N / R2) / S1; ++m) {
-    const int w = gb + m * S1;
+    const int w = bt + m * S1;
     const int cc = w & 1, bf = w >> 1;
     const int blk = bf / L3, b = bf - blk * L3;
     const int p0 = blk * L2 + b;
     float2 v[R2];
 #pragma unroll
-    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz(p0 + r * L3) + cc];
+    for (int r = 0; r < R2; ++r) v[r] = col2[2 * qswz_t<SW>(p0 + r * L3) + cc];
 #pragma unroll
     for (int r = 1; r < R2; ++r) v[r] = cmulc(v[r], tw2[b * (R2 + 1) + r]);
     dft_dir<R2, true>(v);
 #pragma unroll
-    for (int r = 0; r < R2; ++r) col2[2 * qswz(p0 + r * L3) + cc] = v[r];
+    for (int r = 0; r < R2; ++r) col2[2 * qswz_t<SW>(p0 + r * L3) + cc] = v[r];
   }
   __syncthreads();
   {  // pass 1 inverse: shared -> registers -> global
     float2 va[R1], vb[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      const float4 x = col[qswz(gb + r * S1)];
+      const float4 x = gcol[qswz_t<SW>(gb + r * S1)];
       va[r] = make_float2(x.x, x.y);
       vb[r] = make_float2(x.z, x.w);
       if (r > 0) {
@@ -756,18 +764,18 @@ __global__ void __launch_bounds__(R2 * R3 * R4, 1) cols4_fast_kernel(FastColPara
   }
 }
 
-template <int R1, int R2, int R3, int R4>
+template <int R1, int R2, int R3, int R4, int NP>
 int launch_cols4_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
   constexpr int N = R1 * R2 * R3 * R4;
-  const size_t smem = (size_t)N * sizeof(float4) +
+  const size_t smem = (size_t)NP * (N + 2) * sizeof(float4) +
                       ((size_t)(N / R1 / R2) * (R2 + 1) + (size_t)R4 * (R3 + 1)) * sizeof(float2);
-  dim3 grid((P.ncols + 1) / 2, batch);
+  dim3 grid((P.ncols + 2 * NP - 1) / (2 * NP), batch);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(cols4_fast_kernel<R1, R2, R3, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(cols4_fast_kernel<R1, R2, R3, R4, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     configured = true;
   }
-  launch_pdl(16, cols4_fast_kernel<R1, R2, R3, R4>, grid, dim3(N / R1), smem, s, P, spec);
+  launch_pdl(16, cols4_fast_kernel<R1, R2, R3, R4, NP>, grid, dim3(NP * (N / R1)), smem, s, P, spec);
   return check_launch("cols4_fast_kernel");
 }
 
@@ -821,7 +829,7 @@ void fast_radices(int n, int* r) {
     case 512: r[0] = 8; r[1] = 8; r[2] = 8; break;
     case 1024: r[0] = 8; r[1] = 8; r[2] = 16; break;
     case 2048: r[0] = 8; r[1] = 16; r[2] = 16; break;
-    case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;
+    case 4096: r[0] = 16; r[1] = 16; r[2] = 16; break;  // (8, 8, 8, 8) with 2 pairs per CTA measured within 1 %
     case 8192:  // columns only
       if (four_pass_8192()) { r[0] = 8; r[1] = 8; r[2] = 8; r[3] = 16; }
       else { r[0] = 16; r[1] = 32; r[2] = 16; r[3] = 0; }
@@ -858,7 +866,7 @@ void fast_cols_geometry(int nx, int* cols_per_cta, int* ctas_per_sm) {
 }
 
 int launch_cols_fast(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
-  if (P.nx == 8192 && four_pass_8192()) return launch_cols4_t<8, 8, 8, 16>(s, P, batch, spec);
+  if (P.nx == 8192 && four_pass_8192()) return launch_cols4_t<8, 8, 8, 16, 1>(s, P, batch, spec);
 #define CALL_COLS(a, b, c) launch_cols_t<a, b, c>(s, P, batch, spec)
   JAXIB_DISPATCH_COLS(P.nx, CALL_COLS)
 #undef CALL_COLS
