@@ -138,3 +138,47 @@ def test_product_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         demo.make_stepper(configs.small_periodic(32))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """ABI drift guard: sizes and field offsets of jaxib_grid / jaxib_bodies / jaxib_slab as gcc lays them out
+    from include/jaxib_b200.h must equal the ctypes mirrors in jax_ib_b200/_lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probes = {
+        "jaxib_grid": ["nx", "dt", "bc", "force", "ib_window", "row0", "own_hi", "nx_global"],
+        "jaxib_bodies": ["n_markers", "body_offset", "y0", "max_radius"],
+        "jaxib_slab": ["rank", "cpr", "u", "markers", "colbuf", "specbuf", "flags"],
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "jaxib_b200.h"', "int main(void) {"]
+    for st, fields in probes.items():
+        lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for f in fields:
+            lines.append(f'  printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    mirrors = {"jaxib_grid": _lib.Grid, "jaxib_bodies": _lib.Bodies, "jaxib_slab": _lib.Slab}
+    for st, fields in probes.items():
+        assert int(out[st]) == ctypes.sizeof(mirrors[st]), st
+        for f in fields:
+            assert int(out[f"{st}.{f}"]) == getattr(mirrors[st], f).offset, (st, f)
+    assert _lib.MAX_PEERS == 16
+
+
+def test_peer_block_layout_is_aligned_and_disjoint():
+    from jax_ib_b200 import slab
+    L = slab.SlabLayout(8192, 8192, 8, 3, 16)
+    blk = slab.PeerBlock(L, 4768)
+    spans = sorted((off, off + blk.size[name], name) for name, off in blk.offset.items())
+    for (a0, a1, _), (b0, _, _) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert all(off % 256 == 0 for off in blk.offset.values())
+    assert blk.nbytes >= spans[-1][1] and blk.size["flags"] == 4 * slab.PeerBlock.FLAG_WORDS
+    assert blk.size["colbuf"] == 8192 * L.cpr * 8 and blk.size["specbuf"] == (L.nloc + 1) * L.sp * 8
