@@ -61,7 +61,7 @@ def workload_cfg(name):
         return configs.flap600()
     if name.startswith("slab"):  # slab8192 = G4 `multi8192`: (n/2048)^2 flapping ellipses on an n^2 grid
         n = int(name[4:])
-        return configs.ib_periodic(n, max(1, n // 2048))
+        return configs.ib_periodic(n, max(1, n // 1024))  # 8192: 8 x 8 lattice = 64 bodies, 19 072 markers
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -247,9 +247,42 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
                f"{world} slabs of {L.nloc} rows + {L.halo} halo rows; {mode}")
         e_ms = ms_peer if ms_peer is not None else ms_nccl
     ms = max_over_ranks(e0.elapsed_time(e1)) if world == 1 else e_ms
+    # ---- correctness of the decomposition, carried by the driver's own SCALE record: `nv` steps from the initial
+    #      state; `checksum` (sha1 of the u, v, p bytes) must be identical at every N, and at N > 1 rank 0 also
+    #      runs the single-GPU fused step itself and compares bit for bit -------------------------------------
+    import hashlib
+    nv = 3
+    verify = {"steps": nv}
+    try:
+        if world == 1:
+            u, v, p = (torch.from_numpy(a).to(device) for a in fields)
+            tabv, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], nv)
+            stepper.run_block(u, v, p, nv, torch.from_numpy(np.ascontiguousarray(tabv[:, None])).to(device))
+            got = (u, v, p)
+        else:
+            st.load(*(torch.from_numpy(a) for a in fields))
+            st.advance(nv)
+            got = st.gather()
+            st.check()
+        torch.cuda.synchronize()
+        h = hashlib.sha1()
+        for t in got:
+            h.update(t.cpu().numpy().tobytes())
+        verify["checksum"] = h.hexdigest()[:16]
+        if world > 1 and rank == 0:
+            ref_stepper = demo.make_stepper(cfg, device=device)
+            u, v, p = (torch.from_numpy(a).to(device) for a in fields)
+            tabv, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], nv)
+            ref_stepper.run_block(u, v, p, nv, torch.from_numpy(np.ascontiguousarray(tabv[:, None])).to(device))
+            verify["bitwise_vs_1gpu"] = bool(all(torch.equal(a, b) for a, b in zip(got, (u, v, p))))
+            verify["max_abs_diff_vs_1gpu"] = float(max((a - b).abs().max().item() for a, b in zip(got, (u, v, p))))
+            del ref_stepper
+    except Exception as e:  # noqa: BLE001
+        verify["error"] = f"{type(e).__name__}: {e}"[:200]
     out = {"workload": name, "grid": [nx, ny], "bodies": len(cfg["bodies"]["centers"]), "n_gpus": world,
            "scaling": "strong", "steps": K, "ms_per_step": ms / K, "value": cells * K / (ms * 1e-3) / 1e6,
-           "unit": UNIT, "finite": finite, "how": how,
+           "unit": UNIT, "finite": finite, "verify": verify, "markers": int(sum(len(x) for x, _ in configs.body_markers(cfg))),
+           "how": how,
            "l2": "state (5 fields + spectrum buffers) per GPU exceeds the 126 MB L2; steps run back to back"}
     if world > 1 and peer_phases:
         out["phase_us_max_over_ranks"] = peer_phases

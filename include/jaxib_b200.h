@@ -217,11 +217,14 @@ int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const ja
  * bodies == NULL skips the IB stage.  body_table: [nsteps][batch][n_bodies][8] (device).
  * perm (may be NULL): [batch][nx][ny] Brinkman permeability.  incremental_pressure == 0 selects
  * the penalty stepper (no -grad p_old in the predictor, time_stepping.py:345).
- * The clock / wall values / body centres are host-side state (boundaries.py:519-542,
- * particle_motion.py:38-66) and are not touched here.                                         */
+ * wall_table (HOST memory, may be NULL): [nsteps][4] = u_lo, u_hi, v_lo, v_hi, the wall values of a
+ * channel grid at the time stamp of each step -- what update_BC (boundaries.py:519-542) re-evaluates
+ * from the Moving_wall bc_fn every step (:636-663); NULL keeps the plan's constant u_wall / v_wall.
+ * The clock / body centres are host-side state (boundaries.py:519-542, particle_motion.py:38-66)
+ * and are not touched here.                                                                    */
 int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
-               const float* perm, int32_t incremental_pressure, int32_t nsteps, float* u, float* v, float* p,
-               void* scratch, size_t scratch_bytes);
+               const float* perm, const double* wall_table, int32_t incremental_pressure, int32_t nsteps, float* u,
+               float* v, float* p, void* scratch, size_t scratch_bytes);
 
 /* Measurement aid (bench.py): runs `nsteps` steps like jaxib_step but brackets every stage of every
  * step with CUDA events on `stream`, optionally overwrites `flush` (flush_bytes, > L2) before each

@@ -75,7 +75,8 @@ _SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), _P, _P]),
     "jaxib_pressure_solve": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_project": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t]),
-    "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_size_t]),
+    "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.POINTER(C.c_double), C.c_int32, C.c_int32, _P, _P, _P, _P,
+                             C.c_size_t]),
     "jaxib_step_profile": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P,
                                      C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_double)]),
     "jaxib_tracer_step": (C.c_int, [_P, C.POINTER(Grid), _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double,
@@ -104,9 +105,9 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if not os.path.exists(path) or os.environ.get("JAXIB_REBUILD") == "1":
-            path = _build.build()
+        # build() is a no-op when the in-tree .so matches the digest of the sources; it rebuilds a stale one
+        # (edited .cu files) under a file lock, so concurrent ranks do not race on the in-tree build
+        path = _build.build(force=os.environ.get("JAXIB_REBUILD") == "1")
         lib = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError = header / library mismatch: fail loudly

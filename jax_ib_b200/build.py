@@ -50,11 +50,25 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _fresh(digest: str) -> bool:
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    if not force and _fresh(digest):
         return LIB
+    import fcntl
+
+    with open(os.path.join(OUT_DIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # one builder at a time (torchrun ranks share the tree)
+        if not force and _fresh(digest):  # another rank built it while we waited
+            return LIB
+        return _build_locked(digest, verbose)
+
+
+def _build_locked(digest: str, verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []

@@ -264,8 +264,8 @@ int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u,
 }
 
 int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
-               const float* perm, int32_t incremental_pressure, int32_t nsteps, float* u, float* v, float* p,
-               void* scratch, size_t scratch_bytes) {
+               const float* perm, const double* wall_table, int32_t incremental_pressure, int32_t nsteps, float* u,
+               float* v, float* p, void* scratch, size_t scratch_bytes) {
   if (!plan) { set_error("step: plan is null"); return JAXIB_ERR_INVALID; }
   int rc = check_ptrs("step", {u, v, p});
   if (rc) return rc;
@@ -281,13 +281,20 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
   cudaStream_t s = (cudaStream_t)stream;
   const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
   for (int n = 0; n < nsteps; ++n) {
+    // boundaries.py:519-542 update_BC: step n sees the wall values of its own time stamp
+    GridF gn = g;
+    if (wall_table) {
+      const double* w = wall_table + 4 * (size_t)n;
+      gn.uw_lo = (float)w[0]; gn.uw_hi = (float)w[1]; gn.vw_lo = (float)w[2]; gn.vw_hi = (float)w[3];
+    }
+    const GridF* gov = wall_table ? &gn : nullptr;
     // time_stepping.py:191-208
-    if ((rc = launch_explicit(s, g, u, v, incremental_pressure ? p : nullptr, perm, sc.u_star, sc.v_star, true))) return rc;
+    if ((rc = launch_explicit(s, gn, u, v, incremental_pressure ? p : nullptr, perm, sc.u_star, sc.v_star, true))) return rc;
     // time_stepping.py:210-223
-    if (has_ib && (rc = launch_ib_force(s, g, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
+    if (has_ib && (rc = launch_ib_force(s, gn, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
       return rc;
     // time_stepping.py:246
-    if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum))) return rc;
+    if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum, nullptr, gov))) return rc;
   }
   return JAXIB_OK;
 }

@@ -134,16 +134,16 @@ int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, c
                      int* box_scratch);
 int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
                    float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
-                   const StageHook* hook = nullptr);
+                   const StageHook* hook = nullptr, const GridF* gov = nullptr);
 // Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp,
-                    const SpecScatter* sc = nullptr);
+                    const SpecScatter* sc = nullptr, const GridF* gov = nullptr);
 int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0,
                 int col_begin = 0);
 void plan_cols_geometry(const jaxib_plan* plan, int* cols_per_cta, int* ctas_per_sm);
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectrum, int sp, const float* u,
                     const float* v, const float* p, float* u_out, float* v_out, float* p_out, float* q_only,
-                    const HaloOut* ho = nullptr);
+                    const HaloOut* ho = nullptr, const GridF* gov = nullptr);
 bool plan_fast_rows(const jaxib_plan* plan);
 bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);

@@ -407,9 +407,9 @@ struct StageParams {
 };
 
 // sp = spectrum row pitch in complex values (0 = the default ny/2 + 4)
-StageParams stage_params(const jaxib_plan* pl, int sp) {
+StageParams stage_params(const jaxib_plan* pl, int sp, const GridF* gov = nullptr) {
   StageParams S;
-  const GridF& g = pl->gf;
+  const GridF& g = gov ? *gov : pl->gf;  // gov: the plan's grid with this step's wall values (update_BC)
   const int n2 = g.ny / 2;
   const double nxg = g.nx_global > 0 ? g.nx_global : g.nx;  // slab: normalise with the global length
   S.channel = g.bc == JAXIB_BC_CHANNEL;
@@ -433,8 +433,8 @@ StageParams stage_params(const jaxib_plan* pl, int sp) {
 
 // K4: divergence of (u, v) + forward row transform -> spectrum [nx][sp]
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, float* spectrum, int sp,
-                    const SpecScatter* sc) {
-  StageParams S = stage_params(pl, sp);
+                    const SpecScatter* sc, const GridF* gov) {
+  StageParams S = stage_params(pl, sp, gov);
   float2* spec = reinterpret_cast<float2*>(spectrum);
   if (sc && sc->cpr) {
     if (!pl->fast_rows) { set_error("peer-memory slab mode needs ny/2 in {512, 1024, 2048, 4096}"); return JAXIB_ERR_UNSUPPORTED; }
@@ -487,8 +487,9 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
 
 // K6: inverse row transform (+ projection and pressure update unless q_only)
 int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum, int sp, const float* u, const float* v,
-                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const HaloOut* ho) {
-  StageParams S = stage_params(pl, sp);
+                    const float* p, float* u_out, float* v_out, float* p_out, float* q_only, const HaloOut* ho,
+                    const GridF* gov) {
+  StageParams S = stage_params(pl, sp, gov);
   if (ho && ho->halo) {
     if (!pl->fast_rows) { set_error("peer-memory slab mode needs ny/2 in {512, 1024, 2048, 4096}"); return JAXIB_ERR_UNSUPPORTED; }
     S.frp.ho = *ho;
@@ -517,14 +518,14 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum,
 }
 
 int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
-                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook) {
-  int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0);
+                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook, const GridF* gov) {
+  int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0, nullptr, gov);
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);
   rc = launch_cols(s, pl, spectrum, 0, 0, 0);
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[1], s);
-  rc = launch_rows_inv(s, pl, spectrum, 0, u, v, p, u_out, v_out, p_out, q_only);
+  rc = launch_rows_inv(s, pl, spectrum, 0, u, v, p, u_out, v_out, p_out, q_only, nullptr, gov);
   if (hook) cudaEventRecord(hook->ev[2], s);
   return rc;
 }
@@ -646,16 +647,21 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   pl->cols_per_cta = cpc;
   pl->col_smem = cpc * col_bytes;
   pl->col_threads = 256;
-  cudaFuncSetAttribute(cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->col_smem);
-  cudaFuncSetAttribute(rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
-  cudaFuncSetAttribute(rows_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
-  cudaFuncSetAttribute(rows_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pl->row_smem));
-  if (channel) {
-    const int dsm = (int)(pl->row_smem + 2 * (size_t)ny * sizeof(float));
-    cudaFuncSetAttribute(rows_fwd_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->row_smem);
-    cudaFuncSetAttribute(rows_inv_dct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);
-    cudaFuncSetAttribute(rows_inv_dct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsm);
+  // The opt-in is a property of the FUNCTION, not of the plan: a per-plan value would be overwritten by the
+  // next plan (a later, smaller plan would make the launches of a larger one fail).  Every generic kernel
+  // is opted in to the device maximum once; the per-launch size still comes from the plan.
+  if ((size_t)max_smem < pl->col_smem || (size_t)max_smem < 2 * pl->row_smem + 2 * (size_t)ny * sizeof(float)) {
+    set_error("grid %dx%d: a row / column group does not fit the %d bytes of shared memory", nx, ny, max_smem);
+    jaxib_plan_destroy(pl);
+    return JAXIB_ERR_UNSUPPORTED;
   }
+  cudaFuncSetAttribute(cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_fwd_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_inv_dct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(rows_inv_dct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   cudaGetLastError();
   *out = pl;
   return JAXIB_OK;

@@ -66,7 +66,17 @@ int enqueue_barrier(cudaStream_t s, const jaxib_slab& sl, int slot, uint32_t epo
   memset(&a, 0, sizeof(a));
   for (int d = 0; d < sl.world; ++d) a.flags[d] = sl.flags[d];
   a.world = sl.world; a.rank = sl.rank; a.slot = slot; a.epoch = epoch;
-  a.timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
+  // Give-up time of the spin: long enough for any host-side hiccup of a peer (first kinematics evaluation,
+  // GC, a profiler sync), short enough that a dead peer cannot hang the GPU.  JAXIB_SLAB_TIMEOUT_MS overrides.
+  // A give-up is FATAL for the results: the error word stays set until the host clears it and every Python
+  // entry point that hands fields back raises on it (slab.py: PeerRank.check).
+  static long long cycles = 0;
+  if (!cycles) {
+    const char* e = getenv("JAXIB_SLAB_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 20000;
+    cycles = (ms < 1 ? 1 : ms) * 1900000LL;  // ~1.9 GHz
+  }
+  a.timeout_cycles = cycles;
   launch_pdl(64, slab_barrier_kernel, dim3(1), dim3(32), 0, s, a);
   return check_launch("slab_barrier_kernel");
 }

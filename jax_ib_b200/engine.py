@@ -63,7 +63,11 @@ def get_plan(spec: ops.GridSpec, n_markers: int = 0) -> ops.Plan:
 
 def get_bodies(particles, device) -> ops.DeviceBodies:
     dev = cuda_device(device)
-    key = (id(particles.shape), tuple(np.asarray(particles.geometry_param, dtype=np.float64).ravel()), dev.index)
+    # everything the generated body-frame markers depend on: the shape callable, its parameters and the
+    # theta grid (a resolution study keeps shape_fn and geometry but changes Grid1d)
+    G = particles.Grid
+    key = (particles.shape, tuple(np.asarray(particles.geometry_param, dtype=np.float64).ravel()),
+           getattr(G, "shape", None), tuple(getattr(G, "domain", ()) or ()), dev.index)
     b = _BODIES.get(key)
     if b is None:
         x0s, y0s = [], []
@@ -102,15 +106,21 @@ class FusedStepper:
         self.launches_per_step = 4 + (2 if self.bodies else 0)
 
     # -- raw device-level block ---------------------------------------------------------------
-    def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor]):
-        """In place on CUDA tensors (u, v, p)."""
-        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure)
+    def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor], walls=None):
+        """In place on CUDA tensors (u, v, p).  walls: host [nsteps, 4] wall values per step or None."""
+        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure, walls)
 
     # -- All_Variables-level --------------------------------------------------------------------
     def advance(self, all_variables, nsteps: int, move_bodies: bool = True):
         vel = all_variables.velocity
         dev = self.device
         in_dev = vel[0].data.device
+        if self.bodies is not None and all_variables.particles is not None:
+            b = get_bodies(all_variables.particles, dev)  # a different particle set than at build time
+            if b is not self.bodies:
+                self.bodies = b
+                if b.n_markers > self.plan.n_markers:
+                    self.plan = ops.Plan(self.spec, b.n_markers, dev)
         # first touch: copy (functional semantics: the caller's arrays are never modified)
         # (non_blocking: from pinned host arrays the three uploads overlap the host-side kinematics below)
         u = vel[0].data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
@@ -120,14 +130,15 @@ class FusedStepper:
         dt = self.spec.dt
         particles = all_variables.particles
         state = all_variables
+        table_dev, times, centers = self._schedule(particles, t0, dt, nsteps, move_bodies)
+        walls = self._wall_table(vel, times, nsteps)
         if self.md_step is None:
-            table_dev, times, centers = self._schedule(particles, t0, dt, nsteps)
-            self.run_block(u, v, p, nsteps, table_dev)
+            self.run_block(u, v, p, nsteps, table_dev, walls)
         else:
-            table_dev, times, centers = self._schedule(particles, t0, dt, nsteps)
             md = all_variables.MD_var
             for n in range(nsteps):
-                self.run_block(u, v, p, 1, None if table_dev is None else table_dev[n:n + 1])
+                self.run_block(u, v, p, 1, None if table_dev is None else table_dev[n:n + 1],
+                               None if walls is None else walls[n:n + 1])
                 md = self.md_step(self._view(all_variables, u, v, p, times[n + 1], particles, md))
             state = dataclasses.replace(state, MD_var=md)
         new_particles = particles
@@ -143,12 +154,31 @@ class FusedStepper:
         # particle_motion.py:59: the step counter lives in the position update
         return dataclasses.replace(out, Step_count=all_variables.Step_count + (nsteps if move_bodies else 0))
 
-    def _schedule(self, particles, t0, dt, nsteps):
+    def _wall_table(self, vel, times, nsteps):
+        """boundaries.py:519-542 update_BC for a block of steps: step 0 sees the wall values stored in the
+        incoming BC objects, step n >= 1 the Moving_wall functions (:636-663) evaluated at its own time
+        stamp t_n -- exactly what the reference's step n reads after n update_BC calls."""
+        if self.spec.bc != "channel":
+            return None
+        tab = np.empty((nsteps, 4), dtype=np.float64)
+        tab[:] = [float(x) for x in vel[0].bc.bc_values[1]] + [float(x) for x in vel[1].bc.bc_values[1]]
+        fx, fy = vel[0].bc.boundary_fn, vel[1].bc.boundary_fn
+        try:
+            fns = (fx[2], fx[3], fy[2], fy[3])
+        except (TypeError, IndexError):
+            return tab  # no per-wall functions (constant-BC factory): the stored values hold for every step
+        for n in range(1, nsteps):
+            tab[n] = [float(f(times[n])) for f in fns]
+        return tab
+
+    def _schedule(self, particles, t0, dt, nsteps, move_bodies=True):
         f32 = np.float32
         if particles is None:
             times = np.add.accumulate(np.concatenate([[f32(t0)], np.full(nsteps, f32(dt), f32)]).astype(f32), dtype=f32)
             return None, times, None
         table, times, centers = kinematics.body_schedule(particles, t0, dt, nsteps)
+        if not move_bodies:  # Updating_Position=None: the reference never touches particle_center (equations.py:143-158)
+            table[:, :, 2:4] = centers[0]
         table = np.broadcast_to(table[:, None], (nsteps, self.spec.batch) + table.shape[1:]).copy()
         return torch.from_numpy(table).to(self.device, non_blocking=True), times, centers
 

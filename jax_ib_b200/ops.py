@@ -257,8 +257,9 @@ class Plan:
                                                     _ptr(u_out), _ptr(v_out), _ptr(p_out)), "poisson_rows_inv")
 
     def step(self, u, v, p, nsteps=1, bodies: Optional[DeviceBodies] = None, body_table=None, perm=None,
-             incremental_pressure=True):
-        """time_stepping.py:144-255, `nsteps` times, in place on (u, v, p)."""
+             incremental_pressure=True, wall_table=None):
+        """time_stepping.py:144-255, `nsteps` times, in place on (u, v, p).  wall_table: host array
+        [nsteps, 4] = (u_lo, u_hi, v_lo, v_hi) per step (boundaries.py:519-542), None = constant walls."""
         for t, n in ((u, "u"), (v, "v"), (p, "p")):
             _check_field(self.spec, t, n)
         b = bodies.c_struct() if bodies is not None else None
@@ -268,9 +269,15 @@ class Plan:
             need = nsteps * self.spec.batch * bodies.n_bodies * BODY_STATE_STRIDE
             if body_table is None or body_table.numel() < need:
                 raise _lib.JaxibError("body_table too small for nsteps")
+        walls = None
+        if wall_table is not None:
+            w = np.ascontiguousarray(np.asarray(wall_table, dtype=np.float64).reshape(-1, 4))
+            if w.shape[0] < nsteps:
+                raise _lib.JaxibError("wall_table too small for nsteps")
+            walls = w.ctypes.data_as(C.POINTER(C.c_double))
         _lib.check(self._lib.jaxib_step(_stream(), self._h, C.byref(b) if b is not None else None, _ptr(body_table),
-                                        _ptr(perm), 1 if incremental_pressure else 0, int(nsteps), _ptr(u), _ptr(v),
-                                        _ptr(p), _ptr(self.scratch), self.scratch_bytes), "step")
+                                        _ptr(perm), walls, 1 if incremental_pressure else 0, int(nsteps), _ptr(u),
+                                        _ptr(v), _ptr(p), _ptr(self.scratch), self.scratch_bytes), "step")
         return u, v, p
 
 

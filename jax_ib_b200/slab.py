@@ -369,6 +369,17 @@ class PeerRank:
         """True if a barrier of this slab ever gave up waiting for a peer (the results are then invalid)."""
         return bool(self.flags[64].item() != 0)
 
+    def check(self):
+        """Raises if a flag barrier gave up: the fields of this and every later step are then built from stale
+        or partial peer data.  Called wherever fields are handed back to the host (synchronises)."""
+        if self.barrier_timed_out():
+            raise RuntimeError(
+                f"slab {self.lay.rank}: a peer-memory flag barrier timed out at epoch {int(self.flags[64].item())} "
+                "(a peer rank was more than JAXIB_SLAB_TIMEOUT_MS late or died); the fields are invalid")
+
+    def clear_error(self):
+        self.flags[64] = 0
+
 
 def _peer_ranks(spec, particles_bodies, world, halo, device, virtual, group):
     """Allocates the symmetric blocks and returns (ranks, handle)."""
@@ -430,7 +441,24 @@ class SlabStepper:
     def load(self, u, v, p, t0=0.0):
         for r in self.ranks:
             r.load_global(u, v, p)
+            if self.peer:
+                r.clear_error()
         self.time = np.float32(t0)
+        self._synced = False
+
+    def _host_barrier(self):
+        """Before the first peer-memory block after a load: every rank has finished its host-side set-up
+        (first torch.func trace of the kinematic laws, uploads), so no rank spins on a peer that is still
+        seconds away from launching."""
+        if self.peer and not self.virtual and not getattr(self, "_synced", False):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.comm.group)
+            self._synced = True
+
+    def check(self):
+        if self.peer:
+            for r in self.ranks:
+                r.check()
 
     def advance(self, nsteps: int, profile: bool = False):
         """`nsteps` steps in place; returns the body centres after the block (host, float32) or None.
@@ -460,6 +488,7 @@ class SlabStepper:
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
                 names = ("predict_force", "spread_rows_fwd+barrier", "cols_push+barrier", "rows_inv+barrier")
                 evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsteps)]
+                self._host_barrier()
                 for n in range(nsteps):
                     evs[n][0].record()
                     for ph in range(4):
@@ -470,6 +499,7 @@ class SlabStepper:
                 self.last_profile["step"] = sum(e[0].elapsed_time(e[4]) for e in evs)
                 return
             if not self.virtual:
+                self._host_barrier()
                 self.ranks[0].run(tab, nsteps)  # one C call: 4 phases x nsteps with flag barriers
             else:  # several slabs of one GPU: lockstep, phase by phase (a flag barrier would deadlock here)
                 for n in range(nsteps):
@@ -496,6 +526,7 @@ class SlabStepper:
 
     def owned_fields(self):
         """[(own_lo, u_rows, v_rows, p_rows)] for the slabs held by this process."""
+        self.check()
         return [(r.lay.own_lo, r.owned(r.u), r.owned(r.v), r.owned(r.p)) for r in self.ranks]
 
     def gather(self):

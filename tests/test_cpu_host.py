@@ -47,7 +47,7 @@ def test_argument_errors_without_a_gpu():
     h = ctypes.c_void_p()
     assert l.jaxib_plan_create(ctypes.byref(g), ctypes.byref(h)) == -1
     assert b"nx" in l.jaxib_last_error()
-    assert l.jaxib_step(None, None, None, None, None, 1, 1, None, None, None, None, 0) == -1
+    assert l.jaxib_step(None, None, None, None, None, None, 1, 1, None, None, None, None, 0) == -1
 
 
 def test_sass_is_sm100a_only():

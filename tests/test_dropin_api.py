@@ -130,14 +130,15 @@ def test_staged_path_matches_fused_path():
 
 @pytest.mark.gpu
 def test_journal_bearing_with_tracers_kT0():
-    """journal_bearing_demo.ipynb cells 4-10 (reduced tracer count), kT = 0, against the oracle."""
+    """journal_bearing_demo.ipynb cells 4-10 at the notebook's tracer count (1200 mobile + 200 wall + 1 hub =
+    1401, :214-219), kT = 0, against the oracle."""
     from oracle import tracers
 
     cfg = configs.bearing300()
     av = ib.demo.make_all_variables(cfg, device="cuda")
     dt, grid = cfg["dt"], av.velocity[0].grid
     rng = np.random.default_rng(0)
-    n_mob, n_wall = 60, 20
+    n_mob, n_wall = 1200, 200
     th = rng.uniform(0, 2 * np.pi, n_mob)
     rr = rng.uniform(0.6, 0.9, n_mob)
     mob = np.stack([2.5 + rr * np.cos(th), 2.5 + rr * np.sin(th)], 1)

@@ -1,0 +1,217 @@
+"""Parity on what is TIMED and on the paths VERDICT r1 found unverified (all through the C ABI):
+
+  * the bench workloads themselves (ib2048, the slab proxy with 16 bodies) against the windowed NumPy oracle;
+  * time-dependent wall values (boundaries.py:519-542 update_BC + :636-663 Moving_wall) inside fused blocks;
+  * the penalty stepper (time_stepping.py:259-365, penalty/util_funs.py:6-16) on the fast and the generic K1;
+  * Updating_Position=None keeps the centres fixed (equations.py:143-158);
+  * the caller-noise (kT > 0) tracer path (MD/simulate.py:81-97).
+"""
+import dataclasses
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from jax_ib_b200 import boundaries, configs, demo, equations, grids, ops, particle_class as pc
+from jax_ib_b200 import advection, penalty as ppen, pressure as ppressure
+from oracle import field, penalty, stepper, tracers
+
+from _adapter import oracle_state, oracle_step, rel_l2
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def _compare(out, st, tol=1e-5):
+    errs = {"u": rel_l2(host(out.velocity[0].data), st.velocity[0].data),
+            "v": rel_l2(host(out.velocity[1].data), st.velocity[1].data),
+            "p": rel_l2(host(out.pressure.data), st.pressure.data)}
+    assert max(errs.values()) < tol, errs
+    return errs
+
+
+# ------------------------------------------------------------------------------------------------ timed workloads
+@pytest.mark.parametrize("n,axis,steps", [(2048, 2, 3), (1024, 4, 3)])
+def test_bench_workloads_match_windowed_oracle(n, axis, steps):
+    """ib2048 (the bench.py workload: 4 bodies / 1192 markers) and the 1024^2 / 16-body proxy of the slab
+    workload, fused fast path vs the NumPy oracle with the same R = 6 window: fields rel-L2 <= 1e-5,
+    centres to float32 round-off, clock bit-equal."""
+    cfg = configs.ib_periodic(n, axis)
+    st = oracle_state(cfg)
+    step = oracle_step(cfg, ib_window=6)
+    for _ in range(steps):
+        st = step(st)
+    out = demo.make_stepper(cfg).advance(demo.make_all_variables(cfg, device="cuda"), steps)
+    _compare(out, st, 1e-5)
+    np.testing.assert_allclose(np.asarray(out.particles.particle_center), st.particles.centers, rtol=0, atol=2e-6)
+    assert np.float32(out.velocity[0].bc.time_stamp) == np.float32(st.velocity[0].bc.time_stamp)
+    assert out.Step_count == steps
+
+
+# ------------------------------------------------------------------------------------------------ moving walls
+def _moving_wall_case(convect):
+    shape, domain, dt = (64, 48), ((0.0, 2.0), (0.0, 1.5)), 1e-3
+    cfg = dict(configs.channel(shape, domain, seed=5), dt=dt, convect=convect, force=(1e-3, 0.0))
+    lower = lambda t: 0.2 * float(t) * 40.0                       # ramps up
+    upper = lambda t: 0.3 * math.sin(2 * math.pi * float(t) / 0.015)  # oscillates within the block
+    zero = lambda t: 0.0
+    fns_u, fns_v = [zero, zero, lower, upper], [zero, zero, zero, zero]
+    return cfg, fns_u, fns_v
+
+
+@pytest.mark.parametrize("convect", ["van_leer", "upwind"])
+def test_time_dependent_walls_inside_a_fused_block(convect):
+    cfg, fns_u, fns_v = _moving_wall_case(convect)
+    steps = 20
+    u0, v0, p0 = configs.initial_fields(cfg)
+    # oracle: update_bc re-evaluates the wall functions every step (boundaries.py:519-542)
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    t0 = F(0.0)
+    vals_u = ((0.0, 0.0), (fns_u[2](t0), fns_u[3](t0)))
+    vals_v = ((0.0, 0.0), (0.0, 0.0))
+    U = field.Var(u0, (1.0, 0.5), g, field.channel_bc(vals_u, t0, fns_u))
+    V = field.Var(v0, (0.5, 1.0), g, field.channel_bc(vals_v, t0, fns_v))
+    P = field.Var(p0, (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    st = stepper.State(None, (U, V), P)
+    ostep = oracle_step(cfg, ib_window=6)
+    for _ in range(steps):
+        st = ostep(st)
+    # product: one fused block of 20 steps through the reference-shaped API
+    grid = grids.Grid(cfg["shape"], domain=cfg["domain"])
+    bcs = (boundaries.Moving_wall_boundary_conditions(ndim=2, bc_vals=vals_u, bc_fn=fns_u, time_stamp=F(0.0)),
+           boundaries.Moving_wall_boundary_conditions(ndim=2, bc_vals=vals_v, bc_fn=fns_v, time_stamp=F(0.0)))
+    vel = tuple(grids.GridVariable(grids.GridArray(dev(a), off, grid), bc) for a, off, bc in zip((u0, v0), grid.cell_faces, bcs))
+    pres = grids.GridVariable(grids.GridArray(dev(p0), grid.cell_center, grid), boundaries.get_pressure_bc_from_velocity(vel))
+    av = pc.All_Variables(None, vel, pres, [0], 0, [0])
+    adv = {"van_leer": advection.advect_van_leer, "upwind": advection.advect_upwind}[convect]
+    step_fn = equations.semi_implicit_navier_stokes_timeBC(
+        density=cfg["density"], viscosity=cfg["viscosity"], dt=cfg["dt"], grid=grid,
+        convect=lambda v: tuple(adv(u, v, cfg["dt"]) for u in v), pressure_solve=ppressure.solve_fast_diag_moving_wall,
+        forcing=equations.constant_forcing(cfg["force"]))
+    assert step_fn.fused
+    out = step_fn.advance(av, steps)
+    _compare(out, st, 1e-5)
+    # the walls really moved: a frozen-wall run (what round 1 did inside a block) differs visibly
+    stf = stepper.State(None, (field.Var(u0, (1.0, 0.5), g, field.channel_bc(vals_u, t0, None)),
+                               field.Var(v0, (0.5, 1.0), g, field.channel_bc(vals_v, t0, None))), P)
+    for _ in range(steps):
+        stf = ostep(stf)
+    assert rel_l2(stf.velocity[0].data, st.velocity[0].data) > 1e-3
+    # the BC object handed back carries the wall values of the new time stamp
+    t_end = np.float32(out.velocity[0].bc.time_stamp)
+    assert t_end == np.float32(st.velocity[0].bc.time_stamp)
+    assert out.velocity[0].bc.bc_values[1][1] == pytest.approx(fns_u[3](t_end))
+    # a second block continues from the right walls (3 + 17 == 20)
+    out2 = step_fn.advance(step_fn.advance(av, 3), 17)
+    assert rel_l2(host(out2.velocity[0].data), host(out.velocity[0].data)) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ penalty stepper
+@pytest.mark.parametrize("convect", ["upwind", "van_leer"])  # upwind + periodic = the fast K1; van Leer = the generic K1
+def test_penalty_stepper_matches_oracle(convect):
+    """semi_implicit_navier_stokes_penalty (equations.py:245-280): u* = u + dt (F(u) + (g - kappa u)/rho),
+    no stored-pressure gradient, projection, clock -- 20 steps with a two-body mask."""
+    cfg = configs.small_periodic(64, bodies=False, convect=convect)
+    steps = 20
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    theta = np.linspace(0, 2 * np.pi, 65)
+    Rts = np.stack([penalty.param_ellipse([0.6, 0.3], theta), penalty.param_circle([0.4], theta)]).astype(F)
+    centers = np.array([[1.2, 1.7], [2.3, 1.1]], F)
+    perm = penalty.perm_multiple(g, centers, Rts, penalty.tanh_smoothing, (60.0, 0.05), np.float32)
+    grad = (2e-2, -1e-2)
+    st = oracle_state(cfg)
+    ostep = stepper.make_step(cfg["dt"], cfg["viscosity"], cfg["density"], convect, "periodic",
+                              penalty.obstacle_forcing(grad, perm), penalty=True)
+    for _ in range(steps):
+        st = ostep(st)
+    av = demo.make_all_variables(cfg, device="cuda")
+    grid = av.velocity[0].grid
+    adv = {"van_leer": advection.advect_van_leer, "upwind": advection.advect_upwind}[convect]
+    step_fn = equations.semi_implicit_navier_stokes_penalty(
+        density=cfg["density"], viscosity=cfg["viscosity"], dt=cfg["dt"], grid=grid,
+        convect=lambda v: tuple(adv(u, v, cfg["dt"]) for u in v), pressure_solve=ppressure.solve_fast_diag,
+        forcing=ppen.util_funs.arbitrary_obstacle(grad, grids.GridArray(dev(perm), grid.cell_center, grid)))
+    assert step_fn.fused and not step_fn.cfg["incremental"] and step_fn.cfg["perm"] is not None
+    out = step_fn.advance(av, steps)
+    _compare(out, st, 1e-5)
+    assert np.float32(out.velocity[0].bc.time_stamp) == np.float32(st.velocity[0].bc.time_stamp)
+    # the mask matters: without it the flow is different at the 1e-2 level
+    st0 = oracle_state(cfg)
+    free = stepper.make_step(cfg["dt"], cfg["viscosity"], cfg["density"], convect, "periodic",
+                             penalty.obstacle_forcing(grad, np.zeros_like(perm)), penalty=True)
+    for _ in range(steps):
+        st0 = free(st0)
+    assert rel_l2(st0.velocity[0].data, st.velocity[0].data) > 1e-3
+
+
+def test_penalty_predictor_kernel_variants_agree():
+    """-kappa u inside jaxib_explicit_terms / _predict: fast marching kernel (periodic upwind, aligned) vs the
+    generic tile kernel (same grid, JAXIB fast path refused by an unaligned view) vs the oracle."""
+    from oracle import stencils
+    cfg = configs.small_periodic(64, bodies=False)
+    spec = demo.make_spec(cfg)
+    u, v, p = configs.initial_fields(cfg)
+    rng = np.random.default_rng(3)
+    perm = (40.0 * rng.random(u.shape)).astype(F)
+    st = oracle_state(cfg)
+    k = stencils.explicit_terms(st.velocity, cfg["viscosity"], cfg["dt"], "upwind",
+                                penalty.obstacle_forcing((0.0, 0.0), perm), cfg["density"])
+    du, dv = ops.explicit_terms(spec, dev(u), dev(v), dev(perm))
+    assert rel_l2(host(du), k[0]) < 1e-5 and rel_l2(host(dv), k[1]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ fixed bodies
+def test_bodies_stay_put_without_updating_position():
+    """Updating_Position=None: the reference never touches particle_center (equations.py:143-158), the
+    kinematic laws still drive rotation and the body velocity U0(t)."""
+    cfg = configs.small_periodic(64)
+    steps = 6
+    st = oracle_state(cfg)
+    ostep = oracle_step(cfg, ib_window=6)
+    for _ in range(steps):
+        c0 = st.particles.centers
+        st = ostep(st)
+        st = dataclasses.replace(st, particles=st.particles.replace_centers(c0), Step_count=0)
+    stp = demo.make_stepper(cfg)
+    av = demo.make_all_variables(cfg, device="cuda")
+    out = stp.advance(av, steps, move_bodies=False)
+    _compare(out, st, 1e-5)
+    np.testing.assert_array_equal(np.asarray(out.particles.particle_center), np.asarray(av.particles.particle_center))
+    assert out.Step_count == 0
+
+
+# ------------------------------------------------------------------------------------------------ tracers, kT > 0
+def test_tracer_step_with_caller_noise():
+    """MD/simulate.py:81-97 with kT > 0: dR = F dt nu + sqrt(2 kT dt nu) xi, xi supplied by the caller
+    (JAX's threefry stream is not reproduced: DESIGN 7)."""
+    cfg = configs.bearing300()
+    spec = demo.make_spec(cfg)
+    rng = np.random.default_rng(11)
+    u = (0.2 * rng.standard_normal(cfg["shape"])).astype(F)
+    v = (0.2 * rng.standard_normal(cfg["shape"])).astype(F)
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    U = field.Var(u, (1.0, 0.5), g, field.periodic_bc())
+    V = field.Var(v, (0.5, 1.0), g, field.periodic_bc())
+    n = 1401
+    R = rng.uniform(0.2, 4.8, (n, 2)).astype(F)
+    xi = rng.standard_normal((n, 2)).astype(F)
+    mobile = rng.random(n) < 0.85
+    kT, dt_md, gamma = 1e-4, 1e-3, 2.0
+    want = tracers.brownian_step(tracers.BrownianState(R), (U, V), dt_md, gamma, kT, None, mobile, xi).position
+    Rg = dev(R.copy())
+    ops.tracer_step(spec, dev(u), dev(v), Rg, dt_md, gamma=gamma, kT=kT, xi=dev(xi), is_mobile=dev(mobile.astype(np.uint8)))
+    np.testing.assert_allclose(host(Rg), want, rtol=0, atol=1e-6)
+    # noise amplitude: the displacement variance of the mobile tracers is 2 kT dt / (m gamma) per axis
+    d = (host(Rg) - R)[mobile] - (tracers.brownian_step(tracers.BrownianState(R), (U, V), dt_md, gamma, 0.0, None,
+                                                        mobile).position - R)[mobile]
+    assert np.var(d) == pytest.approx(2 * kT * dt_md / gamma, rel=0.1)
+    assert np.array_equal(host(Rg)[~mobile], R[~mobile])
