@@ -127,6 +127,8 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
                             const float* markers, float* u_star, float* v_star);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                           const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
+bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
+                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
                      const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,

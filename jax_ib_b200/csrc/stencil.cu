@@ -272,6 +272,7 @@ int launch_explicit(cudaStream_t s, const GridF& g, const float* u, const float*
     return JAXIB_ERR_UNSUPPORTED;
   }
   int rc = JAXIB_OK;
+  if (launch_explicit_ring(s, g, u, v, p, perm, out_u, out_v, predictor, &rc)) return rc;
   if (launch_explicit_fast(s, g, u, v, p, perm, out_u, out_v, predictor, &rc)) return rc;
   return predictor ? launch_scheme<true>(s, g, u, v, p, perm, out_u, out_v)
                    : launch_scheme<false>(s, g, u, v, p, perm, out_u, out_v);
