@@ -89,6 +89,10 @@ typedef struct {
   const float* x0;            /* device [n_markers]                                             */
   const float* y0;            /* device [n_markers]                                             */
   double max_radius;          /* max over markers of hypot(x0, y0): bounds every body's extent  */
+  /* Optional (may be NULL): device [n_markers][4] floats per marker k of body b = (x0, y0 of the NEXT
+   * marker on b's closed curve -- roll(-1), IBM_Force.py:59-63 --, b as int32 bits, 0).  It removes the
+   * marker -> body search and one dependent memory round trip from the marker-force kernel.          */
+  const float* marker_pack;
 } jaxib_bodies;
 
 /* Per-step, per-body kinematic state, evaluated by the HOST from the user's Displacement_EQ /

@@ -35,6 +35,7 @@ class Bodies(C.Structure):
         ("n_bodies", C.c_int32), ("n_markers", C.c_int32),
         ("body_offset", C.c_void_p), ("x0", C.c_void_p), ("y0", C.c_void_p),
         ("max_radius", C.c_double),
+        ("marker_pack", C.c_void_p),
     ]
 
 

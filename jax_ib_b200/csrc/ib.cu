@@ -123,23 +123,41 @@ __global__ void interp_points_kernel(GridF g, float off_x, float off_y, const fl
 template <int RT>
 __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                                     const float* __restrict__ x0, const float* __restrict__ y0,
-                                    const float* __restrict__ body_state, const float* __restrict__ u_star,
-                                    const float* __restrict__ v_star, float* __restrict__ markers) {
-  // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel
+                                    const float4* __restrict__ pack, const float* __restrict__ body_state,
+                                    const float* __restrict__ u_star, const float* __restrict__ v_star,
+                                    float* __restrict__ markers) {
+  // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel.
+  // Dependent memory round trips: [x0, y0, pack] -> [body state] -> [window of u*] -> store.
   pdl_trigger();
-  pdl_wait();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gw = wid >> 1, comp = wid & 1;
   const int total = g.batch * n_markers;
   if (gw >= total) return;
   const int s = gw / n_markers, k = gw - s * n_markers;
-  int b = 0;
-  while (b + 1 < n_bodies && k >= body_offset[b + 1]) ++b;
-  const int k0 = body_offset[b], k1 = body_offset[b + 1];
-  const int kn = (k + 1 < k1) ? k + 1 : k0;  // roll(-1) within the body's closed curve
-  const float* st = body_state + ((size_t)s * n_bodies + b) * JAXIB_BODY_STATE_STRIDE;
-  const float c = st[0], sn = st[1], xc = st[2], yc = st[3], U0x = st[4], U0y = st[5], om = st[6];
-  const float ax = x0[k], ay = y0[k], bx = x0[kn], by = y0[kn];
+  // body-frame data is constant over the run: fetched before the dependency wait (prologue under the
+  // predictor's tail when launched programmatically)
+  const float ax = __ldg(x0 + k), ay = __ldg(y0 + k);
+  float bx, by;
+  int b;
+  if (pack) {
+    const float4 pk = __ldg(pack + k);
+    bx = pk.x; by = pk.y; b = __float_as_int(pk.z);
+  } else {  // no pack: binary search of the owning body, then the next marker on its closed curve
+    int lo = 0, hi = n_bodies;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (k >= __ldg(body_offset + mid)) lo = mid; else hi = mid;
+    }
+    b = lo;
+    const int k0 = __ldg(body_offset + b), k1 = __ldg(body_offset + b + 1);
+    const int kn = (k + 1 < k1) ? k + 1 : k0;  // roll(-1) within the body's closed curve
+    bx = __ldg(x0 + kn); by = __ldg(y0 + kn);
+  }
+  // the kinematic table was uploaded before the block of steps started: not an output of the previous kernel
+  const float4* st4 = reinterpret_cast<const float4*>(body_state + ((size_t)s * n_bodies + b) * JAXIB_BODY_STATE_STRIDE);
+  const float4 sa = __ldg(st4), sb = __ldg(st4 + 1);
+  pdl_wait();
+  const float c = sa.x, sn = sa.y, xc = sa.z, yc = sa.w, U0x = sb.x, U0y = sb.y, om = sb.z;
   const float xp = __fadd_rn(__fsub_rn(__fmul_rn(ax, c), __fmul_rn(ay, sn)), xc);
   const float yp = __fadd_rn(__fadd_rn(__fmul_rn(ax, sn), __fmul_rn(ay, c)), yc);
   const float xq = __fadd_rn(__fsub_rn(__fmul_rn(bx, c), __fmul_rn(by, sn)), xc);
@@ -248,20 +266,35 @@ __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic
   jc = cell_index(st[3], m.dy, m.off_y);
 }
 
-// grid = (tiles_per_axis^2, n_bodies, batch * 2); block = (TS, TS)
+// grid = (tiles_per_axis^2, n_bodies, batch * 2); block = SPREAD_THREADS; dynamic smem: (3 n_bodies + 1) ints
+// Dependent memory round trips: [all body boxes + marker ranges -> smem, own cell of u* prefetched] -> [the
+// body's markers] -> store (the first generation walked the bodies with one dependent global load each).
 __global__ void __launch_bounds__(SPREAD_THREADS)
 spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                      const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
                      int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star) {
   __shared__ SpreadShared sh;
+  extern __shared__ int sbody[];  // ic[n_bodies] | jc[n_bodies] | offset[n_bodies + 1]
+  int* const sic = sbody;
+  int* const sjc = sbody + n_bodies;
+  int* const soff = sbody + 2 * n_bodies;
   pdl_trigger();
-  pdl_wait();
   const int b = blockIdx.y;
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
   const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
-  int ic, jc;
-  body_box(states + b * JAXIB_BODY_STATE_STRIDE, m, ic, jc);
+  // kinematic table and marker ranges are not outputs of the previous kernel: read before the dependency wait
+  for (int b2 = threadIdx.x; b2 <= n_bodies; b2 += SPREAD_THREADS) {
+    if (b2 < n_bodies) {
+      int ic2, jc2;
+      body_box(states + b2 * JAXIB_BODY_STATE_STRIDE, m, ic2, jc2);
+      sic[b2] = ic2;
+      sjc[b2] = jc2;
+    }
+    soff[b2] = __ldg(body_offset + b2);
+  }
+  __syncthreads();
+  const int ic = sic[b], jc = sjc[b];
   const int ty = blockIdx.x / tiles_per_axis, tx = blockIdx.x - ty * tiles_per_axis;
   const int ti0 = ic - half_extent + ty * TS, tj0 = jc - half_extent + tx * TS;
   if (ti0 >= g.nx || ti0 + TS <= 0 || tj0 >= g.ny || tj0 + TS <= 0) return;  // tile fully outside: no image
@@ -269,31 +302,27 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int i = ti0 + cell / TS, j = tj0 + cell % TS;
   bool valid = i >= 0 && i < g.nx && j >= 0 && j < g.ny && i <= ic + half_extent && j <= jc + half_extent;
   // a cell covered by several bounding boxes belongs to the lowest-numbered body
-  for (int b2 = 0; b2 < b && valid; ++b2) {
-    int ic2, jc2;
-    body_box(states + b2 * JAXIB_BODY_STATE_STRIDE, m, ic2, jc2);
-    if (abs(i - ic2) <= half_extent && abs(j - jc2) <= half_extent) valid = false;
-  }
+  for (int b2 = 0; b2 < b && valid; ++b2)
+    if (abs(i - sic[b2]) <= half_extent && abs(j - sjc[b2]) <= half_extent) valid = false;
   const size_t total = (size_t)g.batch * n_markers;
   const float* mk = markers + (size_t)s * n_markers;
   const float* mF = mk + (comp == 0 ? 3 : 4) * total;
+  pdl_wait();
+  float* const out = (comp == 0 ? u_star : v_star) + (size_t)s * g.nx * g.ny + (size_t)(valid ? i : 0) * g.ny + (valid ? j : 0);
+  const bool writer = valid && threadIdx.x < TS * TS;
+  const float cur = writer ? *out : 0.0f;  // in flight while the markers are gathered
   float f_total = 0.0f;
   bool touched = false;
   for (int b2 = b; b2 < n_bodies; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
-    int ic2, jc2;
-    body_box(states + b2 * JAXIB_BODY_STATE_STRIDE, m, ic2, jc2);
+    const int ic2 = sic[b2], jc2 = sjc[b2];
     if (b2 != b && (ic2 + half_extent < ti0 || ic2 - half_extent >= ti0 + TS || jc2 + half_extent < tj0 ||
                     jc2 - half_extent >= tj0 + TS))
       continue;  // block-uniform
-    float fb = gather_markers(sh, m, mk, mk + total, mF, mk + 2 * total, body_offset[b2], body_offset[b2 + 1], ti0,
-                              tj0, i, j, valid);
+    float fb = gather_markers(sh, m, mk, mk + total, mF, mk + 2 * total, soff[b2], soff[b2 + 1], ti0, tj0, i, j, valid);
     f_total = __fadd_rn(f_total, fb);
     touched = true;
   }
-  if (valid && touched && f_total != 0.0f && threadIdx.x < TS * TS) {
-    float* out = (comp == 0 ? u_star : v_star) + (size_t)s * g.nx * g.ny + (size_t)i * g.ny + j;
-    *out = __fadd_rn(*out, __fmul_rn(g.dt, f_total));  // time_stepping.py:223
-  }
+  if (writer && touched && f_total != 0.0f) *out = __fadd_rn(cur, __fmul_rn(g.dt, f_total));  // time_stepping.py:223
 }
 
 // ---- generic L->E spreading of a point cloud (plug-in granularity, batch = 1) -------------------
@@ -351,10 +380,10 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
   if (g.R == 6)
     launch_pdl(2, interp_force_kernel<6>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
-               b.y0, body_state, u_star, v_star, markers);
+               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers);
   else
     launch_pdl(2, interp_force_kernel<0>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
-               b.y0, body_state, u_star, v_star, markers);
+               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers);
   return check_launch("interp_force_kernel");
 }
 
@@ -366,7 +395,9 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
   const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
   const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
   dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
-  launch_pdl(4, spread_bodies_kernel, grid, block, 0, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
+  const size_t smem = (size_t)(3 * b.n_bodies + 1) * sizeof(int);
+  if (smem > 40 * 1024) { set_error("ib_spread_bodies: %d bodies exceed the shared-memory body table", b.n_bodies); return JAXIB_ERR_UNSUPPORTED; }
+  launch_pdl(4, spread_bodies_kernel, grid, block, smem, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
              half_extent, tiles, u_star, v_star);
   return check_launch("spread_bodies_kernel");
 }

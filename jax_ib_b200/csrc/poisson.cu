@@ -42,11 +42,15 @@ struct jaxib_plan {
   size_t row_smem, col_smem;
   // power-of-two fast paths (poisson_fast.cu)
   bool fast_rows, fast_cols;
+  bool team_cols;               // K5 second generation (poisson_team.cu); implies fast_cols
+  bool team_rows;               // K4 / K6 second generation (poisson_team_rows.cu); implies fast_rows
   int fast_rows_per_group;      // K4
   int fast_rows_per_group_inv;  // K6 (each group also transforms the row after its last one)
   float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
   float* lam_y_f;
   float2* tw_dct;      // channel: exp(-i pi k / (2 ny))
+  float2* tw_team_col; // team column kernel: twiddle tables in shared-memory layout
+  float2* tw_team_row; // team row kernels: ditto
 };
 
 namespace jaxib {
@@ -444,6 +448,7 @@ int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const 
     rows_fwd_dct_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.dp, u, v, spectrum);
     return check_launch("rows_fwd_dct_kernel");
   }
+  if (pl->team_rows) return launch_rows_fwd_team(s, S.frp, pl->tw_team_row, u, v, spec);
   if (pl->fast_rows) return launch_rows_fwd_fast(s, S.frp, u, v, spec);
   rows_fwd_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.rp, u, v, spec);
   return check_launch("rows_fwd_kernel");
@@ -455,7 +460,8 @@ bool plan_fast_rows(const jaxib_plan* pl) { return pl->fast_rows; }
 bool plan_fast_cols(const jaxib_plan* pl) { return pl->fast_cols; }
 
 void plan_cols_geometry(const jaxib_plan* pl, int* cols_per_cta, int* ctas_per_sm) {
-  if (pl->fast_cols) fast_cols_geometry(pl->gf.nx, cols_per_cta, ctas_per_sm);
+  if (pl->team_cols) { *cols_per_cta = pl->gf.nx >= 4096 ? 4 : 8; *ctas_per_sm = 1; }
+  else if (pl->fast_cols) fast_cols_geometry(pl->gf.nx, cols_per_cta, ctas_per_sm);
   else { *cols_per_cta = pl->cols_per_cta; *ctas_per_sm = 1; }
 }
 
@@ -471,8 +477,8 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
     FastColParams fcp;
     fcp.limit = sp - col_begin;
     fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
-    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0;
-    return launch_cols_fast(s, fcp, g.batch, spec);
+    fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0; fcp.tw_team = pl->tw_team_col;
+    return pl->team_cols ? launch_cols_team(s, fcp, g.batch, spec) : launch_cols_fast(s, fcp, g.batch, spec);
   }
   ColParams cp;
   // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
@@ -505,6 +511,9 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum,
       rows_inv_dct_kernel<true><<<S.rgrid, pl->row_threads, smem, s>>>(S.dp, spectrum, u, v, p, u_out, v_out, p_out);
     return check_launch("rows_inv_dct_kernel");
   }
+  if (pl->team_rows)
+    return launch_rows_inv_team(s, S.frp, pl->tw_team_row, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out,
+                                q_only == nullptr);
   if (pl->fast_rows) {
     S.frp.rows_per_group = pl->fast_rows_per_group_inv;
     return launch_rows_inv_fast(s, S.frp, spec, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
@@ -558,9 +567,18 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   const bool aligned = (ny % 4) == 0;
   pl->fast_rows = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_size_supported(n2) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
   pl->fast_cols = grid->bc == JAXIB_BC_PERIODIC && aligned && fast_cols_supported(nx) && getenv("JAXIB_NO_FAST_FFT") == nullptr;
+  {
+    const char* e = getenv("JAXIB_COLS");  // JAXIB_COLS=fast selects the first-generation column kernel (A/B runs)
+    pl->team_cols = pl->fast_cols && team_cols_supported(nx) && !(e && !strcmp(e, "fast"));
+  }
+  {
+    const char* e = getenv("JAXIB_ROWS");  // JAXIB_ROWS=fast selects the first-generation row kernels (A/B runs)
+    pl->team_rows = pl->fast_rows && team_rows_supported(n2) && !(e && !strcmp(e, "fast"));
+  }
   if (pl->fast_cols) {
     pl->col.n = nx;
-    fast_radices(nx, pl->col.radix);  // three radices, four for nx = 8192
+    if (pl->team_cols) team_radices(nx, pl->col.radix);
+    else fast_radices(nx, pl->col.radix);  // three radices, four for nx = 8192
     pl->col.nstages = pl->col.radix[3] ? 4 : 3;
   }
   const double two_pi = 6.283185307179586476925286766559;
@@ -581,6 +599,16 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     rc = upload(&pl->tw_dct, twd);
   } else {
     for (int l = 0; l <= n2; ++l) ly[l] = (2.0 * cos(two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
+  }
+  if (!rc && pl->team_cols) {
+    std::vector<float2> tt;
+    team_twiddle_table(nx, &tt);
+    rc = upload(&pl->tw_team_col, tt);
+  }
+  if (!rc && pl->team_rows) {
+    std::vector<float2> tt;
+    team_row_twiddle_table(n2, &tt);
+    rc = upload(&pl->tw_team_row, tt);
   }
   if (!rc) rc = upload(&pl->tw_row, twr);
   if (!rc) rc = upload(&pl->tw_col, twc);
@@ -671,7 +699,7 @@ extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
   if (!pl) return JAXIB_OK;
   cudaFree(pl->tw_row); cudaFree(pl->tw_col); cudaFree(pl->row_pos); cudaFree(pl->col_pos);
   cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y); cudaFree(pl->lam_x_pos_f); cudaFree(pl->lam_y_f);
-  cudaFree(pl->tw_dct);
+  cudaFree(pl->tw_dct); cudaFree(pl->tw_team_col); cudaFree(pl->tw_team_row);
   delete pl;
   return JAXIB_OK;
 }

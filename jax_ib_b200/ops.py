@@ -157,12 +157,23 @@ class DeviceBodies:
         self.x0 = torch.from_numpy(x0).to(device)
         self.y0 = torch.from_numpy(y0).to(device)
         self.offsets_host = off
+        # per-marker pack (see struct jaxib_bodies): next marker on the closed curve + owning body
+        pack = np.zeros((self.n_markers, 4), dtype=np.float32)
+        body = np.zeros(self.n_markers, dtype=np.int32)
+        for b in range(self.n_bodies):
+            k0, k1 = int(off[b]), int(off[b + 1])
+            nxt = np.roll(np.arange(k0, k1), -1)
+            pack[k0:k1, 0], pack[k0:k1, 1] = x0[nxt], y0[nxt]
+            body[k0:k1] = b
+        pack[:, 2] = body.view(np.float32)
+        self.marker_pack = torch.from_numpy(pack).to(device)
 
     def c_struct(self) -> _lib.Bodies:
         b = _lib.Bodies()
         b.n_bodies, b.n_markers = self.n_bodies, self.n_markers
         b.body_offset, b.x0, b.y0 = self.body_offset.data_ptr(), self.x0.data_ptr(), self.y0.data_ptr()
         b.max_radius = self.max_radius
+        b.marker_pack = self.marker_pack.data_ptr() if self.n_markers else None
         return b
 
 
