@@ -43,7 +43,9 @@ struct jaxib_plan {
   // power-of-two fast paths (poisson_fast.cu)
   bool fast_rows, fast_cols;
   bool team_cols;               // K5 second generation (poisson_team.cu); implies fast_cols
-  bool team_rows;               // K4 / K6 second generation (poisson_team_rows.cu); implies fast_rows
+  bool team_rows;               // K6 second generation (poisson_team_rows.cu); implies fast_rows
+  bool team_rows_fwd;           // K4 second generation: row lengths ny <= 2048 (measured: the radix-16 first pass
+                                // of longer rows spills at 64 registers and loses to the first generation)
   int fast_rows_per_group;      // K4
   int fast_rows_per_group_inv;  // K6 (each group also transforms the row after its last one)
   float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
@@ -448,7 +450,7 @@ int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const 
     rows_fwd_dct_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.dp, u, v, spectrum);
     return check_launch("rows_fwd_dct_kernel");
   }
-  if (pl->team_rows) return launch_rows_fwd_team(s, S.frp, pl->tw_team_row, u, v, spec);
+  if (pl->team_rows_fwd) return launch_rows_fwd_team(s, S.frp, pl->tw_team_row, u, v, spec);
   if (pl->fast_rows) return launch_rows_fwd_fast(s, S.frp, u, v, spec);
   rows_fwd_kernel<<<S.rgrid, pl->row_threads, pl->row_smem, s>>>(S.rp, u, v, spec);
   return check_launch("rows_fwd_kernel");
@@ -574,6 +576,8 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   {
     const char* e = getenv("JAXIB_ROWS");  // JAXIB_ROWS=fast selects the first-generation row kernels (A/B runs)
     pl->team_rows = pl->fast_rows && team_rows_supported(n2) && !(e && !strcmp(e, "fast"));
+    const char* ef = getenv("JAXIB_ROWS_FWD");
+    pl->team_rows_fwd = pl->team_rows && (ef ? !strcmp(ef, "team") : n2 <= 1024);
   }
   if (pl->fast_cols) {
     pl->col.n = nx;

@@ -59,14 +59,14 @@ template <int R1, int R2, int R3, int PS2>
 struct RowTeam {
   static constexpr int N = R1 * R2 * R3;  // complex length ny/2
   static constexpr int T = N / 16;        // threads per row team
-  static constexpr int NT = 1024 / T;     // teams per CTA
+  static constexpr int NT = 1024 / T;     // teams per CTA at most (the launcher may use fewer: small grids)
   static constexpr int SUB1 = N / R1, SUB2 = SUB1 / R2;
   static constexpr int NBA = 16 / R1, NBB = 16 / R2, NBC = 16 / R3;
   __host__ __device__ static constexpr int pad(int p) { return p + (p >> 4) + (p >> PS2); }
   static constexpr int BUF = (pad(N) + 3) & ~1;  // floats2 per team buffer (even: 16-byte aligned buffers)
   static constexpr int TA = (R1 - 1) * SUB1, TB = (R2 - 1) * SUB2, TU = N / 2 + 1;
   static constexpr int TAB = (TA + TB + TU + 1) & ~1;  // table entries (even: bulk copies move 16-byte units)
-  static constexpr size_t SMEM = (size_t)(TAB + NT * BUF) * sizeof(float2);
+  __host__ static size_t smem(int nt) { return (size_t)(TAB + nt * BUF) * sizeof(float2); }
   // position of frequency k after the forward DIF (digit reversal of the radix triple)
   __device__ static __forceinline__ int pos(int k) {
     return (k % R1) * SUB1 + ((k / R1) % R2) * SUB2 + k / (R1 * R2);
@@ -168,7 +168,7 @@ rows_fwd_team_kernel(FastRowParams P, const float2* __restrict__ tables, const f
   if (t == 0) tables_issue<G>(smr, tables, bar);  // independent of the previous kernel
   const GridF& g = P.g;
   const int ny = g.ny;
-  const int i = blockIdx.x * G::NT + team;
+  const int i = blockIdx.x * (blockDim.x / T) + team;
   const bool live = i < g.nx;  // uniform over the team (whole warps)
   const size_t plane = (size_t)g.nx * ny;
   u += blockIdx.y * plane;
@@ -268,8 +268,9 @@ __global__ void __launch_bounds__(1024, 1)
 rows_inv_team_kernel(FastRowParams P, const float2* __restrict__ tables, const float2* __restrict__ spec, const float* u,
                      const float* v, const float* p, float* u_out, float* v_out, float* p_out) {
   using G = RowTeam<R1, R2, R3, PS2>;
-  constexpr int N = G::N, T = G::T, SUB1 = G::SUB1, NT = G::NT;
-  constexpr int ROWS = PROJECT ? NT - 1 : NT;  // rows finalised per CTA (the last team carries the row after them)
+  constexpr int N = G::N, T = G::T, SUB1 = G::SUB1;
+  const int NT = blockDim.x / T;               // teams in this CTA
+  const int ROWS = PROJECT ? NT - 1 : NT;      // rows finalised per CTA (the last team carries the row after them)
   extern __shared__ __align__(16) float2 smr[];
   __shared__ __align__(8) unsigned long long tbar;
   float2* const ta = smr;
@@ -410,17 +411,30 @@ rows_inv_team_kernel(FastRowParams P, const float2* __restrict__ tables, const f
   }
 }
 
+// Teams per CTA: the most that still gives every SM a CTA (small grids would otherwise run on a fraction of the
+// machine: 1024 rows of ny = 1024 are 32 CTAs of 32 teams); `halo` = 1 when one team per CTA carries the extra row.
+int teams_per_cta(int max_nt, int nx, int batch, int halo) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const long long rows = (long long)nx * batch;
+  int nt = max_nt;
+  while (nt > 4 && rows / (nt - halo) < sms) nt /= 2;
+  // a barrier is shared by 128 threads: keep whole barrier groups
+  return nt;
+}
+
 template <int R1, int R2, int R3, int PS2>
 int launch_rows_fwd_team_t(cudaStream_t s, const FastRowParams& P, const float2* tables, const float* u, const float* v,
                            float2* spec) {
   using G = RowTeam<R1, R2, R3, PS2>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(rows_fwd_team_kernel<R1, R2, R3, PS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaFuncSetAttribute(rows_fwd_team_kernel<R1, R2, R3, PS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem(G::NT));
     configured = true;
   }
-  dim3 grid((P.g.nx + G::NT - 1) / G::NT, P.g.batch);
-  launch_pdl(8, rows_fwd_team_kernel<R1, R2, R3, PS2>, grid, dim3(1024), G::SMEM, s, P, tables, u, v, spec);
+  const int nt = teams_per_cta(G::NT, P.g.nx, P.g.batch, 0);
+  dim3 grid((P.g.nx + nt - 1) / nt, P.g.batch);
+  launch_pdl(8, rows_fwd_team_kernel<R1, R2, R3, PS2>, grid, dim3(nt * G::T), G::smem(nt), s, P, tables, u, v, spec);
   return check_launch("rows_fwd_team_kernel");
 }
 
@@ -430,16 +444,17 @@ int launch_rows_inv_team_t(cudaStream_t s, const FastRowParams& P, const float2*
   using G = RowTeam<R1, R2, R3, PS2>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(rows_inv_team_kernel<R1, R2, R3, PS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    cudaFuncSetAttribute(rows_inv_team_kernel<R1, R2, R3, PS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaFuncSetAttribute(rows_inv_team_kernel<R1, R2, R3, PS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem(G::NT));
+    cudaFuncSetAttribute(rows_inv_team_kernel<R1, R2, R3, PS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem(G::NT));
     configured = true;
   }
-  const int rows = project ? G::NT - 1 : G::NT;
+  const int nt = teams_per_cta(G::NT, P.g.nx, P.g.batch, project ? 1 : 0);
+  const int rows = project ? nt - 1 : nt;
   dim3 grid((P.g.nx + rows - 1) / rows, P.g.batch);
   if (project)
-    launch_pdl(32, rows_inv_team_kernel<R1, R2, R3, PS2, true>, grid, dim3(1024), G::SMEM, s, P, tables, spec, u, v, p, uo, vo, po);
+    launch_pdl(32, rows_inv_team_kernel<R1, R2, R3, PS2, true>, grid, dim3(nt * G::T), G::smem(nt), s, P, tables, spec, u, v, p, uo, vo, po);
   else
-    launch_pdl(32, rows_inv_team_kernel<R1, R2, R3, PS2, false>, grid, dim3(1024), G::SMEM, s, P, tables, spec, u, v, p, uo, vo, po);
+    launch_pdl(32, rows_inv_team_kernel<R1, R2, R3, PS2, false>, grid, dim3(nt * G::T), G::smem(nt), s, P, tables, spec, u, v, p, uo, vo, po);
   return check_launch("rows_inv_team_kernel");
 }
 
