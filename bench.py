@@ -346,11 +346,12 @@ def run_b200(args, rank, world, local_rank):
 
     u0, v0, p0 = (torch.from_numpy(a).to(device) for a in _configs.initial_fields(cfg))
     table, times, centers = kinematics.body_schedule(particles, 0.0, cfg["dt"], W + 3 * K)
-    table = torch.from_numpy(np.ascontiguousarray(table[:, None])).to(device)
+    table_host = np.ascontiguousarray(table[:, None])  # the host copy lets the library overlap the IB chain
+    table = torch.from_numpy(table_host).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # 256 MiB > 126 MB L2
 
     u, v, p = u0.clone(), v0.clone(), p0.clone()
-    stepper.run_block(u, v, p, W, table[:W])  # warm-up (untimed)
+    stepper.run_block(u, v, p, W, table[:W], table_host=table_host[:W])  # warm-up (untimed)
     # ---- timed region 1: K steps, each bracketed by a CUDA-event pair on the launching stream, 256 MiB
     #      L2 flush before every step outside the brackets (the launches queue up behind the flush) ------
     sampler = ClockSampler(local_rank)
@@ -360,7 +361,7 @@ def run_b200(args, rank, world, local_rank):
     for n in range(K):
         flush.fill_(n & 0xff)
         evs[n][0].record()
-        stepper.run_block(u, v, p, 1, table[W + n:W + n + 1])
+        stepper.run_block(u, v, p, 1, table[W + n:W + n + 1], table_host=table_host[W + n:W + n + 1])
         evs[n][1].record()
     barrier()
     ms_steps = sum(a.elapsed_time(b) for a, b in evs)
@@ -372,7 +373,7 @@ def run_b200(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    stepper.run_block(u, v, p, K, table[W + K:W + 2 * K])
+    stepper.run_block(u, v, p, K, table[W + K:W + 2 * K], table_host=table_host[W + K:W + 2 * K])
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -435,7 +436,7 @@ def run_b200(args, rank, world, local_rank):
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * cells},
         "clocks": clocks,
-        "gpu_launches": stepper.launches_per_step * K,
+        "gpu_launches": (stepper.launches_per_step + (1 if os.environ.get("JAXIB_IB_OVERLAP", "0") == "1" else 0)) * K,
         "e2e": {"value": world * cells * Ke / e2e_s / 1e6, "unit": UNIT, "steps": Ke,
                 "h2d_bytes_per_step": 3 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
                 "api": "FusedStepper.advance(All_Variables on pinned host memory, 1)"},

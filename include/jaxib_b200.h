@@ -13,7 +13,11 @@
  *     Staggering (grids.py:632-637): u at offset (1, .5), v at (.5, 1), p at (.5, .5).
  *   - Every call only ENQUEUES work on `stream` (a cudaStream_t); none synchronises.
  *   - Return value: 0 on success, negative jaxib_status otherwise; jaxib_last_error() gives text.
- *   - No mutable globals: all state lives in the caller's buffers or in a jaxib_plan.
+ *   - All simulation state lives in the caller's buffers or in a jaxib_plan.  Process-wide, created on
+ *     first use and never part of a result: one internal side stream (+ events) per device for the
+ *     overlapped IB chain (jaxib_step) and for the slab decomposition's overlapped push (jaxib_slab_step),
+ *     the once-per-function shared-memory opt-ins, and the environment switches read once (JAXIB_*).
+ *     One host thread per device may drive the library at a time (the XLA runtime's model as well).
  *   - Inputs are const; in-place use is allowed only where stated.
  */
 #ifndef JAXIB_B200_H_
@@ -219,6 +223,11 @@ int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const ja
 /* time_stepping.py:144-255 step_fn, `nsteps` times, in place on (u, v, p):
  *   predict -> [IB interp / force / spread] -> project.
  * bodies == NULL skips the IB stage.  body_table: [nsteps][batch][n_bodies][8] (device).
+ * body_table_host (may be NULL): the same table in HOST memory.  When given (batch = 1, upwind periodic
+ * grids) the library knows where the bodies are and hides the two latency-bound IB kernels: the
+ * predictor covers the rows near the bodies first, then the IB kernels run on an internal
+ * high-priority side stream while the predictor covers the rest of the grid; the projection waits
+ * for both.  Results are identical to the serial order.
  * perm (may be NULL): [batch][nx][ny] Brinkman permeability.  incremental_pressure == 0 selects
  * the penalty stepper (no -grad p_old in the predictor, time_stepping.py:345).
  * wall_table (HOST memory, may be NULL): [nsteps][4] = u_lo, u_hi, v_lo, v_hi, the wall values of a
@@ -227,8 +236,8 @@ int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const ja
  * The clock / body centres are host-side state (boundaries.py:519-542, particle_motion.py:38-66)
  * and are not touched here.                                                                    */
 int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
-               const float* perm, const double* wall_table, int32_t incremental_pressure, int32_t nsteps, float* u,
-               float* v, float* p, void* scratch, size_t scratch_bytes);
+               const float* body_table_host, const float* perm, const double* wall_table, int32_t incremental_pressure,
+               int32_t nsteps, float* u, float* v, float* p, void* scratch, size_t scratch_bytes);
 
 /* Measurement aid (bench.py): runs `nsteps` steps like jaxib_step but brackets every stage of every
  * step with CUDA events on `stream`, optionally overwrites `flush` (flush_bytes, > L2) before each

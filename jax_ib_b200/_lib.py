@@ -76,8 +76,8 @@ _SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), _P, _P]),
     "jaxib_pressure_solve": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_size_t]),
     "jaxib_project": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t]),
-    "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.POINTER(C.c_double), C.c_int32, C.c_int32, _P, _P, _P, _P,
-                             C.c_size_t]),
+    "jaxib_step": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, _P, C.POINTER(C.c_double), C.c_int32, C.c_int32, _P, _P,
+                             _P, _P, C.c_size_t]),
     "jaxib_step_profile": (C.c_int, [_P, _P, C.POINTER(Bodies), _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P,
                                      C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_double)]),
     "jaxib_tracer_step": (C.c_int, [_P, C.POINTER(Grid), _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double,

@@ -4,7 +4,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
+#include <algorithm>
 #include <initializer_list>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -60,6 +64,80 @@ static int check_ptrs(const char* who, std::initializer_list<const void*> ptrs) 
   for (const void* p : ptrs)
     if (!p) { set_error("%s: null device pointer", who); return JAXIB_ERR_INVALID; }
   return JAXIB_OK;
+}
+
+// ---- immersed-boundary chain on a side stream --------------------------------------------------------------
+// The two IB kernels (marker forces, spreading) are pure latency chains that occupy a few SMs for ~20 us.  When
+// the host knows where the bodies are (body_table_host), the predictor is split: rows near the bodies first
+// (K1a, a short launch), then the IB chain runs on a high-priority side stream WHILE the predictor covers the
+// rest of the grid (K1b); the projection waits for both.  One side stream + two events per device, created on
+// first use (process-wide, like the slab decomposition's side stream: documented in the header).
+struct OverlapCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool tried = false;
+};
+static OverlapCtx* overlap_ctx() {
+  static OverlapCtx ctx[32];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  OverlapCtx& c = ctx[dev];
+  if (!c.tried) {
+    c.tried = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess)
+      c.side = nullptr;
+    cudaGetLastError();
+  }
+  return c.side ? &c : nullptr;
+}
+static bool overlap_enabled() {
+  static int on = -1;
+  // Off by default.  Measured on B200 (profiles/r2h_overlap_trace.log, ib2048): the results are bit-identical, but
+  // next to the bandwidth-saturating predictor the two latency-bound IB kernels take 30 us instead of 22 us, the
+  // short first launch costs ~9 us and each cross-stream hop ~3 us: 92.5 us per step against 86.9 us serial.
+  if (on < 0) { const char* e = getenv("JAXIB_IB_OVERLAP"); on = (e && atoi(e) == 1) ? 1 : 0; }
+  return on == 1;
+}
+
+// Row ranges touched by the IB kernels of one step (interpolation windows and spreading boxes of every body,
+// same extent as launch_ib_spread_bodies) and their complement.  Returns false when splitting is not worth it.
+static bool body_row_bands(const GridF& g, const jaxib_bodies& b, const float* state_host, RowBands* near, RowBands* rest) {
+  const float hmin = g.dx < g.dy ? g.dx : g.dy;
+  const int he = (int)ceil(b.max_radius / hmin) + g.R + 2;
+  int lo[kMaxBands], hi[kMaxBands], n = 0;
+  std::vector<std::pair<int, int>> iv;
+  for (int k = 0; k < b.n_bodies; ++k) {
+    const float xc = state_host[(size_t)k * JAXIB_BODY_STATE_STRIDE + 2];
+    const int ic = (int)floorf(xc / g.dx - 1.0f);
+    int a = ic - he - 2, e = ic + he + 3;
+    if (a < 0) a = 0;
+    if (e > g.nx) e = g.nx;
+    if (a < e) iv.push_back({a, e});
+  }
+  if (iv.empty()) return false;
+  std::sort(iv.begin(), iv.end());
+  for (auto& x : iv) {
+    if (n > 0 && x.first <= hi[n - 1]) { if (x.second > hi[n - 1]) hi[n - 1] = x.second; continue; }
+    if (n == kMaxBands - 1) return false;
+    lo[n] = x.first; hi[n] = x.second; ++n;
+  }
+  int covered = 0;
+  for (int k = 0; k < n; ++k) covered += hi[k] - lo[k];
+  if (covered * 2 > g.nx) return false;  // bodies everywhere: nothing to hide the IB chain behind
+  near->n = n;
+  for (int k = 0; k < n; ++k) { near->start[k] = lo[k]; near->rows[k] = hi[k] - lo[k]; }
+  int m = 0, at = 0;
+  for (int k = 0; k <= n; ++k) {
+    const int end = k < n ? lo[k] : g.nx;
+    if (end > at) { rest->start[m] = at; rest->rows[m] = end - at; ++m; }
+    if (k < n) at = hi[k];
+  }
+  rest->n = m;
+  return m > 0;
 }
 
 struct Scratch {
@@ -264,8 +342,8 @@ int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u,
 }
 
 int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies* bodies, const float* body_table,
-               const float* perm, const double* wall_table, int32_t incremental_pressure, int32_t nsteps, float* u,
-               float* v, float* p, void* scratch, size_t scratch_bytes) {
+               const float* body_table_host, const float* perm, const double* wall_table, int32_t incremental_pressure,
+               int32_t nsteps, float* u, float* v, float* p, void* scratch, size_t scratch_bytes) {
   if (!plan) { set_error("step: plan is null"); return JAXIB_ERR_INVALID; }
   int rc = check_ptrs("step", {u, v, p});
   if (rc) return rc;
@@ -288,11 +366,54 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
       gn.uw_lo = (float)w[0]; gn.uw_hi = (float)w[1]; gn.vw_lo = (float)w[2]; gn.vw_hi = (float)w[3];
     }
     const GridF* gov = wall_table ? &gn : nullptr;
-    // time_stepping.py:191-208
-    if ((rc = launch_explicit(s, gn, u, v, incremental_pressure ? p : nullptr, perm, sc.u_star, sc.v_star, true))) return rc;
-    // time_stepping.py:210-223
-    if (has_ib && (rc = launch_ib_force(s, gn, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
-      return rc;
+    const float* pin = incremental_pressure ? p : nullptr;
+    // IB chain on the side stream behind a split predictor (see OverlapCtx)
+    RowBands near, rest;
+    OverlapCtx* oc = nullptr;
+    if (has_ib && body_table_host && g.batch == 1 && overlap_enabled() && explicit_ring_eligible(gn) &&
+        body_row_bands(gn, *bodies, body_table_host + n * state_stride, &near, &rest))
+      oc = overlap_ctx();
+    bool split = false;
+    static const bool trace = getenv("JAXIB_OVERLAP_TRACE") != nullptr;  // diagnostic: event time stamps of the fork / join
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (oc) {
+      int rc1 = JAXIB_OK;
+      if (trace) { for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], s); }
+      split = launch_explicit_ring(s, gn, u, v, pin, perm, sc.u_star, sc.v_star, true, &rc1, &near);  // K1a
+      if (split) {
+        if (rc1) return rc1;
+        cudaEventRecord(oc->fork, s);
+        if (trace) cudaEventRecord(tev[1], s);
+        cudaStreamWaitEvent(oc->side, oc->fork, 0);
+        if (trace) cudaEventRecord(tev[2], oc->side);
+        if ((rc = launch_ib_force(oc->side, gn, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
+          return rc;
+        cudaEventRecord(oc->join, oc->side);
+        if (trace) cudaEventRecord(tev[3], oc->side);
+        if (!launch_explicit_ring(s, gn, u, v, pin, perm, sc.u_star, sc.v_star, true, &rc1, &rest) || rc1) {  // K1b
+          set_error("step: split predictor launch failed");
+          return rc1 ? rc1 : JAXIB_ERR_CUDA;
+        }
+        if (trace) cudaEventRecord(tev[4], s);
+        cudaStreamWaitEvent(s, oc->join, 0);
+        if (trace) {
+          cudaStreamSynchronize(s);
+          float a, b, c, d;
+          cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[0], tev[2]);
+          cudaEventElapsedTime(&c, tev[0], tev[3]); cudaEventElapsedTime(&d, tev[0], tev[4]);
+          fprintf(stderr, "overlap trace (us from step start): K1a done %.1f | side stream starts %.1f | IB chain done %.1f | K1b done %.1f\n",
+                  a * 1e3, b * 1e3, c * 1e3, d * 1e3);
+          for (auto& e : tev) cudaEventDestroy(e);
+        }
+      }
+    }
+    if (!split) {
+      // time_stepping.py:191-208
+      if ((rc = launch_explicit(s, gn, u, v, pin, perm, sc.u_star, sc.v_star, true))) return rc;
+      // time_stepping.py:210-223
+      if (has_ib && (rc = launch_ib_force(s, gn, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers)))
+        return rc;
+    }
     // time_stepping.py:246
     if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum, nullptr, gov))) return rc;
   }

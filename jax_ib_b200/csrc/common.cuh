@@ -127,8 +127,19 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
                             const float* markers, float* u_star, float* v_star);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                           const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
+// Row ranges of one predictor launch (stencil_ring.cu): the rows near the bodies are computed first so that the
+// immersed-boundary kernels can run on a side stream while the rest of the grid is predicted (capi.cu).
+constexpr int kMaxBands = 16;
+struct RowBands {
+  int n;                       // number of disjoint ranges, sorted
+  int start[kMaxBands];
+  int rows[kMaxBands];
+  int chunk0[kMaxBands + 1];   // filled by the launcher: first CTA row-chunk of each range
+};
+bool explicit_ring_eligible(const GridF& g);
 bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
-                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
+                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc,
+                          const RowBands* bands = nullptr);
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
                      const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,

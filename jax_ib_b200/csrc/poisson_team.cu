@@ -65,11 +65,17 @@ struct TeamGeom {
   __host__ __device__ static constexpr int pad(int p) { return p + (p >> PS); }
 };
 
-template <int R1, int R2, int R3, int CS, int PS>
+// HV = 2: the CTA works as two HALVES of CS/2 columns that only meet at kernel start.  Half 1 issues its column
+// loads after half 0 has issued all of its own (named-barrier arrive / sync), so the memory system serves half 0
+// first: its transform runs while half 1's columns are still streaming in, and it stores while half 1 still
+// computes -- the load / compute / store phases of the two halves overlap inside one SM (the kernel is a single
+// wave: without this every SM loads, then computes, then stores in lockstep; ncu r2d: issue slots 50 % busy).
+template <int R1, int R2, int R3, int CS, int PS, int HV>
 __global__ void __launch_bounds__(CS * (R1 * R2 * R3 / 16), 1)
 cols_team_kernel(FastColParams P, int cpc, float2* __restrict__ spec) {
   using G = TeamGeom<R1, R2, R3, CS, PS>;
   constexpr int N = G::N, T = G::T, SUB1 = G::SUB1, SUB2 = G::SUB2, CP = G::COLPITCH;
+  constexpr int CSH = CS / HV, TH = CSH * T;  // columns / threads per half
   extern __shared__ __align__(16) float2 smt[];
   float2* const ta = smt + CS * CP;  // [q - 1][b]:  W_N^(b q)
   float2* const tb = ta + G::TA;     // [q - 1][b2]: W_N^(b2 q R1)
@@ -90,23 +96,26 @@ cols_team_kernel(FastColParams P, int cpc, float2* __restrict__ spec) {
                  "l"(P.tw_team), "r"(bytes), "r"(bar)
                  : "memory");
   }
-  // ---- G mapping
-  const int c = t % CS, bt = t / CS;
+  // ---- G mapping (inside the thread's half)
+  const int half = t / TH, th = t - half * TH;
+  const int c = half * CSH + th % CSH, bt = th / CSH;
   const int gc = blockIdx.x * cpc + c;
   const bool gvalid = c < cpc && gc < P.ncols && gc < P.limit;
   float2* const gspec = spec + (size_t)blockIdx.y * P.nx * P.sp + gc;
   const size_t rs = (size_t)P.sp;
   float2* const gcol = smt + c * CP;
   pdl_wait();
+  __syncthreads();  // the mbarrier initialisation is visible to every thread
   bool tables_ready = false;
 #pragma unroll
   for (int j = 0; j < G::NBA; ++j) {  // pass A forward: global -> registers -> shared
     const int b = bt + T * j;
     float2 v[R1];
+    if (HV == 2 && j == 0 && half == 1) asm volatile("bar.sync 11, %0;" ::"r"(CS * T) : "memory");  // after half 0's loads
 #pragma unroll
     for (int r = 0; r < R1; ++r) v[r] = gvalid ? gspec[(size_t)(b + SUB1 * r) * rs] : make_float2(0.f, 0.f);
+    if (HV == 2 && j == G::NBA - 1 && half == 0) asm volatile("bar.arrive 11, %0;" ::"r"(CS * T) : "memory");
     if (!tables_ready) {  // the table copy was issued long before: this wait is normally free
-      __syncthreads();    // the barrier initialisation is visible to every thread
       unsigned ok = 0;
       while (!ok)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
@@ -121,7 +130,7 @@ cols_team_kernel(FastColParams P, int cpc, float2* __restrict__ spec) {
       dst[G::pad(SUB1 * q)] = v[q];
     }
   }
-  __syncthreads();
+  if (HV == 2) team_sync(9 + half, TH); else __syncthreads();
   // ---- team mapping
   const int team = t / T, b = t - team * T;
   if (team < cpc) {
@@ -182,7 +191,7 @@ cols_team_kernel(FastColParams P, int cpc, float2* __restrict__ spec) {
       for (int r = 0; r < R2; ++r) e[G::pad(SUB2 * r)] = v[r];
     }
   }
-  __syncthreads();
+  if (HV == 2) team_sync(9 + half, TH); else __syncthreads();
 #pragma unroll
   for (int j = 0; j < G::NBA; ++j) {  // pass A inverse: shared -> registers -> global
     const int bb = bt + T * j;
@@ -204,12 +213,15 @@ cols_team_kernel(FastColParams P, int cpc, float2* __restrict__ spec) {
 template <int R1, int R2, int R3, int CS, int PS>
 int launch_cols_team_t(cudaStream_t s, const FastColParams& P, int batch, float2* spec) {
   using G = TeamGeom<R1, R2, R3, CS, PS>;
-  static int sms = 0;
+  static int sms = 0, halves = 1;  // measured at 2048^2: staggered halves 21.9 us, plain 20.6 us (JAXIB_COLS_HALVES=2 to retry)
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(cols_team_kernel<R1, R2, R3, CS, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaFuncSetAttribute(cols_team_kernel<R1, R2, R3, CS, PS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaFuncSetAttribute(cols_team_kernel<R1, R2, R3, CS, PS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    const char* eh = getenv("JAXIB_COLS_HALVES");
+    if (eh && atoi(eh) == 2) halves = 2;
   }
   // columns per CTA: CS (whole 32-byte sectors per row; measured at 2048^2: 129 CTAs x 8 columns 20.8 us,
   // 147 CTAs x 7 columns 22.2 us -- the 56-byte row segments straddle sectors); fewer only for tiny problems
@@ -219,7 +231,10 @@ int launch_cols_team_t(cudaStream_t s, const FastColParams& P, int batch, float2
   static const char* e = getenv("JAXIB_COLS_CPC");
   if (e && atoi(e) >= 1 && atoi(e) <= CS) cpc = atoi(e);
   dim3 grid((P.ncols + cpc - 1) / cpc, batch);
-  launch_pdl(16, cols_team_kernel<R1, R2, R3, CS, PS>, grid, dim3(CS * G::T), G::SMEM, s, P, cpc, spec);
+  if (halves == 2 && (CS / 2) * G::T >= 32)
+    launch_pdl(16, cols_team_kernel<R1, R2, R3, CS, PS, 2>, grid, dim3(CS * G::T), G::SMEM, s, P, cpc, spec);
+  else
+    launch_pdl(16, cols_team_kernel<R1, R2, R3, CS, PS, 1>, grid, dim3(CS * G::T), G::SMEM, s, P, cpc, spec);
   return check_launch("cols_team_kernel");
 }
 

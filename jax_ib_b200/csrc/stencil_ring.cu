@@ -67,6 +67,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 
 struct RingParams {
+  RowBands bands;  // row ranges this launch covers (one range [0, nx) for the whole grid)
   int nx, ny;
   int W;      // strip width in columns = 4 * consumer threads
   int rpc;    // rows per CTA
@@ -105,8 +106,11 @@ explicit_upwind_ring_kernel(RingParams P, const float* __restrict__ u, const flo
   const int ny = P.ny, nx = P.nx, depth = P.depth;
   const int c0col = blockIdx.x * P.W;
   const int Ws = min(P.W, ny - c0col);
-  const int i0 = blockIdx.y * P.rpc;
-  const int i1 = min(i0 + P.rpc, nx);
+  // blockIdx.y -> (band, chunk of rpc rows inside the band)
+  int band = 0;
+  while (band + 1 < P.bands.n && (int)blockIdx.y >= P.bands.chunk0[band + 1]) ++band;
+  const int i0 = P.bands.start[band] + ((int)blockIdx.y - P.bands.chunk0[band]) * P.rpc;
+  const int i1 = min(i0 + P.rpc, P.bands.start[band] + P.bands.rows[band]);
   const int nload = i1 - i0 + 2;   // rows i0-1 .. i1
   const bool hasp = PREDICT && p != nullptr;
   const size_t boff = (size_t)blockIdx.z * nx * ny;
@@ -265,9 +269,13 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-// Returns true when this path handled the launch (rc holds the status).
+bool explicit_ring_eligible(const GridF& g) {
+  return g.bc == JAXIB_BC_PERIODIC && g.convect == JAXIB_CONVECT_UPWIND && !(g.ny & 3) && g.ny >= 8 && g.nx >= 4;
+}
+
+// Returns true when this path handled the launch (rc holds the status).  bands == nullptr: the whole grid.
 bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
-                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc) {
+                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc, const RowBands* bands) {
   if (g.bc != JAXIB_BC_PERIODIC || g.convect != JAXIB_CONVECT_UPWIND || (g.ny & 3) || g.ny < 8 || g.nx < 4) return false;
   const uintptr_t align = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v) |
                           reinterpret_cast<uintptr_t>(out_u) | reinterpret_cast<uintptr_t>(out_v) |
@@ -303,18 +311,33 @@ bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const 
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, explicit_upwind_ring_kernel<false>, threads, smem);
   if (per_sm < 1) per_sm = 1;
   // rows per CTA: one CTA per resident slot when the grid is small enough, otherwise marches of <= 64 rows
+  RowBands B;
+  if (bands) B = *bands;
+  else { B.n = 1; B.start[0] = 0; B.rows[0] = g.nx; }
+  int band_rows = 0;
+  for (int k = 0; k < B.n; ++k) band_rows += B.rows[k];
+  if (band_rows <= 0) { *rc = JAXIB_OK; return true; }
   const long long slots = (long long)sms * per_sm;
-  const long long row_strips = (long long)g.nx * nstrips * g.batch;
+  const long long row_strips = (long long)band_rows * nstrips * g.batch;
   int rpc = env_int("JAXIB_K1_RPC", 0);
   if (rpc <= 0) {
     rpc = (int)((row_strips + slots - 1) / slots);
     if (rpc < 8) rpc = 8;
     if (rpc > 64) rpc = 64;
     if (rpc > g.nx) rpc = g.nx;
-    const int groups = (g.nx + rpc - 1) / rpc;  // equalise the marches
-    rpc = (g.nx + groups - 1) / groups;
+    if (!bands) {
+      const int groups = (g.nx + rpc - 1) / rpc;  // equalise the marches
+      rpc = (g.nx + groups - 1) / groups;
+    }
   }
+  int chunks = 0;
+  for (int k = 0; k < B.n; ++k) {
+    B.chunk0[k] = chunks;
+    chunks += (B.rows[k] + rpc - 1) / rpc;
+  }
+  B.chunk0[B.n] = chunks;
   RingParams P;
+  P.bands = B;
   P.nx = g.nx; P.ny = g.ny; P.W = W; P.rpc = rpc; P.depth = depth;
   const float S = predictor ? g.dt : 1.0f;
   P.c0 = (predictor ? 1.0f : 0.0f) - 2.0f * S * g.nu * g.ssum;
@@ -327,7 +350,7 @@ bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const 
   P.fx = S * g.fx;
   P.fy = S * g.fy;
   P.pk = S * g.inv_rho;
-  dim3 grid(nstrips, (g.nx + rpc - 1) / rpc, g.batch);
+  dim3 grid(nstrips, chunks, g.batch);
   if (predictor)
     launch_pdl(1, explicit_upwind_ring_kernel<true>, grid, dim3(threads), smem, s, P, u, v, p, perm, out_u, out_v);
   else

@@ -106,9 +106,10 @@ class FusedStepper:
         self.launches_per_step = 4 + (2 if self.bodies else 0)
 
     # -- raw device-level block ---------------------------------------------------------------
-    def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor], walls=None):
-        """In place on CUDA tensors (u, v, p).  walls: host [nsteps, 4] wall values per step or None."""
-        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure, walls)
+    def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor], walls=None, table_host=None):
+        """In place on CUDA tensors (u, v, p).  walls: host [nsteps, 4] wall values per step or None;
+        table_host: the kinematic table as a NumPy array (enables the overlapped IB chain)."""
+        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure, walls, table_host)
 
     # -- All_Variables-level --------------------------------------------------------------------
     def advance(self, all_variables, nsteps: int, move_bodies: bool = True):
@@ -131,14 +132,16 @@ class FusedStepper:
         particles = all_variables.particles
         state = all_variables
         table_dev, times, centers = self._schedule(particles, t0, dt, nsteps, move_bodies)
+        table_host = self._table_host
         walls = self._wall_table(vel, times, nsteps)
         if self.md_step is None:
-            self.run_block(u, v, p, nsteps, table_dev, walls)
+            self.run_block(u, v, p, nsteps, table_dev, walls, table_host)
         else:
             md = all_variables.MD_var
             for n in range(nsteps):
                 self.run_block(u, v, p, 1, None if table_dev is None else table_dev[n:n + 1],
-                               None if walls is None else walls[n:n + 1])
+                               None if walls is None else walls[n:n + 1],
+                               None if table_host is None else table_host[n:n + 1])
                 md = self.md_step(self._view(all_variables, u, v, p, times[n + 1], particles, md))
             state = dataclasses.replace(state, MD_var=md)
         new_particles = particles
@@ -173,6 +176,7 @@ class FusedStepper:
 
     def _schedule(self, particles, t0, dt, nsteps, move_bodies=True):
         f32 = np.float32
+        self._table_host = None
         if particles is None:
             times = np.add.accumulate(np.concatenate([[f32(t0)], np.full(nsteps, f32(dt), f32)]).astype(f32), dtype=f32)
             return None, times, None
@@ -180,6 +184,7 @@ class FusedStepper:
         if not move_bodies:  # Updating_Position=None: the reference never touches particle_center (equations.py:143-158)
             table[:, :, 2:4] = centers[0]
         table = np.broadcast_to(table[:, None], (nsteps, self.spec.batch) + table.shape[1:]).copy()
+        self._table_host = table
         return torch.from_numpy(table).to(self.device, non_blocking=True), times, centers
 
     def _view(self, all_variables, u, v, p, t, particles, md):

@@ -78,8 +78,85 @@ def rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED(parameters, t):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Closed forms of the library's own laws and of their time derivatives, vectorised over the time stamps of a
+# block (NumPy float32).  The reference obtains the rates with jax.jacrev at every step (IBM_Force.py:101-104,
+# particle_motion.py:47-52); torch.func.vmap(jacrev) reproduces that for arbitrary user laws but costs ~2 ms
+# of host time per call, which dominated the end-to-end step.  Same formulas, same float32
+# evaluation order as the functions above; user-supplied laws keep the autodiff path.
+_F32 = np.float32
+
+
+def _cols_np(parameters, n):
+    cols = list(zip(*parameters))
+    return [np.asarray([np.asarray(x, dtype=_F32).reshape(-1) for x in cols[i]], dtype=_F32) for i in range(n)]
+
+
+def _cf_displacement_multi(parameters, tt):
+    A0, f = (c[:, 0] for c in _cols_np(parameters, 2))
+    w = _F32(_TWO_PI) * f
+    ph = w[None, :] * tt[:, None]
+    x = A0[None, :] / _F32(2) * np.cos(ph)
+    dx = -(A0[None, :] / _F32(2)) * np.sin(ph) * w[None, :]
+    z = np.zeros_like(x)
+    return np.stack([x, z], axis=1), np.stack([dx, z], axis=1)  # [n, 2, B]
+
+
+def _cf_rotation_multi(parameters, tt):
+    a0, beta, f, phi = (c[:, 0] for c in _cols_np(parameters, 4))
+    w = _F32(_TWO_PI) * f
+    ph = w[None, :] * tt[:, None] + phi[None, :]
+    return a0[None, :] + beta[None, :] * np.sin(ph), beta[None, :] * np.cos(ph) * w[None, :]  # [n, B]
+
+
+def _cf_series(parameters, tt, n_fields=6, p_index=5):
+    cols = _cols_np(parameters, n_fields)
+    alpha0, f, phi = cols[0][:, 0], cols[1][:, 0], cols[2][:, 0]
+    alpha, beta, p = cols[3], cols[4], cols[p_index][:, 0]
+    nb, nt = alpha.shape
+    freq = np.tile(np.arange(1, nt + 1, dtype=_F32), (nb, 1))
+    w = _F32(_TWO_PI) * freq * f[:, None]                                        # [B, nt]
+    inside = _F32(_TWO_PI) * tt[:, None, None] * freq[None] * f[None, :, None] + phi[None, :, None]  # [n, B, nt]
+    a1 = (alpha[None] * np.sin(inside)).sum(axis=2) + p[None] * (beta[None] * np.cos(inside)).sum(axis=2)
+    d1 = (alpha[None] * np.cos(inside) * w[None]).sum(axis=2) - p[None] * (beta[None] * np.sin(inside) * w[None]).sum(axis=2)
+    return alpha0, a1.astype(_F32), d1.astype(_F32), cols, freq
+
+
+def _cf_displacement_fourier(parameters, tt):
+    alpha0, a1, d1, _, _ = _cf_series(parameters, tt)
+    x = -alpha0[None, :] * tt[:, None]
+    return np.stack([x, a1], axis=1), np.stack([np.broadcast_to(-alpha0[None, :], a1.shape), d1], axis=1)
+
+
+def _cf_rotation_fourier(parameters, tt):
+    alpha0, a1, d1, _, _ = _cf_series(parameters, tt)
+    return alpha0[None, :] * tt[:, None] + a1, alpha0[None, :] + d1
+
+
+def _cf_rotation_fourier_normalized(parameters, tt):
+    alpha0, a1, d1, cols, freq = _cf_series(parameters, tt, 7, 6)
+    theta_av, phi, alpha, beta, p = cols[5][:, 0], cols[2][:, 0], cols[3], cols[4], cols[6][:, 0]
+    in2 = _F32(_TWO_PI) * freq + phi[:, None]
+    a2 = (alpha * np.sin(in2)).sum(axis=1) + p * (beta * np.cos(in2)).sum(axis=1)
+    in3 = _F32(_TWO_PI) * freq * _F32(0) + phi[:, None]
+    a3 = (alpha * np.sin(in3)).sum(axis=1) + p * (beta * np.cos(in3)).sum(axis=1)
+    den = (alpha0 + a2 - a3)[None, :]
+    return theta_av[None, :] * (alpha0[None, :] * tt[:, None] + a1) / den, theta_av[None, :] * (alpha0[None, :] + d1) / den
+
+
+def _closed_form(fn):
+    return _CLOSED_FORM.get(getattr(fn, "__name__", None)) if getattr(fn, "__module__", None) == __name__ else None
+
+
 def _values_and_rates(fn: Callable, params, times: torch.Tensor):
-    """fn(params, t) and d/dt fn(params, t) for a vector of times (vmap over jacrev, like jax)."""
+    """fn(params, t) and d/dt fn(params, t) for a vector of times: the closed form for this module's own laws,
+    vmap over jacrev (like jax) for anything else."""
+    cf = _closed_form(fn)
+    if cf is not None:
+        try:
+            vals, rates = cf(params, np.asarray(times, dtype=_F32))
+            return torch.from_numpy(np.ascontiguousarray(vals, dtype=_F32)), torch.from_numpy(np.ascontiguousarray(rates, dtype=_F32))
+        except Exception:  # unusual parameter layout: fall through to autodiff
+            pass
     f = lambda t: fn(params, t)
     vals = torch.func.vmap(f)(times)
     rates = torch.func.vmap(torch.func.jacrev(f))(times)
@@ -161,3 +238,14 @@ def rotation_multiple(parameters, t):
     """[B]: alpha0 + beta sin(2 pi f t + phi) with parameters = [[alpha0, beta, f, phi], ...]."""
     a0, beta, f, phi = (torch.stack([_as(x, t).reshape(()) for x in _col(parameters, i)]) for i in range(4))
     return a0 + beta * torch.sin(_TWO_PI * f * t + phi)
+
+
+_CLOSED_FORM = {
+    "displacement": _cf_displacement_multi,           # the single-body laws are the B = 1 case
+    "rotation": _cf_rotation_multi,
+    "displacement_multiple": _cf_displacement_multi,
+    "rotation_multiple": _cf_rotation_multi,
+    "Displacement_Foil_Fourier_Dotted_Mutliple": _cf_displacement_fourier,
+    "rotation_Foil_Fourier_Dotted_Mutliple": _cf_rotation_fourier,
+    "rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED": _cf_rotation_fourier_normalized,
+}

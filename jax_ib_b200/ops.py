@@ -268,7 +268,7 @@ class Plan:
                                                     _ptr(u_out), _ptr(v_out), _ptr(p_out)), "poisson_rows_inv")
 
     def step(self, u, v, p, nsteps=1, bodies: Optional[DeviceBodies] = None, body_table=None, perm=None,
-             incremental_pressure=True, wall_table=None):
+             incremental_pressure=True, wall_table=None, body_table_host=None):
         """time_stepping.py:144-255, `nsteps` times, in place on (u, v, p).  wall_table: host array
         [nsteps, 4] = (u_lo, u_hi, v_lo, v_hi) per step (boundaries.py:519-542), None = constant walls."""
         for t, n in ((u, "u"), (v, "v"), (p, "p")):
@@ -286,8 +286,14 @@ class Plan:
             if w.shape[0] < nsteps:
                 raise _lib.JaxibError("wall_table too small for nsteps")
             walls = w.ctypes.data_as(C.POINTER(C.c_double))
+        host = None
+        if body_table_host is not None and bodies is not None:
+            # the same table on the host: lets the library overlap the IB chain with the predictor (see the header)
+            th = np.ascontiguousarray(np.asarray(body_table_host, dtype=np.float32))
+            if th.size >= nsteps * self.spec.batch * bodies.n_bodies * BODY_STATE_STRIDE:
+                host = th.ctypes.data_as(C.c_void_p)
         _lib.check(self._lib.jaxib_step(_stream(), self._h, C.byref(b) if b is not None else None, _ptr(body_table),
-                                        _ptr(perm), walls, 1 if incremental_pressure else 0, int(nsteps), _ptr(u),
+                                        host, _ptr(perm), walls, 1 if incremental_pressure else 0, int(nsteps), _ptr(u),
                                         _ptr(v), _ptr(p), _ptr(self.scratch), self.scratch_bytes), "step")
         return u, v, p
 

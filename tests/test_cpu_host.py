@@ -47,7 +47,25 @@ def test_argument_errors_without_a_gpu():
     h = ctypes.c_void_p()
     assert l.jaxib_plan_create(ctypes.byref(g), ctypes.byref(h)) == -1
     assert b"nx" in l.jaxib_last_error()
-    assert l.jaxib_step(None, None, None, None, None, None, 1, 1, None, None, None, None, 0) == -1
+    assert l.jaxib_step(None, None, None, None, None, None, None, 1, 1, None, None, None, None, 0) == -1
+
+
+def test_plain_c_consumer_of_the_header(tmp_path):
+    """tests/c_abi_smoke.c: gcc (no CUDA, no C++) against include/jaxib_b200.h -- every entry point is resolved
+    through the header's own prototypes and the argument-error paths run without a GPU.  Header drift fails here."""
+    import subprocess
+    exe = str(tmp_path / "c_abi_smoke")
+    src = os.path.join(ROOT, "tests", "c_abi_smoke.c")
+    cc = subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), src, "-ldl", "-o", exe],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe, build.build()], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "25 entry points" in run.stdout
+    # every function the header declares is exercised by the C consumer
+    text = open(src).read()
+    for name in _header_functions():
+        assert f"LOAD({name})" in text, f"{name} is declared in the header but not loaded by c_abi_smoke.c"
 
 
 def test_sass_is_sm100a_only():

@@ -225,3 +225,30 @@ def test_tracer_step_with_caller_noise():
                                                         mobile).position - R)[mobile]
     assert np.var(d) == pytest.approx(2 * kT * dt_md / gamma, rel=0.1)
     assert np.array_equal(host(Rg)[~mobile], R[~mobile])
+
+
+# ------------------------------------------------------------------------------------------------ overlapped IB chain
+def test_overlapped_ib_chain_is_bitwise_the_serial_order():
+    """jaxib_step with the host copy of the kinematic table (split predictor, IB kernels on the side stream) must
+    give exactly the fields of the serial kernel order."""
+    from jax_ib_b200 import kinematics
+    import subprocess, sys, os
+    if os.environ.get("JAXIB_IB_OVERLAP") != "1":  # the switch is read once per process: run this test in a child with it on
+        env = dict(os.environ, JAXIB_IB_OVERLAP="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__ + "::test_overlapped_ib_chain_is_bitwise_the_serial_order"],
+                           env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    cfg = configs.ib_periodic(1024, 2)
+    stp = demo.make_stepper(cfg)
+    table, _, _ = kinematics.body_schedule(demo.make_particles(cfg), 0.0, cfg["dt"], 6)
+    th = np.ascontiguousarray(table[:, None])
+    td = dev(th)
+    outs = []
+    for host in (None, th):
+        u, v, p = (dev(a) for a in configs.initial_fields(cfg))
+        stp.run_block(u, v, p, 6, td, table_host=host)
+        torch.cuda.synchronize()
+        outs.append((u, v, p))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
