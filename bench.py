@@ -57,8 +57,12 @@ def workload_cfg(name):
         return configs.ib_periodic(4096, 4)
     if name == "ib1024":
         return configs.ib_periodic(1024, 1)
-    if name == "flap600":
+    if name in ("flap600", "ens1024"):  # G1 / G5: the Flapping demo grid; ens1024 = 128 of them per GPU
         return configs.flap600()
+    if name == "bearing300":  # G2: journal bearing + 1401 tracers
+        return configs.bearing300()
+    if name == "channel2048":  # G3: Taylor-dispersion channel at 2048^2 cells on [0,8]^2 (the notebook's dx, dt)
+        return configs.channel((2048, 2048), ((0.0, 8.0), (0.0, 8.0)))
     if name.startswith("slab"):  # slab8192 = G4 `multi8192`: (n/2048)^2 flapping ellipses on an n^2 grid
         n = int(name[4:])
         return configs.ib_periodic(n, max(1, n // 1024))  # 8192: 8 x 8 lattice = 64 bodies, 19 072 markers
@@ -71,6 +75,72 @@ def peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name, rank, world, device):
+    """Everything the timed loops need for one named workload: stepper, batched initial fields, the host-side
+    kinematic table builder and an optional per-step hook (tracers)."""
+    import numpy as np
+    import torch
+
+    from jax_ib_b200 import configs, demo, kinematics, ops
+
+    cfg = workload_cfg(name)
+    batch = 128 if name == "ens1024" else 1
+    members = [cfg]
+    if name == "ens1024":
+        # SURVEY 8d G5: copies of G1 with A0 ~ U[2.0, 3.2], f ~ U[0.15, 0.35], beta ~ U[pi/8, 3 pi/8], phi ~ U[0, 2 pi),
+        # seed 1234; member index = rank * 128 + k of the 1024-member sweep
+        import math
+        rng = np.random.default_rng(1234)
+        A0, f = rng.uniform(2.0, 3.2, 1024), rng.uniform(0.15, 0.35, 1024)
+        beta, phi = rng.uniform(math.pi / 8, 3 * math.pi / 8, 1024), rng.uniform(0, 2 * math.pi, 1024)
+        members = []
+        for k in range(batch):
+            m = (rank * batch + k) % 1024
+            b = dict(cfg["bodies"], displacement_param=[[float(A0[m]), float(f[m])]],
+                     rotation_param=[[math.pi / 2, float(beta[m]), float(f[m]), float(phi[m])]])
+            members.append(dict(cfg, bodies=b))
+    elif world > 1 and cfg["bodies"] is not None and name.startswith("ib"):
+        b = dict(cfg["bodies"])  # ensemble sweep: every rank gets its own kinematic phase
+        b["rotation_param"] = [[p[0], p[1], p[2], p[3] + 0.37 * rank] for p in b["rotation_param"]]
+        cfg = dict(cfg, bodies=b)
+        members = [cfg]
+    stepper = demo.make_stepper(cfg, batch=batch, device=device)
+    f0 = configs.initial_fields(cfg)
+    if name == "ens1024":  # a little seeded flow so that the fields are not identically zero
+        f0 = configs.initial_fields(dict(cfg, init=("divfree", 11, 0.05)))
+    fields = [torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (batch,) + a.shape) if batch > 1 else a)).to(device)
+              for a in f0]
+
+    def table(nsteps):
+        if cfg["bodies"] is None:
+            return None
+        tabs = [kinematics.body_schedule(demo.make_particles(m), 0.0, m["dt"], nsteps)[0] for m in members]
+        return np.ascontiguousarray(np.stack(tabs, axis=1))  # [nsteps, batch, B, 8]
+
+    post, extra = None, {}
+    if name == "bearing300":
+        # journal_bearing_demo.ipynb cells 8-10: 1200 mobile tracers + 200 wall + 1 hub, harmonic-Morse walls, kT = 0
+        rng = np.random.default_rng(0)
+        n_mob, n_wall = 1200, 200
+        th, rr = rng.uniform(0, 2 * np.pi, n_mob), rng.uniform(0.6, 0.9, n_mob)
+        tw = np.linspace(0, 2 * np.pi, n_wall)
+        pos = np.concatenate([np.stack([2.5 + rr * np.cos(th), 2.5 + rr * np.sin(th)], 1),
+                              np.stack([2.5 + np.cos(tw), 2.5 + np.sin(tw)], 1), [[2.5, 2.5]]]).astype(np.float32)
+        species = torch.from_numpy(np.concatenate([np.zeros(n_mob), np.ones(n_wall), [2]]).astype(np.int32)).to(device)
+        mobile = torch.from_numpy(np.concatenate([np.ones(n_mob), np.zeros(n_wall + 1)]).astype(np.uint8)).to(device)
+        r0 = torch.tensor([[0.0, 2 * np.pi / n_wall, 0.5], [2 * np.pi / n_wall, 0, 0], [0.5, 0, 0]], dtype=torch.float32, device=device)
+        h = torch.tensor([[0.0, 5, 5], [5, 0, 0], [5, 0, 0]], dtype=torch.float32, device=device)
+        R = torch.from_numpy(pos).to(device)
+        spec = stepper.spec
+
+        def post(u, v):
+            F = ops.pair_force(R, species, h, r0, (5.0, 5.0))
+            ops.tracer_step(spec, u, v, R, cfg["dt"], pair=F, is_mobile=mobile)
+
+        extra = {"tracers": int(R.shape[0]), "tracer_launches_per_step": 2}
+    return dict(cfg=cfg, batch=batch, stepper=stepper, fields=fields, table=table, post=post, extra=extra)
 
 
 class ClockSampler(threading.Thread):
@@ -122,56 +192,51 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def _oracle_worker(args):
-    n, steps = args
+def cpu_reference(workload, steps, threads, warmup=0):
+    """The oracle (NumPy float32 port of the reference's algorithm, dense O(M Nx Ny) IB sums as IBM_Force.py:66-87
+    evaluates them) on the SAME workload as the GPU arm, on `threads` host threads: the markers of every body are
+    sharded over the threads with the grid shared -- the reference's own parallelisation (jax.pmap over marker
+    shards, IBM_Force.py:77-87).  Returns (Mcell-steps/s, seconds per step)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from jax_ib_b200 import configs
     from _adapter import oracle_state, oracle_step
 
-    cfg = configs.ib_periodic(n, 1)
+    cfg = workload_cfg(workload)
+    nx, ny = cfg["shape"]
     st = oracle_state(cfg)
-    step = oracle_step(cfg, ib_window=None)  # dense O(M Nx Ny) sums, as the reference does
+    step = oracle_step(cfg, ib_window=None, ib_threads=threads)
+    for _ in range(warmup):
+        st = step(st)
     t0 = time.perf_counter()
     for _ in range(steps):
         st = step(st)
-    return time.perf_counter() - t0
-
-
-def cpu_reference(steps, procs, n=512):
-    """Oracle (NumPy port of the reference's dense algorithm) on the host cores: `procs` independent
-    ensemble members in parallel processes.  Returns (Mcell-steps/s, seconds)."""
-    import multiprocessing as mp
-
-    procs = max(1, procs)
-    t0 = time.perf_counter()
-    if procs == 1:
-        _oracle_worker((n, steps))
-    else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            pool.map(_oracle_worker, [(n, steps)] * procs)
     wall = time.perf_counter() - t0
-    return procs * n * n * steps / wall / 1e6, wall
+    return nx * ny * steps / wall / 1e6, wall / steps
+
+
+def reference_sample_text(workload, steps, threads, sec_per_step):
+    return (f"{steps} full steps of the {workload} workload itself (same grid, bodies, markers, dt, upwind, FFT Poisson) "
+            f"with the NumPy float32 oracle, dense O(M*Nx*Ny) IB sums as in IBM_Force.py:66-87, markers sharded over "
+            f"{threads} host threads with the grid shared (the reference's pmap layout, IBM_Force.py:77-87): "
+            f"{sec_per_step:.1f} s per step")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = min(cores, 32)
-    n = 512
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference(1, 1, n)
-    steps = max(1, min(args.steps, 3))
-    val, wall = cpu_reference(steps, procs, n)
-    sample = (f"{procs} independent ensemble members x {steps} steps of a {n}^2 tile of the ib2048 workload "
-              f"(same dx, dt, upwind, FFT Poisson; one 298-marker ellipse per tile; dense O(M*Nx*Ny) IB sums as in "
-              f"IBM_Force.py:66-87) in {procs} processes, NumPy float32 oracle")
+    threads = min(os.cpu_count() or 1, 64)
+    steps = max(1, min(args.steps, 2))
+    warm = min(args.warmup, 1)
+    val, sec = cpu_reference(args.workload, steps, threads, warm)
+    cfg = workload_cfg(args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "restated-reference CPU (NumPy oracle), not JAX: jax is not installable in this image"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "grid": list(cfg["shape"]),
+                   "bodies": len(cfg["bodies"]["centers"]) if cfg["bodies"] else 0, "convect": cfg["convect"],
+                   "note": "restated-reference CPU (NumPy oracle), not JAX: jax is not installable in this image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": reference_sample_text(args.workload, steps, threads, sec)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -260,6 +325,7 @@ def measure_slab(name, K, W, rank, world, device, barrier, max_over_ranks):
             stepper.run_block(u, v, p, nv, torch.from_numpy(np.ascontiguousarray(tabv[:, None])).to(device))
             got = (u, v, p)
         else:
+            st.particles = demo.make_particles(cfg)  # the timed blocks moved the bodies: restart from the initial state
             st.load(*(torch.from_numpy(a) for a in fields))
             st.advance(nv)
             got = st.gather()
@@ -332,26 +398,30 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
-    cfg = workload_cfg(args.workload)
-    if world > 1:  # ensemble sweep: every rank gets its own kinematic phase
-        b = dict(cfg["bodies"])
-        b["rotation_param"] = [[p[0], p[1], p[2], p[3] + 0.37 * rank] for p in b["rotation_param"]]
-        cfg = dict(cfg, bodies=b)
+    wl = make_workload(args.workload, rank, world, device)
+    cfg, batch, stepper, post = wl["cfg"], wl["batch"], wl["stepper"], wl["post"]
     nx, ny = cfg["shape"]
-    cells = nx * ny
+    cells = batch * nx * ny
     K, W = args.steps, args.warmup
-    stepper = demo.make_stepper(cfg, device=device)
-    particles = demo.make_particles(cfg)
-    from jax_ib_b200 import configs as _configs
-
-    u0, v0, p0 = (torch.from_numpy(a).to(device) for a in _configs.initial_fields(cfg))
-    table, times, centers = kinematics.body_schedule(particles, 0.0, cfg["dt"], W + 3 * K)
-    table_host = np.ascontiguousarray(table[:, None])  # the host copy lets the library overlap the IB chain
-    table = torch.from_numpy(table_host).to(device)
+    u0, v0, p0 = wl["fields"]
+    table_host = wl["table"](W + 3 * K)  # the host copy also lets the library overlap the IB chain (JAXIB_IB_OVERLAP=1)
+    table = None if table_host is None else torch.from_numpy(table_host).to(device)
+    tsl = lambda a, b: (None if table is None else table[a:b], None if table_host is None else table_host[a:b])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # 256 MiB > 126 MB L2
 
+    def run(u, v, p, a, b):
+        """steps a..b of the schedule; with a per-step hook (tracers) one launch chain per step"""
+        if post is None:
+            d, h = tsl(a, b)
+            stepper.run_block(u, v, p, b - a, d, table_host=h)
+        else:
+            for n in range(a, b):
+                d, h = tsl(n, n + 1)
+                stepper.run_block(u, v, p, 1, d, table_host=h)
+                post(u, v)
+
     u, v, p = u0.clone(), v0.clone(), p0.clone()
-    stepper.run_block(u, v, p, W, table[:W], table_host=table_host[:W])  # warm-up (untimed)
+    run(u, v, p, 0, W)  # warm-up (untimed)
     # ---- timed region 1: K steps, each bracketed by a CUDA-event pair on the launching stream, 256 MiB
     #      L2 flush before every step outside the brackets (the launches queue up behind the flush) ------
     sampler = ClockSampler(local_rank)
@@ -361,19 +431,20 @@ def run_b200(args, rank, world, local_rank):
     for n in range(K):
         flush.fill_(n & 0xff)
         evs[n][0].record()
-        stepper.run_block(u, v, p, 1, table[W + n:W + n + 1], table_host=table_host[W + n:W + n + 1])
+        run(u, v, p, W + n, W + n + 1)
         evs[n][1].record()
     barrier()
     ms_steps = sum(a.elapsed_time(b) for a, b in evs)
     # ---- stage breakdown: same K steps again with an event after every kernel (jaxib_step_profile); the
     #      extra events serialise the kernels (no programmatic dependent launch), so its sum is larger ----
-    prof = ops.step_profile(stepper.plan, u, v, p, K, stepper.bodies, table[W + 2 * K:W + 3 * K], flush=flush)
+    prof = ops.step_profile(stepper.plan, u, v, p, K, stepper.bodies, tsl(W + 2 * K, W + 3 * K)[0], stepper.perm,
+                            stepper.incremental_pressure, flush=flush, tile_flags=stepper.tile_flags)
     barrier()
     # ---- timed region 2: K steps back to back (L2 warm, as consecutive time steps really run) ---
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    stepper.run_block(u, v, p, K, table[W + K:W + 2 * K], table_host=table_host[W + K:W + 2 * K])
+    run(u, v, p, W + K, W + 2 * K)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -381,18 +452,34 @@ def run_b200(args, rank, world, local_rank):
     ms_warm = max_over_ranks(e0.elapsed_time(e1))
     finite = bool(torch.isfinite(u).all().item())
 
-    # ---- e2e: public API with host buffers ---------------------------------------------------
+    # ---- e2e: the same step through the public API with HOST (pinned) arrays: H2D of (u, v, p) and D2H of the
+    #      result inside every timed step ---------------------------------------------------------------------
     Ke = max(3, min(K, 20))
-    av = demo.make_all_variables(cfg, device="cpu")
-    pin = lambda gv: type(gv)(type(gv.array)(gv.data.pin_memory(), gv.offset, gv.grid), gv.bc)
-    av = type(av)(av.particles, tuple(pin(x) for x in av.velocity), pin(av.pressure), av.Drag, av.Step_count, av.MD_var)
-    for _ in range(2):
-        av = stepper.advance(av, 1)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        av = stepper.advance(av, 1)  # H2D (u, v, p) -> step -> D2H (u, v, p)
-    torch.cuda.synchronize()
+    if batch == 1:
+        av = demo.make_all_variables(cfg, device="cpu")
+        pin = lambda gv: type(gv)(type(gv.array)(gv.data.pin_memory(), gv.offset, gv.grid), gv.bc)
+        av = type(av)(av.particles, tuple(pin(x) for x in av.velocity), pin(av.pressure), av.Drag, av.Step_count, av.MD_var)
+        for _ in range(2):
+            av = stepper.advance(av, 1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            av = stepper.advance(av, 1)  # H2D (u, v, p) -> step -> D2H (u, v, p)
+        torch.cuda.synchronize()
+        e2e_api = "FusedStepper.advance(All_Variables on pinned host memory, 1)"
+    else:  # ensemble: the batched block call on pinned host arrays (All_Variables holds one simulation)
+        hu, hv, hp = (t.cpu().pin_memory() for t in (u, v, p))
+        ou, ov, op = (torch.empty_like(t).pin_memory() for t in (hu, hv, hp))
+        barrier()
+        t0 = time.perf_counter()
+        for n in range(Ke):
+            du, dv, dp = (t.to(device, non_blocking=True) for t in (hu, hv, hp))
+            d, h = tsl(n, n + 1)
+            stepper.run_block(du, dv, dp, 1, d, table_host=h)
+            for o, t in zip((ou, ov, op), (du, dv, dp)):
+                o.copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_api = "FusedStepper.run_block on pinned host arrays [batch, nx, ny] (H2D, 1 step, D2H)"
     e2e_s = max_over_ranks(time.perf_counter() - t0)
 
     # second partitioning: one 8192^2 grid slab-decomposed over the same GPUs (strong scaling)
@@ -419,9 +506,12 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "grid": [nx, ny], "bodies": len(cfg["bodies"]["centers"]),
-                   "markers": stepper.bodies.n_markers, "convect": cfg["convect"], "poisson": "periodic FFT",
-                   "ib_window_R": 6, "parallelism": f"ensemble x{world} (one simulation per GPU, no collective)",
+        "config": {"workload": args.workload, "grid": [nx, ny], "batch_per_gpu": batch,
+                   "bodies": len(cfg["bodies"]["centers"]) if cfg["bodies"] else 0,
+                   "markers": stepper.bodies.n_markers if stepper.bodies else 0, "convect": cfg["convect"],
+                   "poisson": "periodic FFT" if cfg["bc"] == "periodic" else "channel: FFT x DCT-II", **wl["extra"],
+                   "ib_window_R": 6,
+                   "parallelism": f"ensemble x{world} ({batch} simulation(s) per GPU, no collective)",
                    "l2": "flushed (256 MiB fill) before every timed step; one event pair per step, the flush is outside it",
                    "finite": finite},
         "value_back_to_back": world * cells * K / (ms_warm * 1e-3) / 1e6,
@@ -436,19 +526,18 @@ def run_b200(args, rank, world, local_rank):
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * cells},
         "clocks": clocks,
-        "gpu_launches": (stepper.launches_per_step + (1 if os.environ.get("JAXIB_IB_OVERLAP", "0") == "1" else 0)) * K,
+        "gpu_launches": (stepper.launches_per_step + wl["extra"].get("tracer_launches_per_step", 0) +
+                         (1 if os.environ.get("JAXIB_IB_OVERLAP", "0") == "1" else 0)) * K,
         "e2e": {"value": world * cells * Ke / e2e_s / 1e6, "unit": UNIT, "steps": Ke,
-                "h2d_bytes_per_step": 3 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4,
-                "api": "FusedStepper.advance(All_Variables on pinned host memory, 1)"},
+                "h2d_bytes_per_step": 3 * cells * 4, "d2h_bytes_per_step": 3 * cells * 4, "api": e2e_api},
     }
     if world == 1 and not args.no_cpu_baseline:
-        steps_cpu = 3
-        val, wall = cpu_reference(steps_cpu, 1, 512)
-        line["cpu_baseline"] = {
-            "value": val, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": (f"{steps_cpu} steps of a 512^2 tile of the same workload (same dx, dt, upwind, FFT Poisson, one "
-                       f"298-marker ellipse, dense O(M*Nx*Ny) IB sums as the reference) with the single-threaded NumPy "
-                       f"float32 oracle: {wall:.1f} s on 1 of {os.cpu_count()} host cores")}
+        threads = min(os.cpu_count() or 1, 64)
+        val, sec = cpu_reference(args.workload, 1, threads)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": reference_sample_text(args.workload, 1, threads, sec) +
+                                ("; ONE member of the ensemble" if batch > 1 else "") +
+                                ("; fluid step only (no tracer sub-step)" if post is not None else "")}
     if slab_res is not None:
         line["slab"] = slab_res
     print(json.dumps(line), flush=True)

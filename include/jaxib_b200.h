@@ -97,6 +97,14 @@ typedef struct {
    * marker on b's closed curve -- roll(-1), IBM_Force.py:59-63 --, b as int32 bits, 0).  It removes the
    * marker -> body search and one dependent memory round trip from the marker-force kernel.          */
   const float* marker_pack;
+  /* Optional (may be NULL): caller-owned device scratch of tile_flags_len int32, ZERO-INITIALISED once.  The
+   * marker-force kernel marks the 8 x 8-cell tiles (of every body's bounding box, per velocity component) that
+   * some marker window touches; the spreading kernel skips unmarked tiles at once and clears the marks it
+   * consumes, so the buffer is all zero again after every step.  Needs batch * n_bodies * 2 * T^2 entries,
+   * T = ceil((2 * (ceil(max_radius / min(dx, dy)) + ib_window + 2) + 1) / 8); too short = not used.  One
+   * buffer per concurrently stepping grid (slab rank / stepper).                                        */
+  int32_t* tile_flags;
+  int32_t tile_flags_len;
 } jaxib_bodies;
 
 /* Per-step, per-body kinematic state, evaluated by the HOST from the user's Displacement_EQ /

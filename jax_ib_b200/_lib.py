@@ -36,6 +36,7 @@ class Bodies(C.Structure):
         ("body_offset", C.c_void_p), ("x0", C.c_void_p), ("y0", C.c_void_p),
         ("max_radius", C.c_double),
         ("marker_pack", C.c_void_p),
+        ("tile_flags", C.c_void_p), ("tile_flags_len", C.c_int32),
     ]
 
 

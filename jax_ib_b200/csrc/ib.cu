@@ -125,7 +125,8 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
                                     const float* __restrict__ x0, const float* __restrict__ y0,
                                     const float4* __restrict__ pack, const float* __restrict__ body_state,
                                     const float* __restrict__ u_star, const float* __restrict__ v_star,
-                                    float* __restrict__ markers) {
+                                    float* __restrict__ markers, int* __restrict__ tile_flags, int half_extent,
+                                    int tiles_per_axis) {
   // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel.
   // Dependent memory round trips: [x0, y0, pack] -> [body state] -> [window of u*] -> store.
   pdl_trigger();
@@ -171,6 +172,21 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
   const bool wanted = g.own_hi <= g.own_lo || (iku >= g.own_lo && iku < g.own_hi);
   float U = 0.0f;
   if (wanted) U = interp_marker<RT>(m, (comp == 0 ? u_star : v_star) + s * plane, xp, yp, nullptr, nullptr);
+  if (tile_flags != nullptr && wanted) {
+    // mark the tiles of this body's bounding box (this component's mesh) that the marker's spreading window
+    // touches: spread_bodies_kernel skips every other tile at once and clears the marks it consumes
+    const int lane = threadIdx.x & 31;
+    const int R = RT > 0 ? RT : g.R;
+    const int ik = cell_index(xp, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.dy, m.off_y);
+    const int ti0 = cell_index(xc, m.dx, m.off_x) - m.row0 - half_extent, tj0 = cell_index(yc, m.dy, m.off_y) - half_extent;
+    const int ta = max((ik - R + 1 - ti0) >> 3, 0), tb = min((ik + R - ti0) >> 3, tiles_per_axis - 1);
+    const int tc = max((jk - R + 1 - tj0) >> 3, 0), td = min((jk + R - tj0) >> 3, tiles_per_axis - 1);
+    const int ny_t = td - tc + 1, nt = (tb - ta + 1) * ny_t;
+    for (int e = lane; e < nt; e += 32) {
+      const int ty = ta + e / ny_t, tx = tc + e % ny_t;
+      tile_flags[(((size_t)s * n_bodies + b) * 2 + comp) * tiles_per_axis * tiles_per_axis + ty * tiles_per_axis + tx] = 1;
+    }
+  }
   if ((threadIdx.x & 31) == 0) {
     const size_t stride = (size_t)total;
     float* mk = markers + gw;
@@ -274,7 +290,8 @@ __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic
 __global__ void __launch_bounds__(SPREAD_THREADS)
 spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                      const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
-                     int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star) {
+                     int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star,
+                     int* __restrict__ tile_flags) {
   __shared__ SpreadShared sh;
   extern __shared__ int sbody[];  // ic[n_bodies] | jc[n_bodies] | offset[n_bodies + 1]
   int* const sic = sbody;
@@ -285,6 +302,17 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
   const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
+  // Occupied-tile marks (written by interp_force_kernel, the previous kernel): a tile no marker of its OWN body
+  // touches can only matter if another body's box overlaps it (checked below, after the body table is in shared
+  // memory); with separated bodies an empty tile leaves here after one load.
+  int* my_flag = nullptr;
+  bool own_marked = true;
+  if (tile_flags != nullptr) {
+    my_flag = tile_flags + (((size_t)s * n_bodies + b) * 2 + comp) * tiles_per_axis * tiles_per_axis + blockIdx.x;
+    pdl_wait();
+    own_marked = *my_flag != 0;
+    if (!own_marked && n_bodies == 1) return;
+  }
   // kinematic table and marker ranges are not outputs of the previous kernel: read before the dependency wait
   for (int b2 = threadIdx.x; b2 <= n_bodies; b2 += SPREAD_THREADS) {
     if (b2 < n_bodies) {
@@ -299,13 +327,33 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int ic = sic[b], jc = sjc[b];
   const int ty = blockIdx.x / tiles_per_axis, tx = blockIdx.x - ty * tiles_per_axis;
   const int ti0 = ic - half_extent + ty * TS, tj0 = jc - half_extent + tx * TS;
-  if (ti0 >= g.nx || ti0 + TS <= 0 || tj0 >= g.ny || tj0 + TS <= 0) return;  // tile fully outside: no image
+  if (ti0 >= g.nx || ti0 + TS <= 0 || tj0 >= g.ny || tj0 + TS <= 0) return;  // tile fully outside: no image (mark kept)
+  // which OTHER bodies' boxes reach this tile?  One body per thread + a block-wide OR: with separated bodies
+  // (the usual case) both answers are "none" and neither the ownership walk nor the multi-body gather runs
+  bool lo_hit = false, hi_hit = false;
+  for (int b2 = threadIdx.x; b2 < n_bodies; b2 += SPREAD_THREADS) {
+    if (b2 == b) continue;
+    const bool hit = !(sic[b2] + half_extent < ti0 || sic[b2] - half_extent >= ti0 + TS || sjc[b2] + half_extent < tj0 ||
+                       sjc[b2] - half_extent >= tj0 + TS);
+    lo_hit |= hit && b2 < b;
+    hi_hit |= hit && b2 > b;
+  }
+  const bool any_lo = __syncthreads_or(lo_hit) != 0;
+  const bool any_hi = __syncthreads_or(hi_hit) != 0;
+  if (my_flag != nullptr) {
+    if (!own_marked) {
+      if (!any_hi) return;  // nothing of this body here and no later body reaches the tile
+    } else if (threadIdx.x == 0) {
+      *my_flag = 0;  // consumed (every thread read it before the barriers above): all marks are zero again after the step
+    }
+  }
   const int cell = threadIdx.x & (TS * TS - 1);
   const int i = ti0 + cell / TS, j = tj0 + cell % TS;
   bool valid = i >= 0 && i < g.nx && j >= 0 && j < g.ny && i <= ic + half_extent && j <= jc + half_extent;
   // a cell covered by several bounding boxes belongs to the lowest-numbered body
-  for (int b2 = 0; b2 < b && valid; ++b2)
-    if (abs(i - sic[b2]) <= half_extent && abs(j - sjc[b2]) <= half_extent) valid = false;
+  if (any_lo)
+    for (int b2 = 0; b2 < b && valid; ++b2)
+      if (abs(i - sic[b2]) <= half_extent && abs(j - sjc[b2]) <= half_extent) valid = false;
   const size_t total = (size_t)g.batch * n_markers;
   const float* mk = markers + (size_t)s * n_markers;
   const float* mF = mk + (comp == 0 ? 3 : 4) * total;
@@ -315,7 +363,8 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const float cur = writer ? *out : 0.0f;  // in flight while the markers are gathered
   float f_total = 0.0f;
   bool touched = false;
-  for (int b2 = b; b2 < n_bodies; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
+  const int b_end = any_hi ? n_bodies : b + 1;
+  for (int b2 = b; b2 < b_end; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
     const int ic2 = sic[b2], jc2 = sjc[b2];
     if (b2 != b && (ic2 + half_extent < ti0 || ic2 - half_extent >= ti0 + TS || jc2 + half_extent < tj0 ||
                     jc2 - half_extent >= tj0 + TS))
@@ -362,6 +411,13 @@ spread_points_kernel(GridF g, float off_x, float off_y, const float* __restrict_
 
 }  // namespace
 
+// bounding box of a body in cells (half edge) and 8 x 8 tiles per axis: shared by the two fused IB kernels
+static void spread_geometry(const GridF& g, const jaxib_bodies& b, int* half_extent, int* tiles) {
+  const float hmin = g.dx < g.dy ? g.dx : g.dy;
+  *half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
+  *tiles = (2 * *half_extent + 1 + TS - 1) / TS;
+}
+
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field, const float* xp,
                      const float* yp, int n, float* out, int32_t* ci, int32_t* cj) {
   if (n <= 0) return JAXIB_OK;
@@ -380,12 +436,18 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   const int threads = 128;
   const long long total = (long long)g.batch * b.n_markers * 2 * 32;
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
+  int half_extent, tiles;
+  spread_geometry(g, b, &half_extent, &tiles);
+  const long long need = (long long)g.batch * b.n_bodies * 2 * tiles * tiles;
+  int* flags = (b.tile_flags && (long long)b.tile_flags_len >= need) ? b.tile_flags : nullptr;
   if (g.R == 6)
     launch_pdl(2, interp_force_kernel<6>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
-               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers);
+               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers, flags, half_extent,
+               tiles);
   else
     launch_pdl(2, interp_force_kernel<0>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
-               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers);
+               b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers, flags, half_extent,
+               tiles);
   return check_launch("interp_force_kernel");
 }
 
@@ -393,14 +455,15 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
                             const float* markers, float* u_star, float* v_star) {
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
-  const float hmin = g.dx < g.dy ? g.dx : g.dy;
-  const int half_extent = (int)ceil(b.max_radius / hmin) + g.R + 2;
-  const int tiles = (2 * half_extent + 1 + TS - 1) / TS;
+  int half_extent, tiles;
+  spread_geometry(g, b, &half_extent, &tiles);
   dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
   const size_t smem = (size_t)(3 * b.n_bodies + 1) * sizeof(int);
   if (smem > 40 * 1024) { set_error("ib_spread_bodies: %d bodies exceed the shared-memory body table", b.n_bodies); return JAXIB_ERR_UNSUPPORTED; }
+  const long long need = (long long)g.batch * b.n_bodies * 2 * tiles * tiles;
+  int* flags = (b.tile_flags && (long long)b.tile_flags_len >= need) ? b.tile_flags : nullptr;
   launch_pdl(4, spread_bodies_kernel, grid, block, smem, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
-             half_extent, tiles, u_star, v_star);
+             half_extent, tiles, u_star, v_star, flags);
   return check_launch("spread_bodies_kernel");
 }
 

@@ -104,12 +104,14 @@ class FusedStepper:
         self.incremental_pressure = incremental_pressure
         self.md_step = md_step
         self.launches_per_step = 4 + (2 if self.bodies else 0)
+        self.tile_flags = self.bodies.tile_flags(spec) if self.bodies is not None else None
 
     # -- raw device-level block ---------------------------------------------------------------
     def run_block(self, u, v, p, nsteps: int, table: Optional[torch.Tensor], walls=None, table_host=None):
         """In place on CUDA tensors (u, v, p).  walls: host [nsteps, 4] wall values per step or None;
         table_host: the kinematic table as a NumPy array (enables the overlapped IB chain)."""
-        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure, walls, table_host)
+        self.plan.step(u, v, p, nsteps, self.bodies, table, self.perm, self.incremental_pressure, walls, table_host,
+                       self.tile_flags)
 
     # -- All_Variables-level --------------------------------------------------------------------
     def advance(self, all_variables, nsteps: int, move_bodies: bool = True):
@@ -120,6 +122,7 @@ class FusedStepper:
             b = get_bodies(all_variables.particles, dev)  # a different particle set than at build time
             if b is not self.bodies:
                 self.bodies = b
+                self.tile_flags = b.tile_flags(self.spec)
                 if b.n_markers > self.plan.n_markers:
                     self.plan = ops.Plan(self.spec, b.n_markers, dev)
         # first touch: copy (functional semantics: the caller's arrays are never modified)
@@ -156,6 +159,77 @@ class FusedStepper:
         out = self._view(state, u, v, p, times[-1], new_particles, state.MD_var)
         # particle_motion.py:59: the step counter lives in the position update
         return dataclasses.replace(out, Step_count=all_variables.Step_count + (nsteps if move_bodies else 0))
+
+    # -- rollout: funcutils.trajectory(funcutils.repeated(step_fn, inner), outer) on the device -----------------
+    def rollout(self, all_variables, inner_steps: int, outer_steps: int, start_with_input: bool = False,
+                move_bodies: bool = True, use_graph: bool = True):
+        """The reference's driver loop (Flapping_Demo.ipynb:225-247: `trajectory(repeated(step_fn, inner), outer)`,
+        two nested lax.scan's) with ONE host round: the kinematic table of all inner * outer steps is evaluated and
+        uploaded once, the inner block is captured in a CUDA graph and replayed per outer step (the launch-bound
+        regime of the 300^2 / 600^2 demo grids), and the snapshots go into a device-resident ring
+        [outer, 3, nx, ny] that is copied to the host once at the end when the input lived on the host.
+        Returns (final All_Variables, [snapshot All_Variables] * outer) like funcutils.trajectory."""
+        if self.md_step is not None:
+            raise NotImplementedError("rollout with a tracer sub-step: use funcutils.trajectory (per-step host hook)")
+        vel = all_variables.velocity
+        dev = self.device
+        in_dev = vel[0].data.device
+        u = vel[0].data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
+        v = vel[1].data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
+        p = all_variables.pressure.data.to(dev, dtype=torch.float32, copy=True, non_blocking=True).contiguous()
+        n_total = inner_steps * outer_steps
+        particles = all_variables.particles
+        table_dev, times, centers = self._schedule(particles, vel[0].bc.time_stamp, self.spec.dt, n_total, move_bodies)
+        walls = self._wall_table(vel, times, n_total)
+        ring = torch.empty((outer_steps, 3) + tuple(u.shape), dtype=torch.float32, device=dev)
+        graph = block = None
+        if use_graph and walls is None and outer_steps > 1:
+            try:  # one un-captured block first: every lazy one-time initialisation of the library happens here
+                block = None if table_dev is None else table_dev[:inner_steps].clone()
+                wu, wv, wp = u.clone(), v.clone(), p.clone()
+                self.run_block(wu, wv, wp, inner_steps, block)
+                torch.cuda.current_stream().synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.run_block(u, v, p, inner_steps, block)
+            except Exception:  # capture not possible on this driver / stream state: plain launches
+                graph = None
+                torch.cuda.synchronize()
+                u.copy_(vel[0].data); v.copy_(vel[1].data); p.copy_(all_variables.pressure.data)
+        self.last_rollout_used_graph = graph is not None
+        if graph is not None:  # the capture itself did not execute: u, v, p still hold the input
+            pass
+        for o in range(outer_steps):
+            a, b = o * inner_steps, (o + 1) * inner_steps
+            if start_with_input:
+                ring[o, 0].copy_(u); ring[o, 1].copy_(v); ring[o, 2].copy_(p)
+            if graph is not None:
+                if block is not None:
+                    block.copy_(table_dev[a:b])
+                graph.replay()
+            else:
+                self.run_block(u, v, p, inner_steps, None if table_dev is None else table_dev[a:b],
+                               None if walls is None else walls[a:b])
+            if not start_with_input:
+                ring[o, 0].copy_(u); ring[o, 1].copy_(v); ring[o, 2].copy_(p)
+        if in_dev.type == "cpu":  # host in, host out: one pinned staging copy of the ring and of the final state
+            hring = torch.empty(ring.shape, dtype=ring.dtype, pin_memory=True)
+            hring.copy_(ring, non_blocking=True)
+            outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (u, v, p)]
+            for o_, t in zip(outs, (u, v, p)):
+                o_.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            ring, (u, v, p) = hring, outs
+
+        def state_at(k, fields):  # All_Variables after k steps
+            parts = particles
+            if particles is not None and move_bodies:
+                parts = dataclasses.replace(particles, particle_center=_like(particles.particle_center, centers[k]))
+            out = self._view(all_variables, fields[0], fields[1], fields[2], times[k], parts, all_variables.MD_var)
+            return dataclasses.replace(out, Step_count=all_variables.Step_count + (k if move_bodies else 0))
+
+        snaps = [state_at((o if start_with_input else o + 1) * inner_steps, ring[o]) for o in range(outer_steps)]
+        return state_at(n_total, (u, v, p)), snaps
 
     def _wall_table(self, vel, times, nsteps):
         """boundaries.py:519-542 update_BC for a block of steps: step 0 sees the wall values stored in the

@@ -116,6 +116,13 @@ class _StepFn:
             return x
         return self._get_stepper(x).advance(x, nsteps, move_bodies=self.cfg["move"])
 
+    def rollout(self, x, inner_steps: int, outer_steps: int, start_with_input: bool = False):
+        """trajectory(repeated(self, inner), outer) on the device; None when this step function is not fused (or
+        carries a per-step host hook), in which case funcutils falls back to the step-by-step loop."""
+        if not self.fused or self.cfg["md_step"] is not None:
+            return None
+        return self._get_stepper(x).rollout(x, inner_steps, outer_steps, start_with_input, move_bodies=self.cfg["move"])
+
     def __call__(self, x):
         return self.advance(x, 1)
 

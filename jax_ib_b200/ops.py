@@ -168,12 +168,21 @@ class DeviceBodies:
         pack[:, 2] = body.view(np.float32)
         self.marker_pack = torch.from_numpy(pack).to(device)
 
-    def c_struct(self) -> _lib.Bodies:
+    def tile_flags(self, spec: "GridSpec") -> torch.Tensor:
+        """Zeroed scratch for the occupied-tile marks of struct jaxib_bodies (one per stepping grid)."""
+        hmin = min(spec.step)
+        he = int(math.ceil(self.max_radius / hmin)) + int(spec.ib_window) + 2
+        tiles = (2 * he + 1 + 7) // 8
+        return torch.zeros(max(1, spec.batch * self.n_bodies * 2 * tiles * tiles), dtype=torch.int32, device=self.x0.device)
+
+    def c_struct(self, flags: Optional[torch.Tensor] = None) -> _lib.Bodies:
         b = _lib.Bodies()
         b.n_bodies, b.n_markers = self.n_bodies, self.n_markers
         b.body_offset, b.x0, b.y0 = self.body_offset.data_ptr(), self.x0.data_ptr(), self.y0.data_ptr()
         b.max_radius = self.max_radius
         b.marker_pack = self.marker_pack.data_ptr() if self.n_markers else None
+        if flags is not None:
+            b.tile_flags, b.tile_flags_len = flags.data_ptr(), flags.numel()
         return b
 
 
@@ -268,12 +277,12 @@ class Plan:
                                                     _ptr(u_out), _ptr(v_out), _ptr(p_out)), "poisson_rows_inv")
 
     def step(self, u, v, p, nsteps=1, bodies: Optional[DeviceBodies] = None, body_table=None, perm=None,
-             incremental_pressure=True, wall_table=None, body_table_host=None):
+             incremental_pressure=True, wall_table=None, body_table_host=None, tile_flags=None):
         """time_stepping.py:144-255, `nsteps` times, in place on (u, v, p).  wall_table: host array
         [nsteps, 4] = (u_lo, u_hi, v_lo, v_hi) per step (boundaries.py:519-542), None = constant walls."""
         for t, n in ((u, "u"), (v, "v"), (p, "p")):
             _check_field(self.spec, t, n)
-        b = bodies.c_struct() if bodies is not None else None
+        b = bodies.c_struct(tile_flags) if bodies is not None else None
         if bodies is not None:
             if bodies.n_markers > self.n_markers:
                 raise _lib.JaxibError("plan scratch was sized for fewer markers")
@@ -302,11 +311,11 @@ STAGES = ("explicit_predict", "ib_interp_force", "ib_spread", "rows_fwd", "cols"
 
 
 def step_profile(plan: Plan, u, v, p, nsteps, bodies=None, body_table=None, perm=None, incremental_pressure=True,
-                 flush: Optional[torch.Tensor] = None):
+                 flush: Optional[torch.Tensor] = None, tile_flags=None):
     """Measurement aid: like Plan.step but returns {stage: summed ms} from per-stage CUDA events.
     `flush` (a device buffer larger than L2) is overwritten before every step, outside the brackets.
     Synchronises the stream."""
-    b = bodies.c_struct() if bodies is not None else None
+    b = bodies.c_struct(tile_flags) if bodies is not None else None
     ms = (C.c_double * len(STAGES))()
     _lib.check(plan._lib.jaxib_step_profile(
         _stream(), plan._h, C.byref(b) if b is not None else None, _ptr(body_table), _ptr(perm),

@@ -358,7 +358,9 @@ class PeerRank:
 
     def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True):
         import ctypes as C
-        b = self.bodies.c_struct() if self.bodies is not None else None
+        if self.bodies is not None and getattr(self, "_tile_flags", None) is None:
+            self._tile_flags = self.bodies.tile_flags(self.spec)  # this slab's own occupied-tile marks
+        b = self.bodies.c_struct(self._tile_flags) if self.bodies is not None else None
         lib = self._lib
         lib.check(lib.load().jaxib_slab_step(
             ops._stream(), self.plan_rows._h, self.plan_cols._h, C.byref(self.c_grid), C.byref(self.c_slab),

@@ -167,6 +167,39 @@ def ibm_force(velocity, bodies: Bodies, dt, R: Optional[int] = None):
     return tuple(out)
 
 
+# ---------------------------------------------------------------- the reference's marker sharding, on host threads
+def ibm_force_threads(velocity, bodies: Bodies, dt, nthreads: int):
+    """Dense ibm_force (R = None) with the MARKERS of every body sharded over `nthreads` host threads and the grid
+    shared -- the reference's own parallelisation (jax.pmap over marker shards, grid replicated:
+    IBM_Force.py:77-87, convolution_functions.py:28-35), with ndev = 1 semantics (no marker dropped).  NumPy
+    releases the GIL inside its array kernels, so the shards run concurrently.  Used by bench.py's reference arm;
+    partial sums are added in shard order, so the result differs from `ibm_force` only by summation order."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = []
+    with ThreadPoolExecutor(max_workers=max(1, nthreads)) as pool:
+        for Xi, field in enumerate(velocity):
+            d = field.data
+            dtype = d.dtype.type
+            t = field.bc.time_stamp
+            f = np.zeros_like(d)
+            for b in range(len(bodies.centers)):
+                xp, yp = body_markers(bodies, b, t, dtype)
+                xc, yc = (dtype(v) for v in bodies.centers[b])
+                shards = [s for s in np.array_split(np.arange(len(xp)), max(1, nthreads)) if len(s)]
+                U = np.concatenate(list(pool.map(lambda s: interpolate_dense(field, xp[s], yp[s]), shards)))
+                r = -(yp - yc) if Xi == 0 else (xp - xc)
+                U0 = np.asarray(bodies.displacement[1]([bodies.displacement_param[b]], t, dtype), dtype=dtype).reshape(2, -1)[:, 0]
+                omega = np.asarray(bodies.rotation[1]([bodies.rotation_param[b]], t, dtype), dtype=dtype).reshape(-1)[0]
+                force = (U0[Xi] + omega * r - U) / dtype(dt)
+                dS = np.sqrt((np.roll(xp, -1) - xp) ** 2 + (np.roll(yp, -1) - yp) ** 2)
+                parts = pool.map(lambda s: spread_dense(force[s], xp[s], yp[s], dS[s], field.grid, field.offset, d.dtype), shards)
+                for part in parts:
+                    f = f + part
+            out.append(f)
+    return tuple(out)
+
+
 # ---------------------------------------------------------------- demo shapes (notebook cells)
 def ellipse_shape(geometry_param, ntheta=150, dtype=np.float32):
     """Flapping_Demo.ipynb cell 5 foil_XY_ELLIPSE: 2*ntheta - 2 markers."""

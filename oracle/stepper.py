@@ -76,6 +76,7 @@ def make_step(
     ib_window: Optional[int] = None,
     md_step: Optional[Callable] = None,
     penalty: bool = False,
+    ib_threads: int = 0,
 ):
     """equations.py:194-242 semi_implicit_navier_stokes_timeBC (penalty=False) or :245-280
     semi_implicit_navier_stokes_penalty (penalty=True), with the forward-Euler stepper."""
@@ -93,7 +94,10 @@ def make_step(
         u_star = tuple(u.data + d(dt) * ki - g for u, ki, g in zip(v, k, dP))  # :208
         vs = tuple(u.with_data(x) for u, x in zip(v, u_star))
         if state.particles is not None:
-            force = ib.ibm_force(vs, state.particles, dt, ib_window)  # :210
+            if ib_threads > 0 and ib_window is None:  # the reference's marker sharding on host threads (bench reference arm)
+                force = ib.ibm_force_threads(vs, state.particles, dt, ib_threads)
+            else:
+                force = ib.ibm_force(vs, state.particles, dt, ib_window)  # :210
             vs = tuple(u.with_data(u.data + d(dt) * f) for u, f in zip(vs, force))  # :223
         new_v, new_p = poisson.projection_and_update_pressure(vs, state.pressure, pressure_solve)  # :246
         out = update_bc(dataclasses.replace(state, velocity=new_v, pressure=new_p), dt)  # :248

@@ -252,3 +252,42 @@ def test_overlapped_ib_chain_is_bitwise_the_serial_order():
         outs.append((u, v, p))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ device rollout
+@pytest.mark.parametrize("host_input", [False, True])
+def test_device_rollout_equals_step_by_step(host_input):
+    """funcutils.trajectory(funcutils.repeated(step_fn, inner), outer) -- the reference's driver loop
+    (Flapping_Demo.ipynb:225-247) -- runs as ONE device rollout (kinematic table uploaded once, inner block in a
+    CUDA graph, snapshot ring on the device) and must reproduce the step-by-step loop bit for bit."""
+    from jax_ib_b200 import funcutils, IBM_Force, convolution_functions, particle_motion
+    cfg = configs.small_periodic(64)
+    av = demo.make_all_variables(cfg, device="cpu" if host_input else "cuda")
+    dt, grid = cfg["dt"], av.velocity[0].grid
+    dd = lambda x, x0, w: convolution_functions.delta_approx_logistjax(x, x0, w)
+    sf = lambda f, xp, yp: convolution_functions.new_surf_fn(f, xp, yp, dd)
+    step_fn = equations.semi_implicit_navier_stokes_timeBC(
+        density=cfg["density"], viscosity=cfg["viscosity"], dt=dt, grid=grid,
+        convect=lambda v: tuple(advection.advect_upwind(u, v, dt) for u in v), pressure_solve=ppressure.solve_fast_diag,
+        IBM_forcing=lambda v, dt: IBM_Force.calc_IBM_force_NEW_MULTIPLE(v, dd, sf, dt),
+        Updating_Position=particle_motion.Update_particle_position_Multiple)
+    assert step_fn.fused
+    inner, outer = 4, 3
+    final, traj = funcutils.trajectory(funcutils.repeated(step_fn, inner), outer, start_with_input=True)(av)
+    assert step_fn._stepper.last_rollout_used_graph
+    # the same thing step by step (the semantics of the two nested scans)
+    x, want = av, []
+    for _ in range(outer):
+        want.append(x)
+        x = step_fn.advance(x, inner)
+    assert len(traj) == outer and final.Step_count == inner * outer == x.Step_count
+    for got, ref in zip(traj + [final], want + [x]):
+        assert got.Step_count == ref.Step_count
+        assert np.float32(got.velocity[0].bc.time_stamp) == np.float32(ref.velocity[0].bc.time_stamp)
+        np.testing.assert_array_equal(np.asarray(got.particles.particle_center), np.asarray(ref.particles.particle_center))
+        for a, b in ((got.velocity[0], ref.velocity[0]), (got.velocity[1], ref.velocity[1]), (got.pressure, ref.pressure)):
+            assert a.data.device.type == ("cpu" if host_input else "cuda")
+            assert torch.equal(a.data.cpu(), b.data.cpu())
+    # start_with_input=False: snapshot o is the state after (o + 1) blocks
+    final2, traj2 = funcutils.trajectory(funcutils.repeated(step_fn, inner), outer)(av)
+    assert torch.equal(traj2[-1].velocity[0].data.cpu(), final.velocity[0].data.cpu()) and traj2[0].Step_count == inner

@@ -28,7 +28,8 @@ def main():
         table = torch.from_numpy(np.ascontiguousarray(table[:, None])).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush_on else None
     st.run_block(u, v, p, 10, None if table is None else table[:10])
-    prof = ops.step_profile(st.plan, u, v, p, K, st.bodies, None if table is None else table[10:], flush=flush)
+    prof = ops.step_profile(st.plan, u, v, p, K, st.bodies, None if table is None else table[10:], flush=flush,
+                            tile_flags=st.tile_flags)
     cells = cfg["shape"][0] * cfg["shape"][1]
     us = {k: round(val / K * 1e3, 2) for k, val in prof.items()}
     knobs = {k: os.environ[k] for k in os.environ if k.startswith("JAXIB_")}
