@@ -43,7 +43,9 @@ typedef enum {
 /* Boundary-condition families (boundaries.py:852-879 periodic; :636-663 moving wall / channel). */
 typedef enum {
   JAXIB_BC_PERIODIC = 0, /* periodic x and y; pressure periodic                                  */
-  JAXIB_BC_CHANNEL = 1   /* periodic x; Dirichlet velocity / homogeneous-Neumann pressure in y   */
+  JAXIB_BC_CHANNEL = 1,  /* periodic x; Dirichlet velocity / homogeneous-Neumann pressure in y   */
+  JAXIB_BC_FAR_FIELD = 2 /* Dirichlet velocity on all four walls (boundaries.py:666-693), homogeneous-
+                            Neumann pressure on both axes: pressure.py:134-154 solve_fast_diag_Far_Field */
 } jaxib_bc;
 
 /* Advection schemes (advection.py:120-124, :206-280, :325-333). */
@@ -81,6 +83,8 @@ typedef struct {
   int32_t row0;
   int32_t own_lo, own_hi;
   int32_t nx_global;
+  double u_wall_x[2];  /* far field: u at the lower / upper x wall (bc_values[0] of velocity[0])       */
+  double v_wall_x[2];  /* far field: v at the lower / upper x wall                                     */
 } jaxib_grid;
 
 /* Rigid bodies of ONE simulation (identical marker topology across the batch).
@@ -112,6 +116,7 @@ typedef struct {
  *   [cos(theta), sin(theta), xc, yc, U0x, U0y, Omega, 0]
  * laid out [step][batch][n_bodies][8]. */
 #define JAXIB_BODY_STATE_STRIDE 8
+#define JAXIB_WALL_STRIDE 8
 #define JAXIB_MAX_PEERS 16
 
 typedef struct jaxib_plan jaxib_plan; /* opaque: FFT twiddles, Laplacian eigenvalues, radix plan */
@@ -238,8 +243,9 @@ int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_rows, const ja
  * for both.  Results are identical to the serial order.
  * perm (may be NULL): [batch][nx][ny] Brinkman permeability.  incremental_pressure == 0 selects
  * the penalty stepper (no -grad p_old in the predictor, time_stepping.py:345).
- * wall_table (HOST memory, may be NULL): [nsteps][4] = u_lo, u_hi, v_lo, v_hi, the wall values of a
- * channel grid at the time stamp of each step -- what update_BC (boundaries.py:519-542) re-evaluates
+ * wall_table (HOST memory, may be NULL): [nsteps][JAXIB_WALL_STRIDE = 8] = u_lo, u_hi, v_lo, v_hi on the y walls
+ * then u_lo, u_hi, v_lo, v_hi on the x walls (far field only), the wall values of a channel / far-field
+ * grid at the time stamp of each step -- what update_BC (boundaries.py:519-542) re-evaluates
  * from the Moving_wall bc_fn every step (:636-663); NULL keeps the plan's constant u_wall / v_wall.
  * The clock / body centres are host-side state (boundaries.py:519-542, particle_motion.py:38-66)
  * and are not touched here.                                                                    */

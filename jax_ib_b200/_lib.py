@@ -25,6 +25,7 @@ class Grid(C.Structure):
         ("u_wall", C.c_double * 2), ("v_wall", C.c_double * 2), ("force", C.c_double * 2),
         ("ib_window", C.c_int32), ("row0", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32),
         ("nx_global", C.c_int32),
+        ("u_wall_x", C.c_double * 2), ("v_wall_x", C.c_double * 2),
     ]
 
 
@@ -50,7 +51,7 @@ class Slab(C.Structure):
         (name, C.c_void_p * MAX_PEERS) for name in ("u", "v", "p", "markers", "colbuf", "specbuf", "flags")]
 
 
-BC = {"periodic": 0, "channel": 1}
+BC = {"periodic": 0, "channel": 1, "far_field": 2}
 CONVECT = {"upwind": 0, "van_leer": 1, "van_leer_limiters": 2, "none": 3}
 BODY_STATE_STRIDE = 8
 

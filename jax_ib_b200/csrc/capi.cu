@@ -49,7 +49,7 @@ int check_grid(const jaxib_grid* g) {
     return JAXIB_ERR_INVALID;
   }
   if (!(g->dx > 0.0) || !(g->dy > 0.0)) { set_error("grid: dx, dy must be positive"); return JAXIB_ERR_INVALID; }
-  if (g->bc != JAXIB_BC_PERIODIC && g->bc != JAXIB_BC_CHANNEL) {
+  if (g->bc != JAXIB_BC_PERIODIC && g->bc != JAXIB_BC_CHANNEL && g->bc != JAXIB_BC_FAR_FIELD) {
     set_error("grid: unknown bc %d", g->bc);
     return JAXIB_ERR_INVALID;
   }
@@ -362,8 +362,9 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
     // boundaries.py:519-542 update_BC: step n sees the wall values of its own time stamp
     GridF gn = g;
     if (wall_table) {
-      const double* w = wall_table + 4 * (size_t)n;
+      const double* w = wall_table + JAXIB_WALL_STRIDE * (size_t)n;
       gn.uw_lo = (float)w[0]; gn.uw_hi = (float)w[1]; gn.vw_lo = (float)w[2]; gn.vw_hi = (float)w[3];
+      gn.uwx_lo = (float)w[4]; gn.uwx_hi = (float)w[5]; gn.vwx_lo = (float)w[6]; gn.vwx_hi = (float)w[7];
     }
     const GridF* gov = wall_table ? &gn : nullptr;
     const float* pin = incremental_pressure ? p : nullptr;

@@ -25,7 +25,8 @@ struct GridF {
   float fx, fy;          // float32(force) / float32(density)
   float inv_rho;
   int bc, convect;
-  float uw_lo, uw_hi, vw_lo, vw_hi;
+  float uw_lo, uw_hi, vw_lo, vw_hi;      // y walls
+  float uwx_lo, uwx_hi, vwx_lo, vwx_hi;  // x walls (far field)
   int R;                 // IB window radius
   int row0, own_lo, own_hi, nx_global;  // slab decomposition (see jaxib_grid)
 };
@@ -47,6 +48,8 @@ inline GridF make_gridf(const jaxib_grid& g) {
   f.bc = g.bc; f.convect = g.convect;
   f.uw_lo = (float)g.u_wall[0]; f.uw_hi = (float)g.u_wall[1];
   f.vw_lo = (float)g.v_wall[0]; f.vw_hi = (float)g.v_wall[1];
+  f.uwx_lo = (float)g.u_wall_x[0]; f.uwx_hi = (float)g.u_wall_x[1];
+  f.vwx_lo = (float)g.v_wall_x[0]; f.vwx_hi = (float)g.v_wall_x[1];
   f.R = g.ib_window > 0 ? g.ib_window : 6;
   f.row0 = g.row0; f.own_lo = g.own_lo; f.own_hi = g.own_hi; f.nx_global = g.nx_global;
   return f;

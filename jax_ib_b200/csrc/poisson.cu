@@ -50,7 +50,9 @@ struct jaxib_plan {
   int fast_rows_per_group_inv;  // K6 (each group also transforms the row after its last one)
   float* lam_x_pos_f;  // float32 copies of the eigenvalue tables (lam_y_f padded to ny/2 + 4)
   float* lam_y_f;
-  float2* tw_dct;      // channel: exp(-i pi k / (2 ny))
+  float2* tw_dct;      // channel / far field: exp(-i pi k / (2 ny))
+  float2* tw_dct_col;  // far field: exp(-i pi k / (2 nx))
+  double* lam_x_nat;   // far field: Neumann eigenvalues (2cos(pi k/nx) - 2)/dx^2 in natural order k < nx
   float2* tw_team_col; // team column kernel: twiddle tables in shared-memory layout
   float2* tw_team_row; // team row kernels: ditto
 };
@@ -263,10 +265,11 @@ __global__ void rows_fwd_dct_kernel(DctParams P, const float* __restrict__ u, co
     const float* ur = u + (size_t)i * N;
     const float* um = u + (size_t)wrapi(i - 1, g.nx) * N;
     const float* vr = v + (size_t)i * N;
+    const bool xwall = g.bc == JAXIB_BC_FAR_FIELD && i == 0;  // u(-1, j) is the lower x wall value (edge-aligned u)
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
       // divergence with the channel ghost rule: v(i,-1) is the lower wall value (boundaries.py:205-220)
       const float vm = j > 0 ? vr[j - 1] : g.vw_lo;
-      const float r = (ur[j] - um[j]) * g.inv_dx + (vr[j] - vm) * g.inv_dy;
+      const float r = (ur[j] - (xwall ? g.uwx_lo : um[j])) * g.inv_dx + (vr[j] - vm) * g.inv_dy;
       const int n = (j & 1) ? N - 1 - (j >> 1) : (j >> 1);
       buf[padi(n)] = make_float2(r, 0.0f);
     }
@@ -314,11 +317,14 @@ __global__ void rows_inv_dct_kernel(DctParams P, const float* __restrict__ spec,
     } else if (ii > i0) {
       const float* prv = qrow[(ii - 1 - i0) & 1];
       const size_t ro = (size_t)(ii - 1) * N;
+      const bool xlast = g.bc == JAXIB_BC_FAR_FIELD && ii - 1 == g.nx - 1;  // q(nx) = q(nx-1) (Neumann); u(nx-1) on the wall
       for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const float q0 = prv[j], q1 = cur[j];
+        const float q0 = prv[j], q1 = xlast ? prv[j] : cur[j];
         const float qn = j + 1 < N ? prv[j + 1] : q0;  // homogeneous Neumann ghost = edge (boundaries.py:247-269)
         float vv = v[ro + j] - (qn - q0) * g.inv_dy;
         if (j + 1 == N) vv = g.vw_hi;                  // impose_bc: the last v row lies on the wall (boundaries.py:405-419)
+        if (xlast) u_out[ro + j] = g.uwx_hi;           // impose_bc on the upper x wall
+        else
         u_out[ro + j] = u[ro + j] - (q1 - q0) * g.inv_dx;
         v_out[ro + j] = vv;
         p_out[ro + j] = q0 + p[ro + j];
@@ -395,6 +401,78 @@ __global__ void cols_kernel(ColParams P, float2* __restrict__ spec) {
   }
 }
 
+// ---- K5, far field: DCT-II along x of PAIRS of real coefficient columns ------------------------------
+// pressure.py:134-154 diagonalises the Neumann x Neumann Laplacian (array_utils.py:254-298) with eigh + tensordot;
+// the eigenbasis is the DCT-II on both axes.  The row kernels leave real DCT-y coefficients [nx][ny]; two adjacent
+// real columns (a, b) are one complex column z = a + i b.  Makhoul along x: reorder v[n] = z[2n], v[N-1-n] = z[2n+1],
+// one complex FFT, split into the transforms A, B of the two real sequences through Hermitian symmetry,
+// C[k] = Re(w_k V[k]), C[N-k] = -Im(w_k V[k]); scale by 1/(lx_k + ly_l) (cut-off 10 eps32); and back:
+// V[k] = conj(w_k)(C[k] - i C[N-k]), recombine, inverse FFT, undo the reorder.  Exact forward/inverse pair: the
+// 1/(nx ny) normalisation stays in the inverse row kernel.
+struct ColDctParams {
+  int nx, sp, ncols;       // spectrum [nx][sp] complex = [nx][2 sp] real; ncols complex columns
+  FftPlan pl;
+  const float2* tw;        // W_nx^k
+  const float2* twd;       // exp(-i pi k / (2 nx))
+  const int* pos;
+  const double* lam_x;     // natural order, k < nx
+  const double* lam_y;     // ly_l, l < ny
+  int cols_per_cta;
+};
+
+__global__ void cols_dct_kernel(ColDctParams P, float2* __restrict__ spec) {
+  extern __shared__ float2 buf[];
+  const int N = P.nx;
+  const int pitch = padi(N) + 1;
+  spec += (size_t)blockIdx.y * N * P.sp;
+  const int c0 = blockIdx.x * P.cols_per_cta;
+  const int nc = min(P.cols_per_cta, P.ncols - c0);
+  const int total = N * nc;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = e / nc, c = e - i * nc;
+    const int n = (i & 1) ? N - 1 - (i >> 1) : (i >> 1);
+    buf[c * pitch + padi(n)] = spec[(size_t)i * P.sp + c0 + c];
+  }
+  __syncthreads();
+  fft_forward(P.pl, buf, nc, pitch, P.tw, 1);
+  for (int c = 0; c < nc; ++c) {
+    float2* col = buf + c * pitch;
+    const double lya = P.lam_y[2 * (c0 + c)], lyb = P.lam_y[2 * (c0 + c) + 1];
+    for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
+      const int km = k == 0 ? 0 : N - k;
+      const int p1 = P.pos[k], p2 = P.pos[km];
+      const float2 z1 = col[padi(p1)], z2 = cconj(col[padi(p2)]);
+      // transforms of the two real sequences at frequency k (at N - k they are the conjugates)
+      const float2 A = cscale(cadd(z1, z2), 0.5f), B = cscale(mul_mi(csub(z1, z2)), 0.5f);
+      const float2 w = __ldg(P.twd + k);
+      const float2 wa = cmul(w, A), wb = cmul(w, B);
+      // DCT coefficients C[k] = Re(w V[k]), C[N-k] = -Im(w V[k]); their eigenvalues differ
+      const double lk = P.lam_x[k], lm = k == 0 ? 0.0 : P.lam_x[km];
+      float ak = wa.x * inv_eig(lk, lya), bk = wb.x * inv_eig(lk, lyb);
+      float am = k == 0 ? 0.0f : -wa.y * inv_eig(lm, lya), bm = k == 0 ? 0.0f : -wb.y * inv_eig(lm, lyb);
+      if (2 * k == N) { am = 0.0f; bm = 0.0f; }  // C[N/2] is its own mirror: V'[N/2] = conj(w)(1 - i) C[N/2] below
+      // back: V'[k] = conj(w_k)(C[k] - i C[N-k])
+      float2 Va, Vb;
+      if (2 * k == N) {
+        Va = cmulc(make_float2(ak, -ak), w);
+        Vb = cmulc(make_float2(bk, -bk), w);
+      } else {
+        Va = cmulc(make_float2(ak, -am), w);
+        Vb = cmulc(make_float2(bk, -bm), w);
+      }
+      col[padi(p1)] = cadd(Va, mul_pi(Vb));                          // Z'[k]   = Va + i Vb
+      if (p2 != p1) col[padi(p2)] = cadd(cconj(Va), mul_pi(cconj(Vb)));  // Z'[N-k] = conj(Va) + i conj(Vb)
+    }
+  }
+  __syncthreads();
+  fft_inverse(P.pl, buf, nc, pitch, P.tw, 1);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = e / nc, c = e - i * nc;
+    const int n = (i & 1) ? N - 1 - (i >> 1) : (i >> 1);
+    spec[(size_t)i * P.sp + c0 + c] = buf[c * pitch + padi(n)];
+  }
+}
+
 }  // namespace
 
 const GridF& plan_grid(const jaxib_plan* plan) { return plan->gf; }
@@ -418,7 +496,7 @@ StageParams stage_params(const jaxib_plan* pl, int sp, const GridF* gov = nullpt
   const GridF& g = gov ? *gov : pl->gf;  // gov: the plan's grid with this step's wall values (update_BC)
   const int n2 = g.ny / 2;
   const double nxg = g.nx_global > 0 ? g.nx_global : g.nx;  // slab: normalise with the global length
-  S.channel = g.bc == JAXIB_BC_CHANNEL;
+  S.channel = g.bc != JAXIB_BC_PERIODIC;
   S.rp.g = g; S.rp.pl = pl->row; S.rp.tw = pl->tw_row; S.rp.pos = pl->row_pos; S.rp.rows_per_cta = pl->rows_per_cta;
   S.rp.sp = sp > 0 ? sp : n2 + 4;
   S.rp.scale = (float)(1.0 / (nxg * (double)n2));
@@ -471,7 +549,7 @@ void plan_cols_geometry(const jaxib_plan* pl, int* cols_per_cta, int* ctas_per_s
 int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int ncols, int col0, int col_begin) {
   const GridF& g = pl->gf;
   const int n2 = g.ny / 2;
-  const bool channel = g.bc == JAXIB_BC_CHANNEL;
+  const bool channel = g.bc != JAXIB_BC_PERIODIC;
   if (sp <= 0) sp = n2 + 4;
   float2* spec = reinterpret_cast<float2*>(spectrum) + col_begin;
   col0 += col_begin;
@@ -481,6 +559,14 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
     fcp.nx = g.nx; fcp.sp = sp; fcp.ncols = ncols > 0 ? ncols : n2 + 1; fcp.tw = pl->tw_col;
     fcp.lam_x_pos = pl->lam_x_pos_f; fcp.lam_y = pl->lam_y_f + col0; fcp.tw_team = pl->tw_team_col;
     return pl->team_cols ? launch_cols_team(s, fcp, g.batch, spec) : launch_cols_fast(s, fcp, g.batch, spec);
+  }
+  if (g.bc == JAXIB_BC_FAR_FIELD) {
+    ColDctParams dp;
+    dp.nx = g.nx; dp.sp = sp; dp.ncols = ncols > 0 ? ncols : n2; dp.pl = pl->col; dp.tw = pl->tw_col; dp.twd = pl->tw_dct_col;
+    dp.pos = pl->col_pos; dp.lam_x = pl->lam_x_nat; dp.lam_y = pl->lam_y + 2 * col0; dp.cols_per_cta = pl->cols_per_cta;
+    dim3 dgrid((dp.ncols + pl->cols_per_cta - 1) / pl->cols_per_cta, g.batch);
+    cols_dct_kernel<<<dgrid, pl->col_threads, pl->col_smem, s>>>(dp, spec);
+    return check_launch("cols_dct_kernel");
   }
   ColParams cp;
   // channel: ny real DCT coefficients per row = ny/2 packed column pairs; periodic: ny/2+1 complex columns
@@ -556,7 +642,8 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   pl->grid = *grid;
   pl->gf = make_gridf(*grid);
   const int nx = grid->nx, ny = grid->ny, n2 = ny / 2;
-  const bool channel = grid->bc == JAXIB_BC_CHANNEL;
+  const bool channel = grid->bc != JAXIB_BC_PERIODIC;  // Neumann pressure in y: row DCT (channel and far field)
+  const bool far = grid->bc == JAXIB_BC_FAR_FIELD;     // Neumann pressure in x as well: column DCT
   const int nrow = channel ? ny : n2;  // complex length of the row transform (DCT via a length-ny FFT)
   if (!factor_plan(nrow, &pl->row) || !factor_plan(nx, &pl->col)) {
     set_error("grid %dx%d: sizes must factor into 2, 3 and 5", nx, ny);
@@ -601,6 +688,16 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     for (int k = 0; k < ny; ++k)
       twd[k] = make_float2((float)cos(0.25 * two_pi * k / ny), (float)-sin(0.25 * two_pi * k / ny));
     rc = upload(&pl->tw_dct, twd);
+    if (!rc && far) {  // eigenvalues of the Neumann Laplacian in x too (array_utils.py:254-298), natural order
+      std::vector<double> lxn(nx);
+      std::vector<float2> twdc(nx);
+      for (int k = 0; k < nx; ++k) {
+        lxn[k] = (2.0 * cos(0.5 * two_pi * k / nx) - 2.0) / (grid->dx * grid->dx);
+        twdc[k] = make_float2((float)cos(0.25 * two_pi * k / nx), (float)-sin(0.25 * two_pi * k / nx));
+      }
+      rc = upload(&pl->lam_x_nat, lxn);
+      if (!rc) rc = upload(&pl->tw_dct_col, twdc);
+    }
   } else {
     for (int l = 0; l <= n2; ++l) ly[l] = (2.0 * cos(two_pi * l / ny) - 2.0) / (grid->dy * grid->dy);
   }
@@ -688,6 +785,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     return JAXIB_ERR_UNSUPPORTED;
   }
   cudaFuncSetAttribute(cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(cols_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   cudaFuncSetAttribute(rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   cudaFuncSetAttribute(rows_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   cudaFuncSetAttribute(rows_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -704,6 +802,7 @@ extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
   cudaFree(pl->tw_row); cudaFree(pl->tw_col); cudaFree(pl->row_pos); cudaFree(pl->col_pos);
   cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y); cudaFree(pl->lam_x_pos_f); cudaFree(pl->lam_y_f);
   cudaFree(pl->tw_dct); cudaFree(pl->tw_team_col); cudaFree(pl->tw_team_row);
+  cudaFree(pl->tw_dct_col); cudaFree(pl->lam_x_nat);
   delete pl;
   return JAXIB_OK;
 }

@@ -26,28 +26,62 @@ __device__ __forceinline__ int wrap(int i, int n) {
   return i < 0 ? i + n : i;
 }
 
+// Far field (Dirichlet on the x walls too, boundaries.py:666-693): the x-direction ghost rules are the y rules
+// with the roles of u and v exchanged -- u is EDGE-aligned in x (offset 1: its last index lies on the upper
+// wall), v is cell-centred in x.  `sgn`/`add` describe the affine map ghost = add + sgn * interior(i').
+struct XGhost {
+  int i;
+  float sgn, add;
+};
+__device__ __forceinline__ XGhost xghost_edge(int i, int nx, float lo, float hi) {  // boundaries.py:205-246
+  if (i == -1) return {0, 0.0f, lo};                       // the wall itself
+  if (i < -1) return {-2 - i, -1.0f, lo};                   // bc - reflect past the wall
+  if (i >= nx) return {2 * nx - 2 - i, -1.0f, hi};
+  return {i, 1.0f, 0.0f};
+}
+__device__ __forceinline__ XGhost xghost_center(int i, int nx, float lo, float hi) {  // boundaries.py:179-188
+  if (i < 0) return {-1 - i, -1.0f, 2.0f * lo};
+  if (i >= nx) return {2 * nx - 1 - i, -1.0f, 2.0f * hi};
+  return {i, 1.0f, 0.0f};
+}
+
 // u is cell-centred in y (offset .5): ghost = 2*bc - symmetric mirror (boundaries.py:179-188)
-__device__ __forceinline__ float load_u(const float* __restrict__ u, const GridF& g, int i, int j) {
-  i = wrap(i, g.nx);
-  if (g.bc == JAXIB_BC_PERIODIC) return u[(size_t)i * g.ny + wrap(j, g.ny)];
+__device__ __forceinline__ float load_u_y(const float* __restrict__ u, const GridF& g, int i, int j) {
   if (j < 0) return 2.0f * g.uw_lo - u[(size_t)i * g.ny + (-1 - j)];
   if (j >= g.ny) return 2.0f * g.uw_hi - u[(size_t)i * g.ny + (2 * g.ny - 1 - j)];
   return u[(size_t)i * g.ny + j];
 }
+__device__ __forceinline__ float load_u(const float* __restrict__ u, const GridF& g, int i, int j) {
+  if (g.bc == JAXIB_BC_FAR_FIELD) {
+    const XGhost x = xghost_edge(i, g.nx, g.uwx_lo, g.uwx_hi);
+    return x.sgn == 0.0f ? x.add : x.add + x.sgn * load_u_y(u, g, x.i, j);
+  }
+  i = wrap(i, g.nx);
+  if (g.bc == JAXIB_BC_PERIODIC) return u[(size_t)i * g.ny + wrap(j, g.ny)];
+  return load_u_y(u, g, i, j);
+}
 
 // v is edge-aligned in y (offset 1, last index on the upper wall): boundaries.py:189-246
-__device__ __forceinline__ float load_v(const float* __restrict__ v, const GridF& g, int i, int j) {
-  i = wrap(i, g.nx);
-  if (g.bc == JAXIB_BC_PERIODIC) return v[(size_t)i * g.ny + wrap(j, g.ny)];
+__device__ __forceinline__ float load_v_y(const float* __restrict__ v, const GridF& g, int i, int j) {
   if (j == -1) return g.vw_lo;                                         // the wall itself
   if (j < -1) return g.vw_lo - v[(size_t)i * g.ny + (-2 - j)];         // bc - reflect past the wall
   if (j >= g.ny) return g.vw_hi - v[(size_t)i * g.ny + (2 * g.ny - 2 - j)];
   return v[(size_t)i * g.ny + j];
 }
+__device__ __forceinline__ float load_v(const float* __restrict__ v, const GridF& g, int i, int j) {
+  if (g.bc == JAXIB_BC_FAR_FIELD) {
+    const XGhost x = xghost_center(i, g.nx, g.vwx_lo, g.vwx_hi);
+    return x.add + x.sgn * load_v_y(v, g, x.i, j);
+  }
+  i = wrap(i, g.nx);
+  if (g.bc == JAXIB_BC_PERIODIC) return v[(size_t)i * g.ny + wrap(j, g.ny)];
+  return load_v_y(v, g, i, j);
+}
 
 // p is cell-centred with homogeneous Neumann in y: ghost = edge (boundaries.py:247-269)
 __device__ __forceinline__ float load_p(const float* __restrict__ p, const GridF& g, int i, int j) {
-  i = wrap(i, g.nx);
+  if (g.bc == JAXIB_BC_FAR_FIELD) i = i < 0 ? 0 : (i >= g.nx ? g.nx - 1 : i);  // Neumann ghost = edge
+  else i = wrap(i, g.nx);
   if (g.bc == JAXIB_BC_PERIODIC) return p[(size_t)i * g.ny + wrap(j, g.ny)];
   j = j < 0 ? 0 : (j >= g.ny ? g.ny - 1 : j);
   return p[(size_t)i * g.ny + j];
@@ -107,34 +141,57 @@ struct Terms {
   __device__ Terms(const GridF& g_, const Tiles& t_) : g(g_), t(t_) {}
 
   // ---- component u (offset (1, .5)) -------------------------------------------------------
-  __device__ __forceinline__ float u_fx(int i, int j) const {  // flux through the x-face i+1/2
+  // The x-direction rules of the far field mirror the y-direction rules of the channel with u <-> v.
+  __device__ __forceinline__ float u_corr_x(int i, int j) const {
+    // correction at offset (1.5, .5), u's BC: cell-centred rule 2*bc - mirror (mirror of v_corr_y)
+    if (g.bc == JAXIB_BC_FAR_FIELD && i >= g.nx) {
+      int ii = 2 * g.nx - 1 - i;
+      return 2.0f * g.uwx_hi - vl_corr(t.u(ii - 1, j), t.u(ii, j), t.u(ii + 1, j));
+    }
+    return vl_corr(t.u(i - 1, j), t.u(i, j), t.u(i + 1, j));
+  }
+  __device__ __forceinline__ float u_fx_raw(int i, int j) const {
     float w = 0.5f * t.u(i, j) + 0.5f * t.u(i + 1, j);
-    float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? vl_corr(t.u(i, j), t.u(i + 1, j), t.u(i + 2, j)) : 0.0f;
+    float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? u_corr_x(i + 1, j) : 0.0f;
     return face_flux<SCHEME>(w, t.u(i - 1, j), t.u(i, j), t.u(i + 1, j), t.u(i + 2, j), cn, g.dt_over_dx);
+  }
+  __device__ __forceinline__ float u_fx(int i, int j) const {  // flux through the x-face i+1/2
+    // far field: flux at offset (1.5, .5) with u's BC, cell-centred ghost 2*bc - mirror (mirror of v_fy)
+    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0) return 2.0f * g.uwx_lo - u_fx_raw(-1 - i, j);
+    return u_fx_raw(i, j);
   }
   __device__ __forceinline__ float u_corr_y(int i, int j) const {
     // correction array carries v's BC at offset (1, 1): ghost = bc - reflect (boundaries.py:238-246)
-    if (g.bc == JAXIB_BC_CHANNEL && j >= g.ny) {
+    if (g.bc != JAXIB_BC_PERIODIC && j >= g.ny) {
       int jj = 2 * g.ny - 2 - j;
       return g.vw_hi - vl_corr(t.u(i, jj - 1), t.u(i, jj), t.u(i, jj + 1));
     }
     return vl_corr(t.u(i, j - 1), t.u(i, j), t.u(i, j + 1));
   }
   __device__ __forceinline__ float u_fy(int i, int j) const {  // flux through the y-face j+1/2
-    if (g.bc == JAXIB_BC_CHANNEL && j < 0) return g.uw_lo;      // flux at offset (1,1) stepping onto the wall
+    if (g.bc != JAXIB_BC_PERIODIC && j < 0) return g.uw_lo;      // flux at offset (1,1) stepping onto the wall
     float w = 0.5f * t.v(i, j) + 0.5f * t.v(i + 1, j);
     float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? u_corr_y(i, j + 1) : 0.0f;
     return face_flux<SCHEME>(w, t.u(i, j - 1), t.u(i, j), t.u(i, j + 1), t.u(i, j + 2), cn, g.dt_over_dy);
   }
   // ---- component v (offset (.5, 1)) -------------------------------------------------------
+  __device__ __forceinline__ float v_corr_x(int i, int j) const {
+    // correction array carries u's BC at offset (1, 1): ghost = bc - reflect (mirror of u_corr_y)
+    if (g.bc == JAXIB_BC_FAR_FIELD && i >= g.nx) {
+      int ii = 2 * g.nx - 2 - i;
+      return g.uwx_hi - vl_corr(t.v(ii - 1, j), t.v(ii, j), t.v(ii + 1, j));
+    }
+    return vl_corr(t.v(i - 1, j), t.v(i, j), t.v(i + 1, j));
+  }
   __device__ __forceinline__ float v_fx(int i, int j) const {
+    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0) return g.vwx_lo;  // flux at offset (1, 1) stepping onto the wall (mirror of u_fy)
     float w = 0.5f * t.u(i, j) + 0.5f * t.u(i, j + 1);
-    float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? vl_corr(t.v(i, j), t.v(i + 1, j), t.v(i + 2, j)) : 0.0f;
+    float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? v_corr_x(i + 1, j) : 0.0f;
     return face_flux<SCHEME>(w, t.v(i - 1, j), t.v(i, j), t.v(i + 1, j), t.v(i + 2, j), cn, g.dt_over_dx);
   }
   __device__ __forceinline__ float v_corr_y(int i, int j) const {
     // correction at offset (.5, 1.5), v's BC: cell-centred rule 2*bc - mirror (boundaries.py:179-188)
-    if (g.bc == JAXIB_BC_CHANNEL && j >= g.ny) {
+    if (g.bc != JAXIB_BC_PERIODIC && j >= g.ny) {
       int jj = 2 * g.ny - 1 - j;
       return 2.0f * g.vw_hi - vl_corr(t.v(i, jj - 1), t.v(i, jj), t.v(i, jj + 1));
     }
@@ -147,7 +204,7 @@ struct Terms {
   }
   __device__ __forceinline__ float v_fy(int i, int j) const {
     // flux at offset (.5, 1.5) with v's BC: cell-centred ghost 2*bc - mirror
-    if (g.bc == JAXIB_BC_CHANNEL && j < 0) return 2.0f * g.vw_lo - v_fy_raw(i, -1 - j);
+    if (g.bc != JAXIB_BC_PERIODIC && j < 0) return 2.0f * g.vw_lo - v_fy_raw(i, -1 - j);
     return v_fy_raw(i, j);
   }
 
@@ -194,6 +251,7 @@ __global__ void __launch_bounds__(256) explicit_kernel(GridF g, const float* __r
     int ti = e / (TJ + 2 * H), tj = e - ti * (TJ + 2 * H);
     int gi = i0 - H + ti, gj = j0 - H + tj;
     bool ok = gj >= -H && gj < g.ny + H;  // tiles overhanging the domain edge
+    if (g.bc == JAXIB_BC_FAR_FIELD) ok = ok && gi >= -H && gi < g.nx + H;
     su[ti * PU + tj] = ok ? load_u(u, g, gi, gj) : 0.0f;
     sv[ti * PU + tj] = ok ? load_v(v, g, gi, gj) : 0.0f;
   }

@@ -20,11 +20,14 @@ from . import boundaries, grids, kinematics, ops, particle_class
 
 def grid_spec_from(grid: grids.Grid, dt, viscosity, density, bc_kind, convect, v=None, force=(0.0, 0.0), ib_window=6,
                    batch=1) -> ops.GridSpec:
-    u_wall = v_wall = (0.0, 0.0)
-    if v is not None and bc_kind == "channel":
+    u_wall = v_wall = u_wall_x = v_wall_x = (0.0, 0.0)
+    if v is not None and bc_kind in ("channel", "far_field"):
         u_wall = tuple(float(x) for x in v[0].bc.bc_values[1])
         v_wall = tuple(float(x) for x in v[1].bc.bc_values[1])
-    return ops.GridSpec(
+    if v is not None and bc_kind == "far_field":
+        u_wall_x = tuple(float(x) for x in v[0].bc.bc_values[0])
+        v_wall_x = tuple(float(x) for x in v[1].bc.bc_values[0])
+    return ops.GridSpec(u_wall_x=u_wall_x, v_wall_x=v_wall_x,
         nx=grid.shape[0], ny=grid.shape[1], lower=(grid.domain[0][0], grid.domain[1][0]), step=grid.step, dt=dt,
         nu=None if viscosity is None else viscosity / density, density=density, bc=bc_kind, convect=convect,
         u_wall=u_wall, v_wall=v_wall, force=force, ib_window=ib_window, batch=batch)
@@ -53,7 +56,8 @@ _BODIES = {}
 def get_plan(spec: ops.GridSpec, n_markers: int = 0) -> ops.Plan:
     """Plans (FFT tables + scratch) are cached per (grid spec, device)."""
     dev = cuda_device()
-    key = (spec.nx, spec.ny, spec.batch, spec.lower, spec.step, spec.bc, spec.u_wall, spec.v_wall, dev.index)
+    key = (spec.nx, spec.ny, spec.batch, spec.lower, spec.step, spec.bc, spec.u_wall, spec.v_wall, spec.u_wall_x,
+           spec.v_wall_x, dev.index)
     plan = _PLANS.get(key)
     if plan is None or plan.n_markers < n_markers:
         plan = ops.Plan(spec, n_markers, dev)
@@ -87,6 +91,8 @@ def bc_kind_of(v) -> str:
     t = v[0].bc.types
     if t[0][0] == boundaries.BCType.PERIODIC and t[1][0] == boundaries.BCType.DIRICHLET:
         return "channel"
+    if all(x == boundaries.BCType.DIRICHLET for ax in t for x in ax):
+        return "far_field"
     raise NotImplementedError(f"no CUDA path for velocity BC types {t}")
 
 
@@ -235,17 +241,20 @@ class FusedStepper:
         """boundaries.py:519-542 update_BC for a block of steps: step 0 sees the wall values stored in the
         incoming BC objects, step n >= 1 the Moving_wall functions (:636-663) evaluated at its own time
         stamp t_n -- exactly what the reference's step n reads after n update_BC calls."""
-        if self.spec.bc != "channel":
+        if self.spec.bc not in ("channel", "far_field"):
             return None
-        tab = np.empty((nsteps, 4), dtype=np.float64)
-        tab[:] = [float(x) for x in vel[0].bc.bc_values[1]] + [float(x) for x in vel[1].bc.bc_values[1]]
+        far = self.spec.bc == "far_field"
+        tab = np.zeros((nsteps, 8), dtype=np.float64)
+        tab[:, :4] = [float(x) for x in vel[0].bc.bc_values[1]] + [float(x) for x in vel[1].bc.bc_values[1]]
+        if far:
+            tab[:, 4:] = [float(x) for x in vel[0].bc.bc_values[0]] + [float(x) for x in vel[1].bc.bc_values[0]]
         fx, fy = vel[0].bc.boundary_fn, vel[1].bc.boundary_fn
         try:
-            fns = (fx[2], fx[3], fy[2], fy[3])
+            fns = (fx[2], fx[3], fy[2], fy[3]) + ((fx[0], fx[1], fy[0], fy[1]) if far else ())
         except (TypeError, IndexError):
             return tab  # no per-wall functions (constant-BC factory): the stored values hold for every step
         for n in range(1, nsteps):
-            tab[n] = [float(f(times[n])) for f in fns]
+            tab[n, :len(fns)] = [float(f(times[n])) for f in fns]
         return tab
 
     def _schedule(self, particles, t0, dt, nsteps, move_bodies=True):

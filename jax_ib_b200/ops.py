@@ -62,6 +62,9 @@ class GridSpec:
     own_lo: int = 0
     own_hi: int = 0
     nx_global: int = 0
+    # far field (Dirichlet on all walls): velocity values on the x walls (u_wall / v_wall are the y walls)
+    u_wall_x: Tuple[float, float] = (0.0, 0.0)
+    v_wall_x: Tuple[float, float] = (0.0, 0.0)
 
     def c_struct(self) -> _lib.Grid:
         g = _lib.Grid()
@@ -78,6 +81,8 @@ class GridSpec:
         g.force[0], g.force[1] = (float(x) for x in self.force)
         g.ib_window = int(self.ib_window)
         g.row0, g.own_lo, g.own_hi, g.nx_global = int(self.row0), int(self.own_lo), int(self.own_hi), int(self.nx_global)
+        g.u_wall_x[0], g.u_wall_x[1] = (float(x) for x in self.u_wall_x)
+        g.v_wall_x[0], g.v_wall_x[1] = (float(x) for x in self.v_wall_x)
         return g
 
     @property
@@ -279,7 +284,8 @@ class Plan:
     def step(self, u, v, p, nsteps=1, bodies: Optional[DeviceBodies] = None, body_table=None, perm=None,
              incremental_pressure=True, wall_table=None, body_table_host=None, tile_flags=None):
         """time_stepping.py:144-255, `nsteps` times, in place on (u, v, p).  wall_table: host array
-        [nsteps, 4] = (u_lo, u_hi, v_lo, v_hi) per step (boundaries.py:519-542), None = constant walls."""
+        [nsteps, 8] = (u_lo, u_hi, v_lo, v_hi) on the y walls, then on the x walls, per step (boundaries.py:519-542);
+        None = constant walls."""
         for t, n in ((u, "u"), (v, "v"), (p, "p")):
             _check_field(self.spec, t, n)
         b = bodies.c_struct(tile_flags) if bodies is not None else None
@@ -291,7 +297,7 @@ class Plan:
                 raise _lib.JaxibError("body_table too small for nsteps")
         walls = None
         if wall_table is not None:
-            w = np.ascontiguousarray(np.asarray(wall_table, dtype=np.float64).reshape(-1, 4))
+            w = np.ascontiguousarray(np.asarray(wall_table, dtype=np.float64).reshape(-1, 8))
             if w.shape[0] < nsteps:
                 raise _lib.JaxibError("wall_table too small for nsteps")
             walls = w.ctypes.data_as(C.POINTER(C.c_double))

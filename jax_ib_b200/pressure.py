@@ -35,8 +35,11 @@ def solve_fast_diag_moving_wall(v, q0=None, implementation: Optional[str] = "mat
 
 
 def solve_fast_diag_Far_Field(v, q0=None, implementation=None):
-    """pressure.py:134-154: Neumann x Neumann -- no CUDA path yet."""
-    raise NotImplementedError("solve_fast_diag_Far_Field has no CUDA path (all-Dirichlet velocity BCs are out of scope)")
+    """pressure.py:134-154: Neumann x Neumann pressure (Dirichlet velocity on all four walls).  The reference's
+    eigh + matmul route over laplacian_matrix_w_boundaries (array_utils.py:254-298) == DCT-II on both axes."""
+    if _probe.is_probe(v):
+        return _probe.Tag("pressure_solve", "far_field")
+    return _solve(v, "far_field")
 
 
 def projection_and_update_pressure(All_variables, solve: Callable = solve_fast_diag):

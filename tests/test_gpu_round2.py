@@ -291,3 +291,95 @@ def test_device_rollout_equals_step_by_step(host_input):
     # start_with_input=False: snapshot o is the state after (o + 1) blocks
     final2, traj2 = funcutils.trajectory(funcutils.repeated(step_fn, inner), outer)(av)
     assert torch.equal(traj2[-1].velocity[0].data.cpu(), final.velocity[0].data.cpu()) and traj2[0].Step_count == inner
+
+
+# ------------------------------------------------------------------------------------------------ far field
+def _far_field_case(shape=(40, 48), seed=2):
+    """Dirichlet velocity on all four walls (boundaries.py:666-693), Neumann x Neumann pressure."""
+    domain = ((0.0, 2.0), (0.0, 2.4))
+    g = field.Grid(shape, domain)
+    rng = np.random.default_rng(seed)
+    u0 = (0.1 * rng.standard_normal(shape)).astype(F)
+    v0 = (0.1 * rng.standard_normal(shape)).astype(F)
+    vals_u = ((0.3, 0.25), (0.1, 0.2))   # (x walls), (y walls)
+    vals_v = ((0.05, -0.05), (0.0, 0.02))
+    U = field.Var(u0, (1.0, 0.5), g, field.far_field_bc(vals_u, F(0))).impose_bc()
+    V = field.Var(v0, (0.5, 1.0), g, field.far_field_bc(vals_v, F(0))).impose_bc()
+    P = field.Var(np.zeros(shape, F), (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    spec = ops.GridSpec(nx=shape[0], ny=shape[1], lower=(0.0, 0.0), step=g.step, dt=1e-3, nu=0.05, bc="far_field",
+                        u_wall=vals_u[1], v_wall=vals_v[1], u_wall_x=vals_u[0], v_wall_x=vals_v[0])
+    return g, U, V, P, spec
+
+
+@pytest.mark.parametrize("convect", ["upwind", "van_leer", "van_leer_limiters"])
+def test_far_field_explicit_terms(convect):
+    """navier_stokes_explicit_terms with the Dirichlet ghost rules on BOTH axes (the x rules mirror the channel's
+    y rules with u <-> v): every scheme against the oracle's generic shift/pad/trim."""
+    from oracle import stencils
+    g, U, V, P, spec = _far_field_case()
+    spec = spec.replace(convect=convect)
+    want = stencils.explicit_terms((U, V), 0.05, 1e-3, convect, None, 1.0)
+    du, dv = ops.explicit_terms(spec, dev(U.data), dev(V.data))
+    assert rel_l2(host(du), want[0]) < 1e-5 and rel_l2(host(dv), want[1]) < 1e-5
+    # rows / columns next to every wall, where the ghost rules act
+    for got, ref in ((host(du), want[0]), (host(dv), want[1])):
+        for sl in (np.s_[:2], np.s_[-2:], np.s_[:, :2], np.s_[:, -2:]):
+            assert rel_l2(got[sl], ref[sl]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(40, 48), (64, 64), (96, 60), (256, 128)])
+def test_far_field_pressure_solve_and_projection(shape):
+    """pressure.py:134-154 solve_fast_diag_Far_Field (eigh + tensordot in the reference) == DCT-II on both axes,
+    and projection_and_update_pressure with impose_bc on the upper x and y walls."""
+    from oracle import poisson
+    g, U, V, P, spec = _far_field_case(shape, seed=5)
+    P = field.Var((0.01 * np.random.default_rng(9).standard_normal(shape)).astype(F), P.offset, g, P.bc)
+    plan = ops.Plan(spec)
+    q = host(plan.pressure_solve(dev(U.data), dev(V.data)))
+    want_q = poisson.solve_fast_diag_far_field((U, V))
+    # white-noise right-hand side: compare against float64 with the float32 oracle's own error as the yardstick
+    U64 = field.Var(U.data.astype(np.float64), U.offset, g, U.bc)
+    V64 = field.Var(V.data.astype(np.float64), V.offset, g, V.bc)
+    q64 = poisson.solve_fast_diag_far_field((U64, V64))
+    q64 = q64 - q64.mean() + np.float64(want_q.mean())  # float64 keeps the constant mode that float32's cut-off drops
+    floor = rel_l2(want_q, q64)
+    assert rel_l2(q, q64) < max(1e-5, 3 * floor), (rel_l2(q, q64), floor)
+    (nu, nv), npres = poisson.projection_and_update_pressure((U, V), P, "far_field")
+    uo, vo, po = plan.project(dev(U.data), dev(V.data), dev(P.data))
+    assert rel_l2(host(uo), nu.data) < max(1e-5, 3 * floor)
+    assert rel_l2(host(vo), nv.data) < max(1e-5, 3 * floor)
+    assert rel_l2(host(po), npres.data) < max(1e-5, 3 * floor)
+    np.testing.assert_array_equal(host(uo)[-1], np.full(shape[1], F(0.25)))      # impose_bc, upper x wall
+    np.testing.assert_array_equal(host(vo)[:, -1], np.full(shape[0], F(0.02)))   # impose_bc, upper y wall
+
+
+@pytest.mark.parametrize("convect", ["upwind", "van_leer"])
+def test_far_field_full_step_through_the_reference_api(convect):
+    """20 steps of semi_implicit_navier_stokes_timeBC with Far_field_boundary_conditions and
+    solve_fast_diag_Far_Field against the oracle."""
+    g, U, V, P, spec = _far_field_case((48, 40), seed=7)
+    steps, dt = 20, 1e-3
+    st = stepper.State(None, (U, V), P)
+    ostep = stepper.make_step(dt, 0.05, 1.0, convect, "far_field", None)
+    sgn = np.random.default_rng(0).choice([-1.0, 1.0], U.data.shape)
+    ulp = stepper.State(None, (field.Var((U.data * (1 + F(6e-8) * sgn)).astype(F), U.offset, g, U.bc).impose_bc(), V), P)
+    for _ in range(steps):
+        st = ostep(st)
+        ulp = ostep(ulp)
+    grid = grids.Grid(g.shape, domain=g.domain)
+    cst = lambda c: (lambda t: c)
+    fns_u = [cst(U.bc.values[0][0]), cst(U.bc.values[0][1]), cst(U.bc.values[1][0]), cst(U.bc.values[1][1])]
+    fns_v = [cst(V.bc.values[0][0]), cst(V.bc.values[0][1]), cst(V.bc.values[1][0]), cst(V.bc.values[1][1])]
+    bcs = (boundaries.Far_field_boundary_conditions(ndim=2, bc_vals=U.bc.values, bc_fn=fns_u, time_stamp=F(0.0)),
+           boundaries.Far_field_boundary_conditions(ndim=2, bc_vals=V.bc.values, bc_fn=fns_v, time_stamp=F(0.0)))
+    vel = tuple(grids.GridVariable(grids.GridArray(dev(a), off, grid), bc)
+                for a, off, bc in zip((U.data, V.data), grid.cell_faces, bcs))
+    pres = grids.GridVariable(grids.GridArray(dev(P.data), grid.cell_center, grid), boundaries.get_pressure_bc_from_velocity(vel))
+    av = pc.All_Variables(None, vel, pres, [0], 0, [0])
+    adv = {"van_leer": advection.advect_van_leer, "upwind": advection.advect_upwind}[convect]
+    step_fn = equations.semi_implicit_navier_stokes_timeBC(
+        density=1.0, viscosity=0.05, dt=dt, grid=grid, convect=lambda v: tuple(adv(u, v, dt) for u in v),
+        pressure_solve=ppressure.solve_fast_diag_Far_Field)
+    assert step_fn.fused and step_fn.cfg["poisson"] == "far_field"
+    out = step_fn.advance(av, steps)
+    _compare(out, st, 1e-5, floor=ulp)
