@@ -68,6 +68,30 @@ def test_plain_c_consumer_of_the_header(tmp_path):
         assert f"LOAD({name})" in text, f"{name} is declared in the header but not loaded by c_abi_smoke.c"
 
 
+def test_xla_ffi_shim_type_checks_against_the_api_shaped_header():
+    """jaxlib is not installable here, so the XLA-FFI shim cannot be built for real; it is type-checked (g++
+    -fsyntax-only) against tests/xla_ffi_stub/xla/ffi/api/ffi.h, an API-shaped stand-in whose handler macro asserts
+    that every implementation is invocable with exactly the arguments its binding declares -- and the shim must
+    wrap every stage entry point of the C ABI."""
+    import subprocess
+    shim = os.path.join(ROOT, "jax_ib_b200", "csrc", "xla_ffi_shim.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "xla_ffi_stub"),
+                        "-I/usr/local/cuda/include", shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    text = open(shim).read()
+    not_wrapped = {"jaxib_version", "jaxib_last_error", "jaxib_compiled_arch", "jaxib_plan_create", "jaxib_plan_destroy",
+                   "jaxib_scratch_bytes", "jaxib_ib_marker_force", "jaxib_ib_spread_bodies", "jaxib_poisson_rows_fwd",
+                   "jaxib_poisson_cols", "jaxib_poisson_rows_inv", "jaxib_slab_step", "jaxib_step_profile"}
+    for name in _header_functions():
+        if name not in not_wrapped:
+            assert name + "(" in text, f"{name} has no XLA-FFI handler"
+    # a mismatched handler is rejected by the stand-in (the check is not vacuous)
+    bad = os.path.join(os.path.dirname(shim), "..", "..", "tests", "xla_ffi_stub", "negative_example.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "xla_ffi_stub"),
+                        "-I/usr/local/cuda/include", bad], capture_output=True, text=True)
+    assert r.returncode != 0 and "not invocable" in r.stderr
+
+
 def test_sass_is_sm100a_only():
     out = os.popen(f"cuobjdump -lelf {build.build()} 2>/dev/null").read()
     archs = set(re.findall(r"sm_(\d+a?)", out))
