@@ -145,12 +145,14 @@ struct Scratch {
   float* v_star;
   float* spectrum;
   float* markers;
+  unsigned* sync;  // kSyncBytes of device words for kernel-to-kernel completion counters (RowDeps)
 };
+constexpr size_t kSyncBytes = 256;
 
 static size_t scratch_need(const GridF& g, int n_markers) {
   size_t plane = (size_t)g.batch * g.nx * g.ny;
   size_t spectrum = (size_t)g.batch * g.nx * (g.ny + 8);  // [nx][ny/2 + 4] complex
-  return (2 * plane + spectrum + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256;
+  return (2 * plane + spectrum + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256 + kSyncBytes;
 }
 
 static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scratch* out) {
@@ -166,6 +168,8 @@ static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scr
   out->v_star = base + plane;
   out->spectrum = base + 2 * plane;
   out->markers = base + 2 * plane + (size_t)g.batch * g.nx * (g.ny + 8);
+  out->sync = reinterpret_cast<unsigned*>(
+      (reinterpret_cast<uintptr_t>(out->markers + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) + 63) & ~uintptr_t(63));
   return JAXIB_OK;
 }
 
@@ -358,6 +362,14 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
   if ((rc = carve(g, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
+  // K4 early start (RowDeps, common.cuh): needs the ring predictor's completion counter and the team row kernel
+  // Off by default: bit-identical (tests/test_gpu_round2.py), but measured on B200 at ib2048 85.8 -> 87.5 us per step (the
+  // row kernel's CTAs only become resident once every CTA of the spreading kernel has started, which is after the
+  // predictor has drained), ib1024 59.0 -> 55.4 us (profiles/r2n_early_start.log).  JAXIB_K4_EARLY=1 turns it on.
+  static const bool k4_early_on = getenv("JAXIB_K4_EARLY") && atoi(getenv("JAXIB_K4_EARLY")) == 1;
+  const bool k4_early = k4_early_on && has_ib && g.batch == 1 && plan_team_rows_fwd(plan) && explicit_ring_eligible(g);
+  unsigned k1_total = 0;
+  if (k4_early) cudaMemsetAsync(sc.sync, 0, sizeof(unsigned), s);
   for (int n = 0; n < nsteps; ++n) {
     // boundaries.py:519-542 update_BC: step n sees the wall values of its own time stamp
     GridF gn = g;
@@ -408,6 +420,21 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
         }
       }
     }
+    RowDeps deps;
+    memset(&deps, 0, sizeof(deps));
+    if (!split && k4_early) {
+      int rc1 = JAXIB_OK;
+      unsigned inc = 0;
+      if (launch_explicit_ring(s, gn, u, v, pin, perm, sc.u_star, sc.v_star, true, &rc1, nullptr, sc.sync, &inc)) {
+        if (rc1) return rc1;
+        k1_total += inc;
+        deps.k1_counter = sc.sync; deps.k1_target = k1_total;
+        deps.body_state = body_table + n * state_stride; deps.n_bodies = bodies->n_bodies;
+        deps.half_extent = ib_half_extent(gn, *bodies);
+        if ((rc = launch_ib_force(s, gn, *bodies, body_table + n * state_stride, sc.u_star, sc.v_star, sc.markers))) return rc;
+        split = true;  // predictor and IB stage are enqueued
+      }
+    }
     if (!split) {
       // time_stepping.py:191-208
       if ((rc = launch_explicit(s, gn, u, v, pin, perm, sc.u_star, sc.v_star, true))) return rc;
@@ -416,7 +443,9 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
         return rc;
     }
     // time_stepping.py:246
-    if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum, nullptr, gov))) return rc;
+    if ((rc = launch_project(s, plan, sc.u_star, sc.v_star, p, u, v, p, nullptr, sc.spectrum, nullptr, gov,
+                             deps.k1_counter ? &deps : nullptr)))
+      return rc;
   }
   return JAXIB_OK;
 }

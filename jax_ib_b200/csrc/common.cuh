@@ -140,9 +140,26 @@ struct RowBands {
   int chunk0[kMaxBands + 1];   // filled by the launcher: first CTA row-chunk of each range
 };
 bool explicit_ring_eligible(const GridF& g);
+// done_counter (device, may be null): every consumer warp adds 1 when its rows are stored and fenced;
+// *done_increment receives the number of such arrivals of this launch.
 bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                           const float* perm, float* out_u, float* out_v, bool predictor, int* rc,
-                          const RowBands* bands = nullptr);
+                          const RowBands* bands = nullptr, unsigned* done_counter = nullptr,
+                          unsigned* done_increment = nullptr);
+
+// Early start of the forward row transform (K4).  Its rows far from every body depend on the predictor (K1) only,
+// not on the two latency-bound IB kernels that sit between K1 and K4 in the stream: a far row waits for K1's
+// completion counter instead of the programmatic dependency on K3, so most of K4 runs UNDER the IB kernels.
+// Forward progress: K4's CTAs can only start after every CTA of K3, hence of K2, hence of K1 has started (each
+// kernel triggers its dependents in its prologue), so K1 is resident or finished whenever a K4 team spins; the
+// spin is bounded and falls back to the ordinary dependency wait.
+struct RowDeps {
+  const unsigned* k1_counter;  // null: off
+  unsigned k1_target;
+  const float* body_state;     // [n_bodies][8] of this step (batch = 1)
+  int n_bodies;
+  int half_extent;             // body box half edge in cells (as the spreading kernel's)
+};
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field,
                      const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,
@@ -150,10 +167,12 @@ int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, c
                      int* box_scratch);
 int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
                    float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
-                   const StageHook* hook = nullptr, const GridF* gov = nullptr);
+                   const StageHook* hook = nullptr, const GridF* gov = nullptr, const RowDeps* deps = nullptr);
 // Poisson stages (sp = spectrum row pitch in complex values, 0 = ny/2 + 4)
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, float* spectrum, int sp,
-                    const SpecScatter* sc = nullptr, const GridF* gov = nullptr);
+                    const SpecScatter* sc = nullptr, const GridF* gov = nullptr, const RowDeps* deps = nullptr);
+bool plan_team_rows_fwd(const jaxib_plan* plan);
+int ib_half_extent(const GridF& g, const jaxib_bodies& b);
 int launch_cols(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int ncols, int col0,
                 int col_begin = 0);
 void plan_cols_geometry(const jaxib_plan* plan, int* cols_per_cta, int* ctas_per_sm);

@@ -418,6 +418,12 @@ static void spread_geometry(const GridF& g, const jaxib_bodies& b, int* half_ext
   *tiles = (2 * *half_extent + 1 + TS - 1) / TS;
 }
 
+int ib_half_extent(const GridF& g, const jaxib_bodies& b) {
+  int he, tiles;
+  spread_geometry(g, b, &he, &tiles);
+  return he;
+}
+
 int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* field, const float* xp,
                      const float* yp, int n, float* out, int32_t* ci, int32_t* cj) {
   if (n <= 0) return JAXIB_OK;

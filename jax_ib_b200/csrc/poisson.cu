@@ -505,6 +505,7 @@ StageParams stage_params(const jaxib_plan* pl, int sp, const GridF* gov = nullpt
   S.frp.scale = S.rp.scale;
   memset(&S.frp.sc, 0, sizeof(S.frp.sc));
   memset(&S.frp.ho, 0, sizeof(S.frp.ho));
+  memset(&S.frp.deps, 0, sizeof(S.frp.deps));
   if (S.channel) {
     S.dp.g = g; S.dp.pl = pl->row; S.dp.tw = pl->tw_row; S.dp.twd = pl->tw_dct; S.dp.pos = pl->row_pos;
     S.dp.rows_per_cta = pl->rows_per_cta; S.dp.sp = S.rp.sp;
@@ -516,9 +517,12 @@ StageParams stage_params(const jaxib_plan* pl, int sp, const GridF* gov = nullpt
 }  // namespace
 
 // K4: divergence of (u, v) + forward row transform -> spectrum [nx][sp]
+bool plan_team_rows_fwd(const jaxib_plan* pl) { return pl->team_rows_fwd; }
+
 int launch_rows_fwd(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, float* spectrum, int sp,
-                    const SpecScatter* sc, const GridF* gov) {
+                    const SpecScatter* sc, const GridF* gov, const RowDeps* deps) {
   StageParams S = stage_params(pl, sp, gov);
+  if (deps && pl->team_rows_fwd) S.frp.deps = *deps;
   float2* spec = reinterpret_cast<float2*>(spectrum);
   if (sc && sc->cpr) {
     if (!pl->fast_rows) { set_error("peer-memory slab mode needs ny/2 in {512, 1024, 2048, 4096}"); return JAXIB_ERR_UNSUPPORTED; }
@@ -615,8 +619,9 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum,
 }
 
 int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
-                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook, const GridF* gov) {
-  int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0, nullptr, gov);
+                   float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook, const GridF* gov,
+                   const RowDeps* deps) {
+  int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0, nullptr, gov, deps);
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);
   rc = launch_cols(s, pl, spectrum, 0, 0, 0);

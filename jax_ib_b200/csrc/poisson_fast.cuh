@@ -24,6 +24,7 @@ struct FastRowParams {
   float scale;       // 1 / (nx * ny/2)
   SpecScatter sc;    // rows_fwd, slab mode: spectrum columns go to the column owners
   HaloOut ho;        // rows_inv, slab mode: boundary rows also go to the neighbours' halos
+  RowDeps deps;      // rows_fwd team kernel: early start of the rows far from every body (k1_counter == null: off)
 };
 
 bool fast_size_supported(int n);

@@ -174,8 +174,35 @@ rows_fwd_team_kernel(FastRowParams P, const float2* __restrict__ tables, const f
   u += blockIdx.y * plane;
   v += blockIdx.y * plane;
   spec += (size_t)blockIdx.y * g.nx * P.sp;
-  pdl_wait();
-  __syncthreads();  // barrier initialisation visible
+  __syncthreads();  // barrier initialisation visible (before the dependency waits: teams wait for different things)
+  // Dependency: a row far from every body only needs the predictor (RowDeps in common.cuh), everything else waits
+  // for the previous kernel as usual.
+  bool far = false;
+  if (P.deps.k1_counter != nullptr && live) {
+    bool hit = false;
+    for (int b2 = lane; b2 < P.deps.n_bodies; b2 += 32) {
+      const float xc = __ldg(P.deps.body_state + (size_t)b2 * JAXIB_BODY_STATE_STRIDE + 2);
+      const int ic = (int)floorf(__fsub_rn(__fdiv_rn(xc, g.dx), 1.0f));  // u-cell row of the centre (ib.cu: cell_index)
+      hit |= i >= ic - P.deps.half_extent - 1 && i <= ic + P.deps.half_extent + 2;
+    }
+    far = !__any_sync(FULLW, hit);
+  }
+  if (far) {
+    bool done = true;
+    if (lane == 0) {
+      const long long t0 = clock64();
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.deps.k1_counter) : "memory");
+        done = (int)(seen - P.deps.k1_target) >= 0;
+      } while (!done && clock64() - t0 < 600000);  // ~0.3 ms: far beyond any predictor; then the ordinary wait
+    }
+    done = __shfl_sync(FULLW, done ? 1 : 0, 0) != 0;
+    __syncwarp();
+    if (!done) pdl_wait();
+  } else {
+    pdl_wait();
+  }
   // slab mode (nx_global > 0): the rows are open -- u row -1 sits next to the array (halo)
   const ptrdiff_t im1 = (i == 0 && g.nx_global == 0) ? g.nx - 1 : i - 1;
   const float2* __restrict__ ur = reinterpret_cast<const float2*>(u + (size_t)i * ny);
@@ -432,7 +459,12 @@ int launch_rows_fwd_team_t(cudaStream_t s, const FastRowParams& P, const float2*
     cudaFuncSetAttribute(rows_fwd_team_kernel<R1, R2, R3, PS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem(G::NT));
     configured = true;
   }
-  const int nt = teams_per_cta(G::NT, P.g.nx, P.g.batch, 0);
+  int nt = teams_per_cta(G::NT, P.g.nx, P.g.batch, 0);
+  if (P.deps.k1_counter != nullptr) {
+    // early start: the CTAs must fit NEXT TO the IB kernels' CTAs (half the registers of an SM at most)
+    static const int cap = getenv("JAXIB_K4_EARLY_THREADS") ? atoi(getenv("JAXIB_K4_EARLY_THREADS")) : 512;
+    while (nt > 2 && nt * G::T > cap) nt /= 2;
+  }
   dim3 grid((P.g.nx + nt - 1) / nt, P.g.batch);
   launch_pdl(8, rows_fwd_team_kernel<R1, R2, R3, PS2>, grid, dim3(nt * G::T), G::smem(nt), s, P, tables, u, v, spec);
   return check_launch("rows_fwd_team_kernel");

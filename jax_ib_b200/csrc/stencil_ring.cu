@@ -97,7 +97,7 @@ template <bool PREDICT>
 __global__ void __launch_bounds__(kRingMaxThreads, 1)
 explicit_upwind_ring_kernel(RingParams P, const float* __restrict__ u, const float* __restrict__ v,
                             const float* __restrict__ p, const float* __restrict__ perm, float* __restrict__ out_u,
-                            float* __restrict__ out_v) {
+                            float* __restrict__ out_v, unsigned* __restrict__ done_counter) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   pdl_trigger();
   const int NT = blockDim.x - 32;  // consumer threads
@@ -260,6 +260,11 @@ explicit_upwind_ring_kernel(RingParams P, const float* __restrict__ u, const flo
     if (i + 1 < i1) step(B, C, A);
     if (i + 2 < i1) step(C, A, B);
   }
+  if (done_counter != nullptr) {  // this warp's rows are stored: publish (see RowDeps in common.cuh)
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) atomicAdd(done_counter, 1u);
+  }
 }
 
 int env_int(const char* name, int dflt) {
@@ -275,12 +280,14 @@ bool explicit_ring_eligible(const GridF& g) {
 
 // Returns true when this path handled the launch (rc holds the status).  bands == nullptr: the whole grid.
 bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
-                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc, const RowBands* bands) {
+                          const float* perm, float* out_u, float* out_v, bool predictor, int* rc, const RowBands* bands,
+                          unsigned* done_counter, unsigned* done_increment) {
   if (g.bc != JAXIB_BC_PERIODIC || g.convect != JAXIB_CONVECT_UPWIND || (g.ny & 3) || g.ny < 8 || g.nx < 4) return false;
   const uintptr_t align = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v) |
                           reinterpret_cast<uintptr_t>(out_u) | reinterpret_cast<uintptr_t>(out_v) |
                           reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(perm);
   if (align & 15) return false;
+  if (done_increment) *done_increment = 0;
   static int mode = -1;  // JAXIB_K1=march selects the first-generation register-marching kernel (A/B runs)
   if (mode < 0) { const char* e = getenv("JAXIB_K1"); mode = (e && !strcmp(e, "march")) ? 0 : 1; }
   if (!mode) return false;
@@ -351,11 +358,12 @@ bool launch_explicit_ring(cudaStream_t s, const GridF& g, const float* u, const 
   P.fy = S * g.fy;
   P.pk = S * g.inv_rho;
   dim3 grid(nstrips, chunks, g.batch);
+  if (done_increment) *done_increment = (unsigned)(grid.x * grid.y * grid.z) * (unsigned)(W / 4 / 32);
   if (predictor)
-    launch_pdl(1, explicit_upwind_ring_kernel<true>, grid, dim3(threads), smem, s, P, u, v, p, perm, out_u, out_v);
+    launch_pdl(1, explicit_upwind_ring_kernel<true>, grid, dim3(threads), smem, s, P, u, v, p, perm, out_u, out_v, done_counter);
   else
     launch_pdl(1, explicit_upwind_ring_kernel<false>, grid, dim3(threads), smem, s, P, u, v, (const float*)nullptr, perm,
-               out_u, out_v);
+               out_u, out_v, done_counter);
   *rc = check_launch("explicit_upwind_ring_kernel");
   return true;
 }

@@ -383,3 +383,21 @@ def test_far_field_full_step_through_the_reference_api(convect):
     assert step_fn.fused and step_fn.cfg["poisson"] == "far_field"
     out = step_fn.advance(av, steps)
     _compare(out, st, 1e-5, floor=ulp)
+
+
+# ------------------------------------------------------------------------------------------------ K4 early start
+@pytest.mark.parametrize("workload", ["ib1024", "ib2048"])
+def test_early_start_of_the_row_transform_is_bitwise_the_serial_order(workload):
+    """Rows far from every body start their forward transform on the predictor's completion counter, under the two
+    IB kernels (RowDeps, csrc/common.cuh).  Same kernels, same arithmetic: the fields must equal the run with the
+    ordinary kernel-to-kernel dependency bit for bit.  The switch is read once per process and is off by default
+    (measured slower at 2048^2, capi.cu): the child process runs with JAXIB_K4_EARLY=1."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import field_checksum
+    here = field_checksum.checksum(workload, 6)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "field_checksum.py"), workload, "6"],
+                       env=dict(os.environ, JAXIB_K4_EARLY="1"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().split()[-1] == here
