@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB = os.path.join(OUT_DIR, "libjaxib_b200.so")
 STAMP = os.path.join(OUT_DIR, "build.stamp")
-SOURCES = ["capi.cu", "stencil.cu", "stencil_fast.cu", "stencil_ring.cu", "ib.cu", "poisson.cu", "poisson_fast.cu", "poisson_team.cu", "poisson_team_rows.cu", "tracer.cu", "slab.cu"]
+SOURCES = ["capi.cu", "stencil.cu", "stencil_fast.cu", "stencil_ring.cu", "ib.cu", "poisson.cu", "poisson_fast.cu", "poisson_team.cu", "poisson_team_rows.cu", "poisson_sweep.cu", "tracer.cu", "slab.cu"]
 HEADERS = ["common.cuh", "fft.cuh", "poisson_fast.cuh", os.path.join("..", "..", "include", "jaxib_b200.h")]
 
 NVCC_FLAGS = [

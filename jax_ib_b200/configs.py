@@ -87,9 +87,10 @@ def _divfree_perturbation(shape, domain, seed, nmodes=16, amp=1e-2):
     return (u * s).astype(F), (v * s).astype(F)
 
 
-def channel(shape=(1024, 256), domain=((0.0, 4.0), (0.0, 1.0)), seed=3):
+def channel(shape=(1024, 256), domain=((0.0, 4.0), (0.0, 1.0)), seed=3, force_x=2e-3):
     """G3: taylor_dispersion_demo.ipynb cells 9-11 -- periodic-x / no-slip-y channel, van Leer,
-    nu = 1e-3, body force 2e-3 in x, dt = min(0.5 dx / 1, dx^2 / (4 nu))."""
+    nu = 1e-3, body force 2e-3 in x, dt = min(0.5 dx / 1, dx^2 / (4 nu)).  The notebook's dt assumes |u| <= 1: a taller
+    channel needs a proportionally smaller force (Poiseuille peak = force H^2 / (8 nu)) to stay inside that CFL bound."""
     nx, ny = shape
     dx = (domain[0][1] - domain[0][0]) / nx
     dy = (domain[1][1] - domain[1][0]) / ny
@@ -98,7 +99,7 @@ def channel(shape=(1024, 256), domain=((0.0, 4.0), (0.0, 1.0)), seed=3):
     dt = min(0.5 * h / 1.0, h ** 2 / (nu * 4))
     return dict(
         name=f"channel{nx}x{ny}", shape=shape, domain=domain, dt=dt, density=1.0, viscosity=nu,
-        bc="channel", convect="van_leer", force=(2e-3, 0.0), wall_u=(0.0, 0.0), wall_v=(0.0, 0.0),
+        bc="channel", convect="van_leer", force=(force_x, 0.0), wall_u=(0.0, 0.0), wall_v=(0.0, 0.0),
         bodies=None, init=("poiseuille+noise", seed),
     )
 

@@ -149,14 +149,16 @@ struct Scratch {
 };
 constexpr size_t kSyncBytes = 256;
 
-static size_t scratch_need(const GridF& g, int n_markers) {
+static size_t scratch_need(const jaxib_plan* plan, int n_markers) {
+  const GridF& g = plan_grid(plan);
   size_t plane = (size_t)g.batch * g.nx * g.ny;
-  size_t spectrum = (size_t)g.batch * g.nx * (g.ny + 8);  // [nx][ny/2 + 4] complex
+  size_t spectrum = spectrum_floats(plan);  // [nx][ny/2 + 4] complex, or the x-sweep's row images + carried values
   return (2 * plane + spectrum + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) * sizeof(float) + 256 + kSyncBytes;
 }
 
-static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scratch* out) {
-  size_t need = scratch_need(g, n_markers);
+static int carve(const jaxib_plan* plan, int n_markers, void* scratch, size_t bytes, Scratch* out) {
+  const GridF& g = plan_grid(plan);
+  size_t need = scratch_need(plan, n_markers);
   if (!scratch || bytes < need) {
     set_error("scratch too small: have %zu bytes, need %zu", bytes, need);
     return JAXIB_ERR_SCRATCH;
@@ -167,7 +169,7 @@ static int carve(const GridF& g, int n_markers, void* scratch, size_t bytes, Scr
   out->u_star = base;
   out->v_star = base + plane;
   out->spectrum = base + 2 * plane;
-  out->markers = base + 2 * plane + (size_t)g.batch * g.nx * (g.ny + 8);
+  out->markers = base + 2 * plane + spectrum_floats(plan);
   out->sync = reinterpret_cast<unsigned*>(
       (reinterpret_cast<uintptr_t>(out->markers + (size_t)5 * g.batch * (n_markers > 0 ? n_markers : 0)) + 63) & ~uintptr_t(63));
   return JAXIB_OK;
@@ -191,7 +193,7 @@ int jaxib_compiled_arch(void) {
 
 size_t jaxib_scratch_bytes(const jaxib_plan* plan, int32_t n_markers) {
   if (!plan) return 0;
-  return scratch_need(plan_grid(plan), n_markers);
+  return scratch_need(plan, n_markers);
 }
 
 int jaxib_explicit_terms(jaxib_stream_t stream, const jaxib_grid* grid, const float* u, const float* v,
@@ -331,7 +333,7 @@ int jaxib_pressure_solve(jaxib_stream_t stream, const jaxib_plan* plan, const fl
   int rc = check_ptrs("pressure_solve", {u, v, q});
   if (rc) return rc;
   Scratch sc;
-  if ((rc = carve(plan_grid(plan), 0, scratch, scratch_bytes, &sc))) return rc;
+  if ((rc = carve(plan, 0, scratch, scratch_bytes, &sc))) return rc;
   return launch_project((cudaStream_t)stream, plan, u, v, nullptr, nullptr, nullptr, nullptr, q, sc.spectrum);
 }
 
@@ -341,7 +343,7 @@ int jaxib_project(jaxib_stream_t stream, const jaxib_plan* plan, const float* u,
   int rc = check_ptrs("project", {u, v, p, u_out, v_out, p_out});
   if (rc) return rc;
   Scratch sc;
-  if ((rc = carve(plan_grid(plan), 0, scratch, scratch_bytes, &sc))) return rc;
+  if ((rc = carve(plan, 0, scratch, scratch_bytes, &sc))) return rc;
   return launch_project((cudaStream_t)stream, plan, u, v, p, u_out, v_out, p_out, nullptr, sc.spectrum);
 }
 
@@ -359,7 +361,7 @@ int jaxib_step(jaxib_stream_t stream, const jaxib_plan* plan, const jaxib_bodies
   }
   const GridF& g = plan_grid(plan);
   Scratch sc;
-  if ((rc = carve(g, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
+  if ((rc = carve(plan, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
   // K4 early start (RowDeps, common.cuh): needs the ring predictor's completion counter and the team row kernel
@@ -465,7 +467,7 @@ int jaxib_step_profile(jaxib_stream_t stream, const jaxib_plan* plan, const jaxi
   }
   const GridF& g = plan_grid(plan);
   Scratch sc;
-  if ((rc = carve(g, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
+  if ((rc = carve(plan, has_ib ? bodies->n_markers : 0, scratch, scratch_bytes, &sc))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t state_stride = has_ib ? (size_t)g.batch * bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
   const int per = JAXIB_N_STAGES;  // start + 6 stage ends

@@ -182,6 +182,7 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* plan, const float* spectru
 bool plan_fast_rows(const jaxib_plan* plan);
 bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);
+bool plan_sweep(const jaxib_plan* plan);
 const GridF& plan_grid(const jaxib_plan* plan);
 
 }  // namespace jaxib

@@ -55,6 +55,17 @@ struct jaxib_plan {
   double* lam_x_nat;   // far field: Neumann eigenvalues (2cos(pi k/nx) - 2)/dx^2 in natural order k < nx
   float2* tw_team_col; // team column kernel: twiddle tables in shared-memory layout
   float2* tw_team_row; // team row kernels: ditto
+  // third generation of the periodic solve (x-sweep, poisson_team_rows.cu): no column transform
+  bool sweep;
+  jaxib::SweepGeom sweep_geo;
+  float* sw_rho;
+  float* sw_lg;
+  float* sw_gain;
+  double* sw_rho_d;
+  // K5 third generation (poisson_sweep.cu): x periodic (periodic and channel grids), any nx
+  bool col_sweep;
+  float2* cs_tab;
+  int cs_pitch;
 };
 
 namespace jaxib {
@@ -477,8 +488,14 @@ __global__ void cols_dct_kernel(ColDctParams P, float2* __restrict__ spec) {
 
 const GridF& plan_grid(const jaxib_plan* plan) { return plan->gf; }
 size_t spectrum_floats(const jaxib_plan* plan) {
-  return (size_t)plan->gf.batch * plan->gf.nx * (plan->gf.ny + 8);  // [nx][ny/2 + 4] complex
+  const size_t plain = (size_t)plan->gf.batch * plan->gf.nx * (plan->gf.ny + 8);  // [nx][ny/2 + 4] complex
+  if (!plan->sweep) return plain;
+  // x-sweep: row images [nx][img] + three [chunks][img] arrays of carried values, complex
+  const SweepGeom& sg = plan->sweep_geo;
+  const size_t sweep = 2 * (size_t)plan->gf.batch * sg.img * ((size_t)plan->gf.nx + 3 * (size_t)sg.C);
+  return sweep > plain ? sweep : plain;
 }
+bool plan_sweep(const jaxib_plan* plan) { return plan->sweep; }
 
 namespace {
 
@@ -555,6 +572,13 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
   const int n2 = g.ny / 2;
   const bool channel = g.bc != JAXIB_BC_PERIODIC;
   if (sp <= 0) sp = n2 + 4;
+  if (pl->col_sweep && ncols <= 0 && col0 == 0 && col_begin == 0) {  // whole grid on this GPU: sweeps instead of a transform
+    ColSweepParams P;
+    P.nx = g.nx; P.sp = sp; P.ncols = channel ? n2 : n2 + 1; P.segs = (g.nx + 15) / 16;
+    P.cst = pl->cs_tab; P.cst_pitch = pl->cs_pitch;
+    P.dx2 = (double)g.dx * (double)g.dx; P.out_scale = (double)g.nx;
+    return launch_cols_sweep(s, P, g.batch, reinterpret_cast<float2*>(spectrum));
+  }
   float2* spec = reinterpret_cast<float2*>(spectrum) + col_begin;
   col0 += col_begin;
   if (pl->fast_cols) {
@@ -621,6 +645,26 @@ int launch_rows_inv(cudaStream_t s, const jaxib_plan* pl, const float* spectrum,
 int launch_project(cudaStream_t s, const jaxib_plan* pl, const float* u, const float* v, const float* p, float* u_out,
                    float* v_out, float* p_out, float* q_only, float* spectrum, const StageHook* hook, const GridF* gov,
                    const RowDeps* deps) {
+  if (pl->sweep) {  // periodic grids with team row kernels: FFT along y, two recurrences along x, no column pass
+    const SweepGeom& sg = pl->sweep_geo;
+    SweepParams P;
+    P.g = gov ? *gov : pl->gf;
+    P.L = sg.L; P.C = sg.C; P.img = sg.img;
+    P.rho = pl->sw_rho; P.lg = pl->sw_lg; P.gain = pl->sw_gain; P.rho_d = pl->sw_rho_d;
+    const size_t rows = (size_t)P.g.batch * P.g.nx * sg.img, carr = (size_t)P.g.batch * sg.C * sg.img;
+    P.a = reinterpret_cast<float2*>(spectrum);
+    P.agg = P.a + rows;
+    P.cA = P.agg + carr;
+    P.cB = P.cA + carr;
+    int rc = launch_rows_fwd_sweep(s, P, sg.ntb, pl->tw_team_row, u, v);
+    if (rc) return rc;
+    if (hook) cudaEventRecord(hook->ev[0], s);
+    if ((rc = launch_sweep_carry(s, P))) return rc;
+    if (hook) cudaEventRecord(hook->ev[1], s);
+    rc = launch_rows_inv_sweep(s, P, sg.ntb, pl->tw_team_row, u, v, p, u_out, v_out, q_only ? q_only : p_out, q_only == nullptr);
+    if (hook) cudaEventRecord(hook->ev[2], s);
+    return rc;
+  }
   int rc = launch_rows_fwd(s, pl, u, v, spectrum, 0, nullptr, gov, deps);
   if (rc) return rc;
   if (hook) cudaEventRecord(hook->ev[0], s);
@@ -716,6 +760,35 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
     team_row_twiddle_table(n2, &tt);
     rc = upload(&pl->tw_team_row, tt);
   }
+  {
+    const char* e = getenv("JAXIB_SWEEP");  // JAXIB_SWEEP=0: keep the FFT x FFT solve (A/B runs)
+    pl->sweep = pl->team_rows && grid->nx_global == 0 && (e && atoi(e) == 1) &&
+                sweep_geometry(nx, ny, pl->gf.batch, &pl->sweep_geo);
+    if (!rc && pl->sweep) {
+      std::vector<float> r, l, gn;
+      std::vector<double> rd;
+      sweep_tables(ny, (double)pl->gf.dx, (double)pl->gf.dy, &r, &l, &gn, &rd);
+      rc = upload(&pl->sw_rho, r);
+      if (!rc) rc = upload(&pl->sw_lg, l);
+      if (!rc) rc = upload(&pl->sw_gain, gn);
+      if (!rc) rc = upload(&pl->sw_rho_d, rd);
+    }
+  }
+  {
+    const char* e = getenv("JAXIB_COL_SWEEP");  // JAXIB_COL_SWEEP=0: keep the column FFT (A/B runs)
+    pl->col_sweep = !far && grid->nx_global == 0 && cols_sweep_supported(nx) && !(e && atoi(e) == 0);
+    if (!rc && pl->col_sweep) {
+      const int nc = channel ? n2 : n2 + 1;
+      std::vector<double> lre(nc), lim(nc);
+      for (int c = 0; c < nc; ++c) {
+        lre[c] = channel ? ly[2 * c] : ly[c];
+        lim[c] = channel ? ly[2 * c + 1] : ly[c];
+      }
+      std::vector<float2> tab;
+      cols_sweep_tables(nx, nc, (double)pl->gf.dx, lre.data(), lim.data(), &tab, &pl->cs_pitch);
+      rc = upload(&pl->cs_tab, tab);
+    }
+  }
   if (!rc) rc = upload(&pl->tw_row, twr);
   if (!rc) rc = upload(&pl->tw_col, twc);
   if (!rc) rc = upload(&pl->row_pos, rpos);
@@ -808,6 +881,7 @@ extern "C" int jaxib_plan_destroy(jaxib_plan* pl) {
   cudaFree(pl->lam_x_pos); cudaFree(pl->lam_y); cudaFree(pl->lam_x_pos_f); cudaFree(pl->lam_y_f);
   cudaFree(pl->tw_dct); cudaFree(pl->tw_team_col); cudaFree(pl->tw_team_row);
   cudaFree(pl->tw_dct_col); cudaFree(pl->lam_x_nat);
+  cudaFree(pl->cs_tab); cudaFree(pl->sw_rho); cudaFree(pl->sw_lg); cudaFree(pl->sw_gain); cudaFree(pl->sw_rho_d);
   delete pl;
   return JAXIB_OK;
 }

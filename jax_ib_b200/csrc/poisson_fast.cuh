@@ -50,4 +50,45 @@ int launch_rows_fwd_team(cudaStream_t s, const FastRowParams& P, const float2* t
 int launch_rows_inv_team(cudaStream_t s, const FastRowParams& P, const float2* tables, const float2* spec, const float* u,
                          const float* v, const float* p, float* uo, float* vo, float* po, bool project);
 
+// third generation of the periodic solve (poisson_team_rows.cu, "x-sweep"): row FFTs + two first-order sweeps along x
+struct SweepParams {
+  GridF g;
+  int L, C, img;          // rows per chunk, chunks per grid, float2 entries of a row image
+  const float* rho;       // [img] rho of the slot's wavenumber; < 0: padding hole; 0: the k = 0 column
+  const float* lg;        // [img] log2(rho), finite
+  const float* gain;      // [img] -dx^2 rho / (ny/2); k = 0: 1 / (ny/2)
+  const double* rho_d;    // [img]
+  float2* a;              // [batch][nx][img]  chunk-local forward sweep
+  float2* agg;            // [batch][C][img]   sum_r rho^r a[r] of each chunk
+  float2* cA;             // [batch][C][img]   forward sweep value entering the chunk
+  float2* cB;             // [batch][C][img]   backward sweep value entering the chunk (= b of the next chunk's first row)
+};
+
+struct SweepGeom {
+  int L, C, img;      // rows per chunk, chunks, float2 entries per row image
+  int ntb;            // teams (rows in flight) per CTA
+  int team_threads, max_teams;
+};
+bool sweep_geometry(int nx, int ny, int batch, SweepGeom* out);  // false: row length not supported
+void sweep_tables(int ny, double dx, double dy, std::vector<float>* rho, std::vector<float>* lg, std::vector<float>* gain,
+                  std::vector<double>* rho_d);
+int launch_rows_fwd_sweep(cudaStream_t s, const SweepParams& P, int ntb, const float2* tables, const float* u, const float* v);
+int launch_sweep_carry(cudaStream_t s, const SweepParams& P);
+int launch_rows_inv_sweep(cudaStream_t s, const SweepParams& P, int ntb, const float2* tables, const float* u, const float* v,
+                          const float* p, float* uo, float* vo, float* po, bool project);
+
+// K5 third generation (poisson_sweep.cu): the periodic x-direction solved by two first-order sweeps, no transform
+struct ColSweepParams {
+  int nx, sp, ncols;    // rows, spectrum row pitch (complex), stored complex columns
+  int segs;             // ceil(nx / 16): segments of rows per column
+  const float2* cst;    // [7][cst_pitch] per-column constants (cols_sweep_tables)
+  int cst_pitch;
+  double dx2;           // dx^2
+  double out_scale;     // nx (see cols_sweep_tables)
+};
+bool cols_sweep_supported(int nx);
+void cols_sweep_tables(int nx, int ncols, double dx, const double* ly_re, const double* ly_im, std::vector<float2>* out,
+                       int* pitch);
+int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec);
+
 }  // namespace jaxib

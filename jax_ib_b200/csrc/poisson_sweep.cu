@@ -1,0 +1,322 @@
+// K5, third generation ("column sweep"): the x-direction of the pressure solve WITHOUT a transform.
+//
+// After the row transform along y (K4: packed real FFT on periodic grids, DCT-II in a channel) every stored
+// column is a 1-D periodic problem along x for one y-eigenvalue ly (pressure.py:94-108, 111-130: the
+// eigenvalues lx + ly of the second-difference operators, array_utils.py:168-182):
+//     Q[i-1] - (2 + mu) Q[i] + Q[i+1] = dx^2 X[i],      mu = -ly dx^2 >= 0.
+// The first two generations diagonalise it with a complex FFT along x, divide and transform back (5 N log N
+// flops per point twice, five shared-memory round trips, 0.25 of the HBM roofline: profiles/r2d).  But a periodic
+// tridiagonal Toeplitz system has a closed-form inverse, a two-sided geometric sequence: with rho in (0, 1)
+// the root of rho + 1/rho = 2 + mu,
+//     a[i] = X[i] + rho a[i-1]  (forward sweep),   b[i] = a[i] + rho b[i+1]  (backward sweep),   Q = -dx^2 rho b,
+// both sweeps periodic.  That is 4 FMAs per point instead of ~110 flops, and it is the SAME linear operator as the
+// reference's pseudo-inverse (the mu = 0 column, singular, is solved with the mean mode projected out exactly as
+// the 10 eps cut-off of the pseudo-inverse does; tests compare against the oracle's FFT solve).
+//
+// Kernel: a CTA owns CS adjacent columns (CS x 8 bytes per row: whole sectors) over ALL nx rows; thread =
+// (column, segment of RS = 16 consecutive rows), the 16 values live in registers.
+//   1. local forward sweep from zero; e = a of the segment's last row, S = sum_r rho^r a[r] (Horner);
+//   2. the carried values of all segments obey  Aout[s] = e_s + P_s Ain[s], Ain[s] = Aout[s-1]  (cyclic; P_s =
+//      rho^rows) and  Bout[s] = T_s + P_s Bin[s], Bin[s] = Bout[s+1],  T_s = S_s + Ain[s] rho (1 - rho^2rows)/(1 - rho^2):
+//      one warp per column composes these affine maps with a shuffle scan and closes the cycle with 1/(1 - rho^nx);
+//   3. a_true[r] = a[r] + rho^(r+1) Ain, backward sweep from Bin, scale, store in place.
+// The real part of column 0 (mu = 0) is solved by the last CTA of the grid with two prefix sums in double.
+// A channel stores two real DCT columns per complex column: real and imaginary parts simply carry their own
+// constants (on periodic grids they are equal).  tools/sweep_model.py restates the arithmetic in NumPy float32:
+// rel-L2 2.4e-7 against the float64 solution at 2048^2 (float32 FFT solve: 1.7e-7).
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "poisson_fast.cuh"
+
+namespace jaxib {
+namespace {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int RS = 16;  // rows per thread
+
+// y = e + P x: composition "first f, then g" = (g.e + g.P f.e, g.P f.P)
+struct Affine {
+  float e, P;
+};
+__device__ __forceinline__ Affine then(const Affine& f, const Affine& g) { return {fmaf(g.P, f.e, g.e), g.P * f.P}; }
+
+// Solves one real channel (re or im) of one column for the warp: lane l owns segments [l m, (l+1) m).
+// e[], S[]: this column's shared arrays in the layout [j][lane] (segment = lane m + j: for a fixed j the lanes read
+// consecutive words -- a [segment] layout would put every lane on the same bank; measured 32-way conflicts on
+// every access, profiles/r2v).  On return e[] holds Ain and S[] holds Bin of every segment.
+__device__ __forceinline__ void carry_scan(float* e, float* S, int segs, int m, float Pseg, float Plast, float rG,
+                                           float rGlast, float close, int lane) {
+  const int s0 = min(lane * m, segs), s1 = min(s0 + m, segs);
+  // ---- forward
+  Affine f = {0.0f, 1.0f};
+  for (int s = s0; s < s1; ++s) f = then(f, Affine{e[(s - s0) * 32 + lane], s == segs - 1 ? Plast : Pseg});
+  Affine inc = f;  // inclusive scan over the lanes: map of segments [0, s1)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Affine up = {__shfl_up_sync(FULLM, inc.e, o), __shfl_up_sync(FULLM, inc.P, o)};
+    if (lane >= o) inc = then(up, inc);
+  }
+  const float all_e = __shfl_sync(FULLM, inc.e, 31);
+  const float ain0 = all_e * close;  // value entering segment 0 = value leaving the last one (cyclic)
+  Affine ex = {__shfl_up_sync(FULLM, inc.e, 1), __shfl_up_sync(FULLM, inc.P, 1)};
+  float cur = lane == 0 ? ain0 : fmaf(ex.P, ain0, ex.e);
+  // ---- walk forward; T_s replaces S_s
+  Affine g = {0.0f, 1.0f};  // backward map of this lane's segments: Bout[s0] = g.e + g.P Bin[s1 - 1]
+  float W = 1.0f;
+  for (int s = s0; s < s1; ++s) {
+    const bool last = s == segs - 1;
+    const float Ps = last ? Plast : Pseg;
+    const int at = (s - s0) * 32 + lane;
+    const float es = e[at];
+    e[at] = cur;                                             // Ain[s]
+    const float T = fmaf(cur, last ? rGlast : rG, S[at]);
+    S[at] = T;
+    g.e = fmaf(T, W, g.e);
+    W *= Ps;
+    cur = fmaf(Ps, cur, es);
+  }
+  g.P = W;
+  // ---- backward: inclusive scan from the last lane down: map of segments [s0, segs)
+  Affine dec = g;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Affine dn = {__shfl_down_sync(FULLM, dec.e, o), __shfl_down_sync(FULLM, dec.P, o)};
+    if (lane + o < 32) dec = then(dn, dec);
+  }
+  const float ball = __shfl_sync(FULLM, dec.e, 0);
+  const float bin_last = ball * close;  // value entering the last segment from above = Bout[0] (cyclic)
+  Affine dx = {__shfl_down_sync(FULLM, dec.e, 1), __shfl_down_sync(FULLM, dec.P, 1)};
+  float b = lane == 31 ? bin_last : fmaf(dx.P, bin_last, dx.e);
+  for (int s = s1 - 1; s >= s0; --s) {
+    const int at = (s - s0) * 32 + lane;
+    const float T = S[at];
+    S[at] = b;                                               // Bin[s]
+    b = fmaf(s == segs - 1 ? Plast : Pseg, b, T);
+  }
+}
+
+template <int NTH>
+__device__ __forceinline__ double cta_sum(double v, double* red, int t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+  __syncthreads();
+  if ((t & 31) == 0) red[t >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+// in-place scan of q[0..n) by the whole CTA (every thread a contiguous piece, piece totals by shuffles)
+__device__ void cta_scan(double* q, int n, bool inclusive, double* red, int t) {
+  const int nth = blockDim.x;
+  const int per = (n + nth - 1) / nth;
+  const int lo = min(t * per, n), hi = min(lo + per, n);
+  __syncthreads();  // q was written with another thread mapping
+  double s = 0.0;
+  for (int i = lo; i < hi; ++i) s += q[i];
+  double inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(FULLM, inc, o);
+    if ((t & 31) >= o) inc += y;
+  }
+  __syncthreads();
+  if ((t & 31) == 31) red[t >> 5] = inc;
+  __syncthreads();
+  double acc = inc - s;
+  for (int w = 0; w < (t >> 5); ++w) acc += red[w];
+  for (int i = lo; i < hi; ++i) {
+    const double x = q[i];
+    if (inclusive) { acc += x; q[i] = acc; } else { q[i] = acc; acc += x; }
+  }
+  __syncthreads();
+}
+
+// blockDim = CS * segs_padded (a multiple of 32); dynamic shared memory: max(4 CS (32 ceil(segs/32) + 1) floats, nx doubles)
+template <int CS>
+__global__ void __launch_bounds__(1024, 1)
+cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
+  extern __shared__ __align__(16) unsigned char sw_raw[];
+  __shared__ double red[32];
+  pdl_trigger();
+  const int t = threadIdx.x;
+  const int nx = P.nx;
+  spec += (size_t)blockIdx.y * nx * P.sp;
+  if (blockIdx.x == gridDim.x - 1) {
+    // ---- real part of column 0: Q[i-1] - 2 Q[i] + Q[i+1] = dx^2 (X[i] - mean X), mean Q = 0  (two prefix sums)
+    double* const q = reinterpret_cast<double*>(sw_raw);
+    const int nth = blockDim.x;
+    pdl_wait();
+    double sum = 0.0;
+    for (int i = t; i < nx; i += nth) { const double x = spec[(size_t)i * P.sp].x; q[i] = x; sum += x; }
+    const double mean = cta_sum<0>(sum, red, t) / nx;
+    for (int i = t; i < nx; i += nth) q[i] = (q[i] - mean) * P.dx2;
+    cta_scan(q, nx, true, red, t);   // s_i = sum_{j <= i}
+    sum = 0.0;
+    for (int i = t; i < nx; i += nth) sum += q[i];
+    const double smean = cta_sum<0>(sum, red, t) / nx;
+    for (int i = t; i < nx; i += nth) q[i] -= smean;  // d_i = Q[i+1] - Q[i]
+    cta_scan(q, nx, false, red, t);  // Q_i - Q_0
+    sum = 0.0;
+    for (int i = t; i < nx; i += nth) sum += q[i];
+    const double qmean = cta_sum<0>(sum, red, t) / nx;
+    for (int i = t; i < nx; i += nth) spec[(size_t)i * P.sp].x = (float)((q[i] - qmean) * P.out_scale);
+    return;
+  }
+  const int segs = P.segs;
+  const int c = t % CS, seg = t / CS;
+  const int col = blockIdx.x * CS + c;
+  const bool active = seg < segs && col < P.ncols;
+  // per-column constants (plan tables): before the dependency wait
+  float2 rho = make_float2(0.f, 0.f), gain = rho;
+  if (active) { rho = __ldg(P.cst + col); gain = __ldg(P.cst + P.cst_pitch + col); }
+  const int r0 = seg * RS;
+  const int rows = active ? min(RS, nx - r0) : 0;
+  float2* const base = spec + (size_t)r0 * P.sp + col;
+  // shared arrays [re | im][column][j][lane] (+ 1 word per column against bank conflicts of the column index);
+  // segment = lane m + j
+  const int m = (segs + 31) / 32;
+  const int cp1 = 32 * m + 1;                          // words per column
+  float* const sE = reinterpret_cast<float*>(sw_raw);  // e, later Ain
+  float* const sS = sE + 2 * CS * cp1;                 // S, later Bin
+  const int at = c * cp1 + (seg % m) * 32 + seg / m;
+  pdl_wait();
+  float2 a[RS];
+#pragma unroll
+  for (int r = 0; r < RS; ++r)
+    if (r < rows) a[r] = base[(size_t)r * P.sp];
+  // ---- 1. local forward sweep, Horner sum
+  float2 ap = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < RS; ++r)
+    if (r < rows) {
+      ap.x = fmaf(rho.x, ap.x, a[r].x);
+      ap.y = fmaf(rho.y, ap.y, a[r].y);
+      a[r] = ap;
+    }
+  float2 h = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = RS - 1; r >= 0; --r)
+    if (r < rows) {
+      h.x = fmaf(rho.x, h.x, a[r].x);
+      h.y = fmaf(rho.y, h.y, a[r].y);
+    }
+  if (active) {
+    sE[at] = ap.x; sE[CS * cp1 + at] = ap.y;
+    sS[at] = h.x;  sS[CS * cp1 + at] = h.y;
+  }
+  __syncthreads();
+  // ---- 2. carried values: warp w solves (column w >> 1, part w & 1)
+  {
+    const int w = t >> 5, lane = t & 31;
+    const int nwarps = blockDim.x >> 5;
+    for (int job = w; job < 2 * CS; job += nwarps) {
+      const int cj = job >> 1, part = job & 1;
+      const int colj = blockIdx.x * CS + cj;
+      if (colj >= P.ncols) continue;
+      const float* k = reinterpret_cast<const float*>(P.cst) + part;  // component `part` of the float2 tables
+      const size_t cp = (size_t)P.cst_pitch * 2;
+      const float Pseg = __ldg(k + 2 * cp + 2 * colj), Plast = __ldg(k + 3 * cp + 2 * colj);
+      const float close = __ldg(k + 4 * cp + 2 * colj), rG = __ldg(k + 5 * cp + 2 * colj), rGl = __ldg(k + 6 * cp + 2 * colj);
+      carry_scan(sE + (part * CS + cj) * cp1, sS + (part * CS + cj) * cp1, segs, m, Pseg, Plast, rG, rGl, close, lane);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  // ---- 3. carried part of the forward sweep, backward sweep, scale, store
+  const float2 ain = make_float2(sE[at], sE[CS * cp1 + at]);
+  float2 b = make_float2(sS[at], sS[CS * cp1 + at]);
+  // rho^n from rho, rho^2, rho^4, rho^8 (at most 4 roundings; n is a compile-time constant after unrolling)
+  const float2 p1 = rho, p2 = make_float2(p1.x * p1.x, p1.y * p1.y), p4 = make_float2(p2.x * p2.x, p2.y * p2.y),
+               p8 = make_float2(p4.x * p4.x, p4.y * p4.y);
+  auto power = [&](int n) {
+    if (n == 16) return make_float2(p8.x * p8.x, p8.y * p8.y);
+    float2 v = make_float2(1.f, 1.f);
+    if (n & 8) v = p8;
+    if (n & 4) v = (n & 8) ? make_float2(v.x * p4.x, v.y * p4.y) : p4;
+    if (n & 2) v = (n & 12) ? make_float2(v.x * p2.x, v.y * p2.y) : p2;
+    if (n & 1) v = (n & 14) ? make_float2(v.x * p1.x, v.y * p1.y) : p1;
+    return v;
+  };
+  const bool skip_re = col == 0;  // the last CTA owns the real part of column 0
+#pragma unroll
+  for (int r = RS - 1; r >= 0; --r)
+    if (r < rows) {
+      const float2 pw = power(r + 1);
+      b.x = fmaf(rho.x, b.x, fmaf(pw.x, ain.x, a[r].x));
+      b.y = fmaf(rho.y, b.y, fmaf(pw.y, ain.y, a[r].y));
+      float2* const o = base + (size_t)r * P.sp;
+      if (skip_re) o->y = gain.y * b.y;
+      else *o = make_float2(gain.x * b.x, gain.y * b.y);
+    }
+}
+
+template <int CS>
+int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(cols_sweep_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = true;
+  }
+  int threads = ((CS * P.segs + 31) / 32) * 32;
+  size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float);
+  const size_t col0 = (size_t)P.nx * sizeof(double);
+  if (col0 > smem) smem = col0;
+  dim3 grid((P.ncols + CS - 1) / CS + 1, batch);
+  launch_pdl(16, cols_sweep_kernel<CS>, grid, dim3(threads), smem, s, P, spec);
+  return check_launch("cols_sweep_kernel");
+}
+
+}  // namespace
+
+bool cols_sweep_supported(int nx) { return nx >= 2 && (nx + RS - 1) / RS <= 1024 && (size_t)nx * sizeof(double) <= 160 * 1024; }
+
+// Table layout [7][pitch] float2: rho, gain, rho^RS, rho^rows_last, 1/(1 - rho^nx), rho (1 - rho^2RS)/(1 - rho^2), same
+// for the last segment.  ly_re / ly_im: y-eigenvalues of the real and imaginary part of each stored column
+// (equal on periodic grids).  out_scale: the row kernels normalise by 1/nx (they were written for an unnormalised
+// forward + inverse column FFT), so the solution is stored times nx.
+void cols_sweep_tables(int nx, int ncols, double dx, const double* ly_re, const double* ly_im, std::vector<float2>* out,
+                       int* pitch) {
+  const int pt = (ncols + 3) & ~3;
+  *pitch = pt;
+  out->assign((size_t)7 * pt, make_float2(0.f, 0.f));
+  const int segs = (nx + RS - 1) / RS, last = nx - (segs - 1) * RS;
+  for (int c = 0; c < ncols; ++c) {
+    float v[7][2];
+    for (int part = 0; part < 2; ++part) {
+      const double mu = -(part ? ly_im[c] : ly_re[c]) * dx * dx;
+      if (!(mu > 1e-14)) {  // singular column (mean mode): the dedicated CTA solves it; the sweep passes it through
+        for (int k = 0; k < 7; ++k) v[k][part] = 0.0f;
+        v[4][part] = 1.0f;
+        continue;
+      }
+      const double r = 1.0 / (1.0 + 0.5 * mu + sqrt(mu + 0.25 * mu * mu));
+      v[0][part] = (float)r;
+      v[1][part] = (float)(-dx * dx * r * nx);
+      v[2][part] = (float)pow(r, RS);
+      v[3][part] = (float)pow(r, last);
+      v[4][part] = (float)(1.0 / (1.0 - pow(r, nx)));
+      v[5][part] = (float)(r * (1.0 - pow(r, 2 * RS)) / (1.0 - r * r));
+      v[6][part] = (float)(r * (1.0 - pow(r, 2 * last)) / (1.0 - r * r));
+    }
+    for (int k = 0; k < 7; ++k) (*out)[(size_t)k * pt + c] = make_float2(v[k][0], v[k][1]);
+  }
+}
+
+int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
+  // columns per CTA: whole 32-byte sectors per row where the thread budget allows (threads = CS * segs <= 1024)
+  if (P.segs <= 0 || P.segs > 1024) { set_error("column sweep: nx=%d unsupported", P.nx); return JAXIB_ERR_UNSUPPORTED; }
+  int cs = 1024 / P.segs;
+  if (const char* e = getenv("JAXIB_SWEEP_CS")) { const int v = atoi(e); if (v >= 1 && v * P.segs <= 1024) cs = v; }
+  if (cs >= 16) return launch_cols_sweep_t<16>(s, P, batch, spec);
+  if (cs >= 8) return launch_cols_sweep_t<8>(s, P, batch, spec);
+  if (cs >= 4) return launch_cols_sweep_t<4>(s, P, batch, spec);
+  if (cs >= 2) return launch_cols_sweep_t<2>(s, P, batch, spec);
+  return launch_cols_sweep_t<1>(s, P, batch, spec);
+}
+
+}  // namespace jaxib
