@@ -183,6 +183,11 @@ bool plan_fast_rows(const jaxib_plan* plan);
 bool plan_fast_cols(const jaxib_plan* plan);
 size_t spectrum_floats(const jaxib_plan* plan);
 bool plan_sweep(const jaxib_plan* plan);
+bool plan_col_sweep(const jaxib_plan* plan);
+int plan_col_sweep_pitch(const jaxib_plan* plan);
+int launch_cols_sweep_slab(cudaStream_t s, const jaxib_plan* plan, float* spectrum, int sp, int world, int rank,
+                           float* const* tables, int mode);
+size_t cols_sweep_slab_table_bytes(int world, int ncols_pad, int nx_global);
 const GridF& plan_grid(const jaxib_plan* plan);
 
 }  // namespace jaxib

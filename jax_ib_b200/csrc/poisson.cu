@@ -496,6 +496,23 @@ size_t spectrum_floats(const jaxib_plan* plan) {
   return sweep > plain ? sweep : plain;
 }
 bool plan_sweep(const jaxib_plan* plan) { return plan->sweep; }
+bool plan_col_sweep(const jaxib_plan* plan) { return plan->col_sweep; }
+int plan_col_sweep_pitch(const jaxib_plan* plan) { return plan->cs_pitch; }
+
+// passes A (mode 1) / B (mode 2) of the slab-decomposed column sweep on this slab's spectrum rows [nloc (+ 1)][sp]
+int launch_cols_sweep_slab(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, int world, int rank,
+                           float* const* tables, int mode) {
+  const GridF& g = pl->gf;
+  if (!pl->col_sweep || g.nx_global <= 0 || g.bc != JAXIB_BC_PERIODIC) { set_error("slab column sweep: plan is not a periodic slab plan"); return JAXIB_ERR_INVALID; }
+  ColSweepParams P;
+  memset(&P, 0, sizeof(P));
+  P.nx = g.nx; P.sp = sp; P.ncols = g.ny / 2 + 1; P.segs = (g.nx + 15) / 16;
+  P.cst = pl->cs_tab; P.cst_pitch = pl->cs_pitch;
+  P.dx2 = (double)g.dx * (double)g.dx; P.out_scale = (double)g.nx_global;
+  P.world = world; P.rank = rank; P.nx_global = g.nx_global; P.ncols_pad = pl->cs_pitch;
+  for (int d = 0; d < world; ++d) P.slab_table[d] = tables[d];
+  return launch_cols_sweep(s, P, 1, reinterpret_cast<float2*>(spectrum), mode);
+}
 
 namespace {
 
@@ -572,8 +589,9 @@ int launch_cols(cudaStream_t s, const jaxib_plan* pl, float* spectrum, int sp, i
   const int n2 = g.ny / 2;
   const bool channel = g.bc != JAXIB_BC_PERIODIC;
   if (sp <= 0) sp = n2 + 4;
-  if (pl->col_sweep && ncols <= 0 && col0 == 0 && col_begin == 0) {  // whole grid on this GPU: sweeps instead of a transform
+  if (pl->col_sweep && g.nx_global == 0 && ncols <= 0 && col0 == 0 && col_begin == 0) {  // whole grid on this GPU: sweeps instead of a transform
     ColSweepParams P;
+    memset(&P, 0, sizeof(P));
     P.nx = g.nx; P.sp = sp; P.ncols = channel ? n2 : n2 + 1; P.segs = (g.nx + 15) / 16;
     P.cst = pl->cs_tab; P.cst_pitch = pl->cs_pitch;
     P.dx2 = (double)g.dx * (double)g.dx; P.out_scale = (double)g.nx;
@@ -776,7 +794,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
   }
   {
     const char* e = getenv("JAXIB_COL_SWEEP");  // JAXIB_COL_SWEEP=0: keep the column FFT (A/B runs)
-    pl->col_sweep = !far && grid->nx_global == 0 && cols_sweep_supported(nx) && !(e && atoi(e) == 0);
+    pl->col_sweep = !far && cols_sweep_supported(nx) && !(e && atoi(e) == 0);  // nx_global > 0: the slab passes
     if (!rc && pl->col_sweep) {
       const int nc = channel ? n2 : n2 + 1;
       std::vector<double> lre(nc), lim(nc);
@@ -785,7 +803,7 @@ extern "C" int jaxib_plan_create(const jaxib_grid* grid, jaxib_plan** out) {
         lim[c] = channel ? ly[2 * c + 1] : ly[c];
       }
       std::vector<float2> tab;
-      cols_sweep_tables(nx, nc, (double)pl->gf.dx, lre.data(), lim.data(), &tab, &pl->cs_pitch);
+      cols_sweep_tables(nx, grid->nx_global, nc, (double)pl->gf.dx, lre.data(), lim.data(), &tab, &pl->cs_pitch);
       rc = upload(&pl->cs_tab, tab);
     }
   }

@@ -84,11 +84,15 @@ struct ColSweepParams {
   const float2* cst;    // [7][cst_pitch] per-column constants (cols_sweep_tables)
   int cst_pitch;
   double dx2;           // dx^2
-  double out_scale;     // nx (see cols_sweep_tables)
+  double out_scale;     // nx of the whole column (see cols_sweep_tables)
+  // slab decomposition (modes 1, 2): this GPU holds rows [rank nx, (rank + 1) nx) of nx_global
+  int world, rank, nx_global, ncols_pad;
+  float* slab_table[kMaxPeers];  // every slab's table of block maps + column 0 (cols_sweep_slab_table_bytes)
 };
 bool cols_sweep_supported(int nx);
-void cols_sweep_tables(int nx, int ncols, double dx, const double* ly_re, const double* ly_im, std::vector<float2>* out,
-                       int* pitch);
-int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec);
+void cols_sweep_tables(int nx, int nx_global, int ncols, double dx, const double* ly_re, const double* ly_im,
+                       std::vector<float2>* out, int* pitch);
+int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec, int mode = 0);
+size_t cols_sweep_slab_table_bytes(int world, int ncols_pad, int nx_global);
 
 }  // namespace jaxib

@@ -21,6 +21,12 @@
 //      one warp per column composes these affine maps with a shuffle scan and closes the cycle with 1/(1 - rho^nx);
 //   3. a_true[r] = a[r] + rho^(r+1) Ain, backward sweep from Bin, scale, store in place.
 // The real part of column 0 (mu = 0) is solved by the last CTA of the grid with two prefix sums in double.
+// Slab decomposition (nx_global > 0; a slab holds nloc rows of every column): the same algebra one level up.  Pass A
+// (kSweepAggregate) runs steps 1-2 on the slab's rows with nothing carried in and stores the slab's own affine maps
+// -- two floats per column and part -- into every peer's table; after ONE flag barrier pass B (kSweepApply) closes
+// the cycle over the `world` slabs in every scanning warp (a few FMAs) and runs steps 1-3 with the carried values
+// entering the slab.  b entering the slab from above is b of the next slab's first row, i.e. the spectrum row the
+// inverse row kernel needs after its last one: no transpose of the spectrum, no second exchange.
 // A channel stores two real DCT columns per complex column: real and imaginary parts simply carry their own
 // constants (on periodic grids they are equal).  tools/sweep_model.py restates the arithmetic in NumPy float32:
 // rel-L2 2.4e-7 against the float64 solution at 2048^2 (float32 FFT solve: 1.7e-7).
@@ -47,8 +53,12 @@ __device__ __forceinline__ Affine then(const Affine& f, const Affine& g) { retur
 // e[], S[]: this column's shared arrays in the layout [j][lane] (segment = lane m + j: for a fixed j the lanes read
 // consecutive words -- a [segment] layout would put every lane on the same bank; measured 32-way conflicts on
 // every access, profiles/r2v).  On return e[] holds Ain and S[] holds Bin of every segment.
+// cyclic: the carried values close on themselves (one GPU).  Otherwise ain0 / bin_last are the values entering the
+// block from below / above (0 for the aggregate pass); *tot_e, *tot_t return the block's own maps: the forward value
+// leaving it and the backward value leaving it, both for ZERO carried-in values when ain0 = bin_last = 0.
 __device__ __forceinline__ void carry_scan(float* e, float* S, int segs, int m, float Pseg, float Plast, float rG,
-                                           float rGlast, float close, int lane) {
+                                           float rGlast, float close, int lane, bool cyclic, float ain0_in,
+                                           float bin_in, float* tot_e, float* tot_t) {
   const int s0 = min(lane * m, segs), s1 = min(s0 + m, segs);
   // ---- forward
   Affine f = {0.0f, 1.0f};
@@ -60,7 +70,8 @@ __device__ __forceinline__ void carry_scan(float* e, float* S, int segs, int m, 
     if (lane >= o) inc = then(up, inc);
   }
   const float all_e = __shfl_sync(FULLM, inc.e, 31);
-  const float ain0 = all_e * close;  // value entering segment 0 = value leaving the last one (cyclic)
+  *tot_e = all_e;
+  const float ain0 = cyclic ? all_e * close : ain0_in;  // cyclic: value entering segment 0 = value leaving the last one
   Affine ex = {__shfl_up_sync(FULLM, inc.e, 1), __shfl_up_sync(FULLM, inc.P, 1)};
   float cur = lane == 0 ? ain0 : fmaf(ex.P, ain0, ex.e);
   // ---- walk forward; T_s replaces S_s
@@ -87,7 +98,8 @@ __device__ __forceinline__ void carry_scan(float* e, float* S, int segs, int m, 
     if (lane + o < 32) dec = then(dn, dec);
   }
   const float ball = __shfl_sync(FULLM, dec.e, 0);
-  const float bin_last = ball * close;  // value entering the last segment from above = Bout[0] (cyclic)
+  *tot_t = ball;
+  const float bin_last = cyclic ? ball * close : bin_in;  // cyclic: value entering the last segment from above = Bout[0]
   Affine dx = {__shfl_down_sync(FULLM, dec.e, 1), __shfl_down_sync(FULLM, dec.P, 1)};
   float b = lane == 31 ? bin_last : fmaf(dx.P, bin_last, dx.e);
   for (int s = s1 - 1; s >= s0; --s) {
@@ -137,7 +149,35 @@ __device__ void cta_scan(double* q, int n, bool inclusive, double* red, int t) {
 }
 
 // blockDim = CS * segs_padded (a multiple of 32); dynamic shared memory: max(4 CS (32 ceil(segs/32) + 1) floats, nx doubles)
-template <int CS>
+// Solves Q[i-1] - 2 Q[i] + Q[i+1] = dx2 (X[i] - mean X), mean Q = 0 in place in q[0..n) (shared, double): two prefix sums
+__device__ void solve_mean_mode(double* q, int n, double dx2, double* red, int t) {
+  const int nth = blockDim.x;
+  double sum = 0.0;
+  for (int i = t; i < n; i += nth) sum += q[i];
+  const double mean = cta_sum<0>(sum, red, t) / n;
+  for (int i = t; i < n; i += nth) q[i] = (q[i] - mean) * dx2;
+  cta_scan(q, n, true, red, t);   // s_i = sum_{j <= i}
+  sum = 0.0;
+  for (int i = t; i < n; i += nth) sum += q[i];
+  const double smean = cta_sum<0>(sum, red, t) / n;
+  for (int i = t; i < n; i += nth) q[i] -= smean;  // d_i = Q[i+1] - Q[i]
+  cta_scan(q, n, false, red, t);  // Q_i - Q_0
+  sum = 0.0;
+  for (int i = t; i < n; i += nth) sum += q[i];
+  const double qmean = cta_sum<0>(sum, red, t) / n;
+  for (int i = t; i < n; i += nth) q[i] -= qmean;
+  __syncthreads();
+}
+
+constexpr int kSweepSingle = 0, kSweepAggregate = 1, kSweepApply = 2;
+
+// slab table of one GPU: [world][ncols_pad][2 parts][2] floats (forward map, backward map of each slab) followed by
+// the real part of column 0 of the WHOLE grid, [nx_global] floats
+__device__ __forceinline__ float* slab_entry(float* table, int ncols_pad, int d, int col, int part) {
+  return table + (((size_t)d * ncols_pad + col) * 2 + part) * 2;
+}
+
+template <int CS, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   extern __shared__ __align__(16) unsigned char sw_raw[];
@@ -147,24 +187,29 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   const int nx = P.nx;
   spec += (size_t)blockIdx.y * nx * P.sp;
   if (blockIdx.x == gridDim.x - 1) {
-    // ---- real part of column 0: Q[i-1] - 2 Q[i] + Q[i+1] = dx^2 (X[i] - mean X), mean Q = 0  (two prefix sums)
+    // ---- real part of column 0 (mu = 0): solved whole, by every slab for itself in the decomposed case
     double* const q = reinterpret_cast<double*>(sw_raw);
     const int nth = blockDim.x;
     pdl_wait();
-    double sum = 0.0;
-    for (int i = t; i < nx; i += nth) { const double x = spec[(size_t)i * P.sp].x; q[i] = x; sum += x; }
-    const double mean = cta_sum<0>(sum, red, t) / nx;
-    for (int i = t; i < nx; i += nth) q[i] = (q[i] - mean) * P.dx2;
-    cta_scan(q, nx, true, red, t);   // s_i = sum_{j <= i}
-    sum = 0.0;
-    for (int i = t; i < nx; i += nth) sum += q[i];
-    const double smean = cta_sum<0>(sum, red, t) / nx;
-    for (int i = t; i < nx; i += nth) q[i] -= smean;  // d_i = Q[i+1] - Q[i]
-    cta_scan(q, nx, false, red, t);  // Q_i - Q_0
-    sum = 0.0;
-    for (int i = t; i < nx; i += nth) sum += q[i];
-    const double qmean = cta_sum<0>(sum, red, t) / nx;
-    for (int i = t; i < nx; i += nth) spec[(size_t)i * P.sp].x = (float)((q[i] - qmean) * P.out_scale);
+    if (MODE == kSweepAggregate) {  // every slab gets this slab's rows of the column
+      for (int i = t; i < nx; i += nth) {
+        const float x = spec[(size_t)i * P.sp].x;
+        for (int d = 0; d < P.world; ++d) (P.slab_table[d] + (size_t)P.world * P.ncols_pad * 4)[P.rank * nx + i] = x;
+      }
+      return;
+    }
+    const int n = MODE == kSweepApply ? P.nx_global : nx;
+    if (MODE == kSweepApply) {
+      const float* col0 = P.slab_table[P.rank] + (size_t)P.world * P.ncols_pad * 4;
+      for (int i = t; i < n; i += nth) q[i] = col0[i];
+    } else {
+      for (int i = t; i < n; i += nth) q[i] = spec[(size_t)i * P.sp].x;
+    }
+    solve_mean_mode(q, n, P.dx2, red, t);
+    const int i0 = MODE == kSweepApply ? P.rank * nx : 0;
+    for (int i = t; i < nx; i += nth) spec[(size_t)i * P.sp].x = (float)(q[i0 + i] * P.out_scale);
+    if (MODE == kSweepApply && t == 0)  // the row after the slab (the inverse row kernel differences q forward in x)
+      spec[(size_t)nx * P.sp].x = (float)(q[(i0 + nx) % n] * P.out_scale);
     return;
   }
   const int segs = P.segs;
@@ -222,9 +267,61 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
       const size_t cp = (size_t)P.cst_pitch * 2;
       const float Pseg = __ldg(k + 2 * cp + 2 * colj), Plast = __ldg(k + 3 * cp + 2 * colj);
       const float close = __ldg(k + 4 * cp + 2 * colj), rG = __ldg(k + 5 * cp + 2 * colj), rGl = __ldg(k + 6 * cp + 2 * colj);
-      carry_scan(sE + (part * CS + cj) * cp1, sS + (part * CS + cj) * cp1, segs, m, Pseg, Plast, rG, rGl, close, lane);
+      float ain0 = 0.0f, bin = 0.0f, tot_e, tot_t;
+      if (MODE == kSweepApply) {
+        // close the cycle over the slabs (the same recurrences one level up; every lane does the few steps itself)
+        const float Pb = __ldg(k + 7 * cp + 2 * colj), rGb = __ldg(k + 8 * cp + 2 * colj);
+        const int W = P.world, me = P.rank;
+        float* const tab = P.slab_table[me];
+        float acc = 0.0f;
+        for (int j = 0; j < W; ++j) {  // slabs me, me+1, ..., me-1: the forward value entering slab `me`
+          const int d = me + j < W ? me + j : me + j - W;
+          acc = fmaf(Pb, acc, slab_entry(tab, P.ncols_pad, d, colj, part)[0]);
+        }
+        ain0 = acc * close;
+        // backward: T_d = T0_d + rGb Ain_d with Ain of every slab from walking the ring once more
+        float ain_d = ain0, bacc = 0.0f;
+        float Tm[kMaxPeers];
+#pragma unroll
+        for (int j = 0; j < kMaxPeers; ++j) {
+          if (j < W) {
+            const int d = me + j < W ? me + j : me + j - W;
+            const float* en = slab_entry(tab, P.ncols_pad, d, colj, part);
+            Tm[j] = fmaf(rGb, ain_d, en[1]);
+            ain_d = fmaf(Pb, ain_d, en[0]);
+          }
+        }
+        // slabs me, me-1, ..., me+1 (ring order j = 0, W-1, ..., 1): the backward value entering slab `me` from above
+#pragma unroll
+        for (int j = 0; j < kMaxPeers; ++j) {
+          const int jj = j == 0 ? 0 : W - j;
+          if (j < W) {
+            float Tj = 0.0f;
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q)
+              if (q == jj) Tj = Tm[q];
+            bacc = fmaf(Pb, bacc, Tj);
+          }
+        }
+        bin = bacc * close;
+      }
+      carry_scan(sE + (part * CS + cj) * cp1, sS + (part * CS + cj) * cp1, segs, m, Pseg, Plast, rG, rGl, close, lane,
+                 MODE == kSweepSingle, ain0, bin, &tot_e, &tot_t);
+      if (MODE == kSweepAggregate && lane == 0) {  // this slab's maps into every slab's table (NVLink stores)
+        for (int d = 0; d < P.world; ++d) {
+          float* en = slab_entry(P.slab_table[d], P.ncols_pad, P.rank, colj, part);
+          en[0] = tot_e;
+          en[1] = tot_t;
+        }
+      }
+      if (MODE == kSweepApply && lane == 0 && !(colj == 0 && part == 0)) {
+        // spectrum row after the slab = gain * (b entering from above)
+        const float gn = __ldg(k + 1 * cp + 2 * colj);
+        reinterpret_cast<float*>(spec + (size_t)nx * P.sp + colj)[part] = gn * bin;
+      }
     }
   }
+  if (MODE == kSweepAggregate) return;
   __syncthreads();
   if (!active) return;
   // ---- 3. carried part of the forward sweep, backward sweep, scale, store
@@ -255,68 +352,88 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
     }
 }
 
-template <int CS>
+template <int CS, int MODE>
 int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(cols_sweep_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     configured = true;
   }
   int threads = ((CS * P.segs + 31) / 32) * 32;
   size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float);
-  const size_t col0 = (size_t)P.nx * sizeof(double);
+  const size_t col0 = (size_t)(MODE == kSweepApply ? P.nx_global : P.nx) * sizeof(double);
   if (col0 > smem) smem = col0;
   dim3 grid((P.ncols + CS - 1) / CS + 1, batch);
-  launch_pdl(16, cols_sweep_kernel<CS>, grid, dim3(threads), smem, s, P, spec);
+  launch_pdl(16, cols_sweep_kernel<CS, MODE>, grid, dim3(threads), smem, s, P, spec);
   return check_launch("cols_sweep_kernel");
+}
+
+template <int MODE>
+int launch_cols_sweep_m(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
+  // columns per CTA: whole 32-byte sectors per row where the thread budget allows (threads = CS * segs <= 1024)
+  if (P.segs <= 0 || P.segs > 1024) { set_error("column sweep: nx=%d unsupported", P.nx); return JAXIB_ERR_UNSUPPORTED; }
+  int cs = 1024 / P.segs;
+  if (const char* e = getenv("JAXIB_SWEEP_CS")) { const int v = atoi(e); if (v >= 1 && v * P.segs <= 1024) cs = v; }
+  if (cs >= 16) return launch_cols_sweep_t<16, MODE>(s, P, batch, spec);
+  if (cs >= 8) return launch_cols_sweep_t<8, MODE>(s, P, batch, spec);
+  if (cs >= 4) return launch_cols_sweep_t<4, MODE>(s, P, batch, spec);
+  if (cs >= 2) return launch_cols_sweep_t<2, MODE>(s, P, batch, spec);
+  return launch_cols_sweep_t<1, MODE>(s, P, batch, spec);
 }
 
 }  // namespace
 
 bool cols_sweep_supported(int nx) { return nx >= 2 && (nx + RS - 1) / RS <= 1024 && (size_t)nx * sizeof(double) <= 160 * 1024; }
 
-// Table layout [7][pitch] float2: rho, gain, rho^RS, rho^rows_last, 1/(1 - rho^nx), rho (1 - rho^2RS)/(1 - rho^2), same
-// for the last segment.  ly_re / ly_im: y-eigenvalues of the real and imaginary part of each stored column
+// Table layout [9][pitch] float2: rho, gain, rho^RS, rho^rows_last, 1/(1 - rho^nx_global), rho (1 - rho^2RS)/(1 - rho^2),
+// same for the last segment, and the last two for the whole block of nx rows (slab level).  ly_re / ly_im: y-eigenvalues of the real and imaginary part of each stored column
 // (equal on periodic grids).  out_scale: the row kernels normalise by 1/nx (they were written for an unnormalised
 // forward + inverse column FFT), so the solution is stored times nx.
-void cols_sweep_tables(int nx, int ncols, double dx, const double* ly_re, const double* ly_im, std::vector<float2>* out,
-                       int* pitch) {
+void cols_sweep_tables(int nx, int nx_global, int ncols, double dx, const double* ly_re, const double* ly_im,
+                       std::vector<float2>* out, int* pitch) {
   const int pt = (ncols + 3) & ~3;
   *pitch = pt;
-  out->assign((size_t)7 * pt, make_float2(0.f, 0.f));
+  const int nxg = nx_global > 0 ? nx_global : nx;  // slab: nx rows here, nxg in the whole column
+  out->assign((size_t)9 * pt, make_float2(0.f, 0.f));
   const int segs = (nx + RS - 1) / RS, last = nx - (segs - 1) * RS;
   for (int c = 0; c < ncols; ++c) {
-    float v[7][2];
+    float v[9][2];
     for (int part = 0; part < 2; ++part) {
       const double mu = -(part ? ly_im[c] : ly_re[c]) * dx * dx;
       if (!(mu > 1e-14)) {  // singular column (mean mode): the dedicated CTA solves it; the sweep passes it through
-        for (int k = 0; k < 7; ++k) v[k][part] = 0.0f;
+        for (int k = 0; k < 9; ++k) v[k][part] = 0.0f;
         v[4][part] = 1.0f;
         continue;
       }
       const double r = 1.0 / (1.0 + 0.5 * mu + sqrt(mu + 0.25 * mu * mu));
       v[0][part] = (float)r;
-      v[1][part] = (float)(-dx * dx * r * nx);
+      v[1][part] = (float)(-dx * dx * r * nxg);
       v[2][part] = (float)pow(r, RS);
       v[3][part] = (float)pow(r, last);
-      v[4][part] = (float)(1.0 / (1.0 - pow(r, nx)));
+      v[4][part] = (float)(1.0 / (1.0 - pow(r, nxg)));
       v[5][part] = (float)(r * (1.0 - pow(r, 2 * RS)) / (1.0 - r * r));
       v[6][part] = (float)(r * (1.0 - pow(r, 2 * last)) / (1.0 - r * r));
+      v[7][part] = (float)pow(r, nx);                                     // the whole block (slab level)
+      v[8][part] = (float)(r * (1.0 - pow(r, 2.0 * nx)) / (1.0 - r * r));
     }
-    for (int k = 0; k < 7; ++k) (*out)[(size_t)k * pt + c] = make_float2(v[k][0], v[k][1]);
+    for (int k = 0; k < 9; ++k) (*out)[(size_t)k * pt + c] = make_float2(v[k][0], v[k][1]);
   }
 }
 
-int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
-  // columns per CTA: whole 32-byte sectors per row where the thread budget allows (threads = CS * segs <= 1024)
-  if (P.segs <= 0 || P.segs > 1024) { set_error("column sweep: nx=%d unsupported", P.nx); return JAXIB_ERR_UNSUPPORTED; }
-  int cs = 1024 / P.segs;
-  if (const char* e = getenv("JAXIB_SWEEP_CS")) { const int v = atoi(e); if (v >= 1 && v * P.segs <= 1024) cs = v; }
-  if (cs >= 16) return launch_cols_sweep_t<16>(s, P, batch, spec);
-  if (cs >= 8) return launch_cols_sweep_t<8>(s, P, batch, spec);
-  if (cs >= 4) return launch_cols_sweep_t<4>(s, P, batch, spec);
-  if (cs >= 2) return launch_cols_sweep_t<2>(s, P, batch, spec);
-  return launch_cols_sweep_t<1>(s, P, batch, spec);
+// mode 0: whole grid on this GPU; 1 / 2: passes A / B of the slab decomposition (see the header comment)
+int launch_cols_sweep(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec, int mode) {
+  if (mode == kSweepSingle) return launch_cols_sweep_m<kSweepSingle>(s, P, batch, spec);
+  if (P.world < 1 || P.world > kMaxPeers || P.nx_global != P.nx * P.world || batch != 1) {
+    set_error("column sweep: bad slab geometry (nx=%d world=%d nx_global=%d)", P.nx, P.world, P.nx_global);
+    return JAXIB_ERR_INVALID;
+  }
+  if ((size_t)P.nx_global * sizeof(double) > 160 * 1024) { set_error("column sweep: nx_global=%d too long", P.nx_global); return JAXIB_ERR_UNSUPPORTED; }
+  return mode == kSweepAggregate ? launch_cols_sweep_m<kSweepAggregate>(s, P, batch, spec)
+                                 : launch_cols_sweep_m<kSweepApply>(s, P, batch, spec);
+}
+
+size_t cols_sweep_slab_table_bytes(int world, int ncols_pad, int nx_global) {
+  return ((size_t)world * ncols_pad * 4 + (size_t)nx_global) * sizeof(float);
 }
 
 }  // namespace jaxib

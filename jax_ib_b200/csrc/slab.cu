@@ -18,6 +18,12 @@
 //   phase 3  K6 inverse row FFT + projection + pressure update: owned rows in place, boundary rows
 //            also into the neighbours' halo rows (the halo exchange)                 | barrier 3
 //
+// Since round 2 the default x-solve is the column SWEEP (poisson_sweep.cu) and phases 1-2 read:
+//   phase 1  K3; K4 into the LOCAL spectrum; sweep pass A: the slab's carried-value maps (2 floats per
+//            column and part) + its rows of column 0 into every slab's table      | barrier 1
+//   phase 2  sweep pass B on the local rows (also writes the spectrum row after the slab)  | --
+// i.e. no transposes, two barriers per step.  JAXIB_SLAB_FFT=1 selects the transpose path above.
+//
 // Barrier = one tiny kernel per GPU: a system-scope release store of the step number into every peer's
 // flag word, then an acquire spin on the own flag words (bounded: a lost peer sets an error word
 // instead of hanging the GPU).  Reuse hazards: a buffer written in phase k of step n+1 was last read
@@ -189,9 +195,19 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
               gr.ny, gr.nx_global, gc.nx, gc.ny);
     return JAXIB_ERR_INVALID;
   }
-  if (!plan_fast_rows(plan_rows) || !plan_fast_cols(plan_cols)) {
+  // Column sweep (poisson_sweep.cu): the x-direction is solved slab by slab with one small exchange of carried
+  // values; JAXIB_SLAB_FFT=1 keeps the transpose + column FFT path (A/B runs, and the only path for plans
+  // without the sweep tables).
+  const char* env_fft = getenv("JAXIB_SLAB_FFT");
+  const bool force_fft = env_fft && atoi(env_fft) == 1;
+  const bool sweep = !force_fft && plan_col_sweep(plan_rows);
+  if (!plan_fast_rows(plan_rows) || (!sweep && !plan_fast_cols(plan_cols))) {
     set_error("slab_step: needs ny/2 in {512..4096} and nx in {512..8192} (powers of two)");
     return JAXIB_ERR_UNSUPPORTED;
+  }
+  if (sweep && cols_sweep_slab_table_bytes(W, plan_col_sweep_pitch(plan_rows), nx) > (size_t)nx * cpr * sizeof(float2)) {
+    set_error("slab_step: column buffer too small for the sweep tables");
+    return JAXIB_ERR_INVALID;
   }
   const bool has_ib = bodies && bodies->n_markers > 0;
   if (has_ib && !body_table) { set_error("slab_step: bodies given without body_table"); return JAXIB_ERR_INVALID; }
@@ -303,9 +319,20 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
               }
             }
           }
+          if (sweep) {
+            // row FFT into the LOCAL spectrum, then pass A of the column sweep: this slab's carried-value maps
+            // (two floats per column and part) and its rows of column 0 go into every slab's table
+            if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, nullptr))) return rc;
+            if ((rc = launch_cols_sweep_slab(s, plan_rows, sl.specbuf[me], sp, W, me, sl.colbuf, 1))) return rc;
+            break;
+          }
           if ((rc = launch_rows_fwd(s, plan_rows, u_star + own_off, v_star + own_off, sl.specbuf[me], sp, &sc))) return rc;
           break;
         case 2:
+          if (sweep) {  // pass B: close the cycle over the slabs, sweep, store rows 0 .. nloc of the local spectrum
+            if ((rc = launch_cols_sweep_slab(s, plan_rows, sl.specbuf[me], sp, W, me, sl.colbuf, 2))) return rc;
+            break;
+          }
           if (split_cols > 0) {
             // K5 in two launches of whole waves; the push of the first part runs on a side stream under
             // the second K5 launch (the push is NVLink-bound and needs few SMs, K5 is latency-bound)
@@ -332,7 +359,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
             return rc;
           break;
       }
-      if (barriers && ph != 0 && (rc = enqueue_barrier(s, sl, ph, ep))) return rc;
+      if (barriers && ph != 0 && !(sweep && ph == 2) && (rc = enqueue_barrier(s, sl, ph, ep))) return rc;
     }
   }
   return JAXIB_OK;

@@ -488,7 +488,7 @@ class SlabStepper:
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
-                names = ("predict_force", "spread_rows_fwd+barrier", "cols_push+barrier", "rows_inv+barrier")
+                names = ("predict_force", "spread_rows_fwd_sweepA+barrier", "cols_sweepB", "rows_inv+barrier")
                 evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsteps)]
                 self._host_barrier()
                 for n in range(nsteps):

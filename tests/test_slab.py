@@ -1,5 +1,6 @@
 """Slab decomposition: index arithmetic and exchanges on CPU (incl. world_size-2 gloo),
 and on the GPU the decomposed step against the single-GPU step -- bit for bit."""
+import contextlib
 import os
 import sys
 
@@ -149,6 +150,34 @@ def _seam_cfg(n):
     return cfg
 
 
+@contextlib.contextmanager
+def _column_fft():
+    """Plans created inside use the column FFT (K5 first / second generation) instead of the column sweep: the
+    transposing slab paths run that kernel and are compared bit for bit with the single-GPU step that runs it too.
+    (The switch is read when a plan is created; the engine caches plans.)"""
+    from jax_ib_b200 import engine
+    old = os.environ.get("JAXIB_COL_SWEEP")
+    os.environ["JAXIB_COL_SWEEP"] = "0"
+    engine._PLANS.clear()
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ["JAXIB_COL_SWEEP"]
+        else:
+            os.environ["JAXIB_COL_SWEEP"] = old
+        engine._PLANS.clear()
+
+
+def _close(got, ref, tol=5e-6):
+    """Sweep-based slabs associate the carried values per slab, one GPU per 32-lane scan: same operator, float32
+    round-off apart.  Bars: rel-L2 5e-6 on the velocities, 10x that on the pressure (|p| << |u| in these flows)."""
+    for name, a, b in zip("uvp", got, ref):
+        assert torch.isfinite(a).all()
+        err = float((a - b).norm() / b.norm())
+        assert err < (10 * tol if name == "p" else tol), (name, err, float((a - b).abs().max()))
+
+
 def _single_gpu(cfg, steps):
     from jax_ib_b200 import configs, demo, kinematics
     stp = demo.make_stepper(cfg)
@@ -179,7 +208,8 @@ def _virtual(cfg, steps, world, chunks=(None,), peer=False):
 def test_virtual_slabs_match_single_gpu_bitwise(n, world):
     cfg = _seam_cfg(n)
     steps = 6
-    ref = _single_gpu(cfg, steps)
+    with _column_fft():
+        ref = _single_gpu(cfg, steps)
     got = _virtual(cfg, steps, world, chunks=(2, None))
     for name, a, b in zip("uvp", got, ref):
         assert torch.isfinite(a).all()
@@ -188,20 +218,36 @@ def test_virtual_slabs_match_single_gpu_bitwise(n, world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,world", [(1024, 1), (1024, 2), (1024, 4), (1024, 8), (2048, 4)])
-def test_peer_memory_slabs_match_single_gpu_bitwise(n, world):
-    """csrc/slab.cu: the kernels scatter into the consuming slab's buffers (here: all on one GPU, phases in
-    lockstep without the flag barrier).  Same arithmetic per cell as on one GPU => identical bits."""
+def test_peer_memory_slabs_match_single_gpu_bitwise(n, world, monkeypatch):
+    """csrc/slab.cu, transpose path (JAXIB_SLAB_FFT=1): the kernels scatter into the consuming slab's buffers (here:
+    all on one GPU, phases in lockstep without the flag barrier).  Same arithmetic per cell as on one GPU with the
+    column FFT => identical bits."""
     cfg = _seam_cfg(n)
     steps = 6
-    ref = _single_gpu(cfg, steps)
-    got = _virtual(cfg, steps, world, chunks=(2, None), peer=True)
+    monkeypatch.setenv("JAXIB_SLAB_FFT", "1")
+    with _column_fft():
+        ref = _single_gpu(cfg, steps)
+        got = _virtual(cfg, steps, world, chunks=(2, None), peer=True)
     for name, a, b in zip("uvp", got, ref):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b), (name, float((a - b).abs().max()))
 
 
 @pytest.mark.gpu
-def test_peer_memory_slabs_8192_rows_split_column_transform():
+@pytest.mark.parametrize("n,world", [(1024, 1), (1024, 2), (1024, 4), (1024, 8), (2048, 8)])
+def test_peer_memory_slabs_with_the_column_sweep_match_single_gpu(n, world):
+    """Default peer-memory path: no transposes; every slab sweeps its own rows of every column and the slabs only
+    exchange their carried-value maps (poisson_sweep.cu, passes A / B).  Bodies on the seam, on a slab boundary
+    and off the grid as in the bitwise tests."""
+    cfg = _seam_cfg(n)
+    steps = 6
+    ref = _single_gpu(cfg, steps)
+    got = _virtual(cfg, steps, world, chunks=(2, None), peer=True)
+    _close(got, ref)
+
+
+@pytest.mark.gpu
+def test_peer_memory_slabs_8192_rows_split_column_transform(monkeypatch):
     """Nx = 8192, 520 spectrum columns per slab: the radix 16x32x16 column kernel (one CTA per SM, 260 CTAs)
     runs in two launches of whole waves and the push of the first part overlaps the second launch on a side
     stream (csrc/slab.cu phase 2)."""
@@ -212,11 +258,15 @@ def test_peer_memory_slabs_8192_rows_split_column_transform():
     cfg["bodies"]["centers"] = [[0.5 * 8192 * 0.025, 0.5 * 2048 * 0.025]]  # on the slab boundary
     assert slab.SlabLayout(8192, 2048, 2, 0, 16).cpr == 520
     steps = 3
-    ref = _single_gpu(cfg, steps)
-    got = _virtual(cfg, steps, 2, peer=True)
+    monkeypatch.setenv("JAXIB_SLAB_FFT", "1")
+    with _column_fft():
+        ref = _single_gpu(cfg, steps)
+        got = _virtual(cfg, steps, 2, peer=True)
     for name, a, b in zip("uvp", got, ref):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b), (name, float((a - b).abs().max()))
+    monkeypatch.delenv("JAXIB_SLAB_FFT")
+    _close(_virtual(cfg, steps, 2, peer=True), _single_gpu(cfg, steps))  # and the sweep path on the same case
 
 
 @pytest.mark.gpu
@@ -225,8 +275,7 @@ def test_peer_memory_slabs_without_bodies():
     cfg = dict(configs.ib_periodic(1024, 1), bodies=None)
     ref = _single_gpu(cfg, 4)
     got = _virtual(cfg, 4, 4, peer=True)
-    for a, b in zip(got, ref):
-        assert torch.equal(a, b)
+    _close(got, ref)
 
 
 @pytest.mark.gpu
@@ -241,7 +290,8 @@ def test_peer_memory_mode_rejects_unsupported_sizes():
 def test_virtual_slabs_without_bodies():
     from jax_ib_b200 import configs
     cfg = configs.small_periodic(64, bodies=False)
-    ref = _single_gpu(cfg, 5)
+    with _column_fft():
+        ref = _single_gpu(cfg, 5)
     got = _virtual(cfg, 5, 2)
     for a, b in zip(got, ref):
         assert torch.equal(a, b)

@@ -3,9 +3,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29533 tools/slab_check.py [--n 1024] [--steps 6]
 
-Every rank advances its slab over NCCL; the gathered fields must equal the single-GPU step (run on
-every rank's own GPU) bit for bit.  Prints one `SLAB_CHECK OK ...` line on rank 0, exits non-zero on
-any mismatch."""
+Every rank advances its slab; the gathered fields are compared with the single-GPU step (run on every
+rank's own GPU): bit for bit on the transposing paths (NCCL, or --peer with JAXIB_SLAB_FFT=1: the same
+column FFT as one GPU with JAXIB_COL_SWEEP=0), rel-L2 <= 5e-6 (pressure 5e-5) on the default peer-memory
+path, whose column sweep associates the carried values per slab.  Prints one `SLAB_CHECK OK ...` line on
+rank 0, exits non-zero on any mismatch."""
 import argparse
 import os
 import sys
@@ -31,10 +33,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from jax_ib_b200 import configs, demo, slab
-    from test_slab import _seam_cfg, _single_gpu
+    from test_slab import _column_fft, _seam_cfg, _single_gpu
 
     cfg = _seam_cfg(args.n)
-    ref = _single_gpu(cfg, args.steps)
+    bitwise = not args.peer or os.environ.get("JAXIB_SLAB_FFT") == "1"
+    if bitwise:
+        with _column_fft():
+            ref = _single_gpu(cfg, args.steps)
+    else:
+        ref = _single_gpu(cfg, args.steps)
     st = slab.SlabStepper(demo.make_spec(cfg), demo.make_particles(cfg), device=device, peer=args.peer)
     st.load(*(torch.from_numpy(a) for a in configs.initial_fields(cfg)))
     st.advance(2)
@@ -43,15 +50,16 @@ def main():
     timed_out = args.peer and st.ranks[0].barrier_timed_out()
     worst = 0.0
     ok = True
-    for a, b in zip(got, ref):
-        ok = ok and bool(torch.equal(a, b)) and bool(torch.isfinite(a).all())
+    for name, a, b in zip("uvp", got, ref):
+        same = bool(torch.equal(a, b)) if bitwise else float((a - b).norm() / b.norm()) < (5e-5 if name == "p" else 5e-6)
+        ok = ok and same and bool(torch.isfinite(a).all())
         worst = max(worst, float((a - b).abs().max()))
     flag = torch.tensor([0 if ok and not timed_out else 1], device=device)
     if world > 1:
         dist.all_reduce(flag)
     if rank == 0:
         print(f"SLAB_CHECK {'OK' if flag.item() == 0 else 'FAIL'} world={world} n={args.n} steps={args.steps} "
-              f"max_abs_diff={worst:.3e} mode={'peer-memory' if args.peer else type(st.comm).__name__}", flush=True)
+              f"max_abs_diff={worst:.3e} compare={'bitwise' if bitwise else 'rel-L2'} mode={'peer-memory' if args.peer else type(st.comm).__name__}", flush=True)
     if world > 1:
         dist.destroy_process_group()
     sys.exit(0 if flag.item() == 0 else 1)
