@@ -148,7 +148,7 @@ __device__ void cta_scan(double* q, int n, bool inclusive, double* red, int t) {
   __syncthreads();
 }
 
-// blockDim = CS * segs_padded (a multiple of 32); dynamic shared memory: max(4 CS (32 ceil(segs/32) + 1) floats, nx doubles)
+// blockDim = CS * segs_padded (a multiple of 32); dynamic shared memory: see launch_cols_sweep_t
 // Solves Q[i-1] - 2 Q[i] + Q[i+1] = dx2 (X[i] - mean X), mean Q = 0 in place in q[0..n) (shared, double): two prefix sums
 __device__ void solve_mean_mode(double* q, int n, double dx2, double* red, int t) {
   const int nth = blockDim.x;
@@ -177,7 +177,21 @@ __device__ __forceinline__ float* slab_entry(float* table, int ncols_pad, int d,
   return table + (((size_t)d * ncols_pad + col) * 2 + part) * 2;
 }
 
-template <int CS, int MODE>
+// lane k < 9 fetches row k of the constant table for (column, part); broadcast later by shuffles
+__device__ __forceinline__ float job_const(const ColSweepParams& P, int col, int part, int lane) {
+  return lane < 9 ? __ldg(reinterpret_cast<const float*>(P.cst) + ((size_t)lane * P.cst_pitch + col) * 2 + part) : 0.0f;
+}
+__device__ __forceinline__ float gain_of(const ColSweepParams& P, int col, int part) {
+  return __ldg(reinterpret_cast<const float*>(P.cst) + ((size_t)P.cst_pitch + col) * 2 + part);
+}
+// lane d < world fetches slab d's pair of maps for (column, part) from this GPU's table
+__device__ __forceinline__ float2 job_entry(const ColSweepParams& P, int col, int part, int lane) {
+  if (lane >= P.world) return make_float2(0.f, 0.f);
+  return *reinterpret_cast<const float2*>(slab_entry(P.slab_table[P.rank], P.ncols_pad, lane, col, part));
+}
+
+// FULL: nx is a multiple of RS (every segment has RS rows: no per-row predicates)
+template <int CS, int MODE, bool FULL>
 __global__ void __launch_bounds__(1024, 1)
 cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   extern __shared__ __align__(16) unsigned char sw_raw[];
@@ -229,16 +243,30 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   float* const sE = reinterpret_cast<float*>(sw_raw);  // e, later Ain
   float* const sS = sE + 2 * CS * cp1;                 // S, later Bin
   const int at = c * cp1 + (seg % m) * 32 + seg / m;
+  // this warp's scanning job (step 2): its nine per-column constants, one per lane, fetched now (plan tables) ...
+  const int wj = t >> 5, lanej = t & 31;
+  float kconst = 0.0f;
+  float2 entry = make_float2(0.f, 0.f);
+  {
+    const int colj = blockIdx.x * CS + (wj >> 1);
+    if (wj < 2 * CS && colj < P.ncols) kconst = job_const(P, colj, wj & 1, lanej);
+  }
   pdl_wait();
+  if (MODE == kSweepApply) {  // ... and the slabs' maps of that column (written by pass A of every slab), one slab per lane
+    const int colj = blockIdx.x * CS + (wj >> 1);
+    if (wj < 2 * CS && colj < P.ncols) entry = job_entry(P, colj, wj & 1, lanej);
+  }
   float2 a[RS];
 #pragma unroll
-  for (int r = 0; r < RS; ++r)
-    if (r < rows) a[r] = base[(size_t)r * P.sp];
+  for (int r = 0; r < RS; ++r) {
+    if (FULL) a[r] = make_float2(0.f, 0.f);
+    if (FULL ? active : r < rows) a[r] = base[(size_t)r * P.sp];
+  }
   // ---- 1. local forward sweep, Horner sum
   float2 ap = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < RS; ++r)
-    if (r < rows) {
+    if (FULL || r < rows) {
       ap.x = fmaf(rho.x, ap.x, a[r].x);
       ap.y = fmaf(rho.y, ap.y, a[r].y);
       a[r] = ap;
@@ -246,7 +274,7 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   float2 h = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = RS - 1; r >= 0; --r)
-    if (r < rows) {
+    if (FULL || r < rows) {
       h.x = fmaf(rho.x, h.x, a[r].x);
       h.y = fmaf(rho.y, h.y, a[r].y);
     }
@@ -257,67 +285,54 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   __syncthreads();
   // ---- 2. carried values: warp w solves (column w >> 1, part w & 1)
   {
-    const int w = t >> 5, lane = t & 31;
     const int nwarps = blockDim.x >> 5;
-    for (int job = w; job < 2 * CS; job += nwarps) {
+    for (int job = wj; job < 2 * CS; job += nwarps) {
       const int cj = job >> 1, part = job & 1;
       const int colj = blockIdx.x * CS + cj;
       if (colj >= P.ncols) continue;
-      const float* k = reinterpret_cast<const float*>(P.cst) + part;  // component `part` of the float2 tables
-      const size_t cp = (size_t)P.cst_pitch * 2;
-      const float Pseg = __ldg(k + 2 * cp + 2 * colj), Plast = __ldg(k + 3 * cp + 2 * colj);
-      const float close = __ldg(k + 4 * cp + 2 * colj), rG = __ldg(k + 5 * cp + 2 * colj), rGl = __ldg(k + 6 * cp + 2 * colj);
+      float kc = kconst;
+      float2 en = entry;
+      if (job != wj) {  // more jobs than warps (small CTAs): load this job's words now
+        kc = job_const(P, colj, part, lanej);
+        if (MODE == kSweepApply) en = job_entry(P, colj, part, lanej);
+      }
+      const float Pseg = __shfl_sync(FULLM, kc, 2), Plast = __shfl_sync(FULLM, kc, 3), close = __shfl_sync(FULLM, kc, 4);
+      const float rG = __shfl_sync(FULLM, kc, 5), rGl = __shfl_sync(FULLM, kc, 6);
       float ain0 = 0.0f, bin = 0.0f, tot_e, tot_t;
       if (MODE == kSweepApply) {
-        // close the cycle over the slabs (the same recurrences one level up; every lane does the few steps itself)
-        const float Pb = __ldg(k + 7 * cp + 2 * colj), rGb = __ldg(k + 8 * cp + 2 * colj);
+        // close the cycle over the slabs (the same recurrences one level up; every lane does the few steps itself,
+        // lane d holds slab d's pair of maps)
+        const float Pb = __shfl_sync(FULLM, kc, 7), rGb = __shfl_sync(FULLM, kc, 8);
         const int W = P.world, me = P.rank;
-        float* const tab = P.slab_table[me];
         float acc = 0.0f;
         for (int j = 0; j < W; ++j) {  // slabs me, me+1, ..., me-1: the forward value entering slab `me`
           const int d = me + j < W ? me + j : me + j - W;
-          acc = fmaf(Pb, acc, slab_entry(tab, P.ncols_pad, d, colj, part)[0]);
+          acc = fmaf(Pb, acc, __shfl_sync(FULLM, en.x, d));
         }
         ain0 = acc * close;
-        // backward: T_d = T0_d + rGb Ain_d with Ain of every slab from walking the ring once more
-        float ain_d = ain0, bacc = 0.0f;
-        float Tm[kMaxPeers];
-#pragma unroll
-        for (int j = 0; j < kMaxPeers; ++j) {
-          if (j < W) {
-            const int d = me + j < W ? me + j : me + j - W;
-            const float* en = slab_entry(tab, P.ncols_pad, d, colj, part);
-            Tm[j] = fmaf(rGb, ain_d, en[1]);
-            ain_d = fmaf(Pb, ain_d, en[0]);
-          }
+        // backward: T_d = T0_d + rGb Ain_d with Ain of every slab from walking the ring once more; lane j keeps T
+        // of slab me + j
+        float ain_d = ain0, Tmine = 0.0f;
+        for (int j = 0; j < W; ++j) {
+          const int d = me + j < W ? me + j : me + j - W;
+          const float Ed = __shfl_sync(FULLM, en.x, d), T0d = __shfl_sync(FULLM, en.y, d);
+          if (lanej == j) Tmine = fmaf(rGb, ain_d, T0d);
+          ain_d = fmaf(Pb, ain_d, Ed);
         }
-        // slabs me, me-1, ..., me+1 (ring order j = 0, W-1, ..., 1): the backward value entering slab `me` from above
-#pragma unroll
-        for (int j = 0; j < kMaxPeers; ++j) {
-          const int jj = j == 0 ? 0 : W - j;
-          if (j < W) {
-            float Tj = 0.0f;
-#pragma unroll
-            for (int q = 0; q < kMaxPeers; ++q)
-              if (q == jj) Tj = Tm[q];
-            bacc = fmaf(Pb, bacc, Tj);
-          }
-        }
+        // slabs me, me-1, ..., me+1 (ring positions 0, W-1, ..., 1): the backward value entering slab `me` from above
+        float bacc = 0.0f;
+        for (int j = 0; j < W; ++j) bacc = fmaf(Pb, bacc, __shfl_sync(FULLM, Tmine, j == 0 ? 0 : W - j));
         bin = bacc * close;
       }
-      carry_scan(sE + (part * CS + cj) * cp1, sS + (part * CS + cj) * cp1, segs, m, Pseg, Plast, rG, rGl, close, lane,
+      carry_scan(sE + (part * CS + cj) * cp1, sS + (part * CS + cj) * cp1, segs, m, Pseg, Plast, rG, rGl, close, lanej,
                  MODE == kSweepSingle, ain0, bin, &tot_e, &tot_t);
-      if (MODE == kSweepAggregate && lane == 0) {  // this slab's maps into every slab's table (NVLink stores)
-        for (int d = 0; d < P.world; ++d) {
-          float* en = slab_entry(P.slab_table[d], P.ncols_pad, P.rank, colj, part);
-          en[0] = tot_e;
-          en[1] = tot_t;
-        }
+      if (MODE == kSweepAggregate && lanej == 0) {  // this slab's maps into every slab's table (NVLink stores)
+        for (int d = 0; d < P.world; ++d)
+          *reinterpret_cast<float2*>(slab_entry(P.slab_table[d], P.ncols_pad, P.rank, colj, part)) = make_float2(tot_e, tot_t);
       }
-      if (MODE == kSweepApply && lane == 0 && !(colj == 0 && part == 0)) {
+      if (MODE == kSweepApply && lanej == 0 && !(colj == 0 && part == 0)) {
         // spectrum row after the slab = gain * (b entering from above)
-        const float gn = __ldg(k + 1 * cp + 2 * colj);
-        reinterpret_cast<float*>(spec + (size_t)nx * P.sp + colj)[part] = gn * bin;
+        reinterpret_cast<float*>(spec + (size_t)nx * P.sp + colj)[part] = bin * gain_of(P, colj, part);
       }
     }
   }
@@ -325,6 +340,9 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   __syncthreads();
   if (!active) return;
   // ---- 3. carried part of the forward sweep, backward sweep, scale, store
+  // (Tried: the column tile moved by one bulk asynchronous copy per row, CS x 8 bytes each, into a bank-staggered
+  // shared tile and back -- 16.5 -> 20.1 us at 2048^2, 1205 -> 1469 us at 8192^2 with 16-byte rows: the copy engine
+  // is slow on such short transfers, profiles/r3d.)
   const float2 ain = make_float2(sE[at], sE[CS * cp1 + at]);
   float2 b = make_float2(sS[at], sS[CS * cp1 + at]);
   // rho^n from rho, rho^2, rho^4, rho^8 (at most 4 roundings; n is a compile-time constant after unrolling)
@@ -342,7 +360,7 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   const bool skip_re = col == 0;  // the last CTA owns the real part of column 0
 #pragma unroll
   for (int r = RS - 1; r >= 0; --r)
-    if (r < rows) {
+    if (FULL ? active : r < rows) {
       const float2 pw = power(r + 1);
       b.x = fmaf(rho.x, b.x, fmaf(pw.x, ain.x, a[r].x));
       b.y = fmaf(rho.y, b.y, fmaf(pw.y, ain.y, a[r].y));
@@ -356,15 +374,18 @@ template <int CS, int MODE>
 int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
   int threads = ((CS * P.segs + 31) / 32) * 32;
-  size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float);
+  size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float);  // the column-0 CTA needs nx doubles
   const size_t col0 = (size_t)(MODE == kSweepApply ? P.nx_global : P.nx) * sizeof(double);
   if (col0 > smem) smem = col0;
+  if (smem > 200 * 1024) { set_error("column sweep: %zu bytes of shared memory", smem); return JAXIB_ERR_UNSUPPORTED; }
   dim3 grid((P.ncols + CS - 1) / CS + 1, batch);
-  launch_pdl(16, cols_sweep_kernel<CS, MODE>, grid, dim3(threads), smem, s, P, spec);
+  if (P.nx % RS == 0) launch_pdl(16, cols_sweep_kernel<CS, MODE, true>, grid, dim3(threads), smem, s, P, spec);
+  else launch_pdl(16, cols_sweep_kernel<CS, MODE, false>, grid, dim3(threads), smem, s, P, spec);
   return check_launch("cols_sweep_kernel");
 }
 
