@@ -207,10 +207,12 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
 }
 
 // ---- spreading: tile gather ---------------------------------------------------------------------
+constexpr int kCullBatches = 8;  // marker batches of SPREAD_THREADS the early cull handles (more: culled after the wait)
 struct SpreadShared {
   float xp[SPREAD_THREADS], yp[SPREAD_THREADS], c[SPREAD_THREADS], part[SPREAD_THREADS];
   int ik[SPREAD_THREADS], jk[SPREAD_THREADS];
   int warp_count[SPREAD_THREADS / 32];
+  int batch_end[kCullBatches + 1];  // early cull: list positions where each marker batch ends
 };
 
 // Culls markers [k0, k1) against the tile [ti0, ti0+TS) x [tj0, tj0+TS) (order-preserving ballot
@@ -279,6 +281,64 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
   return tot;  // meaningful in slice 0 (every slice computes the same value)
 }
 
+// Early cull (BEFORE the dependency wait): the marker positions follow from the body-frame coordinates and the
+// kinematic table with the formulas of interp_force_kernel -- bit for bit what that kernel stores -- so a tile can
+// build its list of markers while the force kernel is still running.  After the wait only the forces are missing:
+// one round trip instead of three (marker coordinates, cull, forces).  The list keeps the batch structure of
+// gather_markers (entries of marker batch n occupy [batch_end[n], batch_end[n+1])), so the later sum runs in exactly
+// the same order and the result is bit-identical.  Returns the list length, or -1 if the list overflowed.
+// sh.c holds dS * pref, sh.part (as int bits) the marker index.
+__device__ int cull_markers_early(SpreadShared& sh, const Mesh& m, const float* __restrict__ x0,
+                                  const float* __restrict__ y0, const float4* __restrict__ pack,
+                                  const float* __restrict__ st, int k0, int k1, int ti0, int tj0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float c = st[0], sn = st[1], xc = st[2], yc = st[3];
+  int count = 0, nb = 0;
+  bool overflow = false;
+  if (tid == 0) sh.batch_end[0] = 0;
+  for (int base = k0; base < k1; base += SPREAD_THREADS, ++nb) {
+    const int k = base + tid;
+    bool keep = false;
+    float xp = 0.f, yp = 0.f, ds = 0.f;
+    int ik = 0, jk = 0;
+    if (k < k1) {
+      const float ax = __ldg(x0 + k), ay = __ldg(y0 + k);
+      const float4 pk = __ldg(pack + k);
+      xp = __fadd_rn(__fsub_rn(__fmul_rn(ax, c), __fmul_rn(ay, sn)), xc);
+      yp = __fadd_rn(__fadd_rn(__fmul_rn(ax, sn), __fmul_rn(ay, c)), yc);
+      ik = cell_index(xp, m.dx, m.off_x) - m.row0;
+      jk = cell_index(yp, m.dy, m.off_y);
+      keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
+      if (keep) {  // arc length to the next marker of the closed curve (interp_force_kernel, IBM_Force.py:59-63)
+        const float xq = __fadd_rn(__fsub_rn(__fmul_rn(pk.x, c), __fmul_rn(pk.y, sn)), xc);
+        const float yq = __fadd_rn(__fadd_rn(__fmul_rn(pk.x, sn), __fmul_rn(pk.y, c)), yc);
+        const float dxl = __fsub_rn(xq, xp), dyl = __fsub_rn(yq, yp);
+        ds = __fsqrt_rn(__fadd_rn(__fmul_rn(dxl, dxl), __fmul_rn(dyl, dyl)));
+      }
+    }
+    const unsigned ballot = __ballot_sync(FULL, keep);
+    if (lane == 0) sh.warp_count[warp] = __popc(ballot);
+    __syncthreads();
+    int offset = 0, totalc = 0;
+#pragma unroll
+    for (int w = 0; w < SPREAD_THREADS / 32; ++w) {
+      const int cw = sh.warp_count[w];
+      if (w < warp) offset += cw;
+      totalc += cw;
+    }
+    if (count + totalc > SPREAD_THREADS) overflow = true;  // block-uniform
+    if (keep && !overflow) {
+      const int pos = count + offset + __popc(ballot & ((1u << lane) - 1u));
+      sh.xp[pos] = xp; sh.yp[pos] = yp; sh.c[pos] = ds; sh.ik[pos] = ik; sh.jk[pos] = jk;
+      sh.part[pos] = __int_as_float(k);
+    }
+    count += totalc;
+    if (tid == 0) sh.batch_end[nb + 1] = count;
+    __syncthreads();
+  }
+  return overflow ? -1 : count;
+}
+
 __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic, int& jc) {
   ic = cell_index(st[2], m.dx, m.off_x) - m.row0;
   jc = cell_index(st[3], m.dy, m.off_y);
@@ -291,7 +351,8 @@ __global__ void __launch_bounds__(SPREAD_THREADS)
 spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __restrict__ body_offset,
                      const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
                      int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star,
-                     int* __restrict__ tile_flags) {
+                     int* __restrict__ tile_flags, const float* __restrict__ x0, const float* __restrict__ y0,
+                     const float4* __restrict__ pack) {
   __shared__ SpreadShared sh;
   extern __shared__ int sbody[];  // ic[n_bodies] | jc[n_bodies] | offset[n_bodies + 1]
   int* const sic = sbody;
@@ -302,18 +363,14 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
   const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
-  // Occupied-tile marks (written by interp_force_kernel, the previous kernel): a tile no marker of its OWN body
-  // touches can only matter if another body's box overlaps it (checked below, after the body table is in shared
-  // memory); with separated bodies an empty tile leaves here after one load.
-  int* my_flag = nullptr;
-  bool own_marked = true;
-  if (tile_flags != nullptr) {
-    my_flag = tile_flags + (((size_t)s * n_bodies + b) * 2 + comp) * tiles_per_axis * tiles_per_axis + blockIdx.x;
-    pdl_wait();
-    own_marked = *my_flag != 0;
-    if (!own_marked && n_bodies == 1) return;
-  }
   // kinematic table and marker ranges are not outputs of the previous kernel: read before the dependency wait
+  {  // a tile that lies off the grid leaves after one load (slab decomposition: most bodies belong to other slabs)
+    int ic0, jc0;
+    body_box(states + b * JAXIB_BODY_STATE_STRIDE, m, ic0, jc0);
+    const int ty0 = blockIdx.x / tiles_per_axis, tx0 = blockIdx.x - ty0 * tiles_per_axis;
+    const int ta = ic0 - half_extent + ty0 * TS, tb = jc0 - half_extent + tx0 * TS;
+    if (ta >= g.nx || ta + TS <= 0 || tb >= g.ny || tb + TS <= 0) return;
+  }
   for (int b2 = threadIdx.x; b2 <= n_bodies; b2 += SPREAD_THREADS) {
     if (b2 < n_bodies) {
       int ic2, jc2;
@@ -340,13 +397,14 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   }
   const bool any_lo = __syncthreads_or(lo_hit) != 0;
   const bool any_hi = __syncthreads_or(hi_hit) != 0;
-  if (my_flag != nullptr) {
-    if (!own_marked) {
-      if (!any_hi) return;  // nothing of this body here and no later body reaches the tile
-    } else if (threadIdx.x == 0) {
-      *my_flag = 0;  // consumed (every thread read it before the barriers above): all marks are zero again after the step
-    }
+  // early cull of this body's markers (see cull_markers_early): only when no later body reaches the tile
+  int early = -1;
+  if (pack != nullptr && !any_hi && soff[b + 1] - soff[b] <= kCullBatches * SPREAD_THREADS) {
+    early = cull_markers_early(sh, m, x0, y0, pack, states + b * JAXIB_BODY_STATE_STRIDE, soff[b], soff[b + 1], ti0, tj0);
+    if (early == 0) return;  // no marker window touches the tile (the force kernel marks by the same test: no mark to clear)
   }
+  // Occupied-tile marks (written by interp_force_kernel, the previous kernel, read below): a tile no marker of its
+  // OWN body touches can only matter if another body's box overlaps it.
   const int cell = threadIdx.x & (TS * TS - 1);
   const int i = ti0 + cell / TS, j = tj0 + cell % TS;
   bool valid = i >= 0 && i < g.nx && j >= 0 && j < g.ny && i <= ic + half_extent && j <= jc + half_extent;
@@ -357,21 +415,69 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const size_t total = (size_t)g.batch * n_markers;
   const float* mk = markers + (size_t)s * n_markers;
   const float* mF = mk + (comp == 0 ? 3 : 4) * total;
-  pdl_wait();
   float* const out = (comp == 0 ? u_star : v_star) + (size_t)s * g.nx * g.ny + (size_t)(valid ? i : 0) * g.ny + (valid ? j : 0);
   const bool writer = valid && threadIdx.x < TS * TS;
-  const float cur = writer ? *out : 0.0f;  // in flight while the markers are gathered
+  int* const my_flag = tile_flags == nullptr ? nullptr :
+      tile_flags + (((size_t)s * n_bodies + b) * 2 + comp) * tiles_per_axis * tiles_per_axis + blockIdx.x;
+  pdl_wait();
+  // one round trip after the wait: the tile's mark, the cell's current value and (early cull) the listed forces
+  const int mark = my_flag != nullptr ? *my_flag : 1;
+  const float cur = writer ? *out : 0.0f;
+  float force = 0.0f;
+  if (early > 0 && (int)threadIdx.x < early) force = mF[__float_as_int(sh.part[threadIdx.x])];
+  if (my_flag != nullptr) {
+    __syncthreads();  // every thread has read the mark before it is cleared
+    if (mark == 0) {
+      if (!any_hi) return;  // nothing of this body here (slab mode: its markers belong to another slab) and no later body reaches the tile
+    } else if (threadIdx.x == 0) {
+      *my_flag = 0;  // consumed: all marks are zero again after the step
+    }
+  }
   float f_total = 0.0f;
   bool touched = false;
-  const int b_end = any_hi ? n_bodies : b + 1;
-  for (int b2 = b; b2 < b_end; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
-    const int ic2 = sic[b2], jc2 = sjc[b2];
-    if (b2 != b && (ic2 + half_extent < ti0 || ic2 - half_extent >= ti0 + TS || jc2 + half_extent < tj0 ||
-                    jc2 - half_extent >= tj0 + TS))
-      continue;  // block-uniform
-    float fb = gather_markers(sh, m, mk, mk + total, mF, mk + 2 * total, soff[b2], soff[b2 + 1], ti0, tj0, i, j, valid);
-    f_total = __fadd_rn(f_total, fb);
+  if (early > 0) {
+    // the list is ready: fetch the forces, then sum batch by batch exactly as gather_markers does
+    const int tid = threadIdx.x;
+    if (tid < early) sh.c[tid] = force * m.pref_x * sh.c[tid];  // F * pref * dS (IBM_Force.py:67)
+    __syncthreads();
+    const int slice = tid / (TS * TS);
+    const float X = mesh_coord(m.lower_x, i + m.row0, m.off_x, m.dx);
+    const float Y = mesh_coord(m.lower_y, j, m.off_y, m.dy);
+    const float mhalf_inv_w2 = -0.5f / (m.dx * m.dx);
+    float acc = 0.0f;
+    const int nb = (soff[b + 1] - soff[b] + SPREAD_THREADS - 1) / SPREAD_THREADS;
+    if (valid) {
+      for (int n = 0; n < nb; ++n) {
+        const int q0 = sh.batch_end[n], q1 = sh.batch_end[n + 1];
+        for (int q = q0 + slice; q < q1; q += SPREAD_SLICES) {
+          const int di = i - sh.ik[q], dj = j - sh.jk[q];
+          if (di > -m.R && di <= m.R && dj > -m.R && dj <= m.R) {
+            const float ddx = sh.xp[q] - X, ddy = sh.yp[q] - Y;
+            acc = fmaf(sh.c[q], expf((ddx * ddx + ddy * ddy) * mhalf_inv_w2), acc);
+          }
+        }
+      }
+    }
+    __syncthreads();  // sh.part is reused for the partial sums
+    sh.part[tid] = acc;
+    __syncthreads();
+    const int cell2 = tid & (TS * TS - 1);
+    float tot = sh.part[cell2];
+#pragma unroll
+    for (int q = 1; q < SPREAD_SLICES; ++q) tot += sh.part[cell2 + q * TS * TS];
+    f_total = __fadd_rn(f_total, tot);
     touched = true;
+  } else {
+    const int b_end = any_hi ? n_bodies : b + 1;
+    for (int b2 = b; b2 < b_end; ++b2) {  // IBM_Force.py:99-105: force += per-body contribution
+      const int ic2 = sic[b2], jc2 = sjc[b2];
+      if (b2 != b && (ic2 + half_extent < ti0 || ic2 - half_extent >= ti0 + TS || jc2 + half_extent < tj0 ||
+                      jc2 - half_extent >= tj0 + TS))
+        continue;  // block-uniform
+      float fb = gather_markers(sh, m, mk, mk + total, mF, mk + 2 * total, soff[b2], soff[b2 + 1], ti0, tj0, i, j, valid);
+      f_total = __fadd_rn(f_total, fb);
+      touched = true;
+    }
   }
   if (writer && touched && f_total != 0.0f) *out = __fadd_rn(cur, __fmul_rn(g.dt, f_total));  // time_stepping.py:223
 }
@@ -469,7 +575,7 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
   const long long need = (long long)g.batch * b.n_bodies * 2 * tiles * tiles;
   int* flags = (b.tile_flags && (long long)b.tile_flags_len >= need) ? b.tile_flags : nullptr;
   launch_pdl(4, spread_bodies_kernel, grid, block, smem, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
-             half_extent, tiles, u_star, v_star, flags);
+             half_extent, tiles, u_star, v_star, flags, b.x0, b.y0, reinterpret_cast<const float4*>(b.marker_pack));
   return check_launch("spread_bodies_kernel");
 }
 

@@ -224,3 +224,31 @@ def test_peer_block_layout_is_aligned_and_disjoint():
     assert all(off % 256 == 0 for off in blk.offset.values())
     assert blk.nbytes >= spans[-1][1] and blk.size["flags"] == 4 * slab.PeerBlock.FLAG_WORDS
     assert blk.size["colbuf"] == 8192 * L.cpr * 8 and blk.size["specbuf"] == (L.nloc + 1) * L.sp * 8
+
+
+# ---- column sweep (csrc/poisson_sweep.cu) restated in NumPy: same operator as the oracle's pseudo-inverse -------------
+@pytest.mark.parametrize("shape,slabs", [((96, 64), 1), ((100, 40), 1), ((600, 24), 1), ((96, 64), 3), ((128, 32), 8)])
+def test_column_sweep_model_matches_the_oracle_pseudoinverse(shape, slabs):
+    """tools/sweep_model.py restates the kernel's arithmetic (16-row segments, 32-lane scan of the carried values,
+    cyclic closure, two-prefix-sum mean mode, slab passes A / B).  Its solution must be the oracle's
+    `pseudoinverse(..., 'rfft')` (pressure.py:94-108 through jax_cfd fast_diagonalization) to float32 round-off:
+    partial last segments (100, 600 rows), several segments per lane (600 rows), 3 and 8 slabs."""
+    import importlib.util
+    import os
+    from oracle import poisson
+    spec = importlib.util.spec_from_file_location(
+        "sweep_model", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sweep_model.py"))
+    sm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sm)
+    nx, ny = shape
+    dx, dy = 0.05, 0.03
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal(shape)
+    rhs -= rhs.mean()
+    ops_p = [poisson.laplacian_matrix(nx, dx), poisson.laplacian_matrix(ny, dy)]
+    want = poisson.pseudoinverse(ops_p, np.float64, True, "rfft")(rhs)
+    got = sm.solve(rhs.astype(np.float32), dx, dy, slabs)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
+    # and it does solve the discrete Poisson equation: the 5-point Laplacian of the solution is the right-hand side
+    lap = ((np.roll(got, 1, 0) - 2 * got + np.roll(got, -1, 0)) / dx ** 2 + (np.roll(got, 1, 1) - 2 * got + np.roll(got, -1, 1)) / dy ** 2)
+    assert np.linalg.norm(lap - rhs) / np.linalg.norm(rhs) < 2e-4
