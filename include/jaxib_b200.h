@@ -153,8 +153,14 @@ int jaxib_ib_interp(jaxib_stream_t stream, const jaxib_grid* grid, double off_x,
                     const float* field, const float* xp, const float* yp, int32_t n, float* out,
                     int32_t* ci, int32_t* cj);
 /* IBM_Force.py:66-87: out[i,j] += scale * sum_k F_k * delta(r_k; dx) * dS_k.  Cells outside every
- * marker window are left untouched (zero `out` first to obtain the bare force field).  Needs 16
- * bytes of device scratch (bounding box of the point cloud).  batch = 1.                       */
+ * marker window are left untouched (zero `out` first to obtain the bare force field).  batch = 1.
+ * Scratch (device, 4-byte aligned): with jaxib_ib_spread_scratch_bytes(grid, n) bytes the markers are
+ * counting-sorted into bins of 32 x 32 cells by their owning cell and every 8 x 8 tile gathers, in marker
+ * order, from the bins its window reaches: O(n x window) work (the north star's "markers sorted by cell,
+ * deterministic gather, no float atomics").  With less scratch (at least 16 bytes: the bounding box)
+ * every tile inside the bounding box culls all n points instead.  Same result either way up to the
+ * summation order of float32 (marker order in both; the tile's partial sums are grouped differently). */
+size_t jaxib_ib_spread_scratch_bytes(const jaxib_grid* grid, int32_t n);
 int jaxib_ib_spread(jaxib_stream_t stream, const jaxib_grid* grid, double off_x, double off_y,
                     const float* F, const float* xp, const float* yp, const float* dS, int32_t n,
                     double scale, float* out, void* scratch, size_t scratch_bytes);
@@ -207,8 +213,14 @@ int jaxib_poisson_rows_inv(jaxib_stream_t stream, const jaxib_plan* plan, const 
  * VMM / IPC peer mappings made by the host side; jax_ib_b200/slab.py uses torch symmetric memory);
  * entry [d] is slab d's buffer as addressed from THIS process, entry [rank] is the local one.
  * The kernels of a step store straight into the buffer of the slab that consumes the data (NVLink
- * stores: both spectrum transposes and the halo rows), with a flag barrier after each of the three
- * exchanging phases -- see jax_ib_b200/csrc/slab.cu.  Needs nx in {512..8192}, ny/2 in {512..4096} (powers of 2). */
+ * stores) with a flag barrier after each exchanging phase -- see jax_ib_b200/csrc/slab.cu:
+ *   default      the x-direction of the pressure solve is the column sweep (csrc/poisson_sweep.cu) run slab by
+ *                slab: every slab stores its two carried-value maps per column and part + its rows of column 0
+ *                into the head of every peer's colbuf, and its boundary rows into the neighbours' halos; 2
+ *                barriers per step; ny/2 in {512..4096}, any nx divisible by world; results equal one GPU's
+ *                to float32 round-off (rel-L2 <= 5e-6);
+ *   JAXIB_SLAB_FFT=1 (environment)  round-1 path: both spectrum transposes through colbuf / specbuf, column FFT,
+ *                3 barriers; additionally nx in {512..8192}; bit-identical to one GPU running the column FFT. */
 typedef struct {
   int32_t world, rank;
   int32_t halo;                      /* halo rows on either side, in [2 * ib_window + 4, nloc]       */
@@ -217,7 +229,7 @@ typedef struct {
   float* v[JAXIB_MAX_PEERS];
   float* p[JAXIB_MAX_PEERS];
   float* markers[JAXIB_MAX_PEERS];   /* [5][n_markers]: xp, yp, dS, Fx, Fy (NULL without bodies)     */
-  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised                          */
+  float* colbuf[JAXIB_MAX_PEERS];    /* [nx][cpr] complex, zero-initialised (sweep path: the slab tables)  */
   float* specbuf[JAXIB_MAX_PEERS];   /* [nloc + 1][world * cpr] complex                              */
   uint32_t* flags[JAXIB_MAX_PEERS];  /* 128 words, zero-initialised: barrier flags + error word [64] */
 } jaxib_slab;

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "jaxib_explicit_terms": (C.c_int, [_P, C.POINTER(Grid), _P, _P, _P, _P, _P]),
     "jaxib_explicit_predict": (C.c_int, [_P, C.POINTER(Grid), _P, _P, _P, _P, _P, _P]),
     "jaxib_ib_interp": (C.c_int, [_P, C.POINTER(Grid), C.c_double, C.c_double, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "jaxib_ib_spread_scratch_bytes": (C.c_size_t, [C.POINTER(Grid), C.c_int32]),
     "jaxib_ib_spread": (C.c_int, [_P, C.POINTER(Grid), C.c_double, C.c_double, _P, _P, _P, _P, C.c_int32,
                                   C.c_double, _P, _P, C.c_size_t]),
     "jaxib_ib_force": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(Bodies), _P, _P, _P, _P, C.c_size_t]),

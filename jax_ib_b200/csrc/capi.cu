@@ -238,7 +238,12 @@ int jaxib_ib_spread(jaxib_stream_t stream, const jaxib_grid* grid, double off_x,
   if ((rc = check_ptrs("ib_spread", {F, xp, yp, dS, out}))) return rc;
   if (!scratch || scratch_bytes < 16) { set_error("ib_spread: needs 16 bytes of scratch"); return JAXIB_ERR_SCRATCH; }
   return launch_ib_spread((cudaStream_t)stream, make_gridf(*grid), (float)off_x, (float)off_y, F, xp, yp, dS, n,
-                          (float)scale, out, reinterpret_cast<int*>(scratch));
+                          (float)scale, out, reinterpret_cast<int*>(scratch), scratch_bytes);
+}
+
+size_t jaxib_ib_spread_scratch_bytes(const jaxib_grid* grid, int32_t n) {
+  if (check_grid(grid)) return 0;
+  return ib_spread_scratch_bytes(make_gridf(*grid), n);
 }
 
 static int check_bodies(const jaxib_bodies* b) {

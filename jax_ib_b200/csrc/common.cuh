@@ -164,7 +164,8 @@ int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, c
                      const float* xp, const float* yp, int n, float* out, int32_t* ci, int32_t* cj);
 int launch_ib_spread(cudaStream_t s, const GridF& g, float off_x, float off_y, const float* F,
                      const float* xp, const float* yp, const float* dS, int n, float scale, float* out,
-                     int* box_scratch);
+                     int* box_scratch, size_t scratch_bytes);
+size_t ib_spread_scratch_bytes(const GridF& g, int n);
 int launch_project(cudaStream_t s, const jaxib_plan* plan, const float* u, const float* v, const float* p,
                    float* u_out, float* v_out, float* p_out, float* q_only, float* spectrum,
                    const StageHook* hook = nullptr, const GridF* gov = nullptr, const RowDeps* deps = nullptr);

@@ -438,6 +438,164 @@ rows_inv_team_kernel(FastRowParams P, const float2* __restrict__ tables, const f
   }
 }
 
+// K6, marching variant: one CTA per CHUNK of L consecutive rows, walked from the chunk's last row to its first in
+// batches of NTB rows (the first batch also transforms the row after the chunk: q of that row feeds the u-correction
+// of the chunk's last row; later batches keep q of the row above them in an extra buffer).  L is chosen so that the
+// grid is one wave: with long rows a CTA only holds NT = 4 teams and the plain kernel finalises 3 rows per CTA
+// -- a 1024-row slab of 8192 columns is 342 CTAs = 3 waves for 2.3 waves of work, while 147 chunks of 7 rows are
+// 2 batches of 4 transforms each (rows_inv_team_kernel: 62 us, this: see profiles/r3h).
+template <int R1, int R2, int R3, int PS2>
+__global__ void __launch_bounds__(1024, 1)
+rows_inv_march_kernel(FastRowParams P, const float2* __restrict__ tables, const float2* __restrict__ spec, const float* u,
+                      const float* v, const float* p, float* u_out, float* v_out, float* p_out, int L) {
+  using G = RowTeam<R1, R2, R3, PS2>;
+  constexpr int N = G::N, T = G::T, SUB1 = G::SUB1;
+  const int NTB = blockDim.x / T;
+  extern __shared__ __align__(16) float2 smr[];
+  __shared__ __align__(8) unsigned long long tbar;
+  float2* const ta = smr;
+  float2* const tb = ta + G::TA;
+  float2* const tu = tb + G::TB;
+  const int t = threadIdx.x;
+  const int team = t / T, b = t - team * T;
+  float2* const buf = smr + G::TAB + team * G::BUF;
+  float2* const qsave = smr + G::TAB + NTB * G::BUF;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tbar);
+  pdl_trigger();
+  if (t == 0) tables_issue<G>(smr, tables, bar);
+  const GridF& g = P.g;
+  const int ny = g.ny;
+  const size_t plane = (size_t)g.nx * ny;
+  spec += (size_t)blockIdx.y * g.nx * P.sp;
+  u += blockIdx.y * plane; v += blockIdx.y * plane; p += blockIdx.y * plane;
+  u_out += blockIdx.y * plane; v_out += blockIdx.y * plane; p_out += blockIdx.y * plane;
+  const int i0 = blockIdx.x * L;
+  const int Lc = min(L, g.nx - i0);
+  pdl_wait();
+  __syncthreads();  // barrier initialisation visible
+  bool have_tables = false;
+  for (int jhi = Lc; jhi >= 0; jhi -= NTB) {
+    const int jbase = jhi - NTB + 1;
+    const int j = jbase + team;  // this team's row of the chunk (Lc: the row after it)
+    const bool live = j >= 0;    // uniform over the team
+    const bool more = jbase > 0;
+    if (live) {
+      // slab mode (nx_global > 0): spectrum row nx exists (halo); otherwise the row after the last one wraps
+      const int ii = i0 + j;
+      const int irow = (ii >= g.nx && g.nx_global == 0) ? ii - g.nx : ii;
+      const float2* __restrict__ in = spec + (size_t)irow * P.sp;
+      float2 xk[(N / 2) / T], xm[(N / 2) / T];
+#pragma unroll
+      for (int m = 0; m < (N / 2) / T; ++m) {
+        const int k = b + T * m;
+        xk[m] = in[k];
+        xm[m] = in[N - k];
+      }
+      float2 xh = make_float2(0.f, 0.f);
+      if (b == 0) xh = in[N / 2];
+      if (!have_tables) { tables_wait(bar); have_tables = true; }
+#pragma unroll
+      for (int m = 0; m < (N / 2) / T; ++m) {
+        const int k = b + T * m;
+        if (k == 0) {
+          const float x0 = xk[m].x, xn = xm[m].x;  // X[0], X[N]: both real
+          buf[0] = make_float2(0.5f * (x0 + xn), 0.5f * (x0 - xn));
+        } else {
+          const float2 a = xk[m], c = cconj(xm[m]);
+          const float2 e = cscale(cadd(a, c), 0.5f);
+          const float2 o = cmulc(cscale(csub(a, c), 0.5f), tu[k]);
+          buf[G::pad(G::pos(k))] = cadd(e, mul_pi(o));
+          buf[G::pad(G::pos(N - k))] = cadd(cconj(e), mul_pi(cconj(o)));
+        }
+      }
+      if (b == 0) {
+        const float2 a = xh, c = cconj(xh);
+        const float2 e = cscale(cadd(a, c), 0.5f);
+        const float2 o = cmulc(cscale(csub(a, c), 0.5f), tu[N / 2]);
+        buf[G::pad(G::pos(N / 2))] = cadd(e, mul_pi(o));
+      }
+    }
+    team_bar<G>(team);
+    team_inner<G, R2, R3, R1, true>(buf, tb, b, team, live);
+    if (live) {
+#pragma unroll
+      for (int jj = 0; jj < G::NBA; ++jj) {  // pass A inverse; q[i][2n], q[i][2n+1] stay at (padded) index n
+        const int bA = b + T * jj;
+        float2* const e = buf + G::pad(bA);
+        float2 z[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          z[r] = e[G::pad(SUB1 * r)];
+          if (r > 0) z[r] = cmulc(z[r], ta[(r - 1) * SUB1 + bA]);
+        }
+        dft_r<R1, true>(z);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) e[G::pad(SUB1 * r)] = cscale(z[r], P.scale);
+      }
+    }
+    __syncthreads();  // every team's q row is complete
+    if (live && j < Lc) {
+      const int ii = i0 + j;
+      const float2* const q0row = buf;
+      const float2* const q1row = team + 1 < NTB ? buf + G::BUF : qsave;  // q[i+1]
+      const size_t ro = (size_t)ii * ny;
+      const float2* u2 = reinterpret_cast<const float2*>(u + ro);
+      const float2* v2 = reinterpret_cast<const float2*>(v + ro);
+      const float2* p2 = reinterpret_cast<const float2*>(p + ro);
+      float2* uo = reinterpret_cast<float2*>(u_out + ro);
+      float2* vo = reinterpret_cast<float2*>(v_out + ro);
+      float2* po = reinterpret_cast<float2*>(p_out + ro);
+      constexpr int CH = 4;
+#pragma unroll 1
+      for (int m0 = 0; m0 < N / T; m0 += CH) {
+        float2 ua[CH], va[CH], pa[CH];  // all loads first: the outputs may alias the inputs
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int n = b + T * (m0 + c);
+          ua[c] = u2[n];
+          va[c] = v2[n];
+          pa[c] = p2[n];
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int n = b + T * (m0 + c);
+          const float2 q0 = q0row[G::pad(n)], q1 = q1row[G::pad(n)];
+          const float qn = q0row[G::pad(n + 1 < N ? n + 1 : 0)].x;  // q[i][2n+2] (periodic)
+          float2 uu = ua[c], vv = va[c];
+          uu.x -= (q1.x - q0.x) * g.inv_dx;
+          uu.y -= (q1.y - q0.y) * g.inv_dx;
+          vv.x -= (q0.y - q0.x) * g.inv_dy;
+          vv.y -= (qn - q0.y) * g.inv_dy;
+          const float2 pn = make_float2(q0.x + pa[c].x, q0.y + pa[c].y);
+          uo[n] = uu;
+          vo[n] = vv;
+          po[n] = pn;
+          if (P.ho.halo) {  // slab mode: boundary rows are also the neighbours' halo rows (NVLink stores)
+            if (ii < P.ho.halo) {
+              const size_t o = (size_t)ii * ny;
+              reinterpret_cast<float2*>(P.ho.lo[0] + o)[n] = uu;
+              reinterpret_cast<float2*>(P.ho.lo[1] + o)[n] = vv;
+              reinterpret_cast<float2*>(P.ho.lo[2] + o)[n] = pn;
+            }
+            if (ii >= g.nx - P.ho.halo) {
+              const size_t o = (size_t)(ii - (g.nx - P.ho.halo)) * ny;
+              reinterpret_cast<float2*>(P.ho.hi[0] + o)[n] = uu;
+              reinterpret_cast<float2*>(P.ho.hi[1] + o)[n] = vv;
+              reinterpret_cast<float2*>(P.ho.hi[2] + o)[n] = pn;
+            }
+          }
+        }
+      }
+    }
+    if (more) {  // keep q of the batch's lowest row (team 0) for the next batch's highest one
+      __syncthreads();
+      if (team == 0)
+        for (int n = b; n < G::BUF; n += T) qsave[n] = buf[n];
+      __syncthreads();
+    }
+  }
+}
+
 // Teams per CTA: the most that still gives every SM a CTA (small grids would otherwise run on a fraction of the
 // machine: 1024 rows of ny = 1024 are 32 CTAs of 32 teams); `halo` = 1 when one team per CTA carries the extra row.
 int teams_per_cta(int max_nt, int nx, int batch, int halo) {
@@ -482,6 +640,32 @@ int launch_rows_inv_team_t(cudaStream_t s, const FastRowParams& P, const float2*
   }
   const int nt = teams_per_cta(G::NT, P.g.nx, P.g.batch, project ? 1 : 0);
   const int rows = project ? nt - 1 : nt;
+  if (project && P.g.batch == 1) {
+    // marching variant (rows_inv_march_kernel): one wave of chunks.  Cost model in row transforms per SM:
+    //   plain: waves * nt;  marching: ceil((L + 1) / nt) * nt with L = ceil(nx / SMs)
+    static int sms = 0;
+    static int mode = -1;  // JAXIB_K6_MARCH=0 / 1 forces the choice (A/B runs)
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const char* e = getenv("JAXIB_K6_MARCH");
+      mode = e ? atoi(e) : -1;
+      const int big = (int)G::smem(G::NT + 1);
+      cudaFuncSetAttribute(rows_inv_march_kernel<R1, R2, R3, PS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    }
+    const int ctas = (P.g.nx + rows - 1) / rows;
+    const int plain = ((ctas + sms - 1) / sms) * nt;
+    const int L = (P.g.nx + sms - 1) / sms;
+    const int march = ((L + 1 + nt - 1) / nt) * nt;
+    const bool fits = G::smem(nt + 1) <= 227 * 1024;
+    if (fits && (mode == 1 || (mode != 0 && march * 10 <= plain * 9))) {  // at least 10 % fewer transforms
+      dim3 grid((P.g.nx + L - 1) / L, 1);
+      launch_pdl(32, rows_inv_march_kernel<R1, R2, R3, PS2>, grid, dim3(nt * G::T), G::smem(nt + 1), s, P, tables, spec, u, v, p,
+                 uo, vo, po, L);
+      return check_launch("rows_inv_march_kernel");
+    }
+  }
   dim3 grid((P.g.nx + rows - 1) / rows, P.g.batch);
   if (project)
     launch_pdl(32, rows_inv_team_kernel<R1, R2, R3, PS2, true>, grid, dim3(nt * G::T), G::smem(nt), s, P, tables, spec, u, v, p, uo, vo, po);

@@ -153,11 +153,13 @@ ffi::Error IbSpreadImpl(cudaStream_t s, ffi::ScratchAllocator scratch, F32 base,
   jaxib_grid g = MakeGrid(base.dimensions(), a);
   double off_x = 1.0, off_y = 0.5, scale = 1.0;
   Get(a, "offset_x", &off_x); Get(a, "offset_y", &off_y); Get(a, "scale", &scale);
-  auto mem = scratch.Allocate(16);
+  // scratch for the cell-binned gather (markers counting-sorted by owning cell)
+  const size_t bytes = jaxib_ib_spread_scratch_bytes(&g, static_cast<int32_t>(xp.element_count()));
+  auto mem = scratch.Allocate(bytes);
   if (!mem.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "jaxib scratch");
   CopyIfDistinct(s, base, out);
   return Status(jaxib_ib_spread(s, &g, off_x, off_y, F.typed_data(), xp.typed_data(), yp.typed_data(), dS.typed_data(),
-                                static_cast<int32_t>(xp.element_count()), scale, out->typed_data(), *mem, 16));
+                                static_cast<int32_t>(xp.element_count()), scale, out->typed_data(), *mem, bytes));
 }
 
 // ---- IBM_Force.py:109-115 calc_IBM_force_NEW_MULTIPLE fused with time_stepping.py:223 (`IBM_forcing`) ----------

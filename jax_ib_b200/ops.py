@@ -135,15 +135,18 @@ def ib_interp(spec: GridSpec, field, offset, xp, yp, return_cells=False):
     return (out, ci, cj) if return_cells else out
 
 
-def ib_spread(spec: GridSpec, offset, F, xp, yp, dS, out=None, scale=1.0):
-    """IBM_Force.py:66-87 (windowed): out += scale * sum_k F_k delta(r_k) dS_k."""
+def ib_spread(spec: GridSpec, offset, F, xp, yp, dS, out=None, scale=1.0, binned=True):
+    """IBM_Force.py:66-87 (windowed): out += scale * sum_k F_k delta(r_k) dS_k.  binned: scratch for the cell-binned
+    gather (markers counting-sorted by cell); False: 16 bytes, every tile of the bounding box culls all points."""
     if out is None:
         out = torch.zeros(spec.nx, spec.ny, dtype=torch.float32, device=F.device)
-    scratch = torch.empty(16, dtype=torch.uint8, device=F.device)
     g = spec.replace(batch=1).c_struct()
-    _lib.check(_lib.load().jaxib_ib_spread(_stream(), C.byref(g), float(offset[0]), float(offset[1]), _ptr(_f32(F)),
-                                           _ptr(_f32(xp)), _ptr(_f32(yp)), _ptr(_f32(dS)), F.numel(), float(scale),
-                                           _ptr(out), _ptr(scratch), 16), "ib_spread")
+    lib = _lib.load()
+    nbytes = int(lib.jaxib_ib_spread_scratch_bytes(C.byref(g), F.numel())) if binned else 16
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=F.device)
+    _lib.check(lib.jaxib_ib_spread(_stream(), C.byref(g), float(offset[0]), float(offset[1]), _ptr(_f32(F)),
+                                   _ptr(_f32(xp)), _ptr(_f32(yp)), _ptr(_f32(dS)), F.numel(), float(scale),
+                                   _ptr(out), _ptr(scratch), scratch.numel()), "ib_spread")
     return out
 
 

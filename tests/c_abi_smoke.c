@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
   LOAD(jaxib_version) LOAD(jaxib_last_error) LOAD(jaxib_compiled_arch)
   LOAD(jaxib_plan_create) LOAD(jaxib_plan_destroy) LOAD(jaxib_scratch_bytes)
   LOAD(jaxib_explicit_terms) LOAD(jaxib_explicit_predict)
-  LOAD(jaxib_ib_interp) LOAD(jaxib_ib_spread) LOAD(jaxib_ib_force) LOAD(jaxib_ib_marker_force) LOAD(jaxib_ib_spread_bodies)
+  LOAD(jaxib_ib_interp) LOAD(jaxib_ib_spread_scratch_bytes) LOAD(jaxib_ib_spread) LOAD(jaxib_ib_force) LOAD(jaxib_ib_marker_force) LOAD(jaxib_ib_spread_bodies)
   LOAD(jaxib_pressure_solve) LOAD(jaxib_project)
   LOAD(jaxib_poisson_rows_fwd) LOAD(jaxib_poisson_cols) LOAD(jaxib_poisson_rows_inv)
   LOAD(jaxib_slab_step) LOAD(jaxib_step) LOAD(jaxib_step_profile)
@@ -71,7 +71,7 @@ int main(int argc, char** argv) {
   memset(&sl, 0, sizeof(sl));
   unsigned epoch = 0;
   EXPECT(p_jaxib_slab_step(NULL, NULL, NULL, &g, &sl, NULL, NULL, 1, 0, 3, 1, &epoch, dummy, dummy) == JAXIB_ERR_INVALID);
-  printf("c_abi_smoke: %s, 25 entry points resolved through the header's prototypes, error paths ok\n", p_jaxib_version());
+  printf("c_abi_smoke: %s, 26 entry points resolved through the header's prototypes, error paths ok\n", p_jaxib_version());
   dlclose(lib);
   return 0;
 }

@@ -401,3 +401,38 @@ def test_early_start_of_the_row_transform_is_bitwise_the_serial_order(workload):
                        env=dict(os.environ, JAXIB_K4_EARLY="1"), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip().split()[-1] == here
+
+
+# ------------------------------------------------------------------------------------------------ cell-binned spreading
+@pytest.mark.parametrize("n,R", [(298, 6), (20000, 6), (20000, 12), (3000, 16)])
+def test_cell_binned_spread_of_a_point_cloud(n, R):
+    """jaxib_ib_spread with the binned scratch: markers counting-sorted into 32 x 32-cell bins, every tile gathers
+    from the bins in reach after sorting its candidates by marker number (IBM_Force.py:66-87, north star: "markers
+    sorted by cell, deterministic gather").  Clouds much larger than a body (20 000 points: several bins crowded,
+    some tiles over the candidate cap and back on the cull-everything path), points off the grid on every side,
+    windows R = 6 / 12 / 16 (1, 2 and 3 bins of reach); against the windowed oracle, the unbinned kernel, and itself
+    (two runs bit for bit: the atomics' fill order must not matter)."""
+    from oracle import field, ib
+    cfg = dict(configs.flap600(), shape=(300, 280))
+    cfg["domain"] = ((0.0, 300 * 0.05), (0.0, 280 * 0.03))
+    g = field.Grid(cfg["shape"], cfg["domain"])
+    spec = demo.make_spec(cfg, ib_window=R)
+    rng = np.random.default_rng(n + R)
+    # a dense blob (crowded bins), a ring, and a uniform cloud that leaves the domain by up to 0.6 units
+    k = n // 3
+    th = rng.uniform(0, 2 * np.pi, k)
+    xp = np.concatenate([7.0 + 0.3 * rng.standard_normal(k), 9.0 + 3.0 * np.cos(th), rng.uniform(-0.6, 15.6, n - 2 * k)]).astype(F)
+    yp = np.concatenate([4.0 + 0.2 * rng.standard_normal(k), 4.2 + 2.5 * np.sin(th), rng.uniform(-0.6, 9.0, n - 2 * k)]).astype(F)
+    Fk = rng.standard_normal(n).astype(F)
+    dS = rng.uniform(0.01, 0.03, n).astype(F)
+    for off in ((1.0, 0.5), (0.5, 1.0)):
+        want = ib.spread_windowed(Fk, xp, yp, dS, g, off, R)
+        a = ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS))
+        b = ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS))
+        plain = ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS), binned=False)
+        assert torch.equal(a, b)
+        # thousands of random-sign terms per cell in the blob: the bar is the float32 summation-order noise
+        assert rel_l2(host(a), want) < 1e-5
+        assert rel_l2(host(a), host(plain)) < 1e-5
+        if R == 6:  # identical support (wider windows end in float32 denormals, where exp implementations differ)
+            assert np.array_equal(host(a) != 0, want != 0)
