@@ -644,16 +644,15 @@ int launch_rows_inv_team_t(cudaStream_t s, const FastRowParams& P, const float2*
     // marching variant (rows_inv_march_kernel): one wave of chunks.  Cost model in row transforms per SM:
     //   plain: waves * nt;  marching: ceil((L + 1) / nt) * nt with L = ceil(nx / SMs)
     static int sms = 0;
-    static int mode = -1;  // JAXIB_K6_MARCH=0 / 1 forces the choice (A/B runs)
     if (!sms) {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      const char* e = getenv("JAXIB_K6_MARCH");
-      mode = e ? atoi(e) : -1;
       const int big = (int)G::smem(G::NT + 1);
       cudaFuncSetAttribute(rows_inv_march_kernel<R1, R2, R3, PS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     }
+    const char* env_march = getenv("JAXIB_K6_MARCH");  // 0 / 1 forces the choice (A/B runs, tests)
+    const int mode = env_march ? atoi(env_march) : -1;
     const int ctas = (P.g.nx + rows - 1) / rows;
     const int plain = ((ctas + sms - 1) / sms) * nt;
     const int L = (P.g.nx + sms - 1) / sms;

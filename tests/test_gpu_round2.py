@@ -436,3 +436,24 @@ def test_cell_binned_spread_of_a_point_cloud(n, R):
         assert rel_l2(host(a), host(plain)) < 1e-5
         if R == 6:  # identical support (wider windows end in float32 denormals, where exp implementations differ)
             assert np.array_equal(host(a) != 0, want != 0)
+
+
+# ------------------------------------------------------------------------------------------------ marching K6
+@pytest.mark.parametrize("shape", [(1024, 2048), (4096, 1024), (512, 8192), (300, 4096)])
+def test_marching_inverse_row_kernel_is_bitwise_the_plain_one(shape, monkeypatch):
+    """rows_inv_march_kernel (one wave of row chunks walked in batches; chosen by a cost model for long rows) performs
+    the same transforms and the same finalisation per row as rows_inv_team_kernel: forced on and off
+    (JAXIB_K6_MARCH), the projection must agree bit for bit -- several batches per chunk (4096 rows), partial last
+    batch and a ragged last chunk (300 rows), 4-team CTAs (8192 columns)."""
+    cfg = dict(configs.ib_periodic(1024, 1), shape=shape, bodies=None)
+    cfg["domain"] = ((0.0, shape[0] * 0.025), (0.0, shape[1] * 0.025))
+    rng = np.random.default_rng(3)
+    u, v, p = (rng.standard_normal(shape).astype(F) for _ in range(3))
+    outs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("JAXIB_K6_MARCH", mode)
+        plan = ops.Plan(demo.make_spec(cfg))
+        outs.append(tuple(t.clone() for t in plan.project(dev(u), dev(v), dev(p))))
+    for a, b in zip(*outs):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b)
