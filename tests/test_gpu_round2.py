@@ -457,3 +457,24 @@ def test_marching_inverse_row_kernel_is_bitwise_the_plain_one(shape, monkeypatch
     for a, b in zip(*outs):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ row-sweep variant
+@pytest.mark.parametrize("shape", [(512, 1024), (2048, 2048), (4096, 1024), (512, 8192)])
+def test_sweeps_fused_into_the_row_kernels_match_the_column_sweep(shape, monkeypatch):
+    """JAXIB_SWEEP=1 (read when a plan is created): the x-sweeps run inside K4 / K6 over row chunks with a separate
+    carry kernel (poisson_team_rows.cu: rows_fwd_sweep_kernel, sweep_carry_kernel, rows_inv_sweep_kernel) instead
+    of the column sweep kernel.  Off by default (slower at 2048^2) but kept: same operator, so the
+    projections agree to float32 round-off; single batch, several batches per chunk (4096 rows), 4-team CTAs."""
+    cfg = dict(configs.ib_periodic(1024, 1), shape=shape, bodies=None)
+    cfg["domain"] = ((0.0, shape[0] * 0.025), (0.0, shape[1] * 0.025))
+    fields = configs.initial_fields(dict(cfg, init=("divfree", 11, 0.5)))
+    rng = np.random.default_rng(4)
+    u, v = (a + 0.05 * rng.standard_normal(shape).astype(F) for a in fields[:2])
+    p = rng.standard_normal(shape).astype(F)
+    want = ops.Plan(demo.make_spec(cfg)).project(dev(u), dev(v), dev(p))
+    monkeypatch.setenv("JAXIB_SWEEP", "1")
+    got = ops.Plan(demo.make_spec(cfg)).project(dev(u), dev(v), dev(p))
+    for name, a, b in zip("uvp", got, want):
+        assert torch.isfinite(a).all()
+        assert rel_l2(host(a), host(b)) < (2e-5 if name == "p" else 2e-6), name
