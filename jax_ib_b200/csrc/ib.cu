@@ -365,6 +365,12 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
   const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
+  if (!early_cull && tile_flags != nullptr && n_bodies == 1) {
+    // grids of many waves (ensembles): most CTAs start after the force kernel has finished -- the tile mark is the
+    // cheapest test, an empty tile leaves after one load
+    pdl_wait();
+    if (tile_flags[(((size_t)s * n_bodies + b) * 2 + comp) * tiles_per_axis * tiles_per_axis + blockIdx.x] == 0) return;
+  }
   // kinematic table and marker ranges are not outputs of the previous kernel: read before the dependency wait
   {  // a tile that lies off the grid leaves after one load (slab decomposition: most bodies belong to other slabs)
     int ic0, jc0;

@@ -443,7 +443,7 @@ rows_inv_team_kernel(FastRowParams P, const float2* __restrict__ tables, const f
 // of the chunk's last row; later batches keep q of the row above them in an extra buffer).  L is chosen so that the
 // grid is one wave: with long rows a CTA only holds NT = 4 teams and the plain kernel finalises 3 rows per CTA
 // -- a 1024-row slab of 8192 columns is 342 CTAs = 3 waves for 2.3 waves of work, while 147 chunks of 7 rows are
-// 2 batches of 4 transforms each (rows_inv_team_kernel: 62 us, this: see profiles/r3h).
+// 2 batches of 4 transforms each.  Measured: no gain (see launch_rows_inv_team_t) -- kept off by default, tested bitwise.
 template <int R1, int R2, int R3, int PS2>
 __global__ void __launch_bounds__(1024, 1)
 rows_inv_march_kernel(FastRowParams P, const float2* __restrict__ tables, const float2* __restrict__ spec, const float* u,
@@ -658,7 +658,12 @@ int launch_rows_inv_team_t(cudaStream_t s, const FastRowParams& P, const float2*
     const int L = (P.g.nx + sms - 1) / sms;
     const int march = ((L + 1 + nt - 1) / nt) * nt;
     const bool fits = G::smem(nt + 1) <= 227 * 1024;
-    if (fits && (mode == 1 || (mode != 0 && march * 10 <= plain * 9))) {  // at least 10 % fewer transforms
+    // Measured on B200 (profiles/r3h): NOT faster -- 63.3 vs 62.2 us on a 1024-row slab of 8192 columns, 1360 vs 1301 us
+    // per step at 8192^2 on one GPU: the batches of a chunk serialise load / transform / finalise phases that the
+    // independent CTAs of the plain kernel overlap across waves.  Off unless forced (JAXIB_K6_MARCH=1); the cost
+    // model is kept for the record.
+    (void)plain; (void)march;
+    if (fits && mode == 1) {
       dim3 grid((P.g.nx + L - 1) / L, 1);
       launch_pdl(32, rows_inv_march_kernel<R1, R2, R3, PS2>, grid, dim3(nt * G::T), G::smem(nt + 1), s, P, tables, spec, u, v, p,
                  uo, vo, po, L);
