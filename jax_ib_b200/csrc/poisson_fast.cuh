@@ -87,6 +87,7 @@ struct ColSweepParams {
   double out_scale;     // nx of the whole column (see cols_sweep_tables)
   // slab decomposition (modes 1, 2): this GPU holds rows [rank nx, (rank + 1) nx) of nx_global
   int world, rank, nx_global, ncols_pad;
+  int use_tma;          // set by the launcher: the strip is moved by tensor copies (cp.async.bulk.tensor.2d)
   float* slab_table[kMaxPeers];  // every slab's table of block maps + column 0 (cols_sweep_slab_table_bytes)
 };
 bool cols_sweep_supported(int nx);

@@ -30,6 +30,7 @@
 // A channel stores two real DCT columns per complex column: real and imaginary parts simply carry their own
 // constants (on periodic grids they are equal).  tools/sweep_model.py restates the arithmetic in NumPy float32:
 // rel-L2 2.9e-7 against the float64 solution at 2048^2 (float32 FFT solve: 1.7e-7; on the GPU both pass the same bars, tests/test_gpu_parity.py).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <math.h>
 #include <stdlib.h>
 
@@ -193,8 +194,8 @@ __device__ __forceinline__ float2 job_entry(const ColSweepParams& P, int col, in
 // FULL: nx is a multiple of RS (every segment has RS rows: no per-row predicates)
 template <int CS, int MODE, bool FULL>
 __global__ void __launch_bounds__(1024, 1)
-cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
-  extern __shared__ __align__(16) unsigned char sw_raw[];
+cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char sw_raw[];
   __shared__ double red[32];
   pdl_trigger();
   const int t = threadIdx.x;
@@ -241,9 +242,27 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   // segment = lane m + j
   const int m = (segs + 31) / 32;
   const int cp1 = 32 * m + 1;                          // words per column
-  float* const sE = reinterpret_cast<float*>(sw_raw);  // e, later Ain
+  // TMA path (P.use_tma, opt-in: see the launcher for the measurements): the strip is moved by tensor copies, one
+  // [RS rows x CS columns] box per segment (cp.async.bulk.tensor.2d, UTMALDG / UTMASTG); the copy engine generates
+  // the strided row requests itself.  Boxes clip at the tensor's edges: partial strips and a partial last segment
+  // need no special case.
+  const bool use_tma = P.use_tma != 0;
+  const bool tma_store = use_tma && strip != 0 && MODE != kSweepAggregate;  // strip 0 holds column 0 (real part: CTA 0's)
+  float2* const tile = reinterpret_cast<float2*>(sw_raw);  // [segs][RS][CS]
+  const size_t tile_floats = use_tma ? (size_t)segs * RS * CS * 2 : 0;
+  float* const sE = reinterpret_cast<float*>(sw_raw) + tile_floats;  // e, later Ain
   float* const sS = sE + 2 * CS * cp1;                 // S, later Bin
+  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(sS + 2 * CS * cp1);
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+  if (use_tma) {
+    if (t == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   const int at = c * cp1 + (seg % m) * 32 + seg / m;
+  const int trow0 = (int)blockIdx.y * nx;  // first row of this batch member in the tensor
   // this warp's scanning job (step 2): its nine per-column constants, one per lane, fetched now (plan tables) ...
   const int wj = t >> 5, lanej = t & 31;
   float kconst = 0.0f;
@@ -258,10 +277,24 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
     if (wj < 2 * CS && colj < P.ncols) entry = job_entry(P, colj, wj & 1, lanej);
   }
   float2 a[RS];
+  if (use_tma) {
+    constexpr unsigned kBoxBytes = RS * CS * sizeof(float2);
+    if (t == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)segs * kBoxBytes) : "memory");
+    if (t < segs)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(tile + (size_t)t * RS * CS)),
+                   "l"(&tmap), "r"(2 * strip * CS), "r"(trow0 + t * RS), "r"(bar)
+                   : "memory");
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar) : "memory");
+  }
+  const float2* const tsrc = tile + (size_t)seg * RS * CS + c;
 #pragma unroll
   for (int r = 0; r < RS; ++r) {
     if (FULL) a[r] = make_float2(0.f, 0.f);
-    if (FULL ? active : r < rows) a[r] = base[(size_t)r * P.sp];
+    if (FULL ? active : r < rows) a[r] = use_tma ? tsrc[r * CS] : base[(size_t)r * P.sp];
   }
   // ---- 1. local forward sweep, Horner sum
   float2 ap = make_float2(0.f, 0.f);
@@ -339,13 +372,18 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
   }
   if (MODE == kSweepAggregate) return;
   __syncthreads();
-  if (!active) return;
+  if (!active && !tma_store) return;
   // ---- 3. carried part of the forward sweep, backward sweep, scale, store
   // (Tried: the column tile moved by one bulk asynchronous copy per row, CS x 8 bytes each, into a bank-staggered
   // shared tile and back -- 16.5 -> 20.1 us at 2048^2, 1205 -> 1469 us at 8192^2 with 16-byte rows: the copy engine
   // is slow on such short transfers, profiles/r3d.)
-  const float2 ain = make_float2(sE[at], sE[CS * cp1 + at]);
-  float2 b = make_float2(sS[at], sS[CS * cp1 + at]);
+  float2 ain = make_float2(0.f, 0.f), b = ain;
+  if (active) {
+    ain = make_float2(sE[at], sE[CS * cp1 + at]);
+    b = make_float2(sS[at], sS[CS * cp1 + at]);
+  }
+  float2* const tdst = tile + (size_t)seg * RS * CS + c;
+  (void)tdst;
   // rho^n from rho, rho^2, rho^4, rho^8 (at most 4 roundings; n is a compile-time constant after unrolling)
   const float2 p1 = rho, p2 = make_float2(p1.x * p1.x, p1.y * p1.y), p4 = make_float2(p2.x * p2.x, p2.y * p2.y),
                p8 = make_float2(p4.x * p4.x, p4.y * p4.y);
@@ -371,22 +409,62 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec) {
     }
 }
 
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+
+// rank-2 float32 view of the spectrum: [rows][2 sp] floats, box = [RS rows][2 CS floats]
+bool make_strip_map(CUtensorMap* map, float2* spec, int sp, long long rows, int cs) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc || cs < 2) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * sp, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)sp * sizeof(float2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(2 * cs), (cuuint32_t)RS};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, spec, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CS, int MODE>
-int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P, int batch, float2* spec) {
+int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P0, int batch, float2* spec) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(cols_sweep_kernel<CS, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
+  ColSweepParams P = P0;
   int threads = ((CS * P.segs + 31) / 32) * 32;
-  size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float);  // the column-0 CTA needs nx doubles
-  const size_t col0 = (size_t)(MODE == kSweepApply ? P.nx_global : P.nx) * sizeof(double);
+  // Tensor copies (JAXIB_SWEEP_TMA=1; off by default).  Measured on B200 (profiles/r3j): bit-identical results, no gain
+  // -- 2048^2 16.58 vs 16.56 us, a 1024-row slab of 8192 columns (128-byte boxes) 27.1 vs 25.5 us, 4096^2 (32-byte
+  // boxes) 282 vs 274 us per step, 8192^2 on one GPU (16-byte boxes) 1302 vs 1197 us: the strip's rows are too short
+  // for the copy engine to beat plain loads.  A partial last segment clips at the tensor's last row, which only is the
+  // grid's last row for batch = 1.
+  const char* env_tma = getenv("JAXIB_SWEEP_TMA");
+  const bool tma_on = env_tma && atoi(env_tma) == 1;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  P.use_tma = 0;
+  if (tma_on && CS >= 2 && (P.nx % RS == 0 || batch == 1) && make_strip_map(&map, spec, P.sp, (long long)batch * P.nx, CS)) P.use_tma = 1;
+  size_t smem = (size_t)4 * CS * (32 * ((P.segs + 31) / 32) + 1) * sizeof(float) + 16;
+  if (P.use_tma) smem += (size_t)P.segs * RS * CS * sizeof(float2);
+  const size_t col0 = (size_t)(MODE == kSweepApply ? P.nx_global : P.nx) * sizeof(double);  // the column-0 CTA needs nx doubles
   if (col0 > smem) smem = col0;
   if (smem > 200 * 1024) { set_error("column sweep: %zu bytes of shared memory", smem); return JAXIB_ERR_UNSUPPORTED; }
   dim3 grid((P.ncols + CS - 1) / CS + 1, batch);
-  if (P.nx % RS == 0) launch_pdl(16, cols_sweep_kernel<CS, MODE, true>, grid, dim3(threads), smem, s, P, spec);
-  else launch_pdl(16, cols_sweep_kernel<CS, MODE, false>, grid, dim3(threads), smem, s, P, spec);
+  if (P.nx % RS == 0) launch_pdl(16, cols_sweep_kernel<CS, MODE, true>, grid, dim3(threads), smem, s, P, spec, map);
+  else launch_pdl(16, cols_sweep_kernel<CS, MODE, false>, grid, dim3(threads), smem, s, P, spec, map);
   return check_launch("cols_sweep_kernel");
 }
 
