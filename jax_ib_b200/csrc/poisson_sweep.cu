@@ -242,12 +242,11 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec, const __grid_cons
   // segment = lane m + j
   const int m = (segs + 31) / 32;
   const int cp1 = 32 * m + 1;                          // words per column
-  // TMA path (P.use_tma, opt-in: see the launcher for the measurements): the strip is moved by tensor copies, one
-  // [RS rows x CS columns] box per segment (cp.async.bulk.tensor.2d, UTMALDG / UTMASTG); the copy engine generates
-  // the strided row requests itself.  Boxes clip at the tensor's edges: partial strips and a partial last segment
-  // need no special case.
+  // TMA path (P.use_tma, opt-in: see the launcher for the measurements): the strip is LOADED by tensor copies, one
+  // [RS rows x CS columns] box per segment (cp.async.bulk.tensor.2d, UTMALDG); the copy engine generates the strided
+  // row requests itself.  Boxes clip at the tensor's edges: partial strips and a partial last segment need no
+  // special case.  The results are stored plainly (the loads showed no gain, so the store side was not built).
   const bool use_tma = P.use_tma != 0;
-  const bool tma_store = use_tma && strip != 0 && MODE != kSweepAggregate;  // strip 0 holds column 0 (real part: CTA 0's)
   float2* const tile = reinterpret_cast<float2*>(sw_raw);  // [segs][RS][CS]
   const size_t tile_floats = use_tma ? (size_t)segs * RS * CS * 2 : 0;
   float* const sE = reinterpret_cast<float*>(sw_raw) + tile_floats;  // e, later Ain
@@ -372,18 +371,13 @@ cols_sweep_kernel(ColSweepParams P, float2* __restrict__ spec, const __grid_cons
   }
   if (MODE == kSweepAggregate) return;
   __syncthreads();
-  if (!active && !tma_store) return;
+  if (!active) return;
   // ---- 3. carried part of the forward sweep, backward sweep, scale, store
   // (Tried: the column tile moved by one bulk asynchronous copy per row, CS x 8 bytes each, into a bank-staggered
   // shared tile and back -- 16.5 -> 20.1 us at 2048^2, 1205 -> 1469 us at 8192^2 with 16-byte rows: the copy engine
   // is slow on such short transfers, profiles/r3d.)
-  float2 ain = make_float2(0.f, 0.f), b = ain;
-  if (active) {
-    ain = make_float2(sE[at], sE[CS * cp1 + at]);
-    b = make_float2(sS[at], sS[CS * cp1 + at]);
-  }
-  float2* const tdst = tile + (size_t)seg * RS * CS + c;
-  (void)tdst;
+  const float2 ain = make_float2(sE[at], sE[CS * cp1 + at]);
+  float2 b = make_float2(sS[at], sS[CS * cp1 + at]);
   // rho^n from rho, rho^2, rho^4, rho^8 (at most 4 roundings; n is a compile-time constant after unrolling)
   const float2 p1 = rho, p2 = make_float2(p1.x * p1.x, p1.y * p1.y), p4 = make_float2(p2.x * p2.x, p2.y * p2.y),
                p8 = make_float2(p4.x * p4.x, p4.y * p4.y);
@@ -446,7 +440,7 @@ int launch_cols_sweep_t(cudaStream_t s, const ColSweepParams& P0, int batch, flo
   }
   ColSweepParams P = P0;
   int threads = ((CS * P.segs + 31) / 32) * 32;
-  // Tensor copies (JAXIB_SWEEP_TMA=1; off by default).  Measured on B200 (profiles/r3j): bit-identical results, no gain
+  // Tensor-copy loads (JAXIB_SWEEP_TMA=1; off by default).  Measured on B200 (profiles/r3j): bit-identical results, no gain
   // -- 2048^2 16.58 vs 16.56 us, a 1024-row slab of 8192 columns (128-byte boxes) 27.1 vs 25.5 us, 4096^2 (32-byte
   // boxes) 282 vs 274 us per step, 8192^2 on one GPU (16-byte boxes) 1302 vs 1197 us: the strip's rows are too short
   // for the copy engine to beat plain loads.  A partial last segment clips at the tensor's last row, which only is the

@@ -483,8 +483,8 @@ def test_sweeps_fused_into_the_row_kernels_match_the_column_sweep(shape, monkeyp
 # ------------------------------------------------------------------------------------------------ tensor-copy variant
 @pytest.mark.parametrize("shape", [(1024, 2048), (600, 600), (4096, 1024), (100, 40)])
 def test_column_sweep_with_tensor_copies_is_bitwise_the_plain_one(shape, monkeypatch):
-    """JAXIB_SWEEP_TMA=1: the column strip is moved by cp.async.bulk.tensor.2d boxes (one per 16-row segment) instead
-    of plain loads / stores (csrc/poisson_sweep.cu).  Same arithmetic on the same values: bit-identical, including
+    """JAXIB_SWEEP_TMA=1: the column strip is loaded by cp.async.bulk.tensor.2d boxes (one per 16-row segment) instead
+    of plain loads (csrc/poisson_sweep.cu).  Same arithmetic on the same values: bit-identical, including
     partial strips (301 and 21 columns), a partial last segment (600 and 100 rows: the boxes clip) and 32-byte boxes."""
     cfg = dict(configs.ib_periodic(1024, 1), shape=shape, bodies=None)
     cfg["domain"] = ((0.0, shape[0] * 0.025), (0.0, shape[1] * 0.025))
