@@ -225,6 +225,10 @@ typedef struct {
   int32_t world, rank;
   int32_t halo;                      /* halo rows on either side, in [2 * ib_window + 4, nloc]       */
   int32_t cpr;                       /* spectrum columns per slab: multiple of 8, world*cpr >= ny/2+4 */
+  int32_t seam_idle;                 /* host hint: no marker window reaches the periodic seam in this block of
+                                      * steps (rows < ib_window + 3 or >= nx - ib_window - 3): the first slab skips
+                                      * the top-marker forces and the seam-row spread.  0 = always run them.      */
+  int32_t reserved_;
   float* u[JAXIB_MAX_PEERS];         /* [nloc + 2 halo][ny], owned rows in the middle                */
   float* v[JAXIB_MAX_PEERS];
   float* p[JAXIB_MAX_PEERS];

@@ -288,7 +288,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
       switch (ph) {
         case 0:
           if ((rc = launch_explicit(s, gf_ext, u, v, p, nullptr, u_star, v_star, true))) return rc;
-          if (has_ib && own_lo == 0 && W > 1) {
+          if (has_ib && own_lo == 0 && W > 1 && !sl.seam_idle) {
             // first slab of several: forces of the markers at the top of the domain (disjoint marker set) and,
             // in phase 1, the seam row they feed -- on the side stream, next to the main IB kernels, so that
             // slab 0 is not 20 us behind the others at every barrier
@@ -308,7 +308,7 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
             if ((rc = launch_ib_spread_bodies(s, gf_ib, *bodies, state, sl.markers[me], u_star + (size_t)seg_a * ny,
                                               v_star + (size_t)seg_a * ny)))
               return rc;
-            if (own_lo == 0) {
+            if (own_lo == 0 && !sl.seam_idle) {
               const bool aside = W > 1 && side.stream;  // the seam row only depends on the top-marker forces
               if ((rc = launch_ib_spread_bodies(aside ? side.stream : s, gf_seam, *bodies, state, sl.markers[me],
                                                 u_star + (size_t)(halo - 1) * ny, v_star + (size_t)(halo - 1) * ny)))

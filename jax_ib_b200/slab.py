@@ -356,8 +356,9 @@ class PeerRank:
     load_global = SlabRank.load_global
     owned = SlabRank.owned
 
-    def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True):
+    def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True, seam_idle: bool = False):
         import ctypes as C
+        self.c_slab.seam_idle = 1 if seam_idle else 0
         if self.bodies is not None and getattr(self, "_tile_flags", None) is None:
             self._tile_flags = self.bodies.tile_flags(self.spec)  # this slab's own occupied-tile marks
         b = self.bodies.c_struct(self._tile_flags) if self.bodies is not None else None
@@ -476,6 +477,7 @@ class SlabStepper:
         if self.particles is not None:
             tab, times, centers = kinematics.body_schedule(self.particles, float(self.time), self.spec.dt, nsteps)
             table = torch.from_numpy(np.ascontiguousarray(tab[:, None])).to(self.device)  # [nsteps, 1, B, 8]
+            self._seam_idle = self._no_marker_near_the_seam(tab)
             self.time = times[-1]
             self.particles = dataclasses.replace(self.particles, particle_center=centers[-1])
         else:
@@ -483,8 +485,21 @@ class SlabStepper:
                 self.time = np.float32(self.time + np.float32(self.spec.dt))
         return table, centers
 
+    def _no_marker_near_the_seam(self, tab) -> bool:
+        """True when, at every step of the block, every body stays clear of the periodic seam by its radius plus the
+        spreading / interpolation reach: the first slab then has no top markers and no seam row to spread onto
+        (struct jaxib_slab.seam_idle).  tab: [nsteps, B, 8] host table (columns 2, 3 = centre)."""
+        bodies = self.ranks[0].bodies
+        if bodies is None:
+            return True
+        reach = bodies.max_radius + (self.spec.ib_window + 4) * self.spec.step[0]
+        lo, hi = self.spec.lower[0], self.spec.lower[0] + self.spec.nx * self.spec.step[0]
+        xc = np.asarray(tab)[:, :, 2]
+        return bool(((xc - reach) > lo).all() and ((xc + reach) < hi).all())
+
     def run(self, table, nsteps: int, profile: bool = False):
         """Device part of a block: enqueues `nsteps` steps on the current stream."""
+        idle = bool(getattr(self, "_seam_idle", False)) and table is not None
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
@@ -494,7 +509,7 @@ class SlabStepper:
                 for n in range(nsteps):
                     evs[n][0].record()
                     for ph in range(4):
-                        self.ranks[0].run(None if tab is None else tab[n:n + 1], 1, ph, ph)
+                        self.ranks[0].run(None if tab is None else tab[n:n + 1], 1, ph, ph, seam_idle=idle)
                         evs[n][ph + 1].record()
                 torch.cuda.synchronize()
                 self.last_profile = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in evs) for k, nm in enumerate(names)}
@@ -502,12 +517,12 @@ class SlabStepper:
                 return
             if not self.virtual:
                 self._host_barrier()
-                self.ranks[0].run(tab, nsteps)  # one C call: 4 phases x nsteps with flag barriers
+                self.ranks[0].run(tab, nsteps, seam_idle=idle)  # one C call: 4 phases x nsteps with flag barriers
             else:  # several slabs of one GPU: lockstep, phase by phase (a flag barrier would deadlock here)
                 for n in range(nsteps):
                     for ph in range(4):
                         for r in self.ranks:
-                            r.run(None if tab is None else tab[n:n + 1], 1, ph, ph, barriers=False)
+                            r.run(None if tab is None else tab[n:n + 1], 1, ph, ph, barriers=False, seam_idle=idle)
             self.last_profile = None
             return
         prof = None
