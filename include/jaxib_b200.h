@@ -228,6 +228,9 @@ typedef struct {
   int32_t seam_idle;                 /* host hint: no marker window reaches the periodic seam in this block of
                                       * steps (rows < ib_window + 3 or >= nx - ib_window - 3): the first slab skips
                                       * the top-marker forces and the seam-row spread.  0 = always run them.      */
+  int32_t body_first, body_count;    /* host hint (0 count = all): in this block of steps only the bodies
+                                      * [body_first, body_first + body_count) and their markers                    */
+  int32_t marker_first, marker_count;/* [marker_first, marker_first + marker_count) come near this slab's rows     */
   int32_t reserved_;
   float* u[JAXIB_MAX_PEERS];         /* [nloc + 2 halo][ny], owned rows in the middle                */
   float* v[JAXIB_MAX_PEERS];

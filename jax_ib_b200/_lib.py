@@ -48,7 +48,8 @@ class Slab(C.Structure):
     """struct jaxib_slab."""
 
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("halo", C.c_int32), ("cpr", C.c_int32),
-                ("seam_idle", C.c_int32), ("reserved_", C.c_int32)] + [
+                ("seam_idle", C.c_int32), ("body_first", C.c_int32), ("body_count", C.c_int32),
+                ("marker_first", C.c_int32), ("marker_count", C.c_int32), ("reserved_", C.c_int32)] + [
         (name, C.c_void_p * MAX_PEERS) for name in ("u", "v", "p", "markers", "colbuf", "specbuf", "flags")]
 
 

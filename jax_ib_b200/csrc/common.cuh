@@ -124,10 +124,15 @@ struct StageHook {
 };
 int launch_ib_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
                     float* u_star, float* v_star, float* marker_scratch, const StageHook* hook = nullptr);
+// Optional restriction of the two fused IB kernels to a range of bodies and of their markers (slab decomposition:
+// the bodies near a slab, a host hint; counts of 0 = everything)
+struct BodyRange {
+  int body_first, body_count, marker_first, marker_count;
+};
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers);
+                           const float* u_star, const float* v_star, float* markers, const BodyRange* range = nullptr);
 int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                            const float* markers, float* u_star, float* v_star);
+                            const float* markers, float* u_star, float* v_star, const BodyRange* range = nullptr);
 bool launch_explicit_fast(cudaStream_t s, const GridF& g, const float* u, const float* v, const float* p,
                           const float* perm, float* out_u, float* out_v, bool predictor, int* rc);
 // Row ranges of one predictor launch (stencil_ring.cu): the rows near the bodies are computed first so that the

@@ -126,15 +126,19 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
                                     const float4* __restrict__ pack, const float* __restrict__ body_state,
                                     const float* __restrict__ u_star, const float* __restrict__ v_star,
                                     float* __restrict__ markers, int* __restrict__ tile_flags, int half_extent,
-                                    int tiles_per_axis) {
+                                    int tiles_per_axis, int marker_first, int marker_count) {
   // one warp per (marker, velocity component): halves the dependent chain of the latency-bound kernel.
   // Dependent memory round trips: [x0, y0, pack] -> [body state] -> [window of u*] -> store.
   pdl_trigger();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int gw = wid >> 1, comp = wid & 1;
+  const int lw = wid >> 1, comp = wid & 1;
+  // marker_count > 0: only the markers [marker_first, marker_first + marker_count) (slab decomposition: the bodies
+  // near this slab, a host hint)
+  const int mcount = marker_count > 0 ? marker_count : n_markers;
+  if (lw >= g.batch * mcount) return;
+  const int s = lw / mcount, k = marker_first + (lw - s * mcount);
+  const int gw = s * n_markers + k;  // index into the marker arrays
   const int total = g.batch * n_markers;
-  if (gw >= total) return;
-  const int s = gw / n_markers, k = gw - s * n_markers;
   // body-frame data is constant over the run: fetched before the dependency wait (prologue under the
   // predictor's tail when launched programmatically)
   const float ax = __ldg(x0 + k), ay = __ldg(y0 + k);
@@ -354,14 +358,14 @@ spread_bodies_kernel(GridF g, int n_bodies, int n_markers, const int32_t* __rest
                      const float* __restrict__ body_state, const float* __restrict__ markers, int half_extent,
                      int tiles_per_axis, float* __restrict__ u_star, float* __restrict__ v_star,
                      int* __restrict__ tile_flags, const float* __restrict__ x0, const float* __restrict__ y0,
-                     const float4* __restrict__ pack, int early_cull) {
+                     const float4* __restrict__ pack, int early_cull, int body_first) {
   __shared__ SpreadShared sh;
   extern __shared__ int sbody[];  // ic[n_bodies] | jc[n_bodies] | offset[n_bodies + 1]
   int* const sic = sbody;
   int* const sjc = sbody + n_bodies;
   int* const soff = sbody + 2 * n_bodies;
   pdl_trigger();
-  const int b = blockIdx.y;
+  const int b = body_first + blockIdx.y;  // body_first > 0: the launch covers a range of bodies (slab hint)
   const int s = blockIdx.z >> 1, comp = blockIdx.z & 1;
   const Mesh m = comp == 0 ? make_mesh(g, 1.0f, 0.5f) : make_mesh(g, 0.5f, 1.0f);
   const float* states = body_state + (size_t)s * n_bodies * JAXIB_BODY_STATE_STRIDE;
@@ -664,11 +668,13 @@ int launch_ib_interp(cudaStream_t s, const GridF& g, float off_x, float off_y, c
 }
 
 int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                           const float* u_star, const float* v_star, float* markers) {
+                           const float* u_star, const float* v_star, float* markers, const BodyRange* range) {
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   const int threads = 128;
-  const long long total = (long long)g.batch * b.n_markers * 2 * 32;
+  const int m_first = range && range->marker_count > 0 ? range->marker_first : 0;
+  const int m_count = range && range->marker_count > 0 ? range->marker_count : 0;
+  const long long total = (long long)g.batch * (m_count > 0 ? m_count : b.n_markers) * 2 * 32;
   const unsigned nblk = (unsigned)((total + threads - 1) / threads);
   int half_extent, tiles;
   spread_geometry(g, b, &half_extent, &tiles);
@@ -677,21 +683,23 @@ int launch_ib_marker_force(cudaStream_t s, const GridF& g, const jaxib_bodies& b
   if (g.R == 6)
     launch_pdl(2, interp_force_kernel<6>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
                b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers, flags, half_extent,
-               tiles);
+               tiles, m_first, m_count);
   else
     launch_pdl(2, interp_force_kernel<0>, dim3(nblk), dim3(threads), 0, s, g, b.n_bodies, b.n_markers, b.body_offset, b.x0,
                b.y0, reinterpret_cast<const float4*>(b.marker_pack), body_state, u_star, v_star, markers, flags, half_extent,
-               tiles);
+               tiles, m_first, m_count);
   return check_launch("interp_force_kernel");
 }
 
 int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& b, const float* body_state,
-                            const float* markers, float* u_star, float* v_star) {
+                            const float* markers, float* u_star, float* v_star, const BodyRange* range) {
   if (b.n_markers <= 0 || b.n_bodies <= 0) return JAXIB_OK;
   if (g.R < 1 || g.R > 16) { set_error("ib_window R=%d outside [1,16]", g.R); return JAXIB_ERR_UNSUPPORTED; }
   int half_extent, tiles;
   spread_geometry(g, b, &half_extent, &tiles);
-  dim3 grid(tiles * tiles, b.n_bodies, g.batch * 2), block(SPREAD_THREADS);
+  const int b_first = range && range->body_count > 0 ? range->body_first : 0;
+  const int b_count = range && range->body_count > 0 ? range->body_count : b.n_bodies;
+  dim3 grid(tiles * tiles, b_count, g.batch * 2), block(SPREAD_THREADS);
   const size_t smem = (size_t)(3 * b.n_bodies + 1) * sizeof(int);
   if (smem > 40 * 1024) { set_error("ib_spread_bodies: %d bodies exceed the shared-memory body table", b.n_bodies); return JAXIB_ERR_UNSUPPORTED; }
   const long long need = (long long)g.batch * b.n_bodies * 2 * tiles * tiles;
@@ -701,7 +709,7 @@ int launch_ib_spread_bodies(cudaStream_t s, const GridF& g, const jaxib_bodies& 
   // is the cheaper test (measured, ens1024: 74 us with the mark first, 113 us with the cull first).
   const int early_cull = (long long)grid.x * grid.y * grid.z <= 4096 ? 1 : 0;
   launch_pdl(4, spread_bodies_kernel, grid, block, smem, s, g, b.n_bodies, b.n_markers, b.body_offset, body_state, markers,
-             half_extent, tiles, u_star, v_star, flags, b.x0, b.y0, reinterpret_cast<const float4*>(b.marker_pack), early_cull);
+             half_extent, tiles, u_star, v_star, flags, b.x0, b.y0, reinterpret_cast<const float4*>(b.marker_pack), early_cull, b_first);
   return check_launch("spread_bodies_kernel");
 }
 

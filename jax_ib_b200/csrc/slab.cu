@@ -280,6 +280,17 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
     if (split_cols >= cpr) split_cols = 0;
   }
   const size_t state_stride = has_ib ? (size_t)bodies->n_bodies * JAXIB_BODY_STATE_STRIDE : 0;
+  // host hint: the bodies (and their markers) that come near this slab during the block; everything else is skipped
+  BodyRange range = {sl.body_first, sl.body_count, sl.marker_first, sl.marker_count};
+  const BodyRange* rg = nullptr;
+  if (has_ib && sl.body_count > 0 && sl.marker_count > 0) {
+    if (sl.body_first < 0 || sl.body_first + sl.body_count > bodies->n_bodies || sl.marker_first < 0 ||
+        sl.marker_first + sl.marker_count > bodies->n_markers) {
+      set_error("slab_step: body / marker range hint outside the bodies");
+      return JAXIB_ERR_INVALID;
+    }
+    rg = &range;
+  }
 
   for (int n = 0; n < nsteps; ++n) {
     const uint32_t ep = ++(*epoch);
@@ -300,13 +311,13 @@ extern "C" int jaxib_slab_step(jaxib_stream_t stream, const jaxib_plan* plan_row
             if ((rc = launch_ib_marker_force(st, gf_top, *bodies, state, u_star, v_star, sl.markers[me]))) return rc;
           }
           if (has_ib && (rc = launch_ib_marker_force(s, gf_ib, *bodies, state, u_star + (size_t)seg_a * ny,
-                                                     v_star + (size_t)seg_a * ny, sl.markers[me])))
+                                                     v_star + (size_t)seg_a * ny, sl.markers[me], rg)))
             return rc;
           break;
         case 1:
           if (has_ib) {
             if ((rc = launch_ib_spread_bodies(s, gf_ib, *bodies, state, sl.markers[me], u_star + (size_t)seg_a * ny,
-                                              v_star + (size_t)seg_a * ny)))
+                                              v_star + (size_t)seg_a * ny, rg)))
               return rc;
             if (own_lo == 0 && !sl.seam_idle) {
               const bool aside = W > 1 && side.stream;  // the seam row only depends on the top-marker forces

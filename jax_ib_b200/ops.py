@@ -161,6 +161,7 @@ class DeviceBodies:
         x0 = np.concatenate([np.asarray(x, dtype=np.float32) for x in x0_list]) if sizes else np.zeros(0, np.float32)
         y0 = np.concatenate([np.asarray(y, dtype=np.float32) for y in y0_list]) if sizes else np.zeros(0, np.float32)
         self.max_radius = float(np.sqrt(x0.astype(np.float64) ** 2 + y0.astype(np.float64) ** 2).max()) if sizes else 0.0
+        self.offset_host = off  # marker range of every body (host copy: slab hints)
         self.body_offset = torch.from_numpy(off).to(device)
         self.x0 = torch.from_numpy(x0).to(device)
         self.y0 = torch.from_numpy(y0).to(device)

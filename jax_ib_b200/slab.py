@@ -356,9 +356,17 @@ class PeerRank:
     load_global = SlabRank.load_global
     owned = SlabRank.owned
 
-    def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True, seam_idle: bool = False):
+    def run(self, table, nsteps: int, phase_lo: int = 0, phase_hi: int = 3, barriers: bool = True, seam_idle: bool = False,
+            body_range=None):
         import ctypes as C
         self.c_slab.seam_idle = 1 if seam_idle else 0
+        b0, b1 = body_range if body_range is not None else (0, 0)
+        self.c_slab.body_first, self.c_slab.body_count = int(b0), int(b1 - b0)
+        if b1 > b0:
+            off = self.bodies.offset_host
+            self.c_slab.marker_first, self.c_slab.marker_count = int(off[b0]), int(off[b1] - off[b0])
+        else:
+            self.c_slab.marker_first = self.c_slab.marker_count = 0
         if self.bodies is not None and getattr(self, "_tile_flags", None) is None:
             self._tile_flags = self.bodies.tile_flags(self.spec)  # this slab's own occupied-tile marks
         b = self.bodies.c_struct(self._tile_flags) if self.bodies is not None else None
@@ -478,6 +486,7 @@ class SlabStepper:
             tab, times, centers = kinematics.body_schedule(self.particles, float(self.time), self.spec.dt, nsteps)
             table = torch.from_numpy(np.ascontiguousarray(tab[:, None])).to(self.device)  # [nsteps, 1, B, 8]
             self._seam_idle = self._no_marker_near_the_seam(tab)
+            self._body_ranges = {r.lay.rank: self._bodies_near(r.lay, tab) for r in self.ranks} if self.peer else {}
             self.time = times[-1]
             self.particles = dataclasses.replace(self.particles, particle_center=centers[-1])
         else:
@@ -497,9 +506,29 @@ class SlabStepper:
         xc = np.asarray(tab)[:, :, 2]
         return bool(((xc - reach) > lo).all() and ((xc + reach) < hi).all())
 
+    def _bodies_near(self, lay, tab):
+        """(first, last + 1) of the bodies that can touch slab `lay` during the block -- a contiguous superset, what
+        struct jaxib_slab.body_first / body_count restrict the two IB kernels to; None = all bodies.  A body counts
+        when its centre track, widened by its radius plus the interpolation and spreading reach (2 R + 8 cells, more
+        than the 2 R + 4 halo), overlaps the slab's rows; the first / last slab also own everything off the grid."""
+        bodies = self.ranks[0].bodies
+        if bodies is None or bodies.n_bodies < 2:
+            return None
+        dx = self.spec.step[0]
+        reach = bodies.max_radius + (2 * self.spec.ib_window + 8) * dx
+        xc = np.asarray(tab)[:, :, 2] - self.spec.lower[0]
+        lo, hi = xc.min(axis=0) - reach, xc.max(axis=0) + reach
+        a = -np.inf if lay.rank == 0 else lay.own_lo * dx
+        b = np.inf if lay.rank == lay.world - 1 else lay.own_hi * dx
+        near = np.nonzero((hi >= a) & (lo <= b))[0]
+        if near.size == 0:
+            return (0, 1)  # nothing comes near: one body keeps the launches well-formed (its tiles leave at once)
+        return (int(near.min()), int(near.max()) + 1)
+
     def run(self, table, nsteps: int, profile: bool = False):
         """Device part of a block: enqueues `nsteps` steps on the current stream."""
         idle = bool(getattr(self, "_seam_idle", False)) and table is not None
+        ranges = getattr(self, "_body_ranges", {}) if table is not None else {}
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
@@ -509,7 +538,8 @@ class SlabStepper:
                 for n in range(nsteps):
                     evs[n][0].record()
                     for ph in range(4):
-                        self.ranks[0].run(None if tab is None else tab[n:n + 1], 1, ph, ph, seam_idle=idle)
+                        self.ranks[0].run(None if tab is None else tab[n:n + 1], 1, ph, ph, seam_idle=idle,
+                                          body_range=ranges.get(self.ranks[0].lay.rank))
                         evs[n][ph + 1].record()
                 torch.cuda.synchronize()
                 self.last_profile = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in evs) for k, nm in enumerate(names)}
@@ -517,12 +547,13 @@ class SlabStepper:
                 return
             if not self.virtual:
                 self._host_barrier()
-                self.ranks[0].run(tab, nsteps, seam_idle=idle)  # one C call: 4 phases x nsteps with flag barriers
+                self.ranks[0].run(tab, nsteps, seam_idle=idle, body_range=ranges.get(self.ranks[0].lay.rank))  # one C call: 4 phases x nsteps with flag barriers
             else:  # several slabs of one GPU: lockstep, phase by phase (a flag barrier would deadlock here)
                 for n in range(nsteps):
                     for ph in range(4):
                         for r in self.ranks:
-                            r.run(None if tab is None else tab[n:n + 1], 1, ph, ph, barriers=False, seam_idle=idle)
+                            r.run(None if tab is None else tab[n:n + 1], 1, ph, ph, barriers=False, seam_idle=idle,
+                                  body_range=ranges.get(r.lay.rank))
             self.last_profile = None
             return
         prof = None

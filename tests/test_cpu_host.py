@@ -193,7 +193,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     probes = {
         "jaxib_grid": ["nx", "dt", "bc", "force", "ib_window", "row0", "own_hi", "nx_global"],
         "jaxib_bodies": ["n_markers", "body_offset", "y0", "max_radius"],
-        "jaxib_slab": ["rank", "cpr", "seam_idle", "u", "markers", "colbuf", "specbuf", "flags"],
+        "jaxib_slab": ["rank", "cpr", "seam_idle", "body_first", "marker_count", "u", "markers", "colbuf", "specbuf", "flags"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "jaxib_b200.h"', "int main(void) {"]
     for st, fields in probes.items():
