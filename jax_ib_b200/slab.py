@@ -487,6 +487,7 @@ class SlabStepper:
             table = torch.from_numpy(np.ascontiguousarray(tab[:, None])).to(self.device)  # [nsteps, 1, B, 8]
             self._seam_idle = self._no_marker_near_the_seam(tab)
             self._body_ranges = {r.lay.rank: self._bodies_near(r.lay, tab) for r in self.ranks} if self.peer else {}
+            self._hints_for = table.data_ptr()  # the hints describe THIS table: run() ignores them for any other
             self.time = times[-1]
             self.particles = dataclasses.replace(self.particles, particle_center=centers[-1])
         else:
@@ -527,8 +528,9 @@ class SlabStepper:
 
     def run(self, table, nsteps: int, profile: bool = False):
         """Device part of a block: enqueues `nsteps` steps on the current stream."""
-        idle = bool(getattr(self, "_seam_idle", False)) and table is not None
-        ranges = getattr(self, "_body_ranges", {}) if table is not None else {}
+        hinted = table is not None and getattr(self, "_hints_for", None) == table.data_ptr()
+        idle = hinted and bool(getattr(self, "_seam_idle", False))
+        ranges = getattr(self, "_body_ranges", {}) if hinted else {}
         if self.peer:
             tab = None if table is None else table.view(nsteps, -1, 8)
             if not self.virtual and profile:  # measurement only: one call per phase, bracketed by events
