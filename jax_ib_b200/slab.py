@@ -262,6 +262,34 @@ class SlabRank:
         return lo_send, hi_send, lo_recv, hi_recv
 
 
+def seam_is_idle(xc, max_radius: float, ib_window: int, dx: float, lower: float, nx: int) -> bool:
+    """Host hint `jaxib_slab.seam_idle`: True when, at every step of the block (xc: [nsteps, B] body-centre x), every
+    body stays clear of both ends of the periodic x-range by its radius plus the spreading / interpolation reach, so
+    the first slab has no top markers and no seam row to spread onto."""
+    reach = max_radius + (ib_window + 4) * dx
+    xc = np.asarray(xc, dtype=np.float64)
+    return bool(((xc - reach) > lower).all() and ((xc + reach) < lower + nx * dx).all())
+
+
+def bodies_near(xc, max_radius: float, ib_window: int, dx: float, lower: float, own_lo: int, own_hi: int, first: bool,
+                last: bool):
+    """Host hint `jaxib_slab.body_first / body_count`: (first, last + 1) of the bodies that can touch the slab
+    of rows [own_lo, own_hi) during the block -- a contiguous superset; None = all bodies.  A body counts when its
+    centre track, widened by its radius plus the interpolation and spreading reach (2 R + 8 cells, more than the
+    2 R + 4 halo), overlaps the slab's rows; the first / last slab also own everything off the grid."""
+    xc = np.asarray(xc, dtype=np.float64) - lower
+    if xc.ndim != 2 or xc.shape[1] < 2:
+        return None
+    reach = max_radius + (2 * ib_window + 8) * dx
+    lo, hi = xc.min(axis=0) - reach, xc.max(axis=0) + reach
+    a = -np.inf if first else own_lo * dx
+    b = np.inf if last else own_hi * dx
+    near = np.nonzero((hi >= a) & (lo <= b))[0]
+    if near.size == 0:
+        return (0, 1)  # nothing comes near: one body keeps the launches well-formed (its tiles leave at once)
+    return (int(near.min()), int(near.max()) + 1)
+
+
 PHASES = ("predict_force", "spread_rows_fwd", "x_transpose_fwd", "cols", "x_transpose_inv", "rows_inv", "x_halos")
 
 
@@ -496,35 +524,18 @@ class SlabStepper:
         return table, centers
 
     def _no_marker_near_the_seam(self, tab) -> bool:
-        """True when, at every step of the block, every body stays clear of the periodic seam by its radius plus the
-        spreading / interpolation reach: the first slab then has no top markers and no seam row to spread onto
-        (struct jaxib_slab.seam_idle).  tab: [nsteps, B, 8] host table (columns 2, 3 = centre)."""
         bodies = self.ranks[0].bodies
         if bodies is None:
             return True
-        reach = bodies.max_radius + (self.spec.ib_window + 4) * self.spec.step[0]
-        lo, hi = self.spec.lower[0], self.spec.lower[0] + self.spec.nx * self.spec.step[0]
-        xc = np.asarray(tab)[:, :, 2]
-        return bool(((xc - reach) > lo).all() and ((xc + reach) < hi).all())
+        return seam_is_idle(np.asarray(tab)[:, :, 2], bodies.max_radius, self.spec.ib_window, self.spec.step[0],
+                            self.spec.lower[0], self.spec.nx)
 
     def _bodies_near(self, lay, tab):
-        """(first, last + 1) of the bodies that can touch slab `lay` during the block -- a contiguous superset, what
-        struct jaxib_slab.body_first / body_count restrict the two IB kernels to; None = all bodies.  A body counts
-        when its centre track, widened by its radius plus the interpolation and spreading reach (2 R + 8 cells, more
-        than the 2 R + 4 halo), overlaps the slab's rows; the first / last slab also own everything off the grid."""
         bodies = self.ranks[0].bodies
-        if bodies is None or bodies.n_bodies < 2:
+        if bodies is None:
             return None
-        dx = self.spec.step[0]
-        reach = bodies.max_radius + (2 * self.spec.ib_window + 8) * dx
-        xc = np.asarray(tab)[:, :, 2] - self.spec.lower[0]
-        lo, hi = xc.min(axis=0) - reach, xc.max(axis=0) + reach
-        a = -np.inf if lay.rank == 0 else lay.own_lo * dx
-        b = np.inf if lay.rank == lay.world - 1 else lay.own_hi * dx
-        near = np.nonzero((hi >= a) & (lo <= b))[0]
-        if near.size == 0:
-            return (0, 1)  # nothing comes near: one body keeps the launches well-formed (its tiles leave at once)
-        return (int(near.min()), int(near.max()) + 1)
+        return bodies_near(np.asarray(tab)[:, :, 2], bodies.max_radius, self.spec.ib_window, self.spec.step[0],
+                           self.spec.lower[0], lay.own_lo, lay.own_hi, lay.rank == 0, lay.rank == lay.world - 1)
 
     def run(self, table, nsteps: int, profile: bool = False):
         """Device part of a block: enqueues `nsteps` steps on the current stream."""

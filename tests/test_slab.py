@@ -314,3 +314,34 @@ def test_slabs_on_several_gpus_match_single_gpu(mode):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "SLAB_CHECK OK" in res.stdout
+
+
+# ---- host hints of the peer-memory slab step (pure host logic) --------------------------------------------------
+def test_slab_hints_are_conservative_supersets():
+    """`jaxib_slab.seam_idle` / `body_first, body_count` (slab.seam_is_idle, slab.bodies_near): every body whose markers
+    can reach a slab's rows (radius + the 2 R + 4 halo rows the kernels read) during the block must be inside the
+    hinted range; bodies far away are left out; the first / last slab own everything off the grid."""
+    dx, R, nx, world = 0.025, 6, 8192, 8
+    nloc = nx // world
+    rng = np.random.default_rng(1)
+    radius = 0.5
+    base = (np.arange(64) // 8 + 0.5) * 25.6                       # the G4 lattice: 8 bodies per slab, sorted by x
+    xc = base[None, :] + 2.8 * np.sin(np.linspace(0, 1.0, 50))[:, None] * rng.uniform(-1, 1, 64)[None, :]
+    assert slab.seam_is_idle(xc, radius, R, dx, 0.0, nx)
+    assert not slab.seam_is_idle(np.concatenate([xc, np.full((50, 1), 0.3)], 1), radius, R, dx, 0.0, nx)
+    assert not slab.seam_is_idle(np.concatenate([xc, np.full((50, 1), nx * dx - 0.3)], 1), radius, R, dx, 0.0, nx)
+    for r in range(world):
+        b0, b1 = slab.bodies_near(xc, radius, R, dx, 0.0, r * nloc, (r + 1) * nloc, r == 0, r == world - 1)
+        # brute force: rows any marker of body k can touch (centre track +- radius, +- the halo the kernels read)
+        lo = (xc.min(0) - radius) / dx - (2 * R + 4)
+        hi = (xc.max(0) + radius) / dx + (2 * R + 4)
+        must = np.nonzero((hi >= r * nloc) & (lo <= (r + 1) * nloc))[0]
+        assert must.size and b0 <= must.min() and must.max() < b1
+        assert b1 - b0 <= 24                                       # and it does prune: 8-16 of the 64 bodies (+ neighbours)
+    # bodies off the grid belong to the first / last slab; unordered bodies give the covering range
+    odd = np.array([[-0.4, 100.0, 205.5, 50.0]])
+    assert slab.bodies_near(odd, radius, R, dx, 0.0, 0, nloc, True, False) == (0, 1)
+    assert slab.bodies_near(odd, radius, R, dx, 0.0, 7 * nloc, 8 * nloc, False, True) == (2, 3)
+    assert slab.bodies_near(odd, radius, R, dx, 0.0, 3 * nloc, 5 * nloc, False, False) == (1, 2)   # 100.0 = row 4000
+    assert slab.bodies_near(odd, radius, R, dx, 0.0, 1 * nloc, 2 * nloc, False, False) == (3, 4)   # 50.0 = row 2000
+    assert slab.bodies_near(odd[:, :1], radius, R, dx, 0.0, 0, nloc, True, False) is None          # one body: no range
