@@ -96,8 +96,7 @@ bool pdl_enabled(int kernel_bit);  // JAXIB_PDL_MASK (default all) selects the k
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int kernel_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
