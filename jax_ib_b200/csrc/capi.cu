@@ -112,7 +112,7 @@ static bool body_row_bands(const GridF& g, const jaxib_bodies& b, const float* s
   std::vector<std::pair<int, int>> iv;
   for (int k = 0; k < b.n_bodies; ++k) {
     const float xc = state_host[(size_t)k * JAXIB_BODY_STATE_STRIDE + 2];
-    const int ic = (int)floorf(xc / g.dx - 1.0f);
+    const int ic = (int)floorf((xc - g.lower_x) / g.dx - 1.0f);
     int a = ic - he - 2, e = ic + he + 3;
     if (a < 0) a = 0;
     if (e > g.nx) e = g.nx;

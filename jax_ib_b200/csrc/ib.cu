@@ -37,9 +37,11 @@ __device__ __forceinline__ float mesh_coord(float lower, int i, float off, float
   // grids.py:665: lower + (arange + offset) * step, each op rounded to float32
   return __fadd_rn(lower, __fmul_rn(__fadd_rn((float)i, off), h));
 }
-__device__ __forceinline__ int cell_index(float x, float h, float off) {
-  // IBM_Force.py:35: floor(xp/dx - offset)
-  return (int)floorf(__fsub_rn(__fdiv_rn(x, h), off));
+__device__ __forceinline__ int cell_index(float x, float lower, float h, float off) {
+  // The cell whose mesh point lower + (i + offset) * h lies at or just below x: floor((x - lower)/h - offset).
+  // IBM_Force.py:35 writes xp/dx - offset (its domains start at 0); x - 0 is exact, so the two agree bit for bit
+  // there, and a domain with a non-zero origin keeps the window centred on the marker.
+  return (int)floorf(__fsub_rn(__fdiv_rn(__fsub_rn(x, lower), h), off));
 }
 __device__ __forceinline__ float gauss(float x, float x0, float w, float pref) {
   float z = __fdiv_rn(__fsub_rn(x, x0), w);
@@ -76,7 +78,7 @@ __device__ __forceinline__ float interp_marker(const Mesh& m, const float* __res
   const int lane = threadIdx.x & 31;
   const int R = RT > 0 ? RT : m.R;
   const int W = 2 * R;
-  const int ik = cell_index(xp, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.dy, m.off_y);
+  const int ik = cell_index(xp, m.lower_x, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.lower_y, m.dy, m.off_y);
   if (ik_out) { *ik_out = ik + m.row0; *jk_out = jk; }
   const int ia = ik - R + 1, ja = jk - R + 1;
   float gx = 0.0f, gy = 0.0f;
@@ -172,7 +174,7 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
   // slab decomposition: a slab only needs the forces of the markers near its rows (u-cell row in
   // [own_lo, own_hi)); the entries of the others are left untouched -- no cell of the slab sees them --
   // and their window sums are skipped (warp-uniform)
-  const int iku = cell_index(xp, g.dx, 1.0f);
+  const int iku = cell_index(xp, g.lower_x, g.dx, 1.0f);
   const bool wanted = g.own_hi <= g.own_lo || (iku >= g.own_lo && iku < g.own_hi);
   float U = 0.0f;
   if (wanted) U = interp_marker<RT>(m, (comp == 0 ? u_star : v_star) + s * plane, xp, yp, nullptr, nullptr);
@@ -181,8 +183,8 @@ __global__ void interp_force_kernel(GridF g, int n_bodies, int n_markers, const 
     // touches: spread_bodies_kernel skips every other tile at once and clears the marks it consumes
     const int lane = threadIdx.x & 31;
     const int R = RT > 0 ? RT : g.R;
-    const int ik = cell_index(xp, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.dy, m.off_y);
-    const int ti0 = cell_index(xc, m.dx, m.off_x) - m.row0 - half_extent, tj0 = cell_index(yc, m.dy, m.off_y) - half_extent;
+    const int ik = cell_index(xp, m.lower_x, m.dx, m.off_x) - m.row0, jk = cell_index(yp, m.lower_y, m.dy, m.off_y);
+    const int ti0 = cell_index(xc, m.lower_x, m.dx, m.off_x) - m.row0 - half_extent, tj0 = cell_index(yc, m.lower_y, m.dy, m.off_y) - half_extent;
     const int ta = max((ik - R + 1 - ti0) >> 3, 0), tb = min((ik + R - ti0) >> 3, tiles_per_axis - 1);
     const int tc = max((jk - R + 1 - tj0) >> 3, 0), td = min((jk + R - tj0) >> 3, tiles_per_axis - 1);
     const int ny_t = td - tc + 1, nt = (tb - ta + 1) * ny_t;
@@ -245,8 +247,8 @@ __device__ float gather_markers(SpreadShared& sh, const Mesh& m, const float* __
       xp = mxp[k]; yp = myp[k];
       // IBM_Force.py:67: F * delta(r, 0, dx) * dS -- the marker's constant factor F * pref * dS
       c = mF[k] * m.pref_x * mdS[k];
-      ik = cell_index(xp, m.dx, m.off_x) - m.row0;
-      jk = cell_index(yp, m.dy, m.off_y);
+      ik = cell_index(xp, m.lower_x, m.dx, m.off_x) - m.row0;
+      jk = cell_index(yp, m.lower_y, m.dy, m.off_y);
       keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
     }
     const unsigned ballot = __ballot_sync(FULL, keep);
@@ -312,8 +314,8 @@ __device__ int cull_markers_early(SpreadShared& sh, const Mesh& m, const float* 
       const float4 pk = __ldg(pack + k);
       xp = __fadd_rn(__fsub_rn(__fmul_rn(ax, c), __fmul_rn(ay, sn)), xc);
       yp = __fadd_rn(__fadd_rn(__fmul_rn(ax, sn), __fmul_rn(ay, c)), yc);
-      ik = cell_index(xp, m.dx, m.off_x) - m.row0;
-      jk = cell_index(yp, m.dy, m.off_y);
+      ik = cell_index(xp, m.lower_x, m.dx, m.off_x) - m.row0;
+      jk = cell_index(yp, m.lower_y, m.dy, m.off_y);
       keep = (ik + m.R >= ti0) && (ik - m.R + 1 < ti0 + TS) && (jk + m.R >= tj0) && (jk - m.R + 1 < tj0 + TS);
       if (keep) {  // arc length to the next marker of the closed curve (interp_force_kernel, IBM_Force.py:59-63)
         const float xq = __fadd_rn(__fsub_rn(__fmul_rn(pk.x, c), __fmul_rn(pk.y, sn)), xc);
@@ -346,8 +348,8 @@ __device__ int cull_markers_early(SpreadShared& sh, const Mesh& m, const float* 
 }
 
 __device__ __forceinline__ void body_box(const float* st, const Mesh& m, int& ic, int& jc) {
-  ic = cell_index(st[2], m.dx, m.off_x) - m.row0;
-  jc = cell_index(st[3], m.dy, m.off_y);
+  ic = cell_index(st[2], m.lower_x, m.dx, m.off_x) - m.row0;
+  jc = cell_index(st[3], m.lower_y, m.dy, m.off_y);
 }
 
 // grid = (tiles_per_axis^2, n_bodies, batch * 2); block = SPREAD_THREADS; dynamic smem: (3 n_bodies + 1) ints
@@ -499,7 +501,7 @@ __global__ void bbox_kernel(GridF g, float off_x, float off_y, const float* __re
                             const float* __restrict__ yp, int n, int* __restrict__ box) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  int ik = cell_index(xp[k], g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.dy, off_y);
+  int ik = cell_index(xp[k], g.lower_x, g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.lower_y, g.dy, off_y);
   atomicMin(box + 0, ik); atomicMax(box + 1, ik);
   atomicMin(box + 2, jk); atomicMax(box + 3, jk);
 }
@@ -545,7 +547,7 @@ __global__ void bin_count_kernel(GridF g, float off_x, float off_y, const float*
                                  const float* __restrict__ yp, int n, int bnx, int bny, int* __restrict__ count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int ik = cell_index(xp[k], g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.dy, off_y);
+  const int ik = cell_index(xp[k], g.lower_x, g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.lower_y, g.dy, off_y);
   atomicAdd(count + bin_of(ik, jk, bnx, bny), 1);
 }
 
@@ -581,7 +583,7 @@ __global__ void bin_fill_kernel(GridF g, float off_x, float off_y, const float* 
                                 int* __restrict__ list) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int ik = cell_index(xp[k], g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.dy, off_y);
+  const int ik = cell_index(xp[k], g.lower_x, g.dx, off_x) - g.row0, jk = cell_index(yp[k], g.lower_y, g.dy, off_y);
   list[atomicAdd(cursor + bin_of(ik, jk, bnx, bny), 1)] = k;
 }
 

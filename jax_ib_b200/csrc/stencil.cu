@@ -138,7 +138,36 @@ template <int SCHEME>
 struct Terms {
   const GridF& g;
   const Tiles& t;
-  __device__ Terms(const GridF& g_, const Tiles& t_) : g(g_), t(t_) {}
+  const float* gu;  // the fields in global memory, for the wrapped upwind flux below
+  const float* gv;
+  __device__ Terms(const GridF& g_, const Tiles& t_, const float* gu_, const float* gv_) : g(g_), t(t_), gu(gu_), gv(gv_) {}
+
+  // Plain upwind hands the interpolated variable back with PERIODIC boundary conditions (interpolation.py:152-156)
+  // and the flux inherits them (advection.py:72-74), so the ghost flux below a wall is the flux of the LAST index
+  // of that direction, wall or not.  It lies outside the tile: read its few inputs from global memory (one row /
+  // one column of threads per step does).  The TVD and van Leer paths keep the scalar's own ghost rule.
+  __device__ __forceinline__ float wrapped_u_fy(int i) const {
+    const int j = g.ny - 1;
+    const float w = 0.5f * load_v(gv, g, i, j) + 0.5f * load_v(gv, g, i + 1, j);
+    return (w > 0.0f ? load_u(gu, g, i, j) : load_u(gu, g, i, j + 1)) * w;
+  }
+  __device__ __forceinline__ float wrapped_v_fy(int i) const {
+    const int j = g.ny - 1;
+    const float c0 = load_v(gv, g, i, j), cp = load_v(gv, g, i, j + 1);
+    const float w = 0.5f * c0 + 0.5f * cp;
+    return (w > 0.0f ? c0 : cp) * w;
+  }
+  __device__ __forceinline__ float wrapped_u_fx(int j) const {
+    const int i = g.nx - 1;
+    const float c0 = load_u(gu, g, i, j), cp = load_u(gu, g, i + 1, j);
+    const float w = 0.5f * c0 + 0.5f * cp;
+    return (w > 0.0f ? c0 : cp) * w;
+  }
+  __device__ __forceinline__ float wrapped_v_fx(int j) const {
+    const int i = g.nx - 1;
+    const float w = 0.5f * load_u(gu, g, i, j) + 0.5f * load_u(gu, g, i, j + 1);
+    return (w > 0.0f ? load_v(gv, g, i, j) : load_v(gv, g, i + 1, j)) * w;
+  }
 
   // ---- component u (offset (1, .5)) -------------------------------------------------------
   // The x-direction rules of the far field mirror the y-direction rules of the channel with u <-> v.
@@ -157,7 +186,8 @@ struct Terms {
   }
   __device__ __forceinline__ float u_fx(int i, int j) const {  // flux through the x-face i+1/2
     // far field: flux at offset (1.5, .5) with u's BC, cell-centred ghost 2*bc - mirror (mirror of v_fy)
-    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0) return 2.0f * g.uwx_lo - u_fx_raw(-1 - i, j);
+    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0)
+      return SCHEME == JAXIB_CONVECT_UPWIND ? wrapped_u_fx(j) : 2.0f * g.uwx_lo - u_fx_raw(-1 - i, j);
     return u_fx_raw(i, j);
   }
   __device__ __forceinline__ float u_corr_y(int i, int j) const {
@@ -169,7 +199,8 @@ struct Terms {
     return vl_corr(t.u(i, j - 1), t.u(i, j), t.u(i, j + 1));
   }
   __device__ __forceinline__ float u_fy(int i, int j) const {  // flux through the y-face j+1/2
-    if (g.bc != JAXIB_BC_PERIODIC && j < 0) return g.uw_lo;      // flux at offset (1,1) stepping onto the wall
+    if (g.bc != JAXIB_BC_PERIODIC && j < 0)                      // flux at offset (1,1) stepping onto the wall
+      return SCHEME == JAXIB_CONVECT_UPWIND ? wrapped_u_fy(i) : g.uw_lo;
     float w = 0.5f * t.v(i, j) + 0.5f * t.v(i + 1, j);
     float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? u_corr_y(i, j + 1) : 0.0f;
     return face_flux<SCHEME>(w, t.u(i, j - 1), t.u(i, j), t.u(i, j + 1), t.u(i, j + 2), cn, g.dt_over_dy);
@@ -184,7 +215,8 @@ struct Terms {
     return vl_corr(t.v(i - 1, j), t.v(i, j), t.v(i + 1, j));
   }
   __device__ __forceinline__ float v_fx(int i, int j) const {
-    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0) return g.vwx_lo;  // flux at offset (1, 1) stepping onto the wall (mirror of u_fy)
+    if (g.bc == JAXIB_BC_FAR_FIELD && i < 0)                   // flux at offset (1, 1) stepping onto the wall (mirror of u_fy)
+      return SCHEME == JAXIB_CONVECT_UPWIND ? wrapped_v_fx(j) : g.vwx_lo;
     float w = 0.5f * t.u(i, j) + 0.5f * t.u(i, j + 1);
     float cn = SCHEME == JAXIB_CONVECT_VAN_LEER ? v_corr_x(i + 1, j) : 0.0f;
     return face_flux<SCHEME>(w, t.v(i - 1, j), t.v(i, j), t.v(i + 1, j), t.v(i + 2, j), cn, g.dt_over_dx);
@@ -204,7 +236,8 @@ struct Terms {
   }
   __device__ __forceinline__ float v_fy(int i, int j) const {
     // flux at offset (.5, 1.5) with v's BC: cell-centred ghost 2*bc - mirror
-    if (g.bc != JAXIB_BC_PERIODIC && j < 0) return 2.0f * g.vw_lo - v_fy_raw(i, -1 - j);
+    if (g.bc != JAXIB_BC_PERIODIC && j < 0)
+      return SCHEME == JAXIB_CONVECT_UPWIND ? wrapped_v_fy(i) : 2.0f * g.vw_lo - v_fy_raw(i, -1 - j);
     return v_fy_raw(i, j);
   }
 
@@ -264,7 +297,7 @@ __global__ void __launch_bounds__(256) explicit_kernel(GridF g, const float* __r
   __syncthreads();
 
   Tiles t{su, sv, i0, j0};
-  Terms<SCHEME> terms(g, t);
+  Terms<SCHEME> terms(g, t, u, v);
   const int j = j0 + threadIdx.x;
   if (j >= g.ny) return;
 #pragma unroll 1

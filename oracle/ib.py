@@ -34,11 +34,12 @@ def gaussian_delta(x, x0, w):
 
 
 def marker_cell_index(xp, yp, grid, offset):
-    """The reference's marker -> fractional-index formula (IBM_Force.py:35,
-    MD/CFD_MD_coupling.py:18): xp/dx - offset, floored to the owning cell."""
+    """The cell whose mesh point lies at or just below the marker: floor((xp - lower)/dx - offset).  The
+    reference writes xp/dx - offset (IBM_Force.py:35, where the value is never used: its sums are dense) for
+    domains that start at 0; subtracting a zero origin is exact, so both forms give the same index there."""
     t = xp.dtype.type
-    si = xp / t(grid.step[0]) - t(offset[0])
-    sj = yp / t(grid.step[1]) - t(offset[1])
+    si = (xp - t(grid.domain[0][0])) / t(grid.step[0]) - t(offset[0])
+    sj = (yp - t(grid.domain[1][0])) / t(grid.step[1]) - t(offset[1])
     return np.floor(si).astype(np.int32), np.floor(sj).astype(np.int32)
 
 

@@ -151,9 +151,12 @@ def tvd_van_leer(c: Var, offset, v, dt) -> Var:
 
 
 # ----------------------------------------------------------------------------- advection
-def _advect_aligned(cs, v, c_bc) -> np.ndarray:
-    """advection.py:33-75: -div(c*u), flux inherits c's BC."""
-    flux = tuple(Var(c.data * u.data, c.offset, c.grid, c_bc) for c, u in zip(cs, v))
+def _advect_aligned(cs, v) -> np.ndarray:
+    """advection.py:33-75: -div(c*u).  Each flux component inherits the BC of the INTERPOLATED variable it was
+    built from (advection.py:72-74), not the BC of the advected scalar: `upwind` hands back a periodic variable
+    (interpolation.py:152-156), so with plain upwind advection the flux wraps around even across a wall, while the
+    TVD and van Leer paths keep the scalar's own BC."""
+    flux = tuple(Var(c.data * u.data, c.offset, c.grid, c.bc) for c, u in zip(cs, v))
     return -divergence(flux)
 
 
@@ -162,7 +165,7 @@ def advect_general(c: Var, v, u_interp, c_interp, dt=None) -> np.ndarray:
     targets = control_volume_offsets(c)
     aligned_v = tuple(u_interp(u, t, v, dt) for u, t in zip(v, targets))
     aligned_c = tuple(c_interp(c, t, aligned_v, dt) for t in targets)
-    return _advect_aligned(aligned_c, aligned_v, c.bc)
+    return _advect_aligned(aligned_c, aligned_v)
 
 
 def advect_upwind(c: Var, v, dt=None) -> np.ndarray:

@@ -1,0 +1,167 @@
+"""Golden vectors from the REFERENCE'S OWN SOURCE FILES (run in the build container only; /root/reference is not on the
+GPU box).
+
+    python tests/golden/make_reference_golden.py            # writes tests/golden/reference_pinned.npz
+
+hashimmg/jax_IB is pure Python on top of JAX, and JAX cannot be installed here.  oracle/jax_standin/ is a NumPy-backed
+stand-in for the handful of `jax` entry points the reference's own modules use (float32 / int32 results, weakly
+typed scalars, vmap / pmap as loops, jacrev as a complex-step derivative -- see its docstring).  With it on sys.path
+the UNMODIFIED files /root/reference/jax_ib/base/{grids, boundaries, finite_differences, interpolation, advection,
+convolution_functions, IBM_Force, kinematics, particle_class, particle_motion}.py are imported -- through stub
+`jax_ib` / `jax_ib.base` packages, because the reference's own __init__ files import the jax_cfd-dependent modules
+(pressure, equations, time_stepping) that cannot load -- and executed on seeded inputs.  Inputs and outputs go into one
+.npz; tests/test_reference_pinned.py feeds the same inputs to oracle/ and compares (CPU, no reference needed).
+
+What this pins: SURVEY 8a rows a1-a13 and a18 (delta, interpolation, direct forcing + spreading, multi-body loop,
+kinematic laws and their time derivatives, body update, advection schemes, diffusion, differences, ghost-cell rules,
+clock).  What it cannot pin: the pressure solve and the assembled step (a14-a17, a19: the reference delegates them to
+jax_cfd, which is absent) -- those stay on the identities of tests/test_oracle_identities.py.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+F = np.float32
+
+
+def load_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_standin"))
+    for name, path in (("jax_ib", REF + "/jax_ib"), ("jax_ib.base", REF + "/jax_ib/base")):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    names = ("grids", "particle_class", "boundaries", "interpolation", "finite_differences", "advection",
+             "convolution_functions", "IBM_Force", "kinematics", "particle_motion")
+    return types.SimpleNamespace(**{n: importlib.import_module("jax_ib.base." + n) for n in names})
+
+
+def ellipse_markers(a, b, n):
+    """The notebooks' shape function (Flapping_Demo.ipynb cell 5) is user code, not library code: both sides get the
+    same body-frame markers."""
+    x = np.linspace(-a, a, n)
+    y = b * np.sqrt(np.maximum(0.0, 1.0 - (x / a) ** 2))
+    return np.concatenate([x, x[::-1][1:-1]]).astype(F), np.concatenate([y, -y[::-1][1:-1]]).astype(F)
+
+
+def main():
+    R = load_reference()
+    import jax.numpy as jnp
+    out = {}
+    rng = np.random.default_rng(2024)
+    shape, domain = (48, 40), ((0.5, 2.9), (0.25, 1.85))
+    grid = R.grids.Grid(shape, domain=domain)
+    out["shape"], out["domain"] = np.array(shape), np.array(domain)
+    u, v, p = (rng.standard_normal(shape).astype(F) for _ in range(3))
+    out.update(u=u, v=v, p=p)
+    dt = 1.0e-3
+    out["dt"] = np.float64(dt)
+
+    def variables(bcu, bcv, bcp):
+        U = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(u), (1.0, 0.5), grid), bcu)
+        V = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(v), (0.5, 1.0), grid), bcv)
+        P = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(p), (0.5, 0.5), grid), bcp)
+        return U, V, P
+
+    # ---- a8-a13: stencils and ghost-cell rules, periodic and moving-wall channel ------------------------------
+    walls = ((0.3, -0.2), (0.0, 0.0))  # u and v on the lower / upper y wall
+    out["walls"] = np.array(walls)
+    per = R.boundaries.periodic_boundary_conditions(2)
+    bcs = {"periodic": (per, per),
+           "channel": tuple(R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), w), 0.0, None) for w in walls)}
+    for tag, (bcu, bcv) in bcs.items():
+        U, V, _ = variables(bcu, bcv, per)
+        P = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(p), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
+        vel = (U, V)
+        for k, c in enumerate(vel):
+            out[f"{tag}_upwind_{k}"] = np.asarray(R.advection.advect_upwind(c, vel, dt).data)
+            out[f"{tag}_van_leer_{k}"] = np.asarray(R.advection.advect_van_leer(c, vel, dt).data)
+            out[f"{tag}_van_leer_limiters_{k}"] = np.asarray(R.advection.advect_van_leer_using_limiters(c, vel, dt).data)
+            out[f"{tag}_laplacian_{k}"] = np.asarray(R.finite_differences.laplacian(c).data)
+            for axis in (0, 1):
+                for s in (-2, -1, 1, 2):
+                    out[f"{tag}_shift_{k}_{axis}_{s}"] = np.asarray(c.shift(s, axis).data)
+        out[f"{tag}_divergence"] = np.asarray(R.finite_differences.divergence(vel).data)
+        for axis in (0, 1):
+            out[f"{tag}_grad_p_{axis}"] = np.asarray(R.finite_differences.forward_difference(P, axis).data)
+            out[f"{tag}_back_u_{axis}"] = np.asarray(R.finite_differences.backward_difference(U, axis).data)
+
+    # ---- a1, a2: discrete delta and Eulerian -> Lagrangian interpolation (dense, as the reference) -------------
+    delta = R.convolution_functions.delta_approx_logistjax
+    xs = rng.uniform(0.5, 2.9, 64).astype(F)
+    out["delta_x"], out["delta_x0"], out["delta_w"] = xs, F(1.7), np.float64(grid.step[0])
+    out["delta_out"] = np.asarray(delta(jnp.asarray(xs), F(1.7), grid.step[0]))
+    x0, y0 = ellipse_markers(0.5, 0.06, 40)
+    out["x0"], out["y0"] = x0, y0
+    U, V, _ = variables(per, per, per)
+    th = F(0.4)
+    xp = (x0 * np.cos(th) - y0 * np.sin(th) + F(1.6)).astype(F)
+    yp = (x0 * np.sin(th) + y0 * np.cos(th) + F(1.0)).astype(F)
+    out["surf_xp"], out["surf_yp"] = xp, yp
+    out["surf_u"] = np.asarray(R.convolution_functions.new_surf_fn(U, jnp.asarray(xp), jnp.asarray(yp), delta))
+    out["surf_v"] = np.asarray(R.convolution_functions.new_surf_fn(V, jnp.asarray(xp), jnp.asarray(yp), delta))
+
+    # ---- a6: kinematic laws and their time derivatives (jax.jacrev in the reference) ---------------------------
+    K = R.kinematics
+    disp_param, rot_param = [[2.8, 0.25]], [[np.pi / 2, np.pi / 4, 0.25, 0.3]]
+    ts = np.array([0.0, 0.37, 1.234, 7.5], dtype=F)
+    out["kin_t"] = ts
+    import jax
+    out["kin_disp"] = np.stack([np.asarray(K.displacement(disp_param, t)) for t in ts])
+    out["kin_rot"] = np.array([np.asarray(K.rotation(rot_param, t)) for t in ts])
+    out["kin_disp_dot"] = np.stack([np.asarray(jax.jacrev(lambda t: K.displacement(disp_param, t))(t)) for t in ts])
+    out["kin_rot_dot"] = np.array([np.asarray(jax.jacrev(lambda t: K.rotation(rot_param, t))(t)) for t in ts])
+    four = [[0.2, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.0], [-0.1, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], 0.5]]
+    out["kin_fourier_disp"] = np.stack([np.asarray(K.Displacement_Foil_Fourier_Dotted_Mutliple(four, t)) for t in ts])
+    out["kin_fourier_rot"] = np.stack([np.asarray(K.rotation_Foil_Fourier_Dotted_Mutliple(four, t)) for t in ts])
+
+    # ---- a3-a5: direct forcing + spreading for two bodies; a7: body update ------------------------------------
+    t0 = F(0.37)
+    pbc = R.boundaries.ConstantBoundaryConditions(values=((0.0, 0.0), (0.0, 0.0)), time_stamp=t0, types=per.types, boundary_fn=None)
+    U, V, P = variables(pbc, pbc, per)
+    centers = jnp.asarray(np.array([[1.2, 0.9], [2.1, 1.2]], dtype=F))
+    dparams = [[0.6, 0.25], [0.4, 0.4]]
+    rparams = [[np.pi / 2, np.pi / 4, 0.25, 0.0], [0.3, 0.5, 0.4, 1.0]]
+    geom = [[0.5, 0.06], [0.5, 0.06]]
+    shape_fn = lambda g, grid_p: (jnp.asarray(x0), jnp.asarray(y0))
+    grid1d = R.particle_class.Grid1d(len(x0), domain=(0, 2 * np.pi))
+    particles = R.particle_class.particle(centers, geom, dparams, rparams, grid1d, shape_fn, K.displacement, K.rotation)
+    av = R.particle_class.All_Variables(particles, (U, V), P, [], 0, None)
+    out["ib_centers"], out["ib_t0"] = np.asarray(centers), t0
+    out["ib_dparams"], out["ib_rparams"] = np.array(dparams), np.array(rparams)
+    surf = lambda field, xp_, yp_: R.convolution_functions.new_surf_fn(field, xp_, yp_, delta)
+    fx, fy = R.IBM_Force.calc_IBM_force_NEW_MULTIPLE(av, delta, surf, dt)
+    out["ib_fx"], out["ib_fy"] = np.asarray(fx.data), np.asarray(fy.data)
+    # body update: the single-body laws take one parameter set (Flapping_Demo.ipynb), so one body here
+    one = R.particle_class.particle(centers[:1], geom[:1], dparams[:1], rparams[:1], grid1d, shape_fn, K.displacement, K.rotation)
+    moved = R.particle_motion.Update_particle_position_Multiple(R.particle_class.All_Variables(one, (U, V), P, [], 3, None), dt)
+    out["ib_new_centers"] = np.asarray(moved.particles.particle_center)
+    out["ib_step_count"] = np.int64(moved.Step_count)
+
+    # ---- a18: the clock and the wall values that update_BC re-evaluates every step -----------------------------
+    wall_u = [lambda t: 0.0, lambda t: 0.0, lambda t: 0.1 * jnp.sin(3.0 * t), lambda t: -0.2 * jnp.cos(2.0 * t)]
+    wall_v = [lambda t: 0.0, lambda t: 0.0, lambda t: 0.0, lambda t: 0.0]
+    bu = R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), (0.0, -0.2)), F(0.0), wall_u)
+    bv = R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), (0.0, 0.0)), F(0.0), wall_v)
+    U, V, P = variables(bu, bv, per)
+    av = R.particle_class.All_Variables(particles, (U, V), P, [], 0, None)
+    stamps, vals = [], []
+    for _ in range(25):
+        av = R.boundaries.update_BC(av, 5.0e-4)
+        stamps.append(np.asarray(av.velocity[0].bc.time_stamp, dtype=F))
+        vals.append(np.asarray([np.asarray(x, dtype=F) for x in av.velocity[0].bc.bc_values[1]] if hasattr(av.velocity[0].bc, "bc_values")
+                               else [np.asarray(x, dtype=F) for x in av.velocity[0].bc._values[1]]))
+    out["clock_stamps"], out["clock_wall_u"] = np.array(stamps), np.array(vals)
+
+    path = os.path.join(HERE, "reference_pinned.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

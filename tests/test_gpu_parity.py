@@ -115,6 +115,34 @@ def test_ib_interp_and_spread_match_windowed_oracle(R):
         assert np.array_equal(sg != 0, sw != 0)  # identical support
 
 
+def test_ib_windows_follow_a_domain_that_does_not_start_at_zero():
+    """The reference's sums are dense (convolution_functions.py:11-37, IBM_Force.py:66-87), so nothing in it
+    depends on where the domain starts; the windows of K2/K3 must be centred on floor((xp - lower)/dx - offset)."""
+    ox, oy = 0.5, -0.25
+    shape = (300, 280)
+    domain = ((ox, ox + 300 * 0.05), (oy, oy + 280 * 0.05))
+    cfg = dict(configs.flap600(), shape=shape, domain=domain)
+    g = field.Grid(shape, domain)
+    spec = demo.make_spec(cfg, ib_window=6)
+    xp, yp = _g1_like_markers()
+    xp, yp = (xp + F(ox)).astype(F), (yp + F(oy)).astype(F)
+    rng = np.random.default_rng(6)
+    fld = rng.standard_normal(shape).astype(F)
+    for off in ((1.0, 0.5), (0.5, 1.0)):
+        var = field.Var(fld, off, g, field.periodic_bc())
+        got, ci, cj = ops.ib_interp(spec, dev(fld), off, dev(xp), dev(yp), return_cells=True)
+        ei, ej = ib.marker_cell_index(xp, yp, g, off)
+        np.testing.assert_array_equal(host(ci), ei)
+        np.testing.assert_array_equal(host(cj), ej)
+        assert rel_l2(host(got), ib.interpolate_windowed(var, xp, yp, 6)) < 2e-6
+        assert rel_l2(host(got), ib.interpolate_dense(var, xp, yp)) < 1e-5  # the reference's own sum
+        Fk = rng.standard_normal(xp.size).astype(F)
+        dS = np.sqrt((np.roll(xp, -1) - xp) ** 2 + (np.roll(yp, -1) - yp) ** 2).astype(F)
+        sg = host(ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS)))
+        assert rel_l2(sg, ib.spread_windowed(Fk, xp, yp, dS, g, off, 6)) < 1e-6
+        assert rel_l2(sg, ib.spread_dense(Fk, xp, yp, dS, g, off)) < 1e-5
+
+
 def test_ib_interp_partition_of_unity_and_edges():
     cfg = configs.flap600()
     spec = demo.make_spec(cfg)

@@ -1,0 +1,130 @@
+"""The oracle against vectors produced by the REFERENCE'S OWN SOURCE FILES (tests/golden/reference_pinned.npz, made by
+tests/golden/make_reference_golden.py in the build container: hashimmg/jax_IB's unmodified modules executed on a
+NumPy-backed stand-in for jax, oracle/jax_standin).  CPU only; /root/reference is not needed here.
+
+Pins SURVEY 8a rows a1-a13 and a18.  Array arithmetic (stencils, ghost cells, differences) is compared BIT FOR BIT:
+both sides are float32 NumPy with the reference's operation order.  Paths through exp / sin / cos carry a 1e-6 bar
+(library transcendental functions), the complex-step derivatives standing in for jax.jacrev 2e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import field, ib, kinematics as okin, stencils, stepper
+
+from _adapter import rel_l2
+
+F = np.float32
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pinned.npz"))
+
+
+def _grid():
+    return field.Grid(tuple(int(x) for x in GOLD["shape"]), tuple(tuple(float(y) for y in x) for x in GOLD["domain"]))
+
+
+def _velocity(tag):
+    g = _grid()
+    if tag == "periodic":
+        bcu = bcv = field.periodic_bc()
+    else:
+        (ulo, uhi), (vlo, vhi) = GOLD["walls"]
+        bcu = field.channel_bc(((0.0, 0.0), (float(ulo), float(uhi))))
+        bcv = field.channel_bc(((0.0, 0.0), (float(vlo), float(vhi))))
+    U = field.Var(GOLD["u"], (1.0, 0.5), g, bcu)
+    V = field.Var(GOLD["v"], (0.5, 1.0), g, bcv)
+    P = field.Var(GOLD["p"], (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    return U, V, P
+
+
+@pytest.mark.parametrize("tag", ["periodic", "channel"])
+def test_stencils_and_ghost_cells_equal_the_reference_bit_for_bit(tag):
+    """advection.py:120-333, finite_differences.py:87-146, grids.py shift / boundaries.py:116-273 pad, trim."""
+    U, V, P = _velocity(tag)
+    vel = (U, V)
+    dt = float(GOLD["dt"])
+    for k, c in enumerate(vel):
+        np.testing.assert_array_equal(stencils.advect_upwind(c, vel, dt), GOLD[f"{tag}_upwind_{k}"])
+        np.testing.assert_array_equal(stencils.advect_van_leer(c, vel, dt), GOLD[f"{tag}_van_leer_{k}"])
+        np.testing.assert_array_equal(stencils.advect_van_leer_using_limiters(c, vel, dt), GOLD[f"{tag}_van_leer_limiters_{k}"])
+        np.testing.assert_array_equal(stencils.laplacian(c), GOLD[f"{tag}_laplacian_{k}"])
+        for axis in (0, 1):
+            for s in (-2, -1, 1, 2):
+                np.testing.assert_array_equal(c.shift(s, axis).data, GOLD[f"{tag}_shift_{k}_{axis}_{s}"])
+    np.testing.assert_array_equal(stencils.divergence(vel), GOLD[f"{tag}_divergence"])
+    for axis in (0, 1):
+        np.testing.assert_array_equal(stencils.forward_difference(P, axis), GOLD[f"{tag}_grad_p_{axis}"])
+        np.testing.assert_array_equal(stencils.backward_difference(U, axis), GOLD[f"{tag}_back_u_{axis}"])
+
+
+def test_delta_and_interpolation_match_the_reference():
+    """convolution_functions.py:5-37."""
+    got = ib.gaussian_delta(GOLD["delta_x"], GOLD["delta_x0"], float(GOLD["delta_w"]))
+    np.testing.assert_allclose(got, GOLD["delta_out"], rtol=1e-6)
+    U, V, _ = _velocity("periodic")
+    np.testing.assert_allclose(ib.interpolate_dense(U, GOLD["surf_xp"], GOLD["surf_yp"]), GOLD["surf_u"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(ib.interpolate_dense(V, GOLD["surf_xp"], GOLD["surf_yp"]), GOLD["surf_v"], rtol=2e-6, atol=1e-6)
+
+
+def test_kinematic_laws_and_their_derivatives_match_the_reference():
+    """kinematics.py:5-105; the derivatives are what jax.jacrev returns in IBM_Force.py:101-102."""
+    disp_param, rot_param = [[2.8, 0.25]], [[np.pi / 2, np.pi / 4, 0.25, 0.3]]
+    four = [[0.2, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.0], [-0.1, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], 0.5]]
+    for i, t in enumerate(GOLD["kin_t"]):
+        np.testing.assert_allclose(okin.displacement(disp_param, t), GOLD["kin_disp"][i], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(okin.rotation(rot_param, t), GOLD["kin_rot"][i], rtol=1e-6)
+        np.testing.assert_allclose(okin.displacement_dot(disp_param, t), GOLD["kin_disp_dot"][i], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(okin.rotation_dot(rot_param, t), GOLD["kin_rot_dot"][i], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(okin.displacement_fourier(four, t), GOLD["kin_fourier_disp"][i], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(okin.rotation_fourier(four, t), GOLD["kin_fourier_rot"][i], rtol=2e-6, atol=2e-6)
+
+
+def _bodies(n):
+    x0, y0 = GOLD["x0"], GOLD["y0"]
+    return ib.Bodies(GOLD["ib_centers"][:n].astype(F), [[0.5, 0.06]] * n, GOLD["ib_dparams"][:n].tolist(), GOLD["ib_rparams"][:n].tolist(),
+                     lambda g: (x0, y0), okin.DISPLACEMENT["harmonic"], okin.ROTATION["harmonic"])
+
+
+def test_direct_forcing_and_spreading_of_two_bodies_match_the_reference():
+    """IBM_Force.py:20-115 calc_IBM_force_NEW_MULTIPLE: marker kinematics, interpolation, (U_body - U) / dt, arc
+    length, dense spreading, sum over bodies -- on both velocity components."""
+    g = _grid()
+    t0 = F(GOLD["ib_t0"])
+    U = field.Var(GOLD["u"], (1.0, 0.5), g, field.periodic_bc(t0))
+    V = field.Var(GOLD["v"], (0.5, 1.0), g, field.periodic_bc(t0))
+    fx, fy = ib.ibm_force((U, V), _bodies(2), float(GOLD["dt"]), R=None)
+    assert rel_l2(fx, GOLD["ib_fx"]) < 1e-6 and rel_l2(fy, GOLD["ib_fy"]) < 1e-6
+    # and the windowed sums the CUDA kernels are compared with agree with the reference's dense ones up to the
+    # taps the window leaves out (beyond 5 cells: below exp(-12.5) = 3.7e-6 of the peak).  The golden grid starts
+    # at (0.5, 0.25), so this also checks that the window follows the domain origin.
+    fxw, fyw = ib.ibm_force((U, V), _bodies(2), float(GOLD["dt"]), R=6)
+    assert rel_l2(fxw, GOLD["ib_fx"]) < 5e-6 and rel_l2(fyw, GOLD["ib_fy"]) < 5e-6
+
+
+def test_body_update_matches_the_reference():
+    """particle_motion.py:38-66 Update_particle_position_Multiple."""
+    g = _grid()
+    t0 = F(GOLD["ib_t0"])
+    U = field.Var(GOLD["u"], (1.0, 0.5), g, field.periodic_bc(t0))
+    V = field.Var(GOLD["v"], (0.5, 1.0), g, field.periodic_bc(t0))
+    P = field.Var(GOLD["p"], (0.5, 0.5), g, field.periodic_bc())
+    st = stepper.State(_bodies(1), (U, V), P, Step_count=3)
+    st = stepper.update_positions(st, float(GOLD["dt"]))
+    np.testing.assert_allclose(st.particles.centers, GOLD["ib_new_centers"], rtol=0, atol=2e-7)
+    assert st.Step_count == int(GOLD["ib_step_count"])
+
+
+def test_clock_and_wall_values_match_the_reference():
+    """boundaries.py:519-542 update_BC: the float32 clock accumulates dt step by step and the wall functions are
+    re-evaluated at the new time stamp."""
+    g = _grid()
+    wall_u = [lambda t: 0.0, lambda t: 0.0, lambda t: 0.1 * np.sin(F(3.0) * t), lambda t: -0.2 * np.cos(F(2.0) * t)]
+    wall_v = [lambda t: 0.0] * 4
+    U = field.Var(GOLD["u"], (1.0, 0.5), g, field.channel_bc(((0.0, 0.0), (0.0, -0.2)), F(0.0), wall_u))
+    V = field.Var(GOLD["v"], (0.5, 1.0), g, field.channel_bc(((0.0, 0.0), (0.0, 0.0)), F(0.0), wall_v))
+    P = field.Var(GOLD["p"], (0.5, 0.5), g, field.periodic_bc())
+    st = stepper.State(None, (U, V), P)
+    for n in range(len(GOLD["clock_stamps"])):
+        st = stepper.update_bc(st, 5.0e-4)
+        assert F(st.velocity[0].bc.time_stamp) == GOLD["clock_stamps"][n]          # bit for bit
+        np.testing.assert_allclose(np.asarray(st.velocity[0].bc.values[1], dtype=F), GOLD["clock_wall_u"][n], rtol=1e-6, atol=1e-7)
