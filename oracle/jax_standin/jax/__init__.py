@@ -24,6 +24,14 @@ Array = Arr
 np = numpy  # the reference's grids.py spells it `jax.np` in one annotation
 
 
+def named_call(f=None, *, name=None):
+    return f
+
+
+def device_get(x):
+    return x
+
+
 def device_count():
     return 1
 

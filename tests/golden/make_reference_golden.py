@@ -7,15 +7,25 @@ hashimmg/jax_IB is pure Python on top of JAX, and JAX cannot be installed here. 
 stand-in for the handful of `jax` entry points the reference's own modules use (float32 / int32 results, weakly
 typed scalars, vmap / pmap as loops, jacrev as a complex-step derivative -- see its docstring).  With it on sys.path
 the UNMODIFIED files /root/reference/jax_ib/base/{grids, boundaries, finite_differences, interpolation, advection,
-convolution_functions, IBM_Force, kinematics, particle_class, particle_motion}.py are imported -- through stub
-`jax_ib` / `jax_ib.base` packages, because the reference's own __init__ files import the jax_cfd-dependent modules
-(pressure, equations, time_stepping) that cannot load -- and executed on seeded inputs.  Inputs and outputs go into one
-.npz; tests/test_reference_pinned.py feeds the same inputs to oracle/ and compares (CPU, no reference needed).
+convolution_functions, IBM_Force, kinematics, particle_class, particle_motion, array_utils, diffusion, pressure,
+time_stepping, equations}.py are imported -- through stub `jax_ib` / `jax_ib.base` packages, because the reference's own
+__init__ files pull in jax_md-dependent modules that cannot load -- and executed on seeded inputs.  Inputs and outputs
+go into one .npz; tests/test_reference_pinned.py feeds the same inputs to oracle/ and compares (CPU, no reference
+needed).
 
-What this pins: SURVEY 8a rows a1-a13 and a18 (delta, interpolation, direct forcing + spreading, multi-body loop,
-kinematic laws and their time derivatives, body update, advection schemes, diffusion, differences, ghost-cell rules,
-clock).  What it cannot pin: the pressure solve and the assembled step (a14-a17, a19: the reference delegates them to
-jax_cfd, which is absent) -- those stay on the identities of tests/test_oracle_identities.py.
+Two third-party dependencies of those files are absent as well and have stand-ins next to jax's:
+  * tree_math (Vector / wrap / unwrap: how equations.py and time_stepping.py add pytrees) -- oracle/jax_standin/tree_math;
+  * jax_cfd (google/jax-cfd; setup.py names it without a version, the reference's files are forks of its 0.2.x modules):
+    only fast_diagonalization.pseudoinverse does work on this path.  oracle/jax_standin/jax_cfd restates its published
+    algorithm (eigh per axis / fft of the first column, outer-summed eigenvalues, 1/lambda with a 10*eps cutoff).
+
+What this pins: SURVEY 8a rows a1-a19 -- delta, interpolation, direct forcing + spreading, multi-body loop, kinematic
+laws and their time derivatives, body update, advection schemes, diffusion, differences, ghost-cell rules, clock; the
+pressure right-hand side, the 1-D operators with their boundary rows, projection, pressure accumulation and re-imposed
+walls for the three boundary types; and the ASSEMBLED step (semi_implicit_navier_stokes_timeBC driven by
+forward_euler_updated exactly as Flapping_Demo.ipynb builds it, one flapping body, 1 and 6 steps, three boundary types).
+What it cannot pin: the eigen-solve inside jax_cfd itself (restated on both sides; anchored on identities in
+tests/test_oracle_identities.py) and XLA's transcendental functions / FFT (1e-6-level differences).
 """
 import importlib
 import os
@@ -37,7 +47,8 @@ def load_reference():
         m.__path__ = [path]
         sys.modules[name] = m
     names = ("grids", "particle_class", "boundaries", "interpolation", "finite_differences", "advection",
-             "convolution_functions", "IBM_Force", "kinematics", "particle_motion")
+             "convolution_functions", "IBM_Force", "kinematics", "particle_motion", "array_utils", "diffusion",
+             "pressure", "time_stepping", "equations")
     return types.SimpleNamespace(**{n: importlib.import_module("jax_ib.base." + n) for n in names})
 
 
@@ -157,6 +168,71 @@ def main():
         vals.append(np.asarray([np.asarray(x, dtype=F) for x in av.velocity[0].bc.bc_values[1]] if hasattr(av.velocity[0].bc, "bc_values")
                                else [np.asarray(x, dtype=F) for x in av.velocity[0].bc._values[1]]))
     out["clock_stamps"], out["clock_wall_u"] = np.array(stamps), np.array(vals)
+
+    # ---- a14-a17: pressure solve and projection through the reference's pressure.py / array_utils.py ----------
+    # (jax_cfd's fast_diagonalization.pseudoinverse, which they call, is the stand-in's restatement)
+    far = tuple(R.boundaries.Far_field_boundary_conditions(2, w, 0.0, None) for w in (((0.5, 0.4), (0.3, -0.2)), ((0.0, 0.1), (0.0, 0.0))))
+    out["far_walls"] = np.array([[[0.5, 0.4], [0.3, -0.2]], [[0.0, 0.1], [0.0, 0.0]]])
+    bcs["far_field"] = far
+    solvers = {"periodic": R.pressure.solve_fast_diag, "channel": R.pressure.solve_fast_diag_moving_wall,
+               "far_field": R.pressure.solve_fast_diag_Far_Field}
+    for tag, (bcu, bcv) in bcs.items():
+        U, V, _ = variables(bcu, bcv, per)
+        P = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(p), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
+        out[f"{tag}_q"] = np.asarray(solvers[tag]((U, V)).data)
+        new = R.pressure.projection_and_update_pressure(R.particle_class.All_Variables(None, (U, V), P, [], 0, None), solvers[tag])
+        out[f"{tag}_proj_u"], out[f"{tag}_proj_v"] = (np.asarray(x.data) for x in new.velocity)
+        out[f"{tag}_proj_p"] = np.asarray(new.pressure.data)
+
+    # ---- a19: the assembled step, as the notebooks build it (Flapping_Demo.ipynb cell 9) ------------------------
+    # equations.semi_implicit_navier_stokes_timeBC + time_stepping.forward_euler_updated, the reference's files
+    # driving the reference's stages; tree_math / jax_cfd.funcutils are the stand-in's.
+    # The notebooks drive the step through jax.lax.scan (funcutils.repeated / trajectory), which turns every pytree
+    # LEAF of the carried state into a float32 array -- including the clock, a leaf of the BC object
+    # (boundaries.py:79-83).  The stand-in has no scan, so the clock starts as float32 here to accumulate as it does
+    # there (the a18 block above pins that accumulation on its own).
+    density, viscosity, nsteps = 1.3, 0.07, 6
+    t_start = F(0.0)
+    out["step_density"], out["step_viscosity"], out["step_n"] = np.float64(density), np.float64(viscosity), np.int64(nsteps)
+    u0s, v0s = (0.3 * u).astype(F), (0.3 * v).astype(F)
+    out["step_u0"], out["step_v0"] = u0s, v0s
+    ib_forcing = lambda av_, dt_: R.IBM_Force.calc_IBM_force_NEW_MULTIPLE(av_, delta, surf, dt_)
+    zero = lambda t: 0.0
+    wall_fns = [zero, zero, lambda t: 0.1 * jnp.sin(3.0 * t), lambda t: -0.2 * jnp.cos(2.0 * t)]
+    step_cases = {
+        "periodic": ("upwind", R.pressure.solve_fast_diag, None,
+                     (R.boundaries.new_periodic_boundary_conditions(ndim=2, bc_vals=((0.0, 0.0), (0.0, 0.0)), bc_fn=[zero] * 4, time_stamp=t_start),) * 2),
+        "channel": ("van_leer_limiters", R.pressure.solve_fast_diag_moving_wall, (0.4, -0.1),
+                    (R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), (0.0, -0.2)), t_start, wall_fns),
+                     R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), (0.0, 0.0)), t_start, [zero] * 4))),
+        "far_field": ("upwind", R.pressure.solve_fast_diag_Far_Field, None,
+                      (R.boundaries.Far_field_boundary_conditions(2, ((0.2, 0.2), (0.2, 0.2)), t_start, [lambda t: 0.2] * 4),
+                       R.boundaries.Far_field_boundary_conditions(2, ((0.0, 0.0), (0.0, 0.0)), t_start, [zero] * 4))),
+    }
+    schemes = {"upwind": R.advection.advect_upwind, "van_leer_limiters": R.advection.advect_van_leer_using_limiters}
+    for tag, (scheme, solver, force, (bcu, bcv)) in step_cases.items():
+        U = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(u0s), (1.0, 0.5), grid), bcu)
+        V = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(v0s), (0.5, 1.0), grid), bcv)
+        P = R.grids.GridVariable(R.grids.GridArray(jnp.zeros(shape), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
+        body = R.particle_class.particle(centers[:1], geom[:1], dparams[:1], rparams[:1], grid1d, shape_fn, K.displacement, K.rotation)
+        av = R.particle_class.All_Variables(body, (U, V), P, [0], 0, [0])
+        convect = lambda vv, fn=schemes[scheme]: tuple(fn(c, vv, dt) for c in vv)
+        forcing = None if force is None else (
+            lambda vv, f=force: tuple(R.grids.GridArray(fk * jnp.ones_like(c.data), c.offset, c.grid) for fk, c in zip(f, vv)))
+        step = R.equations.semi_implicit_navier_stokes_timeBC(
+            density=density, viscosity=viscosity, dt=dt, grid=grid, convect=convect, pressure_solve=solver,
+            forcing=forcing, time_stepper=R.time_stepping.forward_euler_updated, IBM_forcing=ib_forcing,
+            Updating_Position=R.particle_motion.Update_particle_position_Multiple, Drag_fn=lambda av_, dt_: av_)
+        for n in range(nsteps):
+            av = step(av)
+            if n == 0:  # after ONE step: the order of the stages, before round-off has had time to spread
+                out[f"step1_{tag}_u"], out[f"step1_{tag}_v"] = (np.asarray(x.data) for x in av.velocity)
+                out[f"step1_{tag}_p"] = np.asarray(av.pressure.data)
+        out[f"step_{tag}_u"], out[f"step_{tag}_v"] = (np.asarray(x.data) for x in av.velocity)
+        out[f"step_{tag}_p"] = np.asarray(av.pressure.data)
+        out[f"step_{tag}_centers"] = np.asarray(av.particles.particle_center)
+        out[f"step_{tag}_time"] = np.asarray(av.velocity[0].bc.time_stamp, dtype=F)
+        out[f"step_{tag}_count"] = np.int64(av.Step_count)
 
     path = os.path.join(HERE, "reference_pinned.npz")
     np.savez_compressed(path, **out)

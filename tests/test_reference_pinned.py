@@ -2,9 +2,10 @@
 tests/golden/make_reference_golden.py in the build container: hashimmg/jax_IB's unmodified modules executed on a
 NumPy-backed stand-in for jax, oracle/jax_standin).  CPU only; /root/reference is not needed here.
 
-Pins SURVEY 8a rows a1-a13 and a18.  Array arithmetic (stencils, ghost cells, differences) is compared BIT FOR BIT:
-both sides are float32 NumPy with the reference's operation order.  Paths through exp / sin / cos carry a 1e-6 bar
-(library transcendental functions), the complex-step derivatives standing in for jax.jacrev 2e-6.
+Pins SURVEY 8a rows a1-a19.  Array arithmetic (stencils, ghost cells, differences, the channel and far-field pressure
+solves) is compared BIT FOR BIT: both sides are float32 NumPy with the reference's operation order.  Paths through
+exp / sin / cos carry a 1e-6 bar (library transcendental functions), the complex-step derivatives standing in for
+jax.jacrev 2e-6, the assembled step 2e-6 after one step and 1e-5 after six (measured: 1.5e-7 .. 6e-7).
 """
 import os
 
@@ -128,3 +129,82 @@ def test_clock_and_wall_values_match_the_reference():
         st = stepper.update_bc(st, 5.0e-4)
         assert F(st.velocity[0].bc.time_stamp) == GOLD["clock_stamps"][n]          # bit for bit
         np.testing.assert_allclose(np.asarray(st.velocity[0].bc.values[1], dtype=F), GOLD["clock_wall_u"][n], rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- a14-a17, a19 (generator part 2)
+def _bcs(tag):
+    if tag == "periodic":
+        return field.periodic_bc(), field.periodic_bc()
+    if tag == "channel":
+        (ulo, uhi), (vlo, vhi) = GOLD["walls"]
+        return field.channel_bc(((0.0, 0.0), (float(ulo), float(uhi)))), field.channel_bc(((0.0, 0.0), (float(vlo), float(vhi))))
+    wu, wv = GOLD["far_walls"]
+    return (field.far_field_bc(tuple(tuple(float(x) for x in r) for r in wu)),
+            field.far_field_bc(tuple(tuple(float(x) for x in r) for r in wv)))
+
+
+@pytest.mark.parametrize("tag", ["periodic", "channel", "far_field"])
+def test_pressure_solve_and_projection_match_the_reference(tag):
+    """pressure.py:58-154 + array_utils.py laplacian matrices, run from the reference's files: the right-hand side, the
+    1-D operators with their boundary rows, q, p_new = q + p_old, v - grad q, and the wall values re-imposed.  The
+    eigen-solve they call (jax_cfd's pseudoinverse) is a restatement on both sides, so what this pins is everything
+    AROUND it; a wrong operator row, sign or boundary rule shows up at O(1), far above the 1e-5 bar (float32 round-off
+    of two differently ordered transforms of white noise)."""
+    from oracle import poisson
+    g = _grid()
+    bcu, bcv = _bcs(tag)
+    U = field.Var(GOLD["u"], (1.0, 0.5), g, bcu)
+    V = field.Var(GOLD["v"], (0.5, 1.0), g, bcv)
+    P = field.Var(GOLD["p"], (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    q = poisson.SOLVERS[tag]((U, V))
+    assert rel_l2(q, GOLD[f"{tag}_q"]) < 1e-5
+    new_v, new_p = poisson.projection_and_update_pressure((U, V), P, tag)
+    assert rel_l2(new_v[0].data, GOLD[f"{tag}_proj_u"]) < 2e-6
+    assert rel_l2(new_v[1].data, GOLD[f"{tag}_proj_v"]) < 2e-6
+    assert rel_l2(new_p.data, GOLD[f"{tag}_proj_p"]) < 2e-6
+    if tag != "periodic":  # impose_bc: the wall-aligned rows / columns hold the wall values exactly
+        np.testing.assert_array_equal(new_v[1].data[:, -1], GOLD[f"{tag}_proj_v"][:, -1])
+    if tag == "far_field":
+        np.testing.assert_array_equal(new_v[0].data[-1, :], GOLD[f"{tag}_proj_u"][-1, :])
+
+
+STEP_CASES = {
+    # tag: (convect, wall functions of u, wall values of u at t = 0, wall functions of v, constant force)
+    "periodic": ("upwind", None, None, None),
+    "channel": ("van_leer_limiters", [lambda t: 0.0, lambda t: 0.0, lambda t: 0.1 * np.sin(F(3.0) * t), lambda t: -0.2 * np.cos(F(2.0) * t)],
+                ((0.0, 0.0), (0.0, -0.2)), (0.4, -0.1)),
+    "far_field": ("upwind", [lambda t: 0.2] * 4, ((0.2, 0.2), (0.2, 0.2)), None),
+}
+
+
+@pytest.mark.parametrize("tag", ["periodic", "channel", "far_field"])
+def test_assembled_step_matches_the_reference(tag):
+    """equations.py:194-242 semi_implicit_navier_stokes_timeBC driven by time_stepping.py:109-256 navier_stokes_rk_updated
+    (forward Euler), exactly as Flapping_Demo.ipynb cell 9 builds it, with one flapping body: explicit terms, the stored
+    pressure's gradient, direct forcing at the predicted velocity, projection, clock and wall update, body update --
+    after ONE step (the order of the stages) and after six."""
+    convect, fns, vals, force = STEP_CASES[tag]
+    g = _grid()
+    zero = [lambda t: 0.0] * 4
+    make = {"periodic": lambda v, f: field.periodic_bc(F(0.0), f), "channel": lambda v, f: field.channel_bc(v, F(0.0), f),
+            "far_field": lambda v, f: field.far_field_bc(v, F(0.0), f)}[tag]
+    bcu = make(vals, fns if fns is not None else zero)
+    bcv = make(((0.0, 0.0), (0.0, 0.0)), zero)
+    U = field.Var(GOLD["step_u0"], (1.0, 0.5), g, bcu)
+    V = field.Var(GOLD["step_v0"], (0.5, 1.0), g, bcv)
+    P = field.Var(np.zeros(g.shape, F), (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    forcing = None if force is None else (lambda vv: tuple(F(f) * np.ones_like(x.data) for f, x in zip(force, vv)))
+    step = stepper.make_step(float(GOLD["dt"]), float(GOLD["step_viscosity"]), float(GOLD["step_density"]), convect, tag, forcing)
+    st = stepper.State(_bodies(1), (U, V), P)
+    for n in range(int(GOLD["step_n"])):
+        st = step(st)
+        if n == 0:
+            assert rel_l2(st.velocity[0].data, GOLD[f"step1_{tag}_u"]) < 2e-6
+            assert rel_l2(st.velocity[1].data, GOLD[f"step1_{tag}_v"]) < 2e-6
+            assert rel_l2(st.pressure.data, GOLD[f"step1_{tag}_p"]) < 2e-5
+    assert rel_l2(st.velocity[0].data, GOLD[f"step_{tag}_u"]) < 1e-5
+    assert rel_l2(st.velocity[1].data, GOLD[f"step_{tag}_v"]) < 1e-5
+    assert rel_l2(st.pressure.data, GOLD[f"step_{tag}_p"]) < 1e-4
+    np.testing.assert_allclose(st.particles.centers, GOLD[f"step_{tag}_centers"], rtol=0, atol=3e-7)
+    assert F(st.velocity[0].bc.time_stamp) == GOLD[f"step_{tag}_time"]
+    assert st.Step_count == int(GOLD[f"step_{tag}_count"])
