@@ -16,7 +16,7 @@ Nothing under jax_ib_b200/ imports this package; only the fixture generator puts
 import numpy as _np
 
 from . import numpy  # noqa: F401  (jax.numpy)
-from . import core, lax, tree_util  # noqa: F401
+from . import core, lax, random, tree_util  # noqa: F401
 from . import interpreters, scipy  # noqa: F401
 from .numpy import Arr, _wrap
 

@@ -53,3 +53,9 @@ def tree_map(fn, tree, *rest):
 
 
 tree_leaves = lambda tree: tree_flatten(tree)[0]
+
+
+def tree_reduce(fn, tree, initializer=None):
+    import functools
+    leaves = tree_leaves(tree)
+    return functools.reduce(fn, leaves) if initializer is None else functools.reduce(fn, leaves, initializer)

@@ -1,0 +1,14 @@
+import dataclasses as _dc
+
+import numpy as _np
+
+
+@_dc.dataclass
+class BrownianState:
+    position: object
+    mass: object
+    rng: object
+
+
+def canonicalize_mass(state):
+    return state

@@ -46,10 +46,18 @@ def load_reference():
         m = types.ModuleType(name)
         m.__path__ = [path]
         sys.modules[name] = m
+    for name, path in (("jax_ib.MD", REF + "/jax_ib/MD"), ("jax_ib.penalty", REF + "/jax_ib/penalty")):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
     names = ("grids", "particle_class", "boundaries", "interpolation", "finite_differences", "advection",
              "convolution_functions", "IBM_Force", "kinematics", "particle_motion", "array_utils", "diffusion",
              "pressure", "time_stepping", "equations")
-    return types.SimpleNamespace(**{n: importlib.import_module("jax_ib.base." + n) for n in names})
+    ns = {n: importlib.import_module("jax_ib.base." + n) for n in names}
+    for pkg, mods in (("MD", ("CFD_MD_coupling", "simulate", "interaction_potential")), ("penalty", ("util_funs", "parameteric_fns"))):
+        for n in mods:
+            ns[n] = importlib.import_module(f"jax_ib.{pkg}.{n}")
+    return types.SimpleNamespace(**ns)
 
 
 def ellipse_markers(a, b, n):
@@ -233,6 +241,65 @@ def main():
         out[f"step_{tag}_centers"] = np.asarray(av.particles.particle_center)
         out[f"step_{tag}_time"] = np.asarray(av.velocity[0].bc.time_stamp, dtype=F)
         out[f"step_{tag}_count"] = np.int64(av.Step_count)
+
+    # ---- a21: tracer coupling (MD/CFD_MD_coupling.py, MD/simulate.py brownian_cfd at kT = 0) ------------------
+    import jax.random
+    jax.random.ZERO_TEMPERATURE_ONLY = True
+    U, V, P = variables(per, per, per)
+    npts = 200
+    pts = np.stack([rng.uniform(0.5, 2.9, npts), rng.uniform(0.25, 1.85, npts)], axis=1).astype(F)
+    pts[:6] = np.array([[0.5, 0.25], [2.9, 1.85], [0.52, 1.0], [2.89, 0.3], [1.0, 1.849], [0.45, 0.2]], dtype=F)  # edges, outside
+    out["md_pts"] = pts
+    mobile = (np.arange(npts) % 5 != 0)
+    out["md_mobile"] = mobile
+    _, free_shift = __import__("jax_md").space.free()
+    masked_shift = lambda R_, dR_, **k: jnp.where(jnp.asarray(mobile)[:, None], free_shift(R_, dR_), R_)  # the notebooks' masked shift
+    init_fn, apply_fn = R.simulate.brownian_cfd(lambda R_, **k: jnp.zeros_like(R_), masked_shift, dt, 0.0,
+                                               R.CFD_MD_coupling.custom_force_fn_pbc, gamma=0.8)
+    md = init_fn(jax.random.PRNGKey(0), jnp.asarray(pts))
+    av = R.particle_class.All_Variables(particles, (U, V), P, [], 0, md)
+    out["md_force"] = np.asarray(R.CFD_MD_coupling.custom_force_fn_pbc(av))
+    for _ in range(3):
+        av = R.particle_class.All_Variables(particles, (U, V), P, [], 0, apply_fn(av))
+    out["md_pos3"] = np.asarray(av.MD_var.position)
+    dr = jnp.asarray(np.linspace(0.05, 2.0, 64).astype(F))
+    out["morse_dr"] = np.asarray(dr)
+    out["morse_u"] = np.asarray(R.interaction_potential.harmonic_morse(dr, h=jnp.asarray(F(5.0)), D0=jnp.asarray(F(0.7)), alpha=jnp.asarray(F(10.0)),
+                                                                       r0=jnp.asarray(F(0.9)), k=jnp.asarray(F(1.0))))
+
+    # ---- a22: penalty (Brinkman) mask and forcing (penalty/util_funs.py, parameteric_fns.py) -------------------
+    theta = jnp.asarray(np.linspace(0, 2 * np.pi, 61).astype(F))
+    shapes = {"ellipse": R.parameteric_fns.param_ellipse([0.45, 0.2], theta), "circle": R.parameteric_fns.param_circle([0.3], theta),
+              "rose": R.parameteric_fns.param_rose([0.4, 2.0], theta)}
+    smooth = lambda G_, Know: Know[0] / 2.0 * (1.0 + jnp.tanh(G_ / Know[1]))
+    know = (2000.0, 0.01)
+    out["pen_know"] = np.array(know)
+    for name, Rth in shapes.items():
+        out[f"pen_R_{name}"] = np.asarray(Rth)
+        with np.errstate(all="ignore"):
+            _, Rfinal = R.util_funs.project_particle(grid, (1.6, 1.0), Rth, None)
+            out[f"pen_Rfinal_{name}"] = np.asarray(Rfinal)
+            out[f"pen_perm_{name}"] = np.asarray(R.util_funs.calc_perm(grid, (1.6, 1.0), Rth, smooth, know))
+    perm = jnp.asarray(out["pen_perm_ellipse"])
+    frc = R.util_funs.arbitrary_obstacle((0.3, -0.1), perm)((U, V))
+    out["pen_force_u"], out["pen_force_v"] = np.asarray(frc[0].data), np.asarray(frc[1].data)
+    # the penalty stepper: semi_implicit_navier_stokes_penalty + forward_euler_penalty (equations.py:245-280,
+    # time_stepping.py:259-376), channel walls, Brinkman forcing, three steps
+    bu = R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), (0.0, 0.0)), t_start, [zero] * 4)
+    U = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(u0s), (1.0, 0.5), grid), bu)
+    V = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(v0s), (0.5, 1.0), grid), bu)
+    P = R.grids.GridVariable(R.grids.GridArray(jnp.zeros(shape), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
+    pstep = R.equations.semi_implicit_navier_stokes_penalty(
+        density=density, viscosity=viscosity, dt=dt, grid=grid,
+        convect=lambda vv: tuple(R.advection.advect_upwind(c, vv, dt) for c in vv),
+        pressure_solve=R.pressure.solve_fast_diag_moving_wall, forcing=R.util_funs.arbitrary_obstacle((0.3, -0.1), perm),
+        time_stepper=R.time_stepping.forward_euler_penalty)
+    av = R.particle_class.All_Variables(particles, (U, V), P, [0], 0, [0])
+    for _ in range(3):
+        av = pstep(av)
+    out["pen_step_u"], out["pen_step_v"] = (np.asarray(x.data) for x in av.velocity)
+    out["pen_step_p"] = np.asarray(av.pressure.data)
+    out["pen_step_time"] = np.asarray(av.velocity[0].bc.time_stamp, dtype=F)
 
     path = os.path.join(HERE, "reference_pinned.npz")
     np.savez_compressed(path, **out)

@@ -208,3 +208,67 @@ def test_assembled_step_matches_the_reference(tag):
     np.testing.assert_allclose(st.particles.centers, GOLD[f"step_{tag}_centers"], rtol=0, atol=3e-7)
     assert F(st.velocity[0].bc.time_stamp) == GOLD[f"step_{tag}_time"]
     assert st.Step_count == int(GOLD[f"step_{tag}_count"])
+
+
+# ------------------------------------------------------------------------------- a21, a22 (generator part 3)
+def test_tracer_coupling_matches_the_reference():
+    """MD/CFD_MD_coupling.py:7-27 (fractional index x/dx - offset, bilinear, taps outside the array are zero) and
+    MD/simulate.py:81-97 at kT = 0 with the notebooks' masked shift: three Brownian steps in a frozen velocity field."""
+    from oracle import tracers
+    U, V, _ = _velocity("periodic")
+    pts = GOLD["md_pts"]
+    np.testing.assert_array_equal(tracers.cfd_force((U, V), pts), GOLD["md_force"])  # bit for bit, edge and outside points too
+    st = tracers.BrownianState(pts.copy(), 1.0)
+    for _ in range(3):
+        st = tracers.brownian_step(st, (U, V), float(GOLD["dt"]), gamma=0.8, kT=0.0, is_mobile=GOLD["md_mobile"])
+    np.testing.assert_allclose(st.position, GOLD["md_pos3"], rtol=0, atol=3e-7)
+    np.testing.assert_array_equal(st.position[~GOLD["md_mobile"]], pts[~GOLD["md_mobile"]])
+    got = tracers.harmonic_morse(GOLD["morse_dr"], F(5.0), F(0.7), F(10.0), F(0.9), F(1.0))
+    np.testing.assert_allclose(got, GOLD["morse_u"], rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["ellipse", "circle", "rose"])
+def test_penalty_mask_matches_the_reference(name):
+    """penalty/util_funs.py:26-93 project_particle / calc_perm with the shapes of penalty/parameteric_fns.py: polar
+    angle (three-branch arctan), segment lookup, linear R(theta), level set, smoothing."""
+    from oracle import penalty
+    g = _grid()
+    theta = np.linspace(0, 2 * np.pi, 61).astype(F)
+    shape_fn = {"ellipse": lambda: penalty.param_ellipse([0.45, 0.2], theta), "circle": lambda: penalty.param_circle([0.3], theta),
+                "rose": lambda: penalty.param_rose([0.4, 2.0], theta)}[name]
+    Rth = shape_fn()
+    np.testing.assert_allclose(Rth, GOLD[f"pen_R_{name}"], rtol=2e-6, atol=1e-7)
+    Rth = GOLD[f"pen_R_{name}"]  # same table on both sides from here on
+    with np.errstate(all="ignore"):
+        Rfinal, _ = penalty.polar_radius(g, (1.6, 1.0), Rth)
+        perm = penalty.calc_perm(g, (1.6, 1.0), Rth, penalty.tanh_smoothing, tuple(float(x) for x in GOLD["pen_know"]))
+    ok = np.isfinite(GOLD[f"pen_Rfinal_{name}"])
+    assert np.array_equal(ok, np.isfinite(Rfinal))
+    np.testing.assert_array_equal(Rfinal[ok], GOLD[f"pen_Rfinal_{name}"][ok])  # same NumPy operations in the same order
+    np.testing.assert_array_equal(perm, GOLD[f"pen_perm_{name}"])
+
+
+def test_penalty_forcing_and_stepper_match_the_reference():
+    """penalty/util_funs.py:6-16 arbitrary_obstacle and equations.py:245-280 semi_implicit_navier_stokes_penalty with
+    time_stepping.py:259-376 forward_euler_penalty: three steps between channel walls."""
+    from oracle import penalty
+    U, V, _ = _velocity("periodic")
+    perm = GOLD["pen_perm_ellipse"]
+    fu, fv = penalty.obstacle_forcing((0.3, -0.1), perm)((U, V))
+    np.testing.assert_allclose(fu, GOLD["pen_force_u"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(fv, GOLD["pen_force_v"], rtol=1e-6, atol=1e-6)
+    g = _grid()
+    zero = [lambda t: 0.0] * 4
+    bc = field.channel_bc(((0.0, 0.0), (0.0, 0.0)), F(0.0), zero)
+    U = field.Var(GOLD["step_u0"], (1.0, 0.5), g, bc)
+    V = field.Var(GOLD["step_v0"], (0.5, 1.0), g, bc)
+    P = field.Var(np.zeros(g.shape, F), (0.5, 0.5), g, field.pressure_bc_from_velocity((U, V)))
+    step = stepper.make_step(float(GOLD["dt"]), float(GOLD["step_viscosity"]), float(GOLD["step_density"]), "upwind", "channel",
+                             penalty.obstacle_forcing((0.3, -0.1), perm), penalty=True)
+    st = stepper.State(None, (U, V), P)
+    for _ in range(3):
+        st = step(st)
+    assert rel_l2(st.velocity[0].data, GOLD["pen_step_u"]) < 5e-6
+    assert rel_l2(st.velocity[1].data, GOLD["pen_step_v"]) < 5e-6
+    assert rel_l2(st.pressure.data, GOLD["pen_step_p"]) < 5e-5
+    assert F(st.velocity[0].bc.time_stamp) == GOLD["pen_step_time"]
