@@ -10,6 +10,7 @@ the velocity BC, body centres, Step_count) are advanced with the reference's flo
 from __future__ import annotations
 
 import dataclasses
+import math
 from typing import Callable, Optional
 
 import numpy as np
@@ -18,8 +19,18 @@ import torch
 from . import boundaries, grids, kinematics, ops, particle_class
 
 
+def effective_ib_window(window: int, step) -> int:
+    """The window (in cells, same in x and y) that keeps `window` standard deviations of EVERY Gaussian the reference
+    sums: interpolation uses widths (dx, dy) (convolution_functions.py:19-21), spreading a radial Gaussian of width dx
+    in both directions (IBM_Force.py:67), so on a grid with dy < dx the y-window must grow by dx/dy.  Isotropic grids
+    (every reference configuration) are unchanged.  The kernels take windows up to 16."""
+    dx, dy = float(step[0]), float(step[1])
+    return min(16, int(math.ceil(window * max(1.0, dx / dy) - 1e-9)))
+
+
 def grid_spec_from(grid: grids.Grid, dt, viscosity, density, bc_kind, convect, v=None, force=(0.0, 0.0), ib_window=6,
                    batch=1) -> ops.GridSpec:
+    ib_window = effective_ib_window(ib_window, grid.step)
     u_wall = v_wall = u_wall_x = v_wall_x = (0.0, 0.0)
     if v is not None and bc_kind in ("channel", "far_field"):
         u_wall = tuple(float(x) for x in v[0].bc.bc_values[1])

@@ -7,14 +7,22 @@ fast-diagonalisation Poisson projection, clock/body update, tracer coupling and
 the Brinkman penalty mask.  Each function cites the reference file:line it
 follows.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
-this path and cannot be executed in this image (no jax/jaxlib/
-jax_cfd/jax_md).  The oracle is therefore pinned only by
-library-independent identities (partition of unity, div∘grad = Laplacian so
-solve(div grad q) = q, closed-form Laplacian eigenvalues, dense-vs-windowed
-Gaussian sums, Taylor-Green decay, Poiseuille steady state) in
-tests/test_oracle_*.py, and by golden trajectories it generated itself
-(tests/golden/, script tests/golden/make_golden.py).
+PINNED AGAINST THE REFERENCE'S OWN SOURCE FILES, run in the build container.  The
+reference ships no tests, golden vectors or fixtures for this path
+and JAX is not installable here, so oracle/jax_standin/ provides a
+NumPy-backed stand-in for the `jax` entry points the reference uses (plus
+tree_math, and containers of jax_md / jax_cfd): with it on sys.path,
+tests/golden/make_reference_golden.py imports the UNMODIFIED files under
+/root/reference/jax_ib/{base,MD,penalty}/ and executes them on seeded inputs;
+tests/test_reference_pinned.py feeds the same inputs to this package and compares
+(bit for bit for the array arithmetic; 1e-6-level bars through transcendental
+functions and the assembled step).  Covered: SURVEY 8a rows a1-a19, a21, a22,
+including the assembled step built exactly as Flapping_Demo.ipynb builds it.
+NOT covered, and therefore still anchored only on library-independent identities
+(tests/test_oracle_identities.py): the arithmetic INSIDE the absent third-party
+packages -- jax_cfd's eigen-solve (restated on both sides), XLA's FFT and
+transcendental functions, jax_md's pair potentials and JAX's threefry generator
+(kT > 0 takes caller-supplied deviates).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product (jax_ib_b200/) never does.

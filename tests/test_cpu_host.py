@@ -252,3 +252,13 @@ def test_column_sweep_model_matches_the_oracle_pseudoinverse(shape, slabs):
     # and it does solve the discrete Poisson equation: the 5-point Laplacian of the solution is the right-hand side
     lap = ((np.roll(got, 1, 0) - 2 * got + np.roll(got, -1, 0)) / dx ** 2 + (np.roll(got, 1, 1) - 2 * got + np.roll(got, -1, 1)) / dy ** 2)
     assert np.linalg.norm(lap - rhs) / np.linalg.norm(rhs) < 2e-4
+
+
+def test_ib_window_grows_with_the_cell_aspect_ratio():
+    """IBM_Force.py:67 spreads with a radial Gaussian of width dx: the window (in cells) has to cover the same number
+    of standard deviations along y when dy < dx; isotropic grids keep the caller's window."""
+    from jax_ib_b200 import engine
+    assert engine.effective_ib_window(6, (0.025, 0.025)) == 6
+    assert engine.effective_ib_window(6, (0.03, 0.05)) == 6
+    assert engine.effective_ib_window(6, (0.05, 0.03)) == 10
+    assert engine.effective_ib_window(8, (0.1, 0.01)) == 16  # clamped to what the kernels take

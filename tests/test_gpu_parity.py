@@ -143,6 +143,30 @@ def test_ib_windows_follow_a_domain_that_does_not_start_at_zero():
         assert rel_l2(sg, ib.spread_dense(Fk, xp, yp, dS, g, off)) < 1e-5
 
 
+def test_ib_window_widened_for_an_anisotropic_grid_matches_the_dense_sums():
+    """Spreading uses a radial Gaussian of width dx (IBM_Force.py:67): with dy < dx the y-window must cover R * dx/dy
+    cells.  engine.effective_ib_window picks that window for the reference-shaped API; here the kernels are checked
+    at it against the reference's DENSE sums."""
+    shape, domain = (300, 280), ((0.0, 300 * 0.05), (0.0, 280 * 0.03))
+    R = engine.effective_ib_window(6, (0.05, 0.03))
+    assert R == 10
+    cfg = dict(configs.flap600(), shape=shape, domain=domain)
+    g = field.Grid(shape, domain)
+    spec = demo.make_spec(cfg, ib_window=R)
+    xp, yp = _g1_like_markers()
+    rng = np.random.default_rng(8)
+    fld = rng.standard_normal(shape).astype(F)
+    for off in ((1.0, 0.5), (0.5, 1.0)):
+        var = field.Var(fld, off, g, field.periodic_bc())
+        got = host(ops.ib_interp(spec, dev(fld), off, dev(xp), dev(yp)))
+        assert rel_l2(got, ib.interpolate_dense(var, xp, yp)) < 2e-6
+        Fk = rng.standard_normal(xp.size).astype(F)
+        dS = np.sqrt((np.roll(xp, -1) - xp) ** 2 + (np.roll(yp, -1) - yp) ** 2).astype(F)
+        sg = host(ops.ib_spread(spec, off, dev(Fk), dev(xp), dev(yp), dev(dS)))
+        assert rel_l2(sg, ib.spread_windowed(Fk, xp, yp, dS, g, off, R)) < 1e-6
+        assert rel_l2(sg, ib.spread_dense(Fk, xp, yp, dS, g, off)) < 1e-5
+
+
 def test_ib_interp_partition_of_unity_and_edges():
     cfg = configs.flap600()
     spec = demo.make_spec(cfg)
