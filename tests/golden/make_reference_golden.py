@@ -301,6 +301,30 @@ def main():
     out["pen_step_p"] = np.asarray(av.pressure.data)
     out["pen_step_time"] = np.asarray(av.velocity[0].bc.time_stamp, dtype=F)
 
+    # ---- a4-a7 with the multi-body Fourier laws of the journal-bearing notebook (two bodies) --------------------
+    four_d = [[0.2, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.0], [-0.1, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], 0.5]]
+    four_r = [[0.8, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.3, 1.0], [0.5, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], -0.7, 0.5]]
+    out["kin_fourier_norm_rot"] = np.stack([np.asarray(K.rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED(four_r, t)) for t in ts])
+    out["kin_fourier_disp_dot"] = np.stack([np.asarray(jax.jacrev(lambda t: K.Displacement_Foil_Fourier_Dotted_Mutliple(four_d, t))(t)) for t in ts])
+    out["kin_fourier_norm_rot_dot"] = np.stack([np.asarray(jax.jacrev(lambda t: K.rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED(four_r, t))(t)) for t in ts])
+    U = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(u0s), (1.0, 0.5), grid), R.boundaries.new_periodic_boundary_conditions(ndim=2, bc_vals=((0.0, 0.0), (0.0, 0.0)), bc_fn=[zero] * 4, time_stamp=F(0.37)))
+    V = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(v0s), (0.5, 1.0), grid), U.bc)
+    P = R.grids.GridVariable(R.grids.GridArray(jnp.zeros(shape), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
+    two = R.particle_class.particle(centers, geom, four_d, four_r, grid1d, shape_fn, K.Displacement_Foil_Fourier_Dotted_Mutliple,
+                                    K.rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED)
+    av = R.particle_class.All_Variables(two, (U, V), P, [0], 0, [0])
+    fx, fy = R.IBM_Force.calc_IBM_force_NEW_MULTIPLE(av, delta, surf, dt)
+    out["two_fx"], out["two_fy"] = np.asarray(fx.data), np.asarray(fy.data)
+    step = R.equations.semi_implicit_navier_stokes_timeBC(
+        density=density, viscosity=viscosity, dt=dt, grid=grid, convect=lambda vv: tuple(R.advection.advect_upwind(c, vv, dt) for c in vv),
+        pressure_solve=R.pressure.solve_fast_diag, forcing=None, time_stepper=R.time_stepping.forward_euler_updated,
+        IBM_forcing=ib_forcing, Updating_Position=R.particle_motion.Update_particle_position_Multiple, Drag_fn=lambda av_, dt_: av_)
+    for _ in range(3):
+        av = step(av)
+    out["two_step_u"], out["two_step_v"] = (np.asarray(x.data) for x in av.velocity)
+    out["two_step_p"] = np.asarray(av.pressure.data)
+    out["two_step_centers"] = np.asarray(av.particles.particle_center)
+
     path = os.path.join(HERE, "reference_pinned.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

@@ -272,3 +272,36 @@ def test_penalty_forcing_and_stepper_match_the_reference():
     assert rel_l2(st.velocity[1].data, GOLD["pen_step_v"]) < 5e-6
     assert rel_l2(st.pressure.data, GOLD["pen_step_p"]) < 5e-5
     assert F(st.velocity[0].bc.time_stamp) == GOLD["pen_step_time"]
+
+
+# ------------------------------------------------------------------------------- multi-body Fourier laws (generator part 4)
+FOUR_D = [[0.2, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.0], [-0.1, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], 0.5]]
+FOUR_R = [[0.8, 0.3, 0.1, [0.5, 0.25, 0.1], [0.05, 0.02, 0.3], 1.3, 1.0], [0.5, 0.15, 0.7, [0.3, 0.0, 0.2], [0.1, 0.2, 0.0], -0.7, 0.5]]
+
+
+def test_two_bodies_on_the_journal_bearing_laws_match_the_reference():
+    """kinematics.py:14-105 (Fourier displacement, NORMALISED Fourier rotation) with their jacrev derivatives, the
+    per-body loop IBM_Force.py:89-106, and three assembled steps in which particle_motion.py:38-66 moves BOTH centres
+    with the multi-body law evaluated on all parameter sets at once."""
+    for i, t in enumerate(GOLD["kin_t"]):
+        np.testing.assert_allclose(okin.rotation_fourier_normalized(FOUR_R, t), GOLD["kin_fourier_norm_rot"][i], rtol=3e-6, atol=1e-6)
+        np.testing.assert_allclose(okin.displacement_fourier_dot(FOUR_D, t), GOLD["kin_fourier_disp_dot"][i], rtol=5e-6, atol=5e-6)
+        np.testing.assert_allclose(okin.rotation_fourier_normalized_dot(FOUR_R, t), GOLD["kin_fourier_norm_rot_dot"][i], rtol=5e-6, atol=5e-6)
+    g = _grid()
+    x0, y0 = GOLD["x0"], GOLD["y0"]
+    bodies = ib.Bodies(GOLD["ib_centers"].astype(F), [[0.5, 0.06]] * 2, FOUR_D, FOUR_R, lambda gp: (x0, y0),
+                       okin.DISPLACEMENT["fourier"], okin.ROTATION["fourier_normalized"])
+    bc = field.periodic_bc(F(0.37), [lambda t: 0.0] * 4)
+    U = field.Var(GOLD["step_u0"], (1.0, 0.5), g, bc)
+    V = field.Var(GOLD["step_v0"], (0.5, 1.0), g, bc)
+    P = field.Var(np.zeros(g.shape, F), (0.5, 0.5), g, field.periodic_bc())
+    fx, fy = ib.ibm_force((U, V), bodies, float(GOLD["dt"]), R=None)
+    assert rel_l2(fx, GOLD["two_fx"]) < 2e-6 and rel_l2(fy, GOLD["two_fy"]) < 2e-6
+    step = stepper.make_step(float(GOLD["dt"]), float(GOLD["step_viscosity"]), float(GOLD["step_density"]), "upwind", "periodic")
+    st = stepper.State(bodies, (U, V), P)
+    for _ in range(3):
+        st = step(st)
+    assert rel_l2(st.velocity[0].data, GOLD["two_step_u"]) < 5e-6
+    assert rel_l2(st.velocity[1].data, GOLD["two_step_v"]) < 5e-6
+    assert rel_l2(st.pressure.data, GOLD["two_step_p"]) < 5e-5
+    np.testing.assert_allclose(st.particles.centers, GOLD["two_step_centers"], rtol=0, atol=5e-7)
