@@ -62,7 +62,8 @@ typedef enum {
 typedef struct {
   int32_t nx, ny;      /* cells per axis (grids.py:563-624)                                      */
   int32_t batch;       /* independent simulations stacked on the leading axis (>= 1)            */
-  double lower_x, lower_y; /* domain lower corner                                              */
+  double lower_x, lower_y; /* domain lower corner: mesh point i lies at lower + (i + offset) * step (grids.py:665) and
+                            * the marker windows are centred on floor((x - lower) / step - offset)              */
   double dx, dy;       /* grid step = (upper - lower) / n                                       */
   double dt;           /* time step                                                             */
   double nu;           /* viscosity / density (equations.py:73); < 0 disables diffusion        */
@@ -72,7 +73,9 @@ typedef struct {
   double u_wall[2];    /* channel: u at the lower / upper y wall (bc_values[1] of velocity[0])  */
   double v_wall[2];    /* channel: v at the lower / upper y wall                                */
   double force[2];     /* constant body force (forcing(v) of the Taylor demo), per component    */
-  int32_t ib_window;   /* Gaussian truncation radius R in cells (window 2R x 2R); default 6     */
+  int32_t ib_window;   /* Gaussian truncation radius R in cells (window 2R x 2R), 1..16; default 6.  The spreading
+                        * Gaussian has width dx in BOTH directions (IBM_Force.py:67): with dy < dx pass
+                        * ceil(R * dx / dy) to keep R standard deviations along y (the Python API does)    */
   /* Slab decomposition along x (all zero for a full grid): the arrays hold global rows
    * [row0, row0 + nx) (halo rows included).  jaxib_ib_marker_force computes forces only for markers
    * whose u-cell row floor(xp/dx - 1) lies in [own_lo, own_hi) and leaves the entries of the others

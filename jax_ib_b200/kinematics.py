@@ -22,14 +22,21 @@ def _as(x, t):
     return torch.as_tensor(np.asarray(x, dtype=np.float32)) if not isinstance(x, torch.Tensor) else x.to(torch.float32)
 
 
+def _time(t):
+    """The laws take the clock as the reference does: a Python / NumPy scalar or a tensor (under jacrev)."""
+    return t if isinstance(t, torch.Tensor) else torch.as_tensor(np.float32(t))
+
+
 def displacement(parameters, t):
     """kinematics.py:5-7."""
+    t = _time(t)
     A0, f = (_as(x, t) for x in list(*parameters))
     return torch.stack([A0 / 2 * torch.cos(_TWO_PI * f * t), torch.zeros_like(t)])
 
 
 def rotation(parameters, t):
     """kinematics.py:10-12."""
+    t = _time(t)
     alpha0, beta, f, phi = (_as(x, t) for x in list(*parameters))
     return alpha0 + beta * torch.sin(_TWO_PI * f * t + phi)
 
@@ -48,6 +55,7 @@ def _fourier_parts(parameters, t, n_fields=6, p_index=5):
 
 def Displacement_Foil_Fourier_Dotted_Mutliple(parameters, t):
     """kinematics.py:14-38: returns [2, B]."""
+    t = _time(t)
     alpha0, f, phi, alpha, beta, p, freq = _fourier_parts(parameters, t)
     inside = _TWO_PI * t * freq * f + phi
     a1 = (alpha * torch.sin(inside)).sum(dim=1)
@@ -57,6 +65,7 @@ def Displacement_Foil_Fourier_Dotted_Mutliple(parameters, t):
 
 def rotation_Foil_Fourier_Dotted_Mutliple(parameters, t):
     """kinematics.py:41-65: returns [B]."""
+    t = _time(t)
     alpha0, f, phi, alpha, beta, p, freq = _fourier_parts(parameters, t)
     inside = _TWO_PI * t * freq * f + phi
     a1 = (alpha * torch.sin(inside)).sum(dim=1)
@@ -66,6 +75,7 @@ def rotation_Foil_Fourier_Dotted_Mutliple(parameters, t):
 
 def rotation_Foil_Fourier_Dotted_Mutliple_NORMALIZED(parameters, t):
     """kinematics.py:67-105: returns [B]."""
+    t = _time(t)
     alpha0, f, phi, alpha, beta, p, freq = _fourier_parts(parameters, t, 7, 6)
     theta_av = torch.stack([_as(x, t).reshape(()) for x in _col(parameters, 5)])
     inside = _TWO_PI * t * freq * f + phi
@@ -228,6 +238,7 @@ def body_schedule(particles, t0: float, dt: float, nsteps: int):
 # body only -- `list(*parameters)` -- so grids with several flapping bodies need a vectorised form)
 def displacement_multiple(parameters, t):
     """[2, B]: per body [A0/2 cos(2 pi f t), 0] with parameters = [[A0, f], ...]."""
+    t = _time(t)
     A0 = torch.stack([_as(x, t).reshape(()) for x in _col(parameters, 0)])
     f = torch.stack([_as(x, t).reshape(()) for x in _col(parameters, 1)])
     x = A0 / 2 * torch.cos(_TWO_PI * f * t)
@@ -236,6 +247,7 @@ def displacement_multiple(parameters, t):
 
 def rotation_multiple(parameters, t):
     """[B]: alpha0 + beta sin(2 pi f t + phi) with parameters = [[alpha0, beta, f, phi], ...]."""
+    t = _time(t)
     a0, beta, f, phi = (torch.stack([_as(x, t).reshape(()) for x in _col(parameters, i)]) for i in range(4))
     return a0 + beta * torch.sin(_TWO_PI * f * t + phi)
 

@@ -93,6 +93,9 @@ def main():
     per = R.boundaries.periodic_boundary_conditions(2)
     bcs = {"periodic": (per, per),
            "channel": tuple(R.boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), w), 0.0, None) for w in walls)}
+    far = tuple(R.boundaries.Far_field_boundary_conditions(2, w, 0.0, None) for w in (((0.5, 0.4), (0.3, -0.2)), ((0.0, 0.1), (0.0, 0.0))))
+    out["far_walls"] = np.array([[[0.5, 0.4], [0.3, -0.2]], [[0.0, 0.1], [0.0, 0.0]]])
+    bcs["far_field"] = far  # Dirichlet on all four walls, non-zero values on each
     for tag, (bcu, bcv) in bcs.items():
         U, V, _ = variables(bcu, bcv, per)
         P = R.grids.GridVariable(R.grids.GridArray(jnp.asarray(p), (0.5, 0.5), grid), R.boundaries.get_pressure_bc_from_velocity((U, V)))
@@ -179,9 +182,6 @@ def main():
 
     # ---- a14-a17: pressure solve and projection through the reference's pressure.py / array_utils.py ----------
     # (jax_cfd's fast_diagonalization.pseudoinverse, which they call, is the stand-in's restatement)
-    far = tuple(R.boundaries.Far_field_boundary_conditions(2, w, 0.0, None) for w in (((0.5, 0.4), (0.3, -0.2)), ((0.0, 0.1), (0.0, 0.0))))
-    out["far_walls"] = np.array([[[0.5, 0.4], [0.3, -0.2]], [[0.0, 0.1], [0.0, 0.0]]])
-    bcs["far_field"] = far
     solvers = {"periodic": R.pressure.solve_fast_diag, "channel": R.pressure.solve_fast_diag_moving_wall,
                "far_field": R.pressure.solve_fast_diag_Far_Field}
     for tag, (bcu, bcv) in bcs.items():

@@ -81,7 +81,7 @@ IBM = lambda av, dt: IBM_Force.calc_IBM_force_NEW_MULTIPLE(av, DELTA, SURF, dt)
 
 
 # ------------------------------------------------------------------------------------------------ stages
-@pytest.mark.parametrize("tag", ["periodic", "channel"])
+@pytest.mark.parametrize("tag", ["periodic", "channel", "far_field"])
 def test_advection_and_differences_against_the_reference_files(tag):
     """advection.py:120-333 and finite_differences.py on the reference's arrays (random fields, moving-wall values)."""
     bcu, bcv = _bcs(tag)

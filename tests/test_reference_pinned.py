@@ -28,6 +28,10 @@ def _velocity(tag):
     g = _grid()
     if tag == "periodic":
         bcu = bcv = field.periodic_bc()
+    elif tag == "far_field":
+        wu, wv = GOLD["far_walls"]
+        bcu = field.far_field_bc(tuple(tuple(float(x) for x in r) for r in wu))
+        bcv = field.far_field_bc(tuple(tuple(float(x) for x in r) for r in wv))
     else:
         (ulo, uhi), (vlo, vhi) = GOLD["walls"]
         bcu = field.channel_bc(((0.0, 0.0), (float(ulo), float(uhi))))
@@ -38,7 +42,7 @@ def _velocity(tag):
     return U, V, P
 
 
-@pytest.mark.parametrize("tag", ["periodic", "channel"])
+@pytest.mark.parametrize("tag", ["periodic", "channel", "far_field"])
 def test_stencils_and_ghost_cells_equal_the_reference_bit_for_bit(tag):
     """advection.py:120-333, finite_differences.py:87-146, grids.py shift / boundaries.py:116-273 pad, trim."""
     U, V, P = _velocity(tag)
