@@ -325,6 +325,10 @@ def main():
     out["two_step_p"] = np.asarray(av.pressure.data)
     out["two_step_centers"] = np.asarray(av.particles.particle_center)
 
+    # ---- post-processing integral (IBM_Force.py:5-18) ----------------------------------------------------------
+    U, V, P = variables(per, per, per)
+    out["trapz_u"] = np.asarray(R.IBM_Force.Integrate_Field_Fluid_Domain(U))
+
     path = os.path.join(HERE, "reference_pinned.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

@@ -130,6 +130,20 @@ def test_direct_forcing_of_two_bodies_against_the_reference_files():
     np.testing.assert_allclose(host(got), GOLD["surf_u"], rtol=5e-6, atol=2e-6)
 
 
+def test_per_component_forcing_entry_points_against_the_reference_files():
+    """IBM_Force.py:89-106 IBM_Multiple_NEW (all bodies, one component) on top of IBM_force_GENERAL (:20-87, one body,
+    caller-supplied kinematic callables), and the domain integral :5-18."""
+    bcu, bcv = _bcs("periodic", float(GOLD["ib_t0"]))
+    U, V, P = _variables(GOLD["u"], GOLD["v"], GOLD["p"], bcu, bcv)
+    two = _body(2)
+    fx = IBM_Force.IBM_Multiple_NEW(U, 0, two, DELTA, SURF, float(GOLD["dt"]))
+    fy = IBM_Force.IBM_Multiple_NEW(V, 1, two, DELTA, SURF, float(GOLD["dt"]))
+    assert tuple(fx.offset) == (1.0, 0.5) and tuple(fy.offset) == (0.5, 1.0)
+    assert rel_l2(host(fx.data), GOLD["ib_fx"]) < 5e-6
+    assert rel_l2(host(fy.data), GOLD["ib_fy"]) < 5e-6
+    assert float(IBM_Force.Integrate_Field_Fluid_Domain(U)) == pytest.approx(float(GOLD["trapz_u"]), rel=2e-5, abs=1e-6)
+
+
 def test_tracer_coupling_against_the_reference_files():
     """MD/CFD_MD_coupling.py:7-27 (points on the edges and outside the grid included) and three zero-temperature
     Brownian steps of MD/simulate.py:81-97 with the notebooks' masked shift, in a frozen velocity field."""

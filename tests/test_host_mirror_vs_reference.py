@@ -111,3 +111,11 @@ def test_clock_walls_and_body_update_match_the_reference():
     moved = particle_motion.Update_particle_position_Multiple(pc.All_Variables(one, (U, V), P, [], 3, None), float(GOLD["dt"]))
     np.testing.assert_allclose(np.asarray(moved.particles.particle_center), GOLD["ib_new_centers"], rtol=0, atol=2e-7)
     assert moved.Step_count == int(GOLD["ib_step_count"])
+
+
+def test_domain_integral_matches_the_reference():
+    """IBM_Force.py:5-18 Integrate_Field_Fluid_Domain: nested trapezoid rule (last axis with dx, then dy, as written)."""
+    from jax_ib_b200 import IBM_Force
+    U, _, _ = _variables("periodic")
+    got = float(IBM_Force.integrate_trapz(U.data, U.grid.step[0], U.grid.step[1]))
+    assert got == pytest.approx(float(GOLD["trapz_u"]), rel=2e-5, abs=1e-6)
