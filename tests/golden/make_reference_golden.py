@@ -68,7 +68,8 @@ def ellipse_markers(a, b, n):
     return np.concatenate([x, x[::-1][1:-1]]).astype(F), np.concatenate([y, -y[::-1][1:-1]]).astype(F)
 
 
-def main():
+def generate():
+    """Runs the reference's files and returns {name: array}."""
     R = load_reference()
     import jax.numpy as jnp
     out = {}
@@ -329,6 +330,11 @@ def main():
     U, V, P = variables(per, per, per)
     out["trapz_u"] = np.asarray(R.IBM_Force.Integrate_Field_Fluid_Domain(U))
 
+    return out
+
+
+def main():
+    out = generate()
     path = os.path.join(HERE, "reference_pinned.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

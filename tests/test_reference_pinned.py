@@ -309,3 +309,22 @@ def test_two_bodies_on_the_journal_bearing_laws_match_the_reference():
     assert rel_l2(st.velocity[1].data, GOLD["two_step_v"]) < 5e-6
     assert rel_l2(st.pressure.data, GOLD["two_step_p"]) < 5e-5
     np.testing.assert_allclose(st.particles.centers, GOLD["two_step_centers"], rtol=0, atol=5e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/jax_ib"), reason="the reference tree only exists in the build container")
+def test_committed_fixture_is_what_the_reference_files_produce_today():
+    """Regenerates every golden array from /root/reference in a child process (the stand-in shadows `jax` on sys.path,
+    which must not leak into this process) and compares with the committed .npz, bit for bit."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        code = ("import sys, numpy as np; sys.path.insert(0, %r); import make_reference_golden as m; "
+                "np.savez(%r, **m.generate())" % (os.path.join(root, "tests", "golden"), os.path.join(tmp, "fresh.npz")))
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        fresh = np.load(os.path.join(tmp, "fresh.npz"))
+        assert sorted(fresh.files) == sorted(GOLD.files)
+        for k in GOLD.files:
+            np.testing.assert_array_equal(fresh[k], GOLD[k], err_msg=k)
