@@ -8,8 +8,9 @@ stand-in for the handful of `jax` entry points the reference's own modules use (
 typed scalars, vmap / pmap as loops, jacrev as a complex-step derivative -- see its docstring).  With it on sys.path
 the UNMODIFIED files /root/reference/jax_ib/base/{grids, boundaries, finite_differences, interpolation, advection,
 convolution_functions, IBM_Force, kinematics, particle_class, particle_motion, array_utils, diffusion, pressure,
-time_stepping, equations}.py are imported -- through stub `jax_ib` / `jax_ib.base` packages, because the reference's own
-__init__ files pull in jax_md-dependent modules that cannot load -- and executed on seeded inputs.  Inputs and outputs
+time_stepping, equations}.py, MD/{CFD_MD_coupling, simulate, interaction_potential}.py and penalty/{util_funs,
+parameteric_fns}.py are imported -- as the reference's own package, `import jax_ib`, from /root/reference -- and executed on
+seeded inputs.  Inputs and outputs
 go into one .npz; tests/test_reference_pinned.py feeds the same inputs to oracle/ and compares (CPU, no reference
 needed).
 
@@ -41,22 +42,18 @@ F = np.float32
 
 
 def load_reference():
+    """Puts the stand-ins and the reference tree on sys.path and imports the reference's OWN package: with jax,
+    tree_math, jax_cfd and jax_md standing in, `import jax_ib` runs its unmodified __init__ files."""
+    sys.dont_write_bytecode = True  # /root/reference is read-only
     sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_standin"))
-    for name, path in (("jax_ib", REF + "/jax_ib"), ("jax_ib.base", REF + "/jax_ib/base")):
-        m = types.ModuleType(name)
-        m.__path__ = [path]
-        sys.modules[name] = m
-    for name, path in (("jax_ib.MD", REF + "/jax_ib/MD"), ("jax_ib.penalty", REF + "/jax_ib/penalty")):
-        m = types.ModuleType(name)
-        m.__path__ = [path]
-        sys.modules[name] = m
-    names = ("grids", "particle_class", "boundaries", "interpolation", "finite_differences", "advection",
-             "convolution_functions", "IBM_Force", "kinematics", "particle_motion", "array_utils", "diffusion",
-             "pressure", "time_stepping", "equations")
-    ns = {n: importlib.import_module("jax_ib.base." + n) for n in names}
-    for pkg, mods in (("MD", ("CFD_MD_coupling", "simulate", "interaction_potential")), ("penalty", ("util_funs", "parameteric_fns"))):
-        for n in mods:
-            ns[n] = importlib.import_module(f"jax_ib.{pkg}.{n}")
+    sys.path.insert(0, REF)
+    import jax_ib  # noqa: F401
+    names = {"base": ("grids", "particle_class", "boundaries", "interpolation", "finite_differences", "advection",
+                      "convolution_functions", "IBM_Force", "kinematics", "particle_motion", "array_utils", "diffusion",
+                      "pressure", "time_stepping", "equations"),
+             "MD": ("CFD_MD_coupling", "simulate", "interaction_potential"), "penalty": ("util_funs", "parameteric_fns")}
+    ns = {n: importlib.import_module(f"jax_ib.{pkg}.{n}") for pkg, mods in names.items() for n in mods}
+    assert all(m.__file__.startswith(REF + "/") for m in ns.values())
     return types.SimpleNamespace(**ns)
 
 

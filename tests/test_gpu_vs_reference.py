@@ -230,3 +230,25 @@ def test_two_bodies_on_the_journal_bearing_laws_against_the_reference_files():
     assert rel_l2(host(out.velocity[1].data), GOLD["two_step_v"]) < 1e-5
     assert rel_l2(host(out.pressure.data), GOLD["two_step_p"]) < 1e-4
     np.testing.assert_allclose(np.asarray(out.particles.particle_center), GOLD["two_step_centers"], rtol=0, atol=1e-6)
+
+
+def test_flapping_notebook_twenty_steps_against_the_reference_notebook_run():
+    """Flapping_Demo.ipynb as published (600 x 600, 298 markers, upwind, dt = 5e-4) for 20 steps through the reference-shaped
+    API, against what the NOTEBOOK ITSELF produced when its code cells were executed on the stand-in
+    (tests/golden/make_reference_notebook_golden.py; dense marker sums there).  Bars as for the oracle's fixture of
+    the same run: max(1e-5, 2 x the float32 round-off floor of this trajectory)."""
+    from test_dropin_api import flapping_setup
+    here = os.path.dirname(os.path.abspath(__file__))
+    nb = np.load(os.path.join(here, "golden", "reference_notebook_flap600.npz"))
+    floor = np.load(os.path.join(here, "golden", "flap600_20.npz"))
+    step_fn, all_variables = flapping_setup()
+    final, traj = funcutils.trajectory(funcutils.repeated(step_fn, steps=10), 2, start_with_input=True)(all_variables)
+    assert final.Step_count == int(nb["steps"]) and [t.Step_count for t in traj] == list(nb["snapshot_steps"])
+    a, b, c, d = (int(x) for x in nb["crop"])
+    for key, var in (("u", final.velocity[0]), ("v", final.velocity[1]), ("p", final.pressure)):
+        # + 2e-6: two float32 evaluations of the same dense run (the notebook on the stand-in, the oracle) already differ
+        # by 1e-7 (u, v) to 8e-7 (p), tests/test_reference_pinned.py::test_oracle_trajectory_fixture_equals_...
+        bar = max(1e-5, 2.0 * float(floor[key + "_noise"])) + 2e-6
+        assert rel_l2(host(var.data)[a:b, c:d], nb[key + "_crop"]) < bar, key
+    np.testing.assert_allclose(np.asarray(final.particles.particle_center), nb["centers"], atol=2e-6)
+    assert F(final.velocity[0].bc.time_stamp) == F(nb["time"])

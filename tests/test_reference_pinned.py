@@ -328,3 +328,20 @@ def test_committed_fixture_is_what_the_reference_files_produce_today():
         assert sorted(fresh.files) == sorted(GOLD.files)
         for k in GOLD.files:
             np.testing.assert_array_equal(fresh[k], GOLD[k], err_msg=k)
+
+
+def test_oracle_trajectory_fixture_equals_the_reference_notebook_run():
+    """tests/golden/reference_notebook_flap600.npz is Flapping_Demo.ipynb itself -- its code cells executed verbatim on the
+    stand-in (make_reference_notebook_golden.py), 20 steps at 600 x 600 with the 298-marker ellipse and dense sums.
+    tests/golden/flap600_20.npz is the same run from the oracle, the fixture the GPU tests have replayed since round 1.
+    Comparing the two ties every CUDA-vs-golden assertion to the notebook's own output."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    nb = np.load(os.path.join(here, "golden", "reference_notebook_flap600.npz"))
+    gold = np.load(os.path.join(here, "golden", "flap600_20.npz"))
+    assert int(nb["steps"]) == int(gold["step_count"]) == 20 and list(nb["snapshot_steps"]) == [0, 10]
+    assert np.array_equal(nb["crop"], gold["crop"])
+    for key, bar in (("u", 5e-7), ("v", 5e-7), ("p", 3e-6)):
+        assert rel_l2(gold[key + "_crop"], nb[key + "_crop"]) < bar, key
+        assert float(gold[key + "_l2"]) == pytest.approx(float(nb[key + "_l2"]), rel=1e-6)
+    np.testing.assert_array_equal(gold["centers"], nb["centers"])
+    assert F(gold["time"]) == F(nb["time"])
