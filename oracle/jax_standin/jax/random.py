@@ -20,5 +20,13 @@ def normal(key, shape, dtype=_np.float32):
     return _np.zeros(shape, dtype=_np.float32)
 
 
-def uniform(*a, **k):
-    raise NotImplementedError("threefry is not restated")
+NUMPY_UNIFORM_FOR_INPUTS = False
+
+
+def uniform(key, shape=(), dtype=_np.float32, minval=0.0, maxval=1.0):
+    """NOT JAX's stream.  Only for notebook cells that draw INPUT data (tracer start positions) whose values are stored
+    with the fixture or do not influence what is compared; the generator has to opt in through the module flag."""
+    if not NUMPY_UNIFORM_FOR_INPUTS:
+        raise NotImplementedError("threefry is not restated")
+    rng = _np.random.default_rng(int(_np.asarray(key).ravel()[-1]))
+    return (minval + (maxval - minval) * rng.random(shape)).astype(_np.float32)

@@ -330,18 +330,22 @@ def test_committed_fixture_is_what_the_reference_files_produce_today():
             np.testing.assert_array_equal(fresh[k], GOLD[k], err_msg=k)
 
 
-def test_oracle_trajectory_fixture_equals_the_reference_notebook_run():
-    """tests/golden/reference_notebook_flap600.npz is Flapping_Demo.ipynb itself -- its code cells executed verbatim on the
-    stand-in (make_reference_notebook_golden.py), 20 steps at 600 x 600 with the 298-marker ellipse and dense sums.
-    tests/golden/flap600_20.npz is the same run from the oracle, the fixture the GPU tests have replayed since round 1.
-    Comparing the two ties every CUDA-vs-golden assertion to the notebook's own output."""
+@pytest.mark.parametrize("name,oracle_fixture", [("flap600", "flap600_20.npz"), ("bearing300", "bearing300_20.npz")])
+def test_oracle_trajectory_fixtures_equal_the_reference_notebook_runs(name, oracle_fixture):
+    """tests/golden/reference_notebook_<name>.npz are the reference's NOTEBOOKS themselves -- Flapping_Demo.ipynb (600 x 600,
+    one 298-marker ellipse) and journal_bearing_demo.ipynb (300 x 300, two concentric circles on the normalised Fourier
+    laws, passive tracers) with their code cells executed verbatim on the stand-in for 20 steps, dense marker sums
+    (make_reference_notebook_golden.py).  tests/golden/<oracle_fixture> is the same run from the oracle, the fixture the
+    GPU tests have replayed since round 1.  Comparing the two ties every CUDA-vs-golden assertion to the notebooks' own
+    output.  Bars: 2e-6 for the velocities; for the pressure twice the float32 round-off floor the oracle fixture
+    records for its trajectory (|p| << |u| in the bearing run: floor 7e-5)."""
     here = os.path.dirname(os.path.abspath(__file__))
-    nb = np.load(os.path.join(here, "golden", "reference_notebook_flap600.npz"))
-    gold = np.load(os.path.join(here, "golden", "flap600_20.npz"))
+    nb = np.load(os.path.join(here, "golden", f"reference_notebook_{name}.npz"))
+    gold = np.load(os.path.join(here, "golden", oracle_fixture))
     assert int(nb["steps"]) == int(gold["step_count"]) == 20 and list(nb["snapshot_steps"]) == [0, 10]
     assert np.array_equal(nb["crop"], gold["crop"])
-    for key, bar in (("u", 5e-7), ("v", 5e-7), ("p", 3e-6)):
+    for key, bar in (("u", 2e-6), ("v", 2e-6), ("p", 2.0 * float(gold["p_noise"]))):
         assert rel_l2(gold[key + "_crop"], nb[key + "_crop"]) < bar, key
-        assert float(gold[key + "_l2"]) == pytest.approx(float(nb[key + "_l2"]), rel=1e-6)
+        assert float(gold[key + "_l2"]) == pytest.approx(float(nb[key + "_l2"]), rel=1e-6 if key != "p" else 1e-4)
     np.testing.assert_array_equal(gold["centers"], nb["centers"])
     assert F(gold["time"]) == F(nb["time"])
