@@ -68,6 +68,11 @@ def main():
             out[key + "_crop"] = full[a:b, c:d]
             out[key + "_l2"] = np.float64(np.sqrt((full.astype(np.float64) ** 2).sum()))
             out[key + "_sum"] = np.float64(full.astype(np.float64).sum())
+        if name == "bearing300":  # passive tracers (no pair force here, see NOTEBOOKS): start, end, mobility mask
+            out["md_pos0"] = np.asarray(ns["Pos_all"], dtype=np.float32)
+            out["md_pos"] = np.asarray(final.MD_var.position, dtype=np.float32)
+            out["md_mobile"] = np.asarray(ns["is_mobile"]).astype(bool)
+            out["md_gamma"] = np.float64(ns["gamma_val"])
         path = os.path.join(HERE, f"reference_notebook_{name}.npz")
         np.savez_compressed(path, **out)
         print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB in {time.time() - t0:.0f} s")

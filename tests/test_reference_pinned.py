@@ -349,3 +349,29 @@ def test_oracle_trajectory_fixtures_equal_the_reference_notebook_runs(name, orac
         assert float(gold[key + "_l2"]) == pytest.approx(float(nb[key + "_l2"]), rel=1e-6 if key != "p" else 1e-4)
     np.testing.assert_array_equal(gold["centers"], nb["centers"])
     assert F(gold["time"]) == F(nb["time"])
+
+
+def test_tracers_in_the_journal_bearing_notebook_run():
+    """particle_motion.py:6-35 Update_particle_position_Multiple_and_MD_Step inside the assembled step: WHICH velocity
+    field and WHICH body state the Brownian sub-step sees (time_stepping.py:253 runs it last, on the projected field).
+    The notebook's 1401 tracers were advanced for 20 steps by the reference's own files (passive: the jax_md pair
+    potential is not restated, so there is no wall repulsion on either side); the oracle repeats the run from the same
+    start positions."""
+    from jax_ib_b200 import configs
+    from oracle import tracers
+    from _adapter import oracle_state, oracle_step
+    here = os.path.dirname(os.path.abspath(__file__))
+    nb = np.load(os.path.join(here, "golden", "reference_notebook_bearing300.npz"))
+    cfg = configs.bearing300()
+    st = oracle_state(cfg)
+    st.MD_var = tracers.BrownianState(nb["md_pos0"].copy())
+    md = lambda s: tracers.brownian_step(s.MD_var, s.velocity, cfg["dt"], float(nb["md_gamma"]), 0.0, None, nb["md_mobile"])
+    step = oracle_step(cfg, ib_window=6, md_step=md)
+    for _ in range(int(nb["steps"])):
+        st = step(st)
+    moved = np.abs(nb["md_pos"] - nb["md_pos0"]).max()
+    assert moved > 5e-3  # the tracers really travelled (|u| dt steps ~ 4e-4 each)
+    np.testing.assert_allclose(st.MD_var.position, nb["md_pos"], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(st.MD_var.position[~nb["md_mobile"]], nb["md_pos0"][~nb["md_mobile"]])
+    a, b, c, d = (int(x) for x in nb["crop"])
+    assert rel_l2(st.velocity[0].data[a:b, c:d], nb["u_crop"]) < 2e-6
