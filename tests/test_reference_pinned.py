@@ -375,3 +375,29 @@ def test_tracers_in_the_journal_bearing_notebook_run():
     np.testing.assert_array_equal(st.MD_var.position[~nb["md_mobile"]], nb["md_pos0"][~nb["md_mobile"]])
     a, b, c, d = (int(x) for x in nb["crop"])
     assert rel_l2(st.velocity[0].data[a:b, c:d], nb["u_crop"]) < 2e-6
+
+
+def test_bench_workload_three_steps_by_the_reference_files():
+    """ib2048 -- the configuration bench.py times -- advanced three steps by the reference's own files with dense marker
+    sums (tests/golden/make_reference_ib2048_golden.py, ~10 min on NumPy) against the windowed oracle the GPU test of the
+    same workload uses (tests/test_gpu_round2.py::test_bench_workloads_match_windowed_oracle): crops around the four
+    bodies, 64 x 64 block means of the whole field, norms, centres, clock."""
+    from jax_ib_b200 import configs
+    from _adapter import oracle_state, oracle_step
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = np.load(os.path.join(here, "golden", "reference_ib2048_3.npz"))
+    cfg = configs.ib_periodic(2048, 2)
+    st = oracle_state(cfg)
+    step = oracle_step(cfg, ib_window=6)
+    for _ in range(int(ref["steps"])):
+        st = step(st)
+    for key, var in (("u", st.velocity[0]), ("v", st.velocity[1]), ("p", st.pressure)):
+        full = var.data
+        crops = np.stack([full[a:b, c:d] for a, b, c, d in ref["boxes"]])
+        assert rel_l2(crops, ref[key + "_crops"]) < 2e-6, key
+        blocks = full.astype(np.float64).reshape(64, 32, 64, 32).mean(axis=(1, 3))
+        assert rel_l2(blocks, ref[key + "_blocks"]) < 2e-6, key
+        assert float(np.sqrt((full.astype(np.float64) ** 2).sum())) == pytest.approx(float(ref[key + "_l2"]), rel=1e-6)
+    np.testing.assert_allclose(st.particles.centers, ref["centers"], rtol=0, atol=5e-7)
+    assert F(st.velocity[0].bc.time_stamp) == F(ref["time"])
+    assert st.Step_count == int(ref["steps"])
