@@ -3,8 +3,10 @@ reference's dense O(M*Nx*Ny) Gaussian sums exactly as IBM_Force.py / convolution
 
     python tests/golden/make_golden.py            # writes tests/golden/*.npz
 
-The reference itself cannot run in this image (no JAX), so these are outputs of the
-restatement, not of jax_ib: "parity unpinned" applies (oracle/__init__.py).  Each file holds a crop
+These are outputs of the restatement.  Since round 2 each of the three reference configurations is tied to a run of
+the reference's OWN files / notebooks on the NumPy stand-in for jax (make_reference_notebook_golden.py,
+make_reference_workload_golden.py; tests/test_reference_pinned.py compares: flap600 1e-7, bearing300 1e-6,
+channel1024x256 bit-identical).  Each file holds a crop
 of (u, v, p) around the bodies plus full-field norms / sums, the clock, the body centres and the
 step count, so the fixtures stay small.
 """

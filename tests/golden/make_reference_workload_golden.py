@@ -1,8 +1,16 @@
-"""The BENCH WORKLOAD (ib2048: 2048 x 2048 periodic, four flapping 298-marker ellipses, upwind, FFT projection -- the
-configuration `bench.py` times and BASELINE.json's metric is quoted on) advanced for three steps by the REFERENCE'S OWN
-FILES on the NumPy stand-in for jax, wired exactly as Flapping_Demo.ipynb cell 9 wires them.  Build container only.
+"""Two of the measured workloads advanced by the REFERENCE'S OWN FILES on the NumPy stand-in for jax.  Build container only.
 
-    python tests/golden/make_reference_ib2048_golden.py     # ~10 min, ~12 GB peak; writes tests/golden/reference_ib2048_3.npz
+    python tests/golden/make_reference_workload_golden.py ib2048     # ~10 min, ~12 GB peak -> reference_ib2048_3.npz
+    python tests/golden/make_reference_workload_golden.py channel    # seconds              -> reference_channel1024x256_5.npz
+
+channel: G3's parity case (jax_ib_b200/configs.py::channel: 1024 x 256, periodic x / no-slip y, van Leer advection, body
+force, Poiseuille + noise start), five steps, the run tests/golden/channel1024x256_5.npz holds from the oracle.  The
+reference's step function always calls its IBM_forcing and Updating_Position plug-ins (time_stepping.py:210,253), so
+a body-free run passes a zero force and an identity, as a reference user would.
+
+ib2048: the BENCH WORKLOAD ( 2048 x 2048 periodic, four flapping 298-marker ellipses, upwind, FFT projection -- the
+configuration `bench.py` times and BASELINE.json's metric is quoted on) advanced for three steps, wired exactly as
+Flapping_Demo.ipynb cell 9 wires the reference.
 
 The reference sums every marker over the WHOLE grid (1192 markers x 4.2 M cells, twice per component and step), which
 is why this is three steps and why nothing like it can run inside a test.  Inputs are the product's own workload
@@ -25,7 +33,7 @@ STEPS = 3
 HALF = 80  # crop half-width in cells
 
 
-def main():
+def main_ib2048():
     t_start = time.time()
     sys.dont_write_bytecode = True
     sys.path.insert(0, ROOT)
@@ -98,5 +106,55 @@ def main():
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB in {time.time() - t_start:.0f} s")
 
 
+def main_channel():
+    t_start = time.time()
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, ROOT)
+    from jax_ib_b200 import configs
+    cfg = configs.channel()
+    u0, v0, p0 = configs.initial_fields(cfg)
+    gold = np.load(os.path.join(HERE, "channel1024x256_5.npz"))
+    steps = int(gold["steps"])
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_standin"))
+    sys.path.insert(0, REF)
+    import jax.numpy as jnp
+    import jax_cfd.base as cfd
+    import jax_ib.base as ib
+    from jax_ib.base import advection, boundaries, grids, particle_class as pc
+
+    dt = cfg["dt"]
+    grid = grids.Grid(cfg["shape"], domain=cfg["domain"])
+    zero = lambda t: 0.0
+    bcs = tuple(boundaries.Moving_wall_boundary_conditions(2, ((0.0, 0.0), tuple(w)), 0.0, [zero] * 4) for w in (cfg["wall_u"], cfg["wall_v"]))
+    v = tuple(grids.GridVariable(grids.GridArray(jnp.asarray(a), off, grid), bc) for a, off, bc in zip((u0, v0), grid.cell_faces, bcs))
+    p = grids.GridVariable(grids.GridArray(jnp.asarray(p0), grid.cell_center, grid), boundaries.get_pressure_bc_from_velocity(v))
+    fx, fy = cfg["force"]
+    forcing = lambda vv: tuple(grids.GridArray(f * jnp.ones_like(c.data), c.offset, c.grid) for f, c in zip((fx, fy), vv))
+    no_bodies = lambda av, dt_: tuple(grids.GridVariable(grids.GridArray(jnp.zeros_like(c.data), c.offset, c.grid), c.bc) for c in av.velocity)
+    step_fn = cfd.funcutils.repeated(
+        ib.equations.semi_implicit_navier_stokes_timeBC(
+            density=cfg["density"], viscosity=cfg["viscosity"], dt=dt, grid=grid,
+            convect=lambda vv: tuple(advection.advect_van_leer(c, vv, dt) for c in vv),
+            pressure_solve=ib.pressure.solve_fast_diag_moving_wall, forcing=forcing,
+            time_stepper=ib.time_stepping.forward_euler_updated, IBM_forcing=no_bodies,
+            Updating_Position=lambda av, dt_: av, Drag_fn=lambda av, dt_: av),
+        steps=steps)
+    final = step_fn(pc.All_Variables(None, v, p, [0], 0, [0]))
+    a, b, c, d = (int(x) for x in gold["crop"])
+    out = {"crop": gold["crop"], "steps": np.int64(steps), "time": np.asarray(final.velocity[0].bc.time_stamp, dtype=F)}
+    for key, var in (("u", final.velocity[0]), ("v", final.velocity[1]), ("p", final.pressure)):
+        full = np.asarray(var.data, dtype=F)
+        out[key + "_crop"] = full[a:b, c:d]
+        out[key + "_l2"] = np.float64(np.sqrt((full.astype(np.float64) ** 2).sum()))
+    path = os.path.join(HERE, "reference_channel1024x256_5.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB in {time.time() - t_start:.0f} s")
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["channel", "ib2048"]
+    if "channel" in which:
+        main_channel()
+    if "ib2048" in which:
+        main_ib2048()

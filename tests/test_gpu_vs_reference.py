@@ -256,7 +256,7 @@ def test_flapping_notebook_twenty_steps_against_the_reference_notebook_run():
 
 def test_bench_workload_three_steps_against_the_reference_files():
     """ib2048 -- what bench.py times -- through the fused path for three steps, against the same three steps taken by the
-    reference's own files with DENSE marker sums (tests/golden/make_reference_ib2048_golden.py; the oracle agrees with
+    reference's own files with DENSE marker sums (tests/golden/make_reference_workload_golden.py; the oracle agrees with
     that run to 6e-8 .. 2e-7, tests/test_reference_pinned.py).  Only crops around the four bodies, 64 x 64 block means,
     norms, centres and clock of the reference run are stored (the full fields are 50 MB).  Bars: block means of the
     whole field 1e-5 (the north star); the crops isolate the region where the immersed-boundary forcing acts and are

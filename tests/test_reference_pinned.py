@@ -379,7 +379,7 @@ def test_tracers_in_the_journal_bearing_notebook_run():
 
 def test_bench_workload_three_steps_by_the_reference_files():
     """ib2048 -- the configuration bench.py times -- advanced three steps by the reference's own files with dense marker
-    sums (tests/golden/make_reference_ib2048_golden.py, ~10 min on NumPy) against the windowed oracle the GPU test of the
+    sums (tests/golden/make_reference_workload_golden.py, ~10 min on NumPy) against the windowed oracle the GPU test of the
     same workload uses (tests/test_gpu_round2.py::test_bench_workloads_match_windowed_oracle): crops around the four
     bodies, 64 x 64 block means of the whole field, norms, centres, clock."""
     from jax_ib_b200 import configs
@@ -401,3 +401,17 @@ def test_bench_workload_three_steps_by_the_reference_files():
     np.testing.assert_allclose(st.particles.centers, ref["centers"], rtol=0, atol=5e-7)
     assert F(st.velocity[0].bc.time_stamp) == F(ref["time"])
     assert st.Step_count == int(ref["steps"])
+
+
+def test_channel_trajectory_fixture_is_bit_identical_to_the_reference_run():
+    """G3's parity case (1024 x 256 channel, van Leer, body force, Poiseuille + noise, five steps): the oracle's fixture
+    the GPU test replays (tests/golden/channel1024x256_5.npz) against the same run by the reference's own files with its
+    eigh + matmul pressure solve (tests/golden/make_reference_workload_golden.py channel)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = np.load(os.path.join(here, "golden", "reference_channel1024x256_5.npz"))
+    gold = np.load(os.path.join(here, "golden", "channel1024x256_5.npz"))
+    assert int(ref["steps"]) == int(gold["steps"]) == 5 and np.array_equal(ref["crop"], gold["crop"])
+    for key in "uvp":
+        np.testing.assert_array_equal(gold[key + "_crop"], ref[key + "_crop"])
+        assert float(gold[key + "_l2"]) == float(ref[key + "_l2"])
+    assert F(gold["time"]) == F(ref["time"])
