@@ -2,6 +2,7 @@
 
     python tests/golden/make_reference_workload_golden.py ib2048     # ~10 min, ~12 GB peak -> reference_ib2048_3.npz
     python tests/golden/make_reference_workload_golden.py channel    # seconds              -> reference_channel1024x256_5.npz
+    python tests/golden/make_reference_workload_golden.py small64    # seconds              -> reference_small64_50.npz
 
 channel: G3's parity case (jax_ib_b200/configs.py::channel: 1024 x 256, periodic x / no-slip y, van Leer advection, body
 force, Poiseuille + noise start), five steps, the run tests/golden/channel1024x256_5.npz holds from the oracle.  The
@@ -152,8 +153,62 @@ def main_channel():
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB in {time.time() - t_start:.0f} s")
 
 
+def main_small64():
+    """small64_50: the 64 x 64 periodic parity case with one flapping ellipse on the library's own laws, fifty steps."""
+    t_start = time.time()
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, ROOT)
+    from jax_ib_b200 import configs
+    cfg = configs.small_periodic(64)
+    u0, v0, p0 = configs.initial_fields(cfg)
+    gold = np.load(os.path.join(HERE, "small64_50.npz"))
+    steps = int(gold["steps"])
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_standin"))
+    sys.path.insert(0, REF)
+    import jax.numpy as jnp
+    import jax_cfd.base as cfd
+    import jax_ib.base as ib
+    from jax_ib.base import IBM_Force, advection, boundaries, convolution_functions, grids, kinematics as ks, particle_class as pc, particle_motion
+
+    dt = cfg["dt"]
+    grid = grids.Grid(cfg["shape"], domain=cfg["domain"])
+    zero = lambda t: 0.0
+    bc = boundaries.new_periodic_boundary_conditions(ndim=2, bc_vals=((0.0, 0.0), (0.0, 0.0)), bc_fn=[zero] * 4, time_stamp=0.0)
+    v = tuple(grids.GridVariable(grids.GridArray(jnp.asarray(a), off, grid), bc) for a, off in zip((u0, v0), grid.cell_faces))
+    p = grids.GridVariable(grids.GridArray(jnp.asarray(p0), grid.cell_center, grid), boundaries.get_pressure_bc_from_velocity(v))
+    b = cfg["bodies"]
+    shape_fn = lambda geometry_param, theta: tuple(jnp.asarray(a) for a in configs.ellipse_markers(geometry_param, ntheta=b["ntheta"]))
+    particles = pc.particle(jnp.asarray(np.asarray(b["centers"], dtype=F)), jnp.asarray(np.asarray(b["geometry"], dtype=F)),
+                            jnp.asarray(np.asarray(b["displacement_param"], dtype=F)), jnp.asarray(np.asarray(b["rotation_param"], dtype=F)),
+                            pc.Grid1d(2, domain=(0, 2 * np.pi)), shape_fn, ks.displacement, ks.rotation)
+    delta = lambda x, x0, w1: convolution_functions.delta_approx_logistjax(x, x0, w1)
+    surf = lambda field, xp, yp: convolution_functions.new_surf_fn(field, xp, yp, delta)
+    step_fn = cfd.funcutils.repeated(
+        ib.equations.semi_implicit_navier_stokes_timeBC(
+            density=cfg["density"], viscosity=cfg["viscosity"], dt=dt, grid=grid,
+            convect=lambda vv: tuple(advection.advect_upwind(c, vv, dt) for c in vv),
+            pressure_solve=ib.pressure.solve_fast_diag, forcing=None, time_stepper=ib.time_stepping.forward_euler_updated,
+            IBM_forcing=lambda av, dt_: IBM_Force.calc_IBM_force_NEW_MULTIPLE(av, delta, surf, dt_),
+            Updating_Position=particle_motion.Update_particle_position_Multiple, Drag_fn=lambda av, dt_: av),
+        steps=steps)
+    final = step_fn(pc.All_Variables(particles, v, p, [0], 0, [0]))
+    a, b_, c, d = (int(x) for x in gold["crop"])
+    out = {"crop": gold["crop"], "steps": np.int64(final.Step_count), "time": np.asarray(final.velocity[0].bc.time_stamp, dtype=F),
+           "centers": np.asarray(final.particles.particle_center, dtype=F)}
+    for key, var in (("u", final.velocity[0]), ("v", final.velocity[1]), ("p", final.pressure)):
+        full = np.asarray(var.data, dtype=F)
+        out[key + "_crop"] = full[a:b_, c:d]
+        out[key + "_l2"] = np.float64(np.sqrt((full.astype(np.float64) ** 2).sum()))
+    path = os.path.join(HERE, "reference_small64_50.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB in {time.time() - t_start:.0f} s")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["channel", "ib2048"]
+    which = sys.argv[1:] or ["channel", "small64", "ib2048"]
+    if "small64" in which:
+        main_small64()
     if "channel" in which:
         main_channel()
     if "ib2048" in which:

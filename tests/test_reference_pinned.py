@@ -415,3 +415,17 @@ def test_channel_trajectory_fixture_is_bit_identical_to_the_reference_run():
         np.testing.assert_array_equal(gold[key + "_crop"], ref[key + "_crop"])
         assert float(gold[key + "_l2"]) == float(ref[key + "_l2"])
     assert F(gold["time"]) == F(ref["time"])
+
+
+def test_small_periodic_trajectory_fixture_equals_the_reference_run():
+    """small64_50.npz (64 x 64, one flapping ellipse, FIFTY steps -- the longest fixture) against the same run by the
+    reference's files (make_reference_workload_golden.py small64): 1e-7 on the velocities after 50 steps, centre and
+    float32 clock (0.09999994: fifty float32 additions of 2e-3) identical."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = np.load(os.path.join(here, "golden", "reference_small64_50.npz"))
+    gold = np.load(os.path.join(here, "golden", "small64_50.npz"))
+    assert int(ref["steps"]) == int(gold["steps"]) == 50 and np.array_equal(ref["crop"], gold["crop"])
+    for key, bar in (("u", 5e-7), ("v", 5e-7), ("p", 2.0 * float(gold["p_noise"]))):
+        assert rel_l2(gold[key + "_crop"], ref[key + "_crop"]) < bar, key
+    np.testing.assert_array_equal(gold["centers"], ref["centers"])
+    assert F(gold["time"]) == F(ref["time"])
