@@ -1,6 +1,5 @@
 import dataclasses as _dc
 
-import numpy as _np
 
 
 @_dc.dataclass
