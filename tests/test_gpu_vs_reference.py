@@ -230,49 +230,3 @@ def test_two_bodies_on_the_journal_bearing_laws_against_the_reference_files():
     assert rel_l2(host(out.velocity[1].data), GOLD["two_step_v"]) < 1e-5
     assert rel_l2(host(out.pressure.data), GOLD["two_step_p"]) < 1e-4
     np.testing.assert_allclose(np.asarray(out.particles.particle_center), GOLD["two_step_centers"], rtol=0, atol=1e-6)
-
-
-def test_flapping_notebook_twenty_steps_against_the_reference_notebook_run():
-    """Flapping_Demo.ipynb as published (600 x 600, 298 markers, upwind, dt = 5e-4) for 20 steps through the reference-shaped
-    API, against what the NOTEBOOK ITSELF produced when its code cells were executed on the stand-in
-    (tests/golden/make_reference_notebook_golden.py; dense marker sums there).  Bars as for the oracle's fixture of
-    the same run: max(1e-5, 2 x the float32 round-off floor of this trajectory)."""
-    from test_dropin_api import flapping_setup
-    here = os.path.dirname(os.path.abspath(__file__))
-    nb = np.load(os.path.join(here, "golden", "reference_notebook_flap600.npz"))
-    floor = np.load(os.path.join(here, "golden", "flap600_20.npz"))
-    step_fn, all_variables = flapping_setup()
-    final, traj = funcutils.trajectory(funcutils.repeated(step_fn, steps=10), 2, start_with_input=True)(all_variables)
-    assert final.Step_count == int(nb["steps"]) and [t.Step_count for t in traj] == list(nb["snapshot_steps"])
-    a, b, c, d = (int(x) for x in nb["crop"])
-    for key, var in (("u", final.velocity[0]), ("v", final.velocity[1]), ("p", final.pressure)):
-        # + 2e-6: two float32 evaluations of the same dense run (the notebook on the stand-in, the oracle) already differ
-        # by 1e-7 (u, v) to 8e-7 (p), tests/test_reference_pinned.py::test_oracle_trajectory_fixture_equals_...
-        bar = max(1e-5, 2.0 * float(floor[key + "_noise"])) + 2e-6
-        assert rel_l2(host(var.data)[a:b, c:d], nb[key + "_crop"]) < bar, key
-    np.testing.assert_allclose(np.asarray(final.particles.particle_center), nb["centers"], atol=2e-6)
-    assert F(final.velocity[0].bc.time_stamp) == F(nb["time"])
-
-
-def test_bench_workload_three_steps_against_the_reference_files():
-    """ib2048 -- what bench.py times -- through the fused path for three steps, against the same three steps taken by the
-    reference's own files with DENSE marker sums (tests/golden/make_reference_workload_golden.py; the oracle agrees with
-    that run to 6e-8 .. 2e-7, tests/test_reference_pinned.py).  Only crops around the four bodies, 64 x 64 block means,
-    norms, centres and clock of the reference run are stored (the full fields are 50 MB).  Bars: block means of the
-    whole field 1e-5 (the north star); the crops isolate the region where the immersed-boundary forcing acts and are
-    normalised by their own, smaller norm: 2e-5; the pressure carries the solver's round-off (float32 against float64
-    for this trajectory: 1.1e-5 full field, 1.2e-5 on the crops): 2e-5 / 3e-5; norms 1e-5."""
-    from jax_ib_b200 import configs, demo
-    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_ib2048_3.npz"))
-    cfg = configs.ib_periodic(2048, 2)
-    out = demo.make_stepper(cfg).advance(demo.make_all_variables(cfg, device="cuda"), int(ref["steps"]))
-    for key, var in (("u", out.velocity[0]), ("v", out.velocity[1]), ("p", out.pressure)):
-        full = host(var.data)
-        crops = np.stack([full[a:b, c:d] for a, b, c, d in ref["boxes"]])
-        assert rel_l2(crops, ref[key + "_crops"]) < (3e-5 if key == "p" else 2e-5), key
-        blocks = full.astype(np.float64).reshape(64, 32, 64, 32).mean(axis=(1, 3))
-        assert rel_l2(blocks, ref[key + "_blocks"]) < (2e-5 if key == "p" else 1e-5), key
-        assert float(np.sqrt((full.astype(np.float64) ** 2).sum())) == pytest.approx(float(ref[key + "_l2"]), rel=1e-5)
-    np.testing.assert_allclose(np.asarray(out.particles.particle_center), ref["centers"], rtol=0, atol=2e-6)
-    assert F(out.velocity[0].bc.time_stamp) == F(ref["time"])
-    assert out.Step_count == int(ref["steps"])
