@@ -6,7 +6,8 @@ Part 1: 24 random cases over 6 grid shapes (odd sizes included), shifted domain 
 wall values, field scales 0.01 / 1 / 30, a zero component, dt from 1e-4 to 2e-2: the three advection schemes, laplacian
 and divergence must be BIT-IDENTICAL, the three pressure solves within 2e-5.  Part 2: 10 random immersed-body cases (1-3
 bodies anywhere, including across the domain edge; anisotropic cells; random harmonic laws and time stamps): the oracle's
-dense and windowed forces against the reference's dense sums, bar 1e-5."""
+dense and windowed forces against the reference's dense sums, bar 1e-5.  Part 3: 12 random penalty masks (ellipse tables,
+centres, smoothing constants) and 12 x 300 tracer sample points (inside, on the edges, outside; shifted origins): bit-identical."""
 import os
 import sys
 
@@ -98,4 +99,32 @@ for trial in range(10):
     worst=max(worst,e,ew)
     print(trial,(nx,ny),nb,"dense",e,"windowed R=%d"%R_eff,ew)
 print("immersed bodies: worst rel-L2", worst)
-sys.exit(1 if (bad or not worst < 1e-5) else 0)
+
+# ---------------------------------------------------------------- part 3: penalty mask, tracer sampling (bit-identical)
+from oracle import penalty, tracers
+rng=np.random.default_rng(5)
+bad3=0
+for trial in range(12):
+    nx,ny=[(40,36),(33,48),(64,64)][trial%3]
+    dom=((float(rng.uniform(-1,1)),),(float(rng.uniform(-1,1)),)); dom=((dom[0][0],dom[0][0]+rng.uniform(1,3)),(dom[1][0],dom[1][0]+rng.uniform(1,3)))
+    grid=R.grids.Grid((nx,ny),domain=dom); og=field.Grid((nx,ny),dom)
+    n=int(rng.integers(20,90)); theta=np.linspace(0,2*np.pi,n).astype(F)
+    a,b=float(rng.uniform(0.2,0.6)),float(rng.uniform(0.1,0.3))
+    Rth=np.asarray(R.parameteric_fns.param_ellipse([a,b],jnp.asarray(theta)))
+    c=(float(rng.uniform(*dom[0])),float(rng.uniform(*dom[1])))
+    know=(float(rng.uniform(100,5000)),float(rng.uniform(0.005,0.05)))
+    smooth=lambda G_,K: K[0]/2.0*(1.0+jnp.tanh(G_/K[1]))
+    with np.errstate(all="ignore"):
+        ref=np.asarray(R.util_funs.calc_perm(grid,c,jnp.asarray(Rth),smooth,know))
+        got=penalty.calc_perm(og,c,Rth,penalty.tanh_smoothing,know)
+    if not np.array_equal(ref,got,equal_nan=True):
+        bad3+=1; print("perm mismatch",trial,np.nanmax(np.abs(ref-got)))
+    u=rng.standard_normal((nx,ny)).astype(F)
+    U=R.grids.GridVariable(R.grids.GridArray(jnp.asarray(u),(1.0,.5),grid),R.boundaries.periodic_boundary_conditions(2))
+    pts=np.stack([rng.uniform(dom[0][0]-0.2,dom[0][1]+0.2,300),rng.uniform(dom[1][0]-0.2,dom[1][1]+0.2,300)],1).astype(F)
+    ref=np.asarray(R.CFD_MD_coupling.interpolate_pbc(U,jnp.asarray(pts)))
+    got=tracers.interpolate_field(field.Var(u,(1.0,.5),og,field.periodic_bc()),pts)
+    if not np.array_equal(ref,got):
+        bad3+=1; print("sample mismatch",trial,np.abs(ref-got).max())
+print("penalty mask and tracer sampling: mismatches:", bad3)
+sys.exit(1 if (bad or bad3 or not worst < 1e-5) else 0)
